@@ -1,0 +1,226 @@
+"""oracle/port.py — TEST INFRASTRUCTURE ONLY: ctypes view of oracle/libvs_oracle.so.
+
+libvs_oracle.so is the plain-C restatement (oracle/vs_oracle.c) of the reference's CPU algorithm for
+the flat top-K / range / batch-iterator path. Only tests/, bench.py's cpu_baseline leg and
+__graft_entry__.smoke() may import this module; the product path never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvs_oracle.so")
+
+FLOAT32, FLOAT64, BFLOAT16, FLOAT16, INT8, UINT8 = range(6)
+L2, IP, COSINE = range(3)
+BY_SCORE, BY_ID = 0, 1
+TIER_AVX512, TIER_AVX512_NOBF16, TIER_NAIVE = range(3)
+
+NP_DTYPE = {FLOAT32: np.float32, FLOAT64: np.float64, BFLOAT16: np.uint16, FLOAT16: np.float16,
+            INT8: np.int8, UINT8: np.uint8}
+
+_lib = None
+
+
+def build():
+    """Compile the C restatement (gcc only; no reference sources involved)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "port"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        vp, sz, i32, dbl = C.c_void_p, C.c_size_t, C.c_int, C.c_double
+        L.vso_set_tier.argtypes = [i32]
+        L.vso_stored_size.restype = sz
+        L.vso_stored_size.argtypes = [i32, i32, sz]
+        L.vso_distance.restype = dbl
+        L.vso_distance.argtypes = [i32, i32, sz, vp, vp]
+        L.vso_normalize.argtypes = [i32, sz, vp]
+        L.vso_f32_to_bf16.restype = C.c_uint16
+        L.vso_f32_to_bf16.argtypes = [C.c_float]
+        L.vso_bf16_to_f32.restype = C.c_float
+        L.vso_bf16_to_f32.argtypes = [C.c_uint16]
+        L.vso_f32_to_fp16.restype = C.c_uint16
+        L.vso_f32_to_fp16.argtypes = [C.c_float]
+        L.vso_fp16_to_f32.restype = C.c_float
+        L.vso_fp16_to_f32.argtypes = [C.c_uint16]
+        L.vso_flat_new.restype = vp
+        L.vso_flat_new.argtypes = [i32, sz, i32, i32, sz]
+        L.vso_flat_free.argtypes = [vp]
+        L.vso_flat_add.argtypes = [vp, vp, sz]
+        L.vso_flat_delete.argtypes = [vp, sz]
+        L.vso_flat_size.restype = sz
+        L.vso_flat_size.argtypes = [vp]
+        L.vso_flat_label_count.restype = sz
+        L.vso_flat_label_count.argtypes = [vp]
+        L.vso_flat_row.restype = vp
+        L.vso_flat_row.argtypes = [vp, sz]
+        L.vso_flat_label_of.restype = sz
+        L.vso_flat_label_of.argtypes = [vp, sz]
+        L.vso_flat_topk.restype = sz
+        L.vso_flat_topk.argtypes = [vp, vp, sz, i32, i32, vp, vp, C.POINTER(i32)]
+        L.vso_flat_range.restype = C.c_long
+        L.vso_flat_range.argtypes = [vp, vp, dbl, i32, i32, sz, vp, vp, C.POINTER(i32)]
+        L.vso_flat_distance_from.restype = dbl
+        L.vso_flat_distance_from.argtypes = [vp, sz, vp]
+        L.vso_bi_new.restype = vp
+        L.vso_bi_new.argtypes = [vp, vp]
+        L.vso_bi_next.restype = sz
+        L.vso_bi_next.argtypes = [vp, sz, i32, vp, vp, C.POINTER(i32)]
+        L.vso_bi_has_next.argtypes = [vp]
+        L.vso_bi_reset.argtypes = [vp]
+        L.vso_bi_free.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def set_tier(tier):
+    lib().vso_set_tier(tier)
+
+
+def stored_size(vtype, metric, dim):
+    return lib().vso_stored_size(vtype, metric, dim)
+
+
+def distance(vtype, metric, a, b, dim=None):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    if dim is None:
+        dim = a.size
+    return lib().vso_distance(vtype, metric, dim, _ptr(a), _ptr(b))
+
+
+def distance_many(vtype, metric, dim, A, B):
+    A = np.ascontiguousarray(A)
+    B = np.ascontiguousarray(B)
+    L = lib()
+    out = np.empty(A.shape[0], dtype=np.float64)
+    for i in range(A.shape[0]):
+        out[i] = L.vso_distance(vtype, metric, dim, A[i].ctypes.data, B[i].ctypes.data)
+    return out
+
+
+def normalize(vtype, dim, blob):
+    lib().vso_normalize(vtype, dim, _ptr(blob))
+    return blob
+
+
+def to_bf16(x):
+    """float32 array -> uint16 bf16 bits, round-to-nearest-even (types/bfloat16.h:23-30)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    u = u + (((u >> 16) & 1) + 0x7FFF)
+    return (u >> 16).astype(np.uint16)
+
+
+def from_bf16(h):
+    return (np.ascontiguousarray(h, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+class PortIndex:
+    def __init__(self, vtype, dim, metric, multi=False, block_size=1024):
+        self.vtype, self.dim, self.metric = vtype, dim, metric
+        self.h = lib().vso_flat_new(vtype, dim, metric, int(multi), block_size)
+
+    def close(self):
+        if self.h:
+            lib().vso_flat_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, blob, label):
+        blob = np.ascontiguousarray(blob)
+        return lib().vso_flat_add(self.h, _ptr(blob), label)
+
+    def add_many(self, blobs, labels=None, first_label=0):
+        blobs = np.ascontiguousarray(blobs)
+        L = lib()
+        n = 0
+        for i in range(blobs.shape[0]):
+            n += L.vso_flat_add(self.h, blobs[i].ctypes.data,
+                                int(labels[i]) if labels is not None else first_label + i)
+        return n
+
+    def delete(self, label):
+        return lib().vso_flat_delete(self.h, label)
+
+    def size(self):
+        return lib().vso_flat_size(self.h)
+
+    def distance_from(self, label, blob):
+        blob = np.ascontiguousarray(blob)
+        return lib().vso_flat_distance_from(self.h, label, _ptr(blob))
+
+    def stored_rows(self):
+        """(n x stored_bytes) uint8 copy of the processed rows + labels, in internal-id order."""
+        n = self.size()
+        sb = stored_size(self.vtype, self.metric, self.dim)
+        rows = np.empty((n, sb), dtype=np.uint8)
+        labels = np.empty(n, dtype=np.uint64)
+        L = lib()
+        for i in range(n):
+            C.memmove(rows[i].ctypes.data, L.vso_flat_row(self.h, i), sb)
+            labels[i] = L.vso_flat_label_of(self.h, i)
+        return rows, labels
+
+    def topk(self, q, k, order=BY_SCORE, timeout=0):
+        q = np.ascontiguousarray(q)
+        labels = np.empty(max(k, 1), dtype=np.uint64)
+        scores = np.empty(max(k, 1), dtype=np.float64)
+        code = C.c_int()
+        n = lib().vso_flat_topk(self.h, _ptr(q), k, order, timeout, _ptr(labels), _ptr(scores),
+                                C.byref(code))
+        return labels[:n].copy(), scores[:n].copy(), code.value
+
+    def range(self, q, radius, order=BY_SCORE, timeout=0):
+        q = np.ascontiguousarray(q)
+        cap = max(self.size(), 1)
+        labels = np.empty(cap, dtype=np.uint64)
+        scores = np.empty(cap, dtype=np.float64)
+        code = C.c_int()
+        n = lib().vso_flat_range(self.h, _ptr(q), float(radius), order, timeout, cap, _ptr(labels),
+                                 _ptr(scores), C.byref(code))
+        if n < 0:
+            raise RuntimeError("rangeQuery: invalid radius / order")
+        return labels[:n].copy(), scores[:n].copy(), code.value
+
+    def batch_iterator(self, q):
+        return PortBatchIterator(self, q)
+
+
+class PortBatchIterator:
+    def __init__(self, index, q):
+        q = np.ascontiguousarray(q)
+        self.index = index
+        self.it = lib().vso_bi_new(index.h, _ptr(q))
+
+    def next(self, n, order=BY_SCORE):
+        labels = np.empty(max(n, 1), dtype=np.uint64)
+        scores = np.empty(max(n, 1), dtype=np.float64)
+        code = C.c_int()
+        m = lib().vso_bi_next(self.it, n, order, _ptr(labels), _ptr(scores), C.byref(code))
+        return labels[:m].copy(), scores[:m].copy(), code.value
+
+    def has_next(self):
+        return bool(lib().vso_bi_has_next(self.it))
+
+    def reset(self):
+        lib().vso_bi_reset(self.it)
+
+    def close(self):
+        if self.it:
+            lib().vso_bi_free(self.it)
+            self.it = None

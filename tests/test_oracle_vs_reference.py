@@ -1,0 +1,188 @@
+"""Pins the C restatement (oracle/vs_oracle.c) against the UNMODIFIED reference (oracle/_ref),
+bit for bit. Mirrors the reference's own strategy of walking the dispatcher down tier by tier
+(tests/unit/test_spaces.cpp:703-709) by masking CPU feature bits."""
+import numpy as np
+import pytest
+
+from datagen import (BFLOAT16, COSINE, FLOAT16, FLOAT32, FLOAT64, INT8, IP, L2, METRIC_NAMES,
+                     TYPE_NAMES, UINT8, make_vectors)
+
+ALL_SIMD = ["sse", "sse3", "sse4_1", "avx", "avx2", "fma3", "f16c", "avx512f", "avx512bw",
+            "avx512vl", "avx512vnni", "avx512vbmi2", "avx512_bf16", "avx512_fp16"]
+NEEDED = {"avx512f", "avx512bw", "avx512vl", "avx512vnni", "avx512vbmi2", "fma3", "f16c"}
+
+
+def _processed(port, vtype, metric, dim, raw):
+    """raw caller blob -> processed blob as the index would store/query it."""
+    if metric == COSINE:
+        if vtype in (INT8, UINT8):
+            b = np.zeros(dim + 4, dtype=np.uint8)
+            b[:dim] = raw.view(np.uint8)
+            port.normalize(vtype, dim, b)
+            return b
+        b = raw.copy()
+        port.normalize(vtype, dim, b)
+        return b
+    return raw
+
+
+DIMS = list(range(1, 100)) + [127, 128, 129, 255, 256, 512, 768, 777, 1000, 1024]
+
+
+@pytest.mark.parametrize("vtype", range(6), ids=TYPE_NAMES)
+@pytest.mark.parametrize("metric", range(3), ids=METRIC_NAMES)
+@pytest.mark.parametrize("tier", ["avx512", "avx512_nobf16", "naive"])
+def test_distance_bit_exact(ref, port, vtype, metric, tier):
+    feats = set(ref.host_features())
+    if tier != "naive" and not NEEDED <= feats:
+        pytest.skip("host lacks the AVX512 feature set the restated tier models")
+    if tier == "avx512":
+        if vtype == BFLOAT16 and "avx512_bf16" not in feats:
+            pytest.skip("no avx512_bf16 on this host")
+        ref.set_disabled_features("avx512_fp16")
+        port.set_tier(port.TIER_AVX512)
+    elif tier == "avx512_nobf16":
+        ref.set_disabled_features("avx512_fp16", "avx512_bf16")
+        port.set_tier(port.TIER_AVX512_NOBF16)
+    else:
+        ref.set_disabled_features(*ALL_SIMD)
+        port.set_tier(port.TIER_NAIVE)
+    try:
+        bad = []
+        for dim in DIMS:
+            A = make_vectors(vtype, 4, dim, seed=dim * 7 + vtype)
+            B = make_vectors(vtype, 4, dim, seed=dim * 13 + metric + 1000)
+            for i in range(4):
+                a = _processed(port, vtype, metric, dim, A[i])
+                b = _processed(port, vtype, metric, dim, B[i])
+                r = ref.distance(vtype, metric, a, b, dim)
+                p = port.distance(vtype, metric, a, b, dim)
+                if not (r == p or (np.isnan(r) and np.isnan(p))):
+                    bad.append((dim, r, p))
+        assert not bad, bad[:5]
+    finally:
+        ref.set_disabled_features()
+        port.set_tier(port.TIER_AVX512)
+
+
+@pytest.mark.parametrize("vtype", range(6), ids=TYPE_NAMES)
+def test_normalize_bit_exact(ref, port, vtype):
+    for dim in [1, 3, 4, 17, 128, 513]:
+        raw = make_vectors(vtype, 3, dim, seed=dim + 5)
+        for i in range(3):
+            if vtype in (INT8, UINT8):
+                a = np.zeros(dim + 4, dtype=np.uint8)
+                a[:dim] = raw[i].view(np.uint8)
+            else:
+                a = raw[i].copy()
+            b = a.copy()
+            ref.normalize(vtype, dim, a)
+            port.normalize(vtype, dim, b)
+            assert a.tobytes() == b.tobytes()
+
+
+def _flat_pair(ref, port, vtype, dim, metric, n, seed, block_size=1024, labels=None, dist="uniform"):
+    X = make_vectors(vtype, n, dim, seed, dist)
+    R = ref.RefIndex(vtype, dim, metric, block_size=block_size)
+    P = port.PortIndex(vtype, dim, metric, block_size=block_size)
+    R.add_many(X, labels=labels)
+    P.add_many(X, labels=labels)
+    return X, R, P
+
+
+@pytest.mark.parametrize("vtype", range(6), ids=TYPE_NAMES)
+@pytest.mark.parametrize("metric", range(3), ids=METRIC_NAMES)
+def test_flat_topk_range_identical(ref, port, vtype, metric):
+    feats = set(ref.host_features())
+    if not NEEDED <= feats or (vtype == BFLOAT16 and "avx512_bf16" not in feats):
+        pytest.skip("host lacks the modelled AVX512 tier")
+    ref.set_disabled_features("avx512_fp16")
+    try:
+        for dim, n, k in [(4, 300, 11), (33, 500, 10), (128, 1000, 100)]:
+            X, R, P = _flat_pair(ref, port, vtype, dim, metric, n, seed=n + dim)
+            Q = make_vectors(vtype, 5, dim, seed=99 + dim)
+            for q in Q:
+                for order in (0, 1):
+                    rl, rs, rc = R.topk(q, k, order)
+                    pl, ps, pc = P.topk(q, k, order)
+                    assert rc == pc == 0
+                    assert np.array_equal(rl, pl)
+                    assert np.array_equal(rs, ps)
+                # a radius that catches ~5% of the rows
+                _, allscores, _ = P.topk(q, n)
+                radius = float(allscores[n // 20])
+                if radius >= 0:
+                    rl, rs, _ = R.range(q, radius, 1)
+                    pl, ps, _ = P.range(q, radius, 1)
+                    assert np.array_equal(rl, pl) and np.array_equal(rs, ps)
+                    rl, rs, _ = R.range(q, radius, 0)
+                    pl, ps, _ = P.range(q, radius, 0)
+                    assert np.array_equal(rs, ps)
+                    assert sorted(rl.tolist()) == sorted(pl.tolist())
+            R.close()
+            P.close()
+    finally:
+        ref.set_disabled_features()
+
+
+def test_flat_ties_shuffled_labels(ref, port):
+    """int8 L2 on tiny dims gives surplus ties at the k-th score; with shuffled
+    labels the result depends on scan order AND labels. 200 random trials."""
+    rng = np.random.default_rng(7)
+    for trial in range(200):
+        n, dim, k = int(rng.integers(20, 120)), int(rng.integers(1, 4)), int(rng.integers(1, 30))
+        X = rng.integers(-3, 4, (n, dim)).astype(np.int8)
+        labels = rng.permutation(n * 3)[:n].astype(np.uint64)
+        R = ref.RefIndex(INT8, dim, L2, block_size=7)
+        P = port.PortIndex(INT8, dim, L2, block_size=7)
+        R.add_many(X, labels=labels)
+        P.add_many(X, labels=labels)
+        # a few deletes: swap-with-last changes the scan order
+        for lab in labels[: n // 5]:
+            assert R.delete(int(lab)) == P.delete(int(lab)) == 1
+        q = rng.integers(-3, 4, dim).astype(np.int8)
+        rl, rs, _ = R.topk(q, k)
+        pl, ps, _ = P.topk(q, k)
+        assert np.array_equal(rl, pl), trial
+        assert np.array_equal(rs, ps), trial
+        R.close()
+        P.close()
+
+
+def test_batch_iterator_matches_up_to_ties(ref, port):
+    n, dim = 500, 8
+    X, R, P = _flat_pair(ref, port, FLOAT32, dim, L2, n, seed=3, dist="grid")
+    q = make_vectors(FLOAT32, 1, dim, seed=4, dist="grid")[0]
+    ri, pi = R.batch_iterator(q), P.batch_iterator(q)
+    seen_r, seen_p = [], []
+    while ri.has_next():
+        assert pi.has_next()
+        rl, rs, _ = ri.next(37)
+        pl, ps, _ = pi.next(37)
+        assert np.array_equal(rs, ps)          # score sequence identical
+        seen_r += rl.tolist()
+        seen_p += pl.tolist()
+        # label sets may differ only inside the boundary tie group: compare via scores of labels
+    assert not pi.has_next()
+    assert sorted(seen_r) == sorted(seen_p) == list(range(n))
+    ri.close()
+    pi.close()
+
+
+def test_timeout_and_range_errors(ref, port):
+    X, R, P = _flat_pair(ref, port, FLOAT32, 4, L2, 50, seed=1)
+    q = X[0]
+    ref.set_timeout(1)
+    try:
+        rl, rs, rc = R.topk(q, 5)
+        rrl, _, rrc = R.range(q, 1.0)
+    finally:
+        ref.set_timeout(0)
+    pl, ps, pc = P.topk(q, 5, timeout=1)
+    prl, _, prc = P.range(q, 1.0, timeout=1)
+    assert rc == pc == 1 and len(rl) == len(pl) == 0
+    assert rrc == prc == 1 and len(rrl) == len(prl) == 0
+    with pytest.raises(RuntimeError):
+        R.range(q, -1.0)
+    with pytest.raises(RuntimeError):
+        P.range(q, -1.0)
