@@ -1,0 +1,126 @@
+/* include/vsgpu.h — the thin C-ABI between the host index code and the sm_100a CUDA kernels
+ * (libvsgpu.so). Plain pointers and sizes only; no C++/torch types cross this line.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference/src/VecSim):
+ *   vsgpu_store_*      containers/data_blocks_container.{h,cpp} + data_block.{h,cpp}: the
+ *                      "VectorBlock" store (addElement :30-39, updateElement, removeElement :41-56)
+ *                      and the idToLabelMapping of algorithms/brute_force/brute_force.h:35,174-224.
+ *   vsgpu_topk         the scan + max-heap loop of BruteForceIndex::topKQuery
+ *                      (algorithms/brute_force/brute_force.h:262-288), for a batch of queries.
+ *   vsgpu_range        BruteForceIndex::rangeQuery's scan (brute_force.h:304-321).
+ *   vsgpu_scores       BFS_BatchIterator::calculateScores (bfs_batch_iterator.h:24-41).
+ *   vsgpu_distances    calcDistance over chosen ids (vec_sim_index.h:175-190) — ad-hoc BF and
+ *                      getDistanceFrom_Unsafe (brute_force_single.h:200-212).
+ *   vsgpu_hnsw_*       HNSWIndex::topKQuery's traversal (algorithms/hnsw/hnsw.h:530-613,
+ *                      1210-1258, 1967-2084) over a graph built on the host.
+ * Distances reproduce the reference's x86 AVX512 dispatch tier bit for bit.
+ *
+ * All functions return VSGPU_OK (0) or a negative error; vsgpu_last_error() gives the text.
+ * A store is bound to one device and one stream; calls on one store must be serialised by the
+ * caller (the host index holds a mutex), different stores are independent.
+ */
+#ifndef VSGPU_H
+#define VSGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* numbering = VecSimType / VecSimMetric (vec_sim_common.h:60-69,84-88) */
+enum { VSGPU_FLOAT32 = 0, VSGPU_FLOAT64 = 1, VSGPU_BFLOAT16 = 2, VSGPU_FLOAT16 = 3, VSGPU_INT8 = 4, VSGPU_UINT8 = 5 };
+enum { VSGPU_L2 = 0, VSGPU_IP = 1, VSGPU_COSINE = 2 };
+
+enum {
+    VSGPU_OK = 0,
+    VSGPU_ERR_CUDA = -1,     /* a CUDA call failed */
+    VSGPU_ERR_ARG = -2,      /* bad argument */
+    VSGPU_ERR_NOMEM = -3,    /* device allocation failed */
+    VSGPU_ERR_NODEVICE = -4, /* no usable sm_100 device */
+    VSGPU_ERR_OVERFLOW = -5  /* caller's output buffer too small (range query) */
+};
+
+/* vsgpu_topk flags */
+enum {
+    VSGPU_TOPK_AUTO = 0,       /* tensor-core coarse pass + exact re-rank when the shape allows */
+    VSGPU_TOPK_EXACT_ONLY = 1, /* force the exact SIMT scan */
+    VSGPU_TOPK_TENSOR_ONLY = 2 /* fail instead of falling back (tests / benchmarks) */
+};
+
+typedef struct vsgpu_store vsgpu_store;
+
+const char *vsgpu_last_error(void);
+int vsgpu_device_count(void);
+/* free / total bytes of HBM on `device` */
+int vsgpu_mem_info(int device, size_t *free_bytes, size_t *total_bytes);
+
+/* A store holds processed rows (what the reference keeps in its DataBlocks): dim elements of
+ * `type`, plus — for int8/uint8 cosine — the fp32 norm that the reference appends to the blob.
+ * `capacity_hint` rows are reserved up front (0 = grow on demand). */
+vsgpu_store *vsgpu_store_create(int device, int type, int metric, size_t dim, size_t capacity_hint);
+void vsgpu_store_destroy(vsgpu_store *s);
+size_t vsgpu_store_size(const vsgpu_store *s);
+size_t vsgpu_store_row_bytes(const vsgpu_store *s); /* = VecSimParams_GetStoredDataSize */
+size_t vsgpu_store_device_bytes(const vsgpu_store *s);
+
+/* Append n processed rows from HOST memory (`stride` bytes apart) with their labels. */
+int vsgpu_store_append(vsgpu_store *s, const void *rows, size_t stride, const uint64_t *labels, size_t n);
+/* Same, rows and labels already in DEVICE memory of the store's device (bulk loaders). For
+ * int8/uint8 cosine `norms` (device, fp32) replaces the appended norm; NULL = compute on device. */
+int vsgpu_store_append_device(vsgpu_store *s, const void *rows, size_t stride, const uint64_t *labels,
+                              const float *norms, size_t n);
+/* Overwrite row `id` (label update in place). */
+int vsgpu_store_update(vsgpu_store *s, size_t id, const void *row, uint64_t label);
+/* Delete-by-swap (brute_force.h:195-224): row `src` (the last one) moves to `dst`; count -= 1. */
+int vsgpu_store_remove_swap(vsgpu_store *s, size_t dst);
+/* Copy rows back to the host (tests, serialisation). */
+int vsgpu_store_read(const vsgpu_store *s, size_t first, size_t n, void *rows, size_t stride, uint64_t *labels);
+
+/* Batched top-k. `queries`: nq processed query blobs in HOST memory, `qstride` bytes apart.
+ * Outputs (HOST, any may be NULL): [nq][k] row-major, padded with label=UINT64_MAX/score=NaN/
+ * id=UINT32_MAX; out_counts[q] = number of valid entries = min(k, size).
+ * Order: ascending (score, internal id). With labels that grow with the internal id this IS the
+ * reference's result order; the host index resolves the general tie rule from out_ids. */
+int vsgpu_topk(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k, unsigned flags,
+               uint64_t *out_labels, double *out_scores, uint32_t *out_ids, uint32_t *out_counts);
+/* Same with queries and outputs in DEVICE memory (scores as the index's DistType widened to
+ * double is a host concern: here fp32, or fp64 for FLOAT64 stores, in `out_scores`). Work is
+ * enqueued on the store's stream; call vsgpu_store_sync before reading. */
+int vsgpu_topk_device(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k,
+                      unsigned flags, uint64_t *out_labels, void *out_scores, uint32_t *out_ids);
+int vsgpu_store_sync(vsgpu_store *s);
+void *vsgpu_store_stream(vsgpu_store *s); /* cudaStream_t */
+
+/* Range scan for ONE query: every row with score <= radius (already cast to the DistType by the
+ * caller). Unordered. Returns VSGPU_ERR_OVERFLOW and sets *out_count to the needed capacity when
+ * `cap` is too small. */
+int vsgpu_range(vsgpu_store *s, const void *query, double radius, size_t cap, uint64_t *out_labels,
+                double *out_scores, uint32_t *out_ids, size_t *out_count);
+/* All scores of ONE query, by internal id (out_scores: size() doubles, HOST). */
+int vsgpu_scores(vsgpu_store *s, const void *query, double *out_scores);
+/* Scores of chosen rows (ids: HOST). */
+int vsgpu_distances(vsgpu_store *s, const void *query, const uint32_t *ids, size_t n, double *out_scores);
+
+/* Counters of the last vsgpu_topk call on this store (for benchmarks and tests). */
+typedef struct {
+    uint32_t path;            /* 0 exact scan, 1 tensor coarse + re-rank */
+    uint32_t kernel_launches; /* kernels launched by the call */
+    uint64_t candidates;      /* rows re-ranked exactly (tensor path) */
+    uint32_t fallback_queries;/* queries redone on the exact path (candidate overflow) */
+    float scan_ms;            /* device time of the dominant scan kernel(s), CUDA events */
+    float total_ms;           /* device time of the whole call */
+} vsgpu_stats;
+int vsgpu_last_stats(const vsgpu_store *s, vsgpu_stats *out);
+
+/* Merge per-shard top-k lists (DEVICE memory): `parts` lists of [nq][k] (score fp32/fp64, label)
+ * laid out part-major, into [nq][k] by ascending (score, label). Used after the all-gather of the
+ * sharded flat index. dtype_f64 != 0 for FLOAT64 indexes. */
+int vsgpu_merge_topk_device(int device, void *stream, int dtype_f64, size_t parts, size_t nq, size_t k,
+                            const void *scores, const uint64_t *labels, void *out_scores,
+                            uint64_t *out_labels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,117 @@
+"""CPU-only checks of the product's host side: the C-ABI libraries load and export every symbol the
+headers declare, fail loudly without a device, and the tie-resolution logic that
+turns the device's (score, id)-ordered candidates into the reference's reply matches the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from vectorsimilarity_b200 import build, capi as c
+    build.build()
+    c.lib()
+    return c
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:VecSim|vsgpu_)[A-Za-z0-9_]*)\s*\(", src)) - {"VecSim_OK"})
+
+
+def test_vecsim_header_symbols_exported(capi):
+    L = capi.lib()
+    names = _declared("vecsim_b200.h")
+    assert len(names) > 50
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(capi.EXPORTS) == sorted(names)
+
+
+def test_vsgpu_header_symbols_exported(capi):
+    G = C.CDLL(os.path.join(ROOT, "vectorsimilarity_b200", "libvsgpu.so"))
+    names = _declared("vsgpu.h")
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(G, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    p = capi.BFParams(type=0, dim=4, metric=0, multi=False, initialCapacity=0, blockSize=0)
+    with pytest.raises(RuntimeError, match="no such CUDA device|NULL"):
+        capi.BFIndex(p)
+
+
+def test_product_does_not_touch_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "vectorsimilarity_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "vs_oracle" not in text and "libvecsim_ref" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_blob_sizes_and_normalize_match_oracle(capi, port):
+    L = capi.lib()
+    rng = np.random.default_rng(3)
+    for vtype in range(6):
+        for metric in range(3):
+            for dim in (1, 7, 128, 513):
+                assert L.VecSimParams_GetQueryBlobSize(vtype, dim, metric) == port.stored_size(vtype, metric, dim)
+    from datagen import make_vectors
+    for vtype in range(6):
+        for dim in (3, 16, 100):
+            raw = make_vectors(vtype, 2, dim, seed=dim)
+            for i in range(2):
+                if vtype in (4, 5):
+                    a = np.zeros(dim + 4, dtype=np.uint8)
+                    a[:dim] = raw[i].view(np.uint8)
+                else:
+                    a = raw[i].copy()
+                b = a.copy()
+                capi.normalize(a, dim, vtype)
+                port.normalize(vtype, dim, b)
+                assert a.tobytes() == b.tobytes()
+
+
+def test_tie_resolution_matches_oracle(capi, port):
+    """Feed the host resolver what the device would return — the min(2k, n) best rows by
+    (score, internal id) — and compare with the oracle's sequential heap scan."""
+    L = capi.lib()
+    L.vsb_test_resolve.restype = C.c_size_t
+    L.vsb_test_resolve.argtypes = [C.c_void_p] * 3 + [C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        n, dim, k = int(rng.integers(5, 150)), int(rng.integers(1, 4)), int(rng.integers(1, 40))
+        X = rng.integers(-2, 3, (n, dim)).astype(np.int8)
+        labels = rng.permutation(n * 4)[:n].astype(np.uint64)
+        q = rng.integers(-2, 3, dim).astype(np.int8)
+        P = port.PortIndex(4, dim, 0)
+        P.add_many(X, labels=labels)
+        want_l, want_s, _ = P.topk(q, k)
+        P.close()
+        scores = ((X.astype(np.int64) - q.astype(np.int64)) ** 2).sum(1).astype(np.float64)
+        order = np.lexsort((np.arange(n), scores))          # ascending (score, id)
+        k_sel = n if k > n // 2 else min(2 * k, n)
+        sel = order[:k_sel]
+        cl = np.ascontiguousarray(labels[sel])
+        cs = np.ascontiguousarray(scores[sel])
+        ci = np.ascontiguousarray(sel.astype(np.uint32))
+        out_l = np.empty(max(k, 1), dtype=np.uint64)
+        out_s = np.empty(max(k, 1), dtype=np.float64)
+        m = L.vsb_test_resolve(cl.ctypes.data, cs.ctypes.data, ci.ctypes.data, k_sel, k, out_l.ctypes.data,
+                               out_s.ctypes.data)
+        assert m == len(want_l), trial
+        assert np.array_equal(out_l[:m], want_l), trial
+        assert np.array_equal(out_s[:m], want_s), trial

@@ -1,0 +1,296 @@
+// extern "C" surface of libvecsim_b200.so: the reference's VecSimIndex_* / VecSimQueryReply_* /
+// VecSimBatchIterator_* entry points (see include/vecsim_b200.h for the file:line each replaces)
+// plus the batched / GPU additions. Thin: argument checks, ordering, object lifetime.
+#include "vecsim_index.h"
+#include "vecsim_numeric.h"
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <strings.h>
+
+// ABI pins, measured from the reference headers with g++ 13 on x86-64 (SURVEY §8b "Struct ABI").
+static_assert(sizeof(BFParams) == 40 && offsetof(BFParams, blockSize) == 32, "BFParams ABI");
+static_assert(sizeof(HNSWParams) == 72 && offsetof(HNSWParams, epsilon) == 64, "HNSWParams ABI");
+static_assert(sizeof(AlgoParams) == 120, "AlgoParams ABI");
+static_assert(sizeof(VecSimParams) == 136 && offsetof(VecSimParams, logCtx) == 128, "VecSimParams ABI");
+static_assert(sizeof(VecSimQueryParams) == 56 && offsetof(VecSimQueryParams, batchSize) == 32 &&
+                  offsetof(VecSimQueryParams, timeoutCtx) == 48, "VecSimQueryParams ABI");
+static_assert(sizeof(VecSimIndexBasicInfo) == 32 && sizeof(VecSimIndexStatsInfo) == 32, "info ABI");
+static_assert(sizeof(CommonInfo) == 64 && sizeof(VecSimIndexDebugInfo) == 360, "debug info ABI");
+static_assert(sizeof(VecSimQueryResult) == 16 && sizeof(VecSimRawParam) == 32, "result ABI");
+
+using namespace vsb;
+
+static thread_local std::string g_api_err;
+
+static void sort_reply(VecSimQueryReply *rep, VecSimQueryReply_Order order) {
+    if (order == BY_ID)
+        std::sort(rep->results.begin(), rep->results.end(),
+                  [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id < b.id; });
+    // BY_SCORE / BY_SCORE_THEN_ID: replies are produced in ascending (score, id) order already
+}
+
+extern "C" {
+
+/* ---- replies ---- */
+int64_t VecSimQueryResult_GetId(const VecSimQueryResult *item) { return item ? (int64_t)item->id : -1; }
+double VecSimQueryResult_GetScore(const VecSimQueryResult *item) {
+    return item ? item->score : std::numeric_limits<double>::quiet_NaN();
+}
+size_t VecSimQueryReply_Len(VecSimQueryReply *r) { return r->results.size(); }
+VecSimQueryReply_Code VecSimQueryReply_GetCode(VecSimQueryReply *r) { return r->code; }
+void VecSimQueryReply_Free(VecSimQueryReply *r) { delete r; }
+VecSimQueryReply_Iterator *VecSimQueryReply_GetIterator(VecSimQueryReply *r) { return new VecSimQueryReply_Iterator{r, 0}; }
+VecSimQueryResult *VecSimQueryReply_IteratorNext(VecSimQueryReply_Iterator *it) {
+    if (it->pos >= it->reply->results.size()) return nullptr;
+    return &it->reply->results[it->pos++];
+}
+bool VecSimQueryReply_IteratorHasNext(VecSimQueryReply_Iterator *it) { return it->pos < it->reply->results.size(); }
+void VecSimQueryReply_IteratorReset(VecSimQueryReply_Iterator *it) { it->pos = 0; }
+void VecSimQueryReply_IteratorFree(VecSimQueryReply_Iterator *it) { delete it; }
+
+VecSimQueryReply *VecSimBatchIterator_Next(VecSimBatchIterator *it, size_t n, VecSimQueryReply_Order order) {
+    return it->next(n, order);
+}
+bool VecSimBatchIterator_HasNext(VecSimBatchIterator *it) { return it->hasNext(); }
+void VecSimBatchIterator_Free(VecSimBatchIterator *it) { delete it; }
+void VecSimBatchIterator_Reset(VecSimBatchIterator *it) { it->reset(); }
+
+/* ---- index ---- */
+VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
+    // any failure -> NULL (index_factories/index_factory.cpp:40-43)
+    try {
+        if (!params) return nullptr;
+        if (params->algo == VecSimAlgo_BF) {
+            const BFParams &p = params->algoParams.bfParams;
+            if (p.dim == 0 || p.type > VecSimType_UINT8 || p.metric > VecSimMetric_Cosine) return nullptr;
+            if (p.multi) {
+                g_api_err = "multi-value flat indexes are not built yet (SURVEY §8 row f2)";
+                return nullptr;
+            }
+            auto *idx = new FlatIndex(p, params->logCtx);
+            if (!idx->ok()) {
+                g_api_err = std::string("device store: ") + vsgpu_last_error();
+                delete idx;
+                return nullptr;
+            }
+            return idx;
+        }
+        g_api_err = "only VecSimAlgo_BF is served by this library (HNSW search: vsgpu_hnsw_*)";
+        return nullptr;
+    } catch (...) {
+        return nullptr;
+    }
+}
+size_t VecSimIndex_EstimateInitialSize(const VecSimParams *) { return sizeof(FlatIndex); }
+size_t VecSimIndex_EstimateElementSize(const VecSimParams *params) {
+    if (!params || params->algo != VecSimAlgo_BF) return 0;
+    const BFParams &p = params->algoParams.bfParams;
+    return stored_size(p.type, p.dim, p.metric) + sizeof(size_t) + sizeof(idType);
+}
+void VecSimIndex_Free(VecSimIndex *index) { delete index; }
+int VecSimIndex_AddVector(VecSimIndex *index, const void *blob, size_t label) { return index->addVector(blob, label); }
+int VecSimIndex_DeleteVector(VecSimIndex *index, size_t label) { return index->deleteVector(label); }
+double VecSimIndex_GetDistanceFrom_Unsafe(VecSimIndex *index, size_t label, const void *blob) {
+    return index->getDistanceFrom(label, blob);
+}
+void VecSim_Normalize(void *blob, size_t dim, VecSimType type) { normalize_blob(blob, dim, type); }
+size_t VecSimParams_GetQueryBlobSize(VecSimType type, size_t dim, VecSimMetric metric) { return stored_size(type, dim, metric); }
+size_t VecSimIndex_IndexSize(VecSimIndex *index) { return index->indexSize(); }
+
+static bool parse_positive(const VecSimRawParam &p, long long *out) {
+    if (!p.value || p.valLen == 0) return false;
+    char *end = nullptr;
+    errno = 0;
+    const long long v = strtoll(p.value, &end, 0);
+    if (errno || end != p.value + p.valLen || v <= 0) return false;
+    *out = v;
+    return true;
+}
+static bool parse_positive_double(const VecSimRawParam &p, double *out) {
+    if (!p.value || p.valLen == 0) return false;
+    char *end = nullptr;
+    errno = 0;
+    const double v = strtod(p.value, &end);
+    if (errno || end != p.value + p.valLen || !(v > 0) || std::isinf(v)) return false;
+    *out = v;
+    return true;
+}
+
+// vec_sim.cpp:270-343 restricted to the parameters a flat / HNSW index understands
+VecSimResolveCode VecSimIndex_ResolveParams(VecSimIndex *index, VecSimRawParam *rparams, int paramNum,
+                                            VecSimQueryParams *qparams, VecsimQueryType query_type) {
+    if (!qparams || (!rparams && paramNum != 0)) return VecSimParamResolverErr_NullParam;
+    const VecSimAlgo algo = index->basicInfo().algo;
+    std::memset(qparams, 0, sizeof(*qparams));
+    for (int i = 0; i < paramNum; i++) {
+        const VecSimRawParam &p = rparams[i];
+        long long iv;
+        double dv;
+        if (!strcasecmp(p.name, "EF_RUNTIME")) {
+            if (algo != VecSimAlgo_HNSWLIB || query_type == QUERY_TYPE_RANGE) return VecSimParamResolverErr_UnknownParam;
+            if (qparams->hnswRuntimeParams.efRuntime != 0) return VecSimParamResolverErr_AlreadySet;
+            if (!parse_positive(p, &iv)) return VecSimParamResolverErr_BadValue;
+            qparams->hnswRuntimeParams.efRuntime = (size_t)iv;
+        } else if (!strcasecmp(p.name, "EPSILON")) {
+            if (algo != VecSimAlgo_HNSWLIB) return VecSimParamResolverErr_UnknownParam;
+            if (query_type != QUERY_TYPE_RANGE) return VecSimParamResolverErr_InvalidPolicy_NRange;
+            if (qparams->hnswRuntimeParams.epsilon != 0) return VecSimParamResolverErr_AlreadySet;
+            if (!parse_positive_double(p, &dv)) return VecSimParamResolverErr_BadValue;
+            qparams->hnswRuntimeParams.epsilon = dv;
+        } else if (!strcasecmp(p.name, "BATCH_SIZE")) {
+            if (query_type != QUERY_TYPE_HYBRID) return VecSimParamResolverErr_InvalidPolicy_NHybrid;
+            if (qparams->batchSize != 0) return VecSimParamResolverErr_AlreadySet;
+            if (!parse_positive(p, &iv)) return VecSimParamResolverErr_BadValue;
+            qparams->batchSize = (size_t)iv;
+        } else if (!strcasecmp(p.name, "HYBRID_POLICY")) {
+            if (query_type != QUERY_TYPE_HYBRID) return VecSimParamResolverErr_InvalidPolicy_NHybrid;
+            if (qparams->searchMode != 0) return VecSimParamResolverErr_AlreadySet;
+            if (p.value && !strcasecmp(p.value, "batches")) qparams->searchMode = HYBRID_BATCHES;
+            else if (p.value && !strcasecmp(p.value, "adhoc_bf")) qparams->searchMode = HYBRID_ADHOC_BF;
+            else return VecSimParamResolverErr_InvalidPolicy_NExits;
+        } else {
+            return VecSimParamResolverErr_UnknownParam;
+        }
+    }
+    if (qparams->searchMode == HYBRID_ADHOC_BF && qparams->batchSize > 0)
+        return VecSimParamResolverErr_InvalidPolicy_AdHoc_With_BatchSize;
+    if (qparams->searchMode == HYBRID_ADHOC_BF && algo == VecSimAlgo_HNSWLIB && qparams->hnswRuntimeParams.efRuntime > 0)
+        return VecSimParamResolverErr_InvalidPolicy_AdHoc_With_EfRuntime;
+    if (qparams->searchMode != 0) index->setLastSearchMode(qparams->searchMode);
+    return VecSimParamResolver_OK;
+}
+
+VecSimQueryReply *VecSimIndex_TopKQuery(VecSimIndex *index, const void *queryBlob, size_t k, VecSimQueryParams *queryParams,
+                                        VecSimQueryReply_Order order) {
+    VecSimQueryReply *rep = index->topKQuery(queryBlob, k, queryParams);
+    sort_reply(rep, order);
+    return rep;
+}
+
+VecSimQueryReply *VecSimIndex_RangeQuery(VecSimIndex *index, const void *queryBlob, double radius,
+                                         VecSimQueryParams *queryParams, VecSimQueryReply_Order order) {
+    // the reference throws through the C boundary here (vec_sim.cpp:362-367); kept for parity
+    if (order != BY_ID && order != BY_SCORE && order != BY_SCORE_THEN_ID)
+        throw std::runtime_error("Possible order values are only 'BY_ID' or 'BY_SCORE'");
+    if (radius < 0) throw std::runtime_error("radius must be non-negative");
+    return index->rangeQuery(queryBlob, radius, queryParams, order);
+}
+
+VecSimIndexDebugInfo VecSimIndex_DebugInfo(VecSimIndex *index) { return index->debugInfo(); }
+VecSimIndexBasicInfo VecSimIndex_BasicInfo(VecSimIndex *index) { return index->basicInfo(); }
+VecSimIndexStatsInfo VecSimIndex_StatsInfo(VecSimIndex *index) { return index->statsInfo(); }
+VecSimBatchIterator *VecSimBatchIterator_New(VecSimIndex *index, const void *queryBlob, VecSimQueryParams *queryParams) {
+    return index->newBatchIterator(queryBlob, queryParams);
+}
+bool VecSimIndex_PreferAdHocSearch(VecSimIndex *index, size_t subsetSize, size_t k, bool initial_check) {
+    return index->preferAdHocSearch(subsetSize, k, initial_check);
+}
+
+struct VecSimAdhocBfCtx {
+    VecSimIndex *index;
+    std::vector<uint8_t> query; // preprocessed once (vec_sim.h:240-274)
+};
+VecSimAdhocBfCtx *VecSimIndex_AdhocBfCtx_New(VecSimIndex *index, const void *queryBlob) {
+    return new VecSimAdhocBfCtx{index, index->preprocessQuery(queryBlob)};
+}
+void VecSimIndex_AdhocBfCtx_Free(VecSimAdhocBfCtx *ctx) { delete ctx; }
+double VecSimIndex_AdhocBfCtx_GetDistanceFrom(VecSimAdhocBfCtx *ctx, size_t label) {
+    double d;
+    ctx->index->exactDistances(ctx->query.data(), &label, &d, 1);
+    return d;
+}
+void VecSimIndex_AdhocBfCtx_GetExactDistances(VecSimAdhocBfCtx *ctx, const size_t *labels, double *distances_out, size_t count) {
+    ctx->index->exactDistances(ctx->query.data(), labels, distances_out, count);
+}
+
+void VecSimTieredIndex_GC(VecSimIndex *) {}
+void VecSimTieredIndex_AcquireSharedLocks(VecSimIndex *) {}
+void VecSimTieredIndex_ReleaseSharedLocks(VecSimIndex *) {}
+void VecSim_SetMemoryFunctions(VecSimMemoryFunctions f) {
+    globals().mem = f;
+    globals().mem_set = true;
+}
+void VecSim_SetTimeoutCallbackFunction(timeoutCallbackFunction cb) { globals().timeout_cb = cb; }
+void VecSim_SetLogCallbackFunction(logCallbackFunction cb) { globals().log_cb = cb; }
+void VecSim_SetTestLogContext(const char *, const char *) {}
+void VecSim_SetWriteMode(VecSimWriteMode mode) { globals().write_mode = mode; }
+void VecSim_UpdateThreadPoolSize(size_t new_size) { globals().write_mode = new_size == 0 ? VecSim_WriteInPlace : VecSim_WriteAsync; }
+size_t VecSim_GetSharedMemory(void) { return 0; }
+
+/* ---- additions ---- */
+int VecSimIndex_TopKQueryBatchRaw(VecSimIndex *index, const void *queries, size_t nq, size_t k, VecSimQueryParams *qp,
+                                  size_t *out_labels, double *out_scores) {
+    const int rc = index->topKBatch(queries, nq, k, qp, out_labels, out_scores, nullptr);
+    return rc == 0 ? 0 : (rc == 1 ? 1 : -1);
+}
+
+int VecSimIndex_TopKQueryBatch(VecSimIndex *index, const void *queries, size_t nq, size_t k, VecSimQueryParams *qp,
+                               VecSimQueryReply_Order order, VecSimQueryReply **out) {
+    if (nq == 0) return 0;
+    const size_t kk = std::max<size_t>(std::min(k, index->indexSize()), 1);
+    std::vector<size_t> labels(nq * kk);
+    std::vector<double> scores(nq * kk);
+    std::vector<uint32_t> counts(nq, 0);
+    int rc = 0;
+    if (k > 0 && index->indexSize() > 0) rc = index->topKBatch(queries, nq, kk, qp, labels.data(), scores.data(), counts.data());
+    if (rc < 0) return -1;
+    for (size_t q = 0; q < nq; q++) {
+        auto *rep = new VecSimQueryReply();
+        if (rc == 1) rep->code = VecSim_QueryReply_TimedOut;
+        else {
+            rep->results.resize(counts[q]);
+            for (uint32_t j = 0; j < counts[q]; j++) rep->results[j] = {labels[q * kk + j], scores[q * kk + j]};
+            sort_reply(rep, order);
+        }
+        out[q] = rep;
+    }
+    return 0;
+}
+
+long VecSimIndex_AddVectorBatch(VecSimIndex *index, const void *blobs, size_t n, const size_t *labels, size_t first_label) {
+    return index->addVectorBatch(blobs, n, labels, first_label);
+}
+
+int VecSimGPU_SetDevice(int device) {
+    if (device < 0 || device >= vsgpu_device_count()) return -1;
+    globals().device = device;
+    return 0;
+}
+int VecSimGPU_GetDevice(void) { return globals().device; }
+int VecSimGPU_DeviceCount(void) { return vsgpu_device_count(); }
+void VecSimGPU_SetTopKMode(int mode) { globals().topk_mode = mode; }
+void VecSimGPU_LastQueryStats(VecSimIndex *index, unsigned *path, unsigned *launches, uint64_t *candidates,
+                              unsigned *fallbacks, float *scan_ms, float *total_ms) {
+    vsgpu_stats st{};
+    index->lastStats(&st);
+    if (path) *path = st.path;
+    if (launches) *launches = st.kernel_launches;
+    if (candidates) *candidates = st.candidates;
+    if (fallbacks) *fallbacks = st.fallback_queries;
+    if (scan_ms) *scan_ms = st.scan_ms;
+    if (total_ms) *total_ms = st.total_ms;
+}
+void *VecSimGPU_GetStore(VecSimIndex *index) { return index->deviceStore(); }
+const char *VecSimGPU_LastError(void) {
+    if (!g_api_err.empty()) return g_api_err.c_str();
+    return vsgpu_last_error();
+}
+
+/* host-logic hook for the CPU test-suite (no device needed): SURVEY App. A2 tie rule */
+size_t vsb_test_resolve(const size_t *labels, const double *scores, const uint32_t *ids, size_t cnt, size_t k,
+                        size_t *out_labels, double *out_scores) {
+    std::vector<VecSimQueryResult> res;
+    FlatIndex::resolve(labels, scores, ids, cnt, k, res);
+    for (size_t i = 0; i < res.size(); i++) {
+        out_labels[i] = res[i].id;
+        out_scores[i] = res[i].score;
+    }
+    return res.size();
+}
+
+} // extern "C"

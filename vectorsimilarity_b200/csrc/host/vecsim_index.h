@@ -1,0 +1,133 @@
+// Host-side index objects behind the VecSimIndex_* C API (include/vecsim_b200.h).
+// Mirrors the reference's VecSimIndexInterface / BruteForceIndex_Single split
+// (/root/reference/src/VecSim/vec_sim_interface.h:23-243, algorithms/brute_force/brute_force.h,
+// brute_force_single.h) but keeps only host bookkeeping here: rows live in HBM behind vsgpu_store.
+#pragma once
+#include "../../../include/vecsim_b200.h"
+#include "../../../include/vsgpu.h"
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+struct VecSimQueryResult {
+    size_t id;
+    double score;
+};
+struct VecSimQueryReply {
+    std::vector<VecSimQueryResult> results;
+    VecSimQueryReply_Code code = VecSim_QueryReply_OK;
+};
+struct VecSimQueryReply_Iterator {
+    VecSimQueryReply *reply;
+    size_t pos;
+};
+
+namespace vsb {
+struct Globals {
+    timeoutCallbackFunction timeout_cb = nullptr;
+    logCallbackFunction log_cb = nullptr;
+    VecSimMemoryFunctions mem{};
+    bool mem_set = false;
+    VecSimWriteMode write_mode = VecSim_WriteAsync;
+    int device = 0;
+    int topk_mode = 0;
+};
+Globals &globals();
+inline bool timed_out(void *ctx) { return globals().timeout_cb && globals().timeout_cb(ctx) != 0; }
+size_t type_size(VecSimType t);
+size_t stored_size(VecSimType t, size_t dim, VecSimMetric m);
+void normalize_blob(void *blob, size_t dim, VecSimType type); // VecSim_Normalize
+} // namespace vsb
+
+struct VecSimBatchIterator {
+    virtual ~VecSimBatchIterator() = default;
+    virtual VecSimQueryReply *next(size_t n, VecSimQueryReply_Order order) = 0;
+    virtual bool hasNext() = 0;
+    virtual void reset() = 0;
+};
+
+struct VecSimIndexInterface {
+    virtual ~VecSimIndexInterface() = default;
+    virtual int addVector(const void *blob, size_t label) = 0;
+    virtual long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) = 0;
+    virtual int deleteVector(size_t label) = 0;
+    virtual double getDistanceFrom(size_t label, const void *blob) = 0;
+    virtual size_t indexSize() = 0;
+    virtual size_t indexLabelCount() = 0;
+    virtual VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) = 0;
+    virtual int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels,
+                          double *scores, uint32_t *counts) = 0;
+    virtual VecSimQueryReply *rangeQuery(const void *blob, double radius, VecSimQueryParams *qp,
+                                         VecSimQueryReply_Order order) = 0;
+    virtual VecSimBatchIterator *newBatchIterator(const void *blob, VecSimQueryParams *qp) = 0;
+    virtual VecSimIndexBasicInfo basicInfo() = 0;
+    virtual VecSimIndexDebugInfo debugInfo() = 0;
+    virtual VecSimIndexStatsInfo statsInfo() = 0;
+    virtual bool preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) = 0;
+    virtual void setLastSearchMode(VecSearchMode m) = 0;
+    virtual void exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) = 0;
+    virtual std::vector<uint8_t> preprocessQuery(const void *blob) = 0;
+    virtual vsgpu_store *deviceStore() = 0;
+    virtual void lastStats(vsgpu_stats *out) = 0;
+};
+
+namespace vsb {
+
+class FlatIndex final : public VecSimIndexInterface {
+  public:
+    FlatIndex(const BFParams &p, void *logCtx);
+    ~FlatIndex() override;
+    bool ok() const { return store_ != nullptr; }
+
+    int addVector(const void *blob, size_t label) override;
+    long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) override;
+    int deleteVector(size_t label) override;
+    double getDistanceFrom(size_t label, const void *blob) override;
+    size_t indexSize() override { return id_to_label_.size(); }
+    size_t indexLabelCount() override { return id_to_label_.size(); }
+    VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) override;
+    int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels, double *scores,
+                  uint32_t *counts) override;
+    VecSimQueryReply *rangeQuery(const void *blob, double radius, VecSimQueryParams *qp,
+                                 VecSimQueryReply_Order order) override;
+    VecSimBatchIterator *newBatchIterator(const void *blob, VecSimQueryParams *qp) override;
+    VecSimIndexBasicInfo basicInfo() override;
+    VecSimIndexDebugInfo debugInfo() override;
+    VecSimIndexStatsInfo statsInfo() override;
+    bool preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) override;
+    void setLastSearchMode(VecSearchMode m) override { last_mode_ = m; }
+    void exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) override;
+    std::vector<uint8_t> preprocessQuery(const void *blob) override;
+    vsgpu_store *deviceStore() override;
+    void lastStats(vsgpu_stats *out) override;
+
+    // resolves the reference's admission/tie rule for one query from the
+    // (score, id)-ordered candidates the device returned
+    static void resolve(const size_t *labels, const double *scores, const uint32_t *ids, size_t cnt, size_t k,
+                        std::vector<VecSimQueryResult> &out);
+    // used by the batch iterator
+    int allScores(const void *processed_query, std::vector<std::pair<double, size_t>> &out);
+
+  private:
+    void preprocess(const void *blob, uint8_t *out) const;
+    int flush();
+
+    VecSimType type_;
+    VecSimMetric metric_;
+    size_t dim_, block_size_, data_size_, stored_size_;
+    void *log_ctx_;
+    vsgpu_store *store_ = nullptr;
+    std::unordered_map<size_t, idType> label_to_id_;
+    std::vector<size_t> id_to_label_;
+    bool labels_monotone_ = true;
+    size_t max_label_ = 0;
+    std::vector<uint8_t> pending_rows_;
+    std::vector<uint64_t> pending_labels_;
+    VecSearchMode last_mode_ = EMPTY_MODE;
+    std::mutex mu_;
+};
+
+} // namespace vsb

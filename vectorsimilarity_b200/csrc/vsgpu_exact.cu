@@ -1,0 +1,741 @@
+// Exact distance kernels: every (row, query) score is computed with the same floating-point
+// operation order as the reference's x86 AVX512 dispatch tier, so scores are bit-identical to the
+// CPU path (reference: spaces/IP/IP_AVX512F_FP32.h:19-56, L2/L2_AVX512F_FP32.h:21-59,
+// IP/IP_AVX512F_FP64.h, IP/IP_AVX512_BF16_VL_BF16.h:23-47, L2/L2_AVX512BW_VBMI2_BF16.h:42-78,
+// IP/IP_AVX512F_FP16.h:27-68, IP/IP.cpp:185-286, L2/L2.cpp:76-174, VNNI int8/uint8 kernels).
+//
+// Mapping: one x86 SIMD lane of one accumulator register == one CUDA thread ("chain"): G threads
+// own the G sequential FMA recurrences of a (row, query) pair and finish with the same butterfly
+// the CPU's _mm512_reduce_add_ps performs. Rows stream from HBM once per query chunk, R rows per
+// thread group are register-tiled against QC queries held in shared memory.
+#include "vsgpu_internal.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace vsgpu {
+
+ChainPlan make_plan(int type, int metric, size_t dim_) {
+    ChainPlan p{};
+    const int dim = (int)dim_;
+    p.dim = dim;
+    p.is_l2 = metric == VSGPU_L2;
+    auto lanes = [&](int G) {
+        p.kind = CK_LANES;
+        p.G = G;
+        const int L = G / 2;
+        p.r = dim % G;
+        p.head = p.r % L;
+        p.nfull = p.r / L;
+        p.prefix = p.r ? 1 : 0;
+        p.S = p.prefix + dim / G;
+    };
+    auto seq = [&]() {
+        p.kind = CK_SEQ;
+        p.G = 1;
+        p.S = dim;
+    };
+    switch (type) {
+    case VSGPU_FLOAT32:
+        if (dim < 8) seq(); else lanes(32);
+        break;
+    case VSGPU_FLOAT64:
+        if (dim < 4) seq(); else lanes(16);
+        break;
+    case VSGPU_BFLOAT16:
+        if (dim < 32) {
+            seq();
+        } else if (p.is_l2) {
+            p.kind = CK_BF16_VBMI2;
+            p.G = 16;
+            p.r = dim % 32;
+            p.prefix = (p.r >= 16 ? 1 : 0) + ((p.r % 16) ? 1 : 0);
+            p.S = p.prefix + 2 * (dim / 32);
+        } else {
+            p.kind = CK_BF16_DP;
+            p.G = 16;
+            p.r = dim % 32;
+            p.prefix = p.r ? 1 : 0;
+            p.S = 2 * (p.prefix + dim / 32);
+            p.ftz = 1;
+        }
+        break;
+    case VSGPU_FLOAT16:
+        if (dim < 8) {
+            seq();
+        } else if (dim < 16) {
+            seq();
+            p.seq_f16c = 1;
+        } else {
+            lanes(32);
+        }
+        break;
+    default:
+        p.kind = CK_INT;
+        p.G = 8;
+        p.S = 0;
+        break;
+    }
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// element loads: stored type -> compute type, exact conversions only
+template <typename CT> struct Loader;
+template <> struct Loader<float> {
+    static __device__ __forceinline__ float load(const uint8_t *row, int type, int e) {
+        if (type == VSGPU_FLOAT32) return __ldg(reinterpret_cast<const float *>(row) + e);
+        const unsigned short h = __ldg(reinterpret_cast<const unsigned short *>(row) + e);
+        if (type == VSGPU_BFLOAT16) return __uint_as_float((unsigned)h << 16);
+        return __half2float(__ushort_as_half(h));
+    }
+};
+template <> struct Loader<double> {
+    static __device__ __forceinline__ double load(const uint8_t *row, int, int e) {
+        return __ldg(reinterpret_cast<const double *>(row) + e);
+    }
+};
+
+template <bool FTZ> __device__ __forceinline__ float fma_step(float a, float b, float c) {
+    if constexpr (FTZ) {
+        float d;
+        asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+        return d;
+    } else {
+        return __fmaf_rn(a, b, c);
+    }
+}
+template <bool FTZ> __device__ __forceinline__ double fma_step(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+
+template <typename CT, int G> __device__ __forceinline__ CT butterfly(CT v) {
+#pragma unroll
+    for (int w = G / 2; w >= 1; w >>= 1) v = add_rn(v, __shfl_xor_sync(0xffffffffu, v, w));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// queries -> chain layout: qc[q][s][c] (compute type, zero in padded slots)
+template <typename CT>
+__global__ void prep_queries_kernel(const uint8_t *__restrict__ q, size_t q_stride, int type, ChainPlan plan,
+                                    CT *__restrict__ qc, size_t nq) {
+    const size_t per_q = (size_t)plan.S * plan.G;
+    const size_t total = per_q * nq;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t qi = i / per_q;
+        const int rem = (int)(i % per_q);
+        const int s = rem / plan.G, c = rem % plan.G;
+        const int e = chain_elem(plan, c, s);
+        qc[i] = e < 0 ? CT(0) : Loader<CT>::load(q + qi * q_stride, type, e);
+    }
+}
+
+struct ScanArgs {
+    const uint8_t *rows;
+    size_t row_stride;
+    size_t n;
+    int type;
+    ChainPlan plan;
+    const void *qchain; // [nq][S][G]
+    size_t nq;
+    void *scores; // [nq][ld]
+    size_t ld;
+    int q_in_smem;
+};
+
+// R rows x QC queries per thread group of G chains.
+template <typename CT, int G, bool FTZ, bool L2, int QC, int R>
+__global__ void __launch_bounds__(256) exact_scan_kernel(ScanArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int SC = 8;
+    constexpr int GROUPS = 32 / G;
+    const ChainPlan plan = a.plan;
+    const int S = plan.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = lane % G, grp = lane / G;
+    const int warps = blockDim.x >> 5;
+    const size_t per_q = (size_t)S * G;
+    const bool fast = plan.kind == CK_LANES && plan.prefix == 0;
+
+    for (size_t q0 = 0; q0 < a.nq; q0 += QC) {
+        const int nqc = (int)min((size_t)QC, a.nq - q0);
+        const CT *qbase = reinterpret_cast<const CT *>(a.qchain) + q0 * per_q;
+        if (a.q_in_smem) {
+            CT *qs = reinterpret_cast<CT *>(smem_raw);
+            __syncthreads();
+            for (size_t i = threadIdx.x; i < per_q * nqc; i += blockDim.x) qs[i] = qbase[i];
+            __syncthreads();
+            qbase = qs;
+        }
+        const size_t rows_per_block = (size_t)warps * GROUPS * R;
+        for (size_t tile = (size_t)blockIdx.x * rows_per_block; tile < a.n; tile += (size_t)gridDim.x * rows_per_block) {
+            const size_t row0 = tile + ((size_t)warp * GROUPS + grp) * R;
+            const uint8_t *rp[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                size_t row = row0 + r;
+                if (row >= a.n) row = a.n - 1;
+                rp[r] = a.rows + row * a.row_stride;
+            }
+            CT acc[R][QC];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int q = 0; q < QC; q++) acc[r][q] = CT(0);
+
+            for (int s0 = 0; s0 < S; s0 += SC) {
+                CT rv[R][SC];
+#pragma unroll
+                for (int j = 0; j < SC; j++) {
+                    const int s = s0 + j;
+                    int e = -1;
+                    if (s < S) e = fast ? G * s + c : chain_elem(plan, c, s);
+#pragma unroll
+                    for (int r = 0; r < R; r++) rv[r][j] = e < 0 ? CT(0) : Loader<CT>::load(rp[r], a.type, e);
+                }
+#pragma unroll
+                for (int q = 0; q < QC; q++) {
+                    if (q < nqc) {
+                        const CT *qp = qbase + (size_t)q * per_q + (size_t)s0 * G + c;
+#pragma unroll
+                        for (int j = 0; j < SC; j++) {
+                            if (s0 + j < S) {
+                                const CT qv = qp[j * G];
+#pragma unroll
+                                for (int r = 0; r < R; r++) {
+                                    if constexpr (L2) {
+                                        const CT d = sub_rn(rv[r][j], qv);
+                                        acc[r][q] = fma_step<FTZ>(d, d, acc[r][q]);
+                                    } else {
+                                        acc[r][q] = fma_step<FTZ>(rv[r][j], qv, acc[r][q]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < QC; q++) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    CT v = butterfly<CT, G>(acc[r][q]);
+                    if (!L2) v = sub_rn(CT(1), v);
+                    if (c == 0 && q < nqc && row0 + r < a.n)
+                        reinterpret_cast<CT *>(a.scores)[(q0 + q) * a.ld + row0 + r] = v;
+                }
+            }
+        }
+    }
+}
+
+// Scalar tiers: the reference's naive loops (multiply and add rounded separately), and the F16C
+// fp16 tier for 8 <= dim < 16 (8 lanes, acc0 = head elements, acc1 = next 8, sequential lane sum).
+template <typename CT>
+__global__ void seq_scan_kernel(const uint8_t *__restrict__ rows, size_t row_stride, size_t n, int type,
+                                ChainPlan plan, const uint8_t *__restrict__ q, size_t q_stride, size_t nq,
+                                const uint32_t *__restrict__ ids, size_t ids_ld, CT *__restrict__ out, size_t ld,
+                                size_t per_q) {
+    const size_t total = per_q * nq;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t qi = i / per_q, j = i % per_q;
+        size_t row = j;
+        if (ids) {
+            const uint32_t id = ids[qi * ids_ld + j];
+            if (id == 0xffffffffu) continue;
+            row = id;
+        }
+        const uint8_t *rp = rows + row * row_stride;
+        const uint8_t *qp = q + qi * q_stride;
+        CT res;
+        if (plan.seq_f16c) {
+            // IP_F16C_FP16.h:28-80 / L2_F16C_FP16.h:28-82 with dim in [8,16): sum0 lanes < head hold
+            // the first `head` elements, sum1 the next 8; (s0+s1)+(s2+s3) then lanes 0..7 in order.
+            const int head = plan.dim % 8;
+            CT tot = CT(0);
+            for (int l = 0; l < 8; l++) {
+                CT s0 = CT(0), s1;
+                if (l < head) {
+                    const CT x = Loader<CT>::load(rp, type, l), y = Loader<CT>::load(qp, type, l);
+                    if (plan.is_l2) { const CT d = sub_rn(x, y); s0 = mul_rn(d, d); } else s0 = mul_rn(x, y);
+                }
+                const CT x = Loader<CT>::load(rp, type, head + l), y = Loader<CT>::load(qp, type, head + l);
+                if (plan.is_l2) { const CT d = sub_rn(x, y); s1 = fma_step<false>(d, d, CT(0)); } else s1 = fma_step<false>(x, y, CT(0));
+                const CT lane_sum = add_rn(add_rn(s0, s1), CT(0));
+                tot = l == 0 ? lane_sum : add_rn(tot, lane_sum);
+            }
+            res = tot;
+        } else {
+            res = CT(0);
+            for (int e = 0; e < plan.dim; e++) {
+                const CT x = Loader<CT>::load(rp, type, e), y = Loader<CT>::load(qp, type, e);
+                if (plan.is_l2) {
+                    const CT d = sub_rn(x, y);
+                    res = add_rn(res, mul_rn(d, d));
+                } else {
+                    res = add_rn(res, mul_rn(x, y));
+                }
+            }
+        }
+        if (!plan.is_l2) res = sub_rn(CT(1), res);
+        out[qi * ld + j] = res;
+    }
+}
+
+// Chosen rows (re-rank / ad-hoc distances): one thread group per (query, candidate) pair.
+template <typename CT, int G, bool FTZ, bool L2>
+__global__ void __launch_bounds__(256) exact_gather_kernel(ScanArgs a, const uint32_t *__restrict__ ids, size_t ids_ld,
+                                                           const uint32_t *__restrict__ counts, size_t max_count) {
+    constexpr int GROUPS = 32 / G;
+    const ChainPlan plan = a.plan;
+    const int S = plan.S;
+    const int lane = threadIdx.x & 31;
+    const int c = lane % G, grp = lane / G;
+    const size_t per_q = (size_t)S * G;
+    const size_t group_id = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + grp;
+    const size_t n_groups = (size_t)gridDim.x * (blockDim.x >> 5) * GROUPS;
+    const size_t total = a.nq * max_count;
+    // all groups of a warp iterate the same number of times (shuffles need the full warp)
+    const size_t iters = (total + n_groups - 1) / n_groups;
+    for (size_t it = 0; it < iters; it++) {
+        const size_t pair = it * n_groups + group_id;
+        bool valid = pair < total;
+        size_t qi = 0, j = 0;
+        uint32_t id = 0xffffffffu;
+        if (valid) {
+            qi = pair / max_count;
+            j = pair % max_count;
+            const uint32_t cnt = counts ? counts[qi] : (uint32_t)max_count;
+            if (j < cnt) id = ids[qi * ids_ld + j];
+            valid = id != 0xffffffffu;
+        }
+        const uint8_t *rp = a.rows + (valid ? (size_t)id : 0) * a.row_stride;
+        const CT *qp = reinterpret_cast<const CT *>(a.qchain) + qi * per_q + c;
+        CT acc = CT(0);
+        if (valid) {
+            for (int s = 0; s < S; s++) {
+                const int e = chain_elem(plan, c, s);
+                const CT x = e < 0 ? CT(0) : Loader<CT>::load(rp, a.type, e);
+                const CT y = qp[(size_t)s * G];
+                if constexpr (L2) {
+                    const CT d = sub_rn(x, y);
+                    acc = fma_step<FTZ>(d, d, acc);
+                } else {
+                    acc = fma_step<FTZ>(x, y, acc);
+                }
+            }
+        }
+        CT v = butterfly<CT, G>(acc);
+        if (!L2) v = sub_rn(CT(1), v);
+        if (valid && c == 0) reinterpret_cast<CT *>(a.scores)[qi * a.ld + j] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// integer types: exact in any order. 8 threads per row, 16-byte chunks, dp4a.
+struct IntArgs {
+    const uint8_t *rows;
+    size_t row_stride; // multiple of 16, zero padded
+    size_t n;
+    int is_unsigned;
+    int metric;
+    int dim;
+    const uint8_t *q; // [nq][row_stride], zero padded
+    size_t nq;
+    const float *row_norms; // cosine
+    const float *q_norms;
+    float *scores;
+    size_t ld;
+    const uint32_t *ids; // gather mode (else NULL)
+    size_t ids_ld;
+    const uint32_t *counts;
+    size_t max_count;
+};
+
+template <bool U> __device__ __forceinline__ int dot4(unsigned a, unsigned b, int c) {
+    if constexpr (U) return (int)__dp4a(a, b, (unsigned)c);
+    else return __dp4a((int)a, (int)b, c);
+}
+
+__device__ __forceinline__ float int_score(int metric, long long dot, long long aa, long long qq, float rn, float qn) {
+    if (metric == VSGPU_L2) return __ll2float_rn(aa + qq - 2 * dot);     // float(sum (a-b)^2), L2.cpp:164-174
+    if (metric == VSGPU_IP) return __ll2float_rn(1 - dot);                // float(1 - sum), IP.cpp:258-277
+    // 1.0f - float(ip) / (norm_a * norm_b), IP_AVX512F_BW_VL_VNNI_INT8.h:70-77
+    return __fsub_rn(1.0f, __fdiv_rn(__ll2float_rn(dot), __fmul_rn(rn, qn)));
+}
+
+template <bool U, int QC>
+__global__ void __launch_bounds__(256) int_scan_kernel(IntArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int G = 8, R = 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int c = lane % G, grp = lane / G;
+    const int chunks = (int)(a.row_stride / 16);
+    uint4 *qs = reinterpret_cast<uint4 *>(smem_raw);
+    long long *qq_s = reinterpret_cast<long long *>(smem_raw + (size_t)QC * a.row_stride);
+    for (size_t q0 = 0; q0 < a.nq; q0 += QC) {
+        const int nqc = (int)min((size_t)QC, a.nq - q0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nqc * chunks; i += blockDim.x)
+            qs[i] = reinterpret_cast<const uint4 *>(a.q + q0 * a.row_stride)[i];
+        __syncthreads();
+        if (threadIdx.x < nqc) {
+            long long t = 0;
+            for (int i = 0; i < chunks; i++) {
+                const uint4 v = qs[threadIdx.x * chunks + i];
+                t += dot4<U>(v.x, v.x, 0) + (long long)dot4<U>(v.y, v.y, 0) + dot4<U>(v.z, v.z, 0) + (long long)dot4<U>(v.w, v.w, 0);
+            }
+            qq_s[threadIdx.x] = t;
+        }
+        __syncthreads();
+        const size_t rows_per_block = (size_t)warps * 4 * R;
+        for (size_t tile = (size_t)blockIdx.x * rows_per_block; tile < a.n; tile += (size_t)gridDim.x * rows_per_block) {
+            const size_t row0 = tile + ((size_t)warp * 4 + grp) * R;
+            const uint4 *rp[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                size_t row = row0 + r;
+                if (row >= a.n) row = a.n - 1;
+                rp[r] = reinterpret_cast<const uint4 *>(a.rows + row * a.row_stride);
+            }
+            long long dot[R][QC], aa[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                aa[r] = 0;
+#pragma unroll
+                for (int q = 0; q < QC; q++) dot[r][q] = 0;
+            }
+            // int32 partial sums are flushed to 64 bits every 1024 chunks (16 KB): 255^2*16384 < 2^31
+            for (int base = 0; base < chunks; base += 1024 * G) {
+                int d32[R][QC], a32[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    a32[r] = 0;
+#pragma unroll
+                    for (int q = 0; q < QC; q++) d32[r][q] = 0;
+                }
+                const int end = min(chunks, base + 1024 * G);
+                for (int ch = base + c; ch < end; ch += G) {
+                    uint4 rv[R];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        rv[r] = __ldg(rp[r] + ch);
+                        a32[r] = dot4<U>(rv[r].x, rv[r].x, a32[r]);
+                        a32[r] = dot4<U>(rv[r].y, rv[r].y, a32[r]);
+                        a32[r] = dot4<U>(rv[r].z, rv[r].z, a32[r]);
+                        a32[r] = dot4<U>(rv[r].w, rv[r].w, a32[r]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < QC; q++) {
+                        if (q < nqc) {
+                            const uint4 qv = qs[q * chunks + ch];
+#pragma unroll
+                            for (int r = 0; r < R; r++) {
+                                d32[r][q] = dot4<U>(rv[r].x, qv.x, d32[r][q]);
+                                d32[r][q] = dot4<U>(rv[r].y, qv.y, d32[r][q]);
+                                d32[r][q] = dot4<U>(rv[r].z, qv.z, d32[r][q]);
+                                d32[r][q] = dot4<U>(rv[r].w, qv.w, d32[r][q]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    aa[r] += a32[r];
+#pragma unroll
+                    for (int q = 0; q < QC; q++) dot[r][q] += d32[r][q];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+#pragma unroll
+                for (int w = G / 2; w >= 1; w >>= 1) aa[r] += __shfl_xor_sync(0xffffffffu, aa[r], w);
+#pragma unroll
+                for (int q = 0; q < QC; q++) {
+#pragma unroll
+                    for (int w = G / 2; w >= 1; w >>= 1) dot[r][q] += __shfl_xor_sync(0xffffffffu, dot[r][q], w);
+                    if (c == 0 && q < nqc && row0 + r < a.n) {
+                        const size_t row = row0 + r;
+                        const float rn = a.row_norms ? a.row_norms[row] : 0.f;
+                        const float qn = a.q_norms ? a.q_norms[q0 + q] : 0.f;
+                        a.scores[(q0 + q) * a.ld + row] = int_score(a.metric, dot[r][q], aa[r], qq_s[q], rn, qn);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool U>
+__global__ void __launch_bounds__(256) int_gather_kernel(IntArgs a) {
+    constexpr int G = 8;
+    const int lane = threadIdx.x & 31;
+    const int c = lane % G, grp = lane / G;
+    const int chunks = (int)(a.row_stride / 16);
+    const size_t group_id = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + grp;
+    const size_t n_groups = (size_t)gridDim.x * (blockDim.x >> 5) * 4;
+    const size_t total = a.nq * a.max_count;
+    const size_t iters = (total + n_groups - 1) / n_groups;
+    for (size_t it = 0; it < iters; it++) {
+        const size_t pair = it * n_groups + group_id;
+        bool valid = pair < total;
+        size_t qi = 0, j = 0;
+        uint32_t id = 0xffffffffu;
+        if (valid) {
+            qi = pair / a.max_count;
+            j = pair % a.max_count;
+            const uint32_t cnt = a.counts ? a.counts[qi] : (uint32_t)a.max_count;
+            if (j < cnt) id = a.ids[qi * a.ids_ld + j];
+            valid = id != 0xffffffffu;
+        }
+        const uint4 *rp = reinterpret_cast<const uint4 *>(a.rows + (valid ? (size_t)id : 0) * a.row_stride);
+        const uint4 *qp = reinterpret_cast<const uint4 *>(a.q + qi * a.row_stride);
+        long long dot = 0, aa = 0, qq = 0;
+        if (valid) {
+            for (int ch = c; ch < chunks; ch += G) {
+                const uint4 rv = __ldg(rp + ch), qv = __ldg(qp + ch);
+                dot += (long long)dot4<U>(rv.x, qv.x, 0) + dot4<U>(rv.y, qv.y, 0) + (long long)dot4<U>(rv.z, qv.z, 0) + dot4<U>(rv.w, qv.w, 0);
+                aa += (long long)dot4<U>(rv.x, rv.x, 0) + dot4<U>(rv.y, rv.y, 0) + (long long)dot4<U>(rv.z, rv.z, 0) + dot4<U>(rv.w, rv.w, 0);
+                qq += (long long)dot4<U>(qv.x, qv.x, 0) + dot4<U>(qv.y, qv.y, 0) + (long long)dot4<U>(qv.z, qv.z, 0) + dot4<U>(qv.w, qv.w, 0);
+            }
+        }
+#pragma unroll
+        for (int w = G / 2; w >= 1; w >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, w);
+            aa += __shfl_xor_sync(0xffffffffu, aa, w);
+            qq += __shfl_xor_sync(0xffffffffu, qq, w);
+        }
+        if (valid && c == 0) {
+            const float rn = a.row_norms ? a.row_norms[id] : 0.f;
+            const float qn = a.q_norms ? a.q_norms[qi] : 0.f;
+            a.scores[qi * a.ld + j] = int_score(a.metric, dot, aa, qq, rn, qn);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int grid_for(int device, int blocks_per_sm) {
+    static int sms[64] = {0};
+    if (device < 0 || device >= 64) return 148 * blocks_per_sm;
+    if (!sms[device]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        sms[device] = v;
+    }
+    return sms[device] * blocks_per_sm;
+}
+
+template <typename CT, int G, bool FTZ, bool L2>
+static int launch_scan_t(vsgpu_store *s, ScanArgs &a) {
+    const size_t per_q_bytes = (size_t)a.plan.S * G * sizeof(CT);
+    constexpr int R = sizeof(CT) == 8 ? 2 : 4;
+    // query chunk: as many as fit in ~96 KB of shared memory, capped at 16 (accumulator registers)
+    int qc = 16;
+    if (a.nq <= 1) qc = 1;
+    else if (a.nq <= 4) qc = 4;
+    size_t smem = per_q_bytes * qc;
+    const size_t smem_cap = 160 * 1024;
+    while (qc > 1 && smem > smem_cap) {
+        qc = qc == 16 ? 4 : 1;
+        smem = per_q_bytes * qc;
+    }
+    a.q_in_smem = smem <= smem_cap;
+    if (!a.q_in_smem) smem = 0;
+    const size_t rows_per_block = 8 * (32 / G) * R;
+    size_t blocks = (a.n + rows_per_block - 1) / rows_per_block;
+    const size_t max_blocks = (size_t)grid_for(s->device, 2);
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks == 0) blocks = 1;
+#define VS_LAUNCH_SCAN(QCV)                                                                                    \
+    do {                                                                                                       \
+        auto kern = exact_scan_kernel<CT, G, FTZ, L2, QCV, R>;                                                 \
+        if (smem > 48 * 1024) VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<(unsigned)blocks, 256, smem, s->stream>>>(a);                                                   \
+    } while (0)
+    if (qc == 16) VS_LAUNCH_SCAN(16);
+    else if (qc == 4) VS_LAUNCH_SCAN(4);
+    else VS_LAUNCH_SCAN(1);
+#undef VS_LAUNCH_SCAN
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
+}
+
+template <typename CT, int G, bool FTZ, bool L2>
+static int launch_gather_t(vsgpu_store *s, ScanArgs &a, const uint32_t *ids, size_t ids_ld, const uint32_t *counts,
+                           size_t max_count) {
+    const size_t pairs = a.nq * max_count;
+    const size_t groups_per_block = 8 * (32 / G);
+    size_t blocks = (pairs + groups_per_block - 1) / groups_per_block;
+    const size_t max_blocks = (size_t)grid_for(s->device, 8);
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks == 0) blocks = 1;
+    exact_gather_kernel<CT, G, FTZ, L2><<<(unsigned)blocks, 256, 0, s->stream>>>(a, ids, ids_ld, counts, max_count);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
+}
+
+// chain-layout copy of the queries lives in s->misc
+static int prep_queries(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const void **qchain) {
+    const ChainPlan &p = s->plan;
+    const size_t csz = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    const size_t bytes = (size_t)p.S * p.G * nq * csz;
+    VS_TRY(ensure_scratch(s, s->misc, bytes));
+    const size_t total = (size_t)p.S * p.G * nq;
+    unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 4096);
+    if (blocks == 0) blocks = 1;
+    if (csz == 8)
+        prep_queries_kernel<double><<<blocks, 256, 0, s->stream>>>((const uint8_t *)q_dev, q_stride, s->type, p, (double *)s->misc.ptr, nq);
+    else
+        prep_queries_kernel<float><<<blocks, 256, 0, s->stream>>>((const uint8_t *)q_dev, q_stride, s->type, p, (float *)s->misc.ptr, nq);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    *qchain = s->misc.ptr;
+    return VSGPU_OK;
+}
+
+static int launch_int(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, void *scores,
+                      size_t ld, const uint32_t *ids, size_t ids_ld, const uint32_t *counts, size_t max_count) {
+    if (q_stride != s->row_stride) {
+        set_error("integer queries must be staged with the store's padded row stride");
+        return VSGPU_ERR_ARG;
+    }
+    IntArgs a{};
+    a.rows = s->rows;
+    a.row_stride = s->row_stride;
+    a.n = s->count;
+    a.is_unsigned = s->type == VSGPU_UINT8;
+    a.metric = s->metric;
+    a.dim = (int)s->dim;
+    a.q = (const uint8_t *)q_dev;
+    a.nq = nq;
+    a.row_norms = s->has_norm ? s->norms : nullptr;
+    a.q_norms = s->has_norm ? q_norms : nullptr;
+    a.scores = (float *)scores;
+    a.ld = ld;
+    a.ids = ids;
+    a.ids_ld = ids_ld;
+    a.counts = counts;
+    a.max_count = max_count;
+    if (ids) {
+        const size_t pairs = nq * max_count;
+        size_t blocks = std::min<size_t>((pairs + 31) / 32, (size_t)grid_for(s->device, 8));
+        if (blocks == 0) blocks = 1;
+        if (a.is_unsigned) int_gather_kernel<true><<<(unsigned)blocks, 256, 0, s->stream>>>(a);
+        else int_gather_kernel<false><<<(unsigned)blocks, 256, 0, s->stream>>>(a);
+    } else {
+        int qc = nq <= 1 ? 1 : (nq <= 4 ? 4 : 16);
+        size_t smem = (size_t)qc * s->row_stride + 16 * sizeof(long long);
+        while (qc > 1 && smem > 160 * 1024) {
+            qc = qc == 16 ? 4 : 1;
+            smem = (size_t)qc * s->row_stride + 16 * sizeof(long long);
+        }
+        if (smem > 200 * 1024) {
+            set_error("dimension too large for the integer scan kernel");
+            return VSGPU_ERR_ARG;
+        }
+        const size_t rows_per_block = 8 * 4 * 2;
+        size_t blocks = std::min<size_t>((a.n + rows_per_block - 1) / rows_per_block, (size_t)grid_for(s->device, 2));
+        if (blocks == 0) blocks = 1;
+#define VS_LAUNCH_INT(UV, QCV)                                                                                 \
+    do {                                                                                                       \
+        auto kern = int_scan_kernel<UV, QCV>;                                                                  \
+        if (smem > 48 * 1024) VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<(unsigned)blocks, 256, smem, s->stream>>>(a);                                                   \
+    } while (0)
+        if (a.is_unsigned) {
+            if (qc == 16) VS_LAUNCH_INT(true, 16); else if (qc == 4) VS_LAUNCH_INT(true, 4); else VS_LAUNCH_INT(true, 1);
+        } else {
+            if (qc == 16) VS_LAUNCH_INT(false, 16); else if (qc == 4) VS_LAUNCH_INT(false, 4); else VS_LAUNCH_INT(false, 1);
+        }
+#undef VS_LAUNCH_INT
+    }
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
+}
+
+static int launch_seq(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, void *scores, size_t ld,
+                      const uint32_t *ids, size_t ids_ld, size_t per_q) {
+    const size_t total = per_q * nq;
+    unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)grid_for(s->device, 8));
+    if (blocks == 0) blocks = 1;
+    if (s->type == VSGPU_FLOAT64)
+        seq_scan_kernel<double><<<blocks, 256, 0, s->stream>>>(s->rows, s->row_stride, s->count, s->type, s->plan,
+                                                               (const uint8_t *)q_dev, q_stride, nq, ids, ids_ld,
+                                                               (double *)scores, ld, per_q);
+    else
+        seq_scan_kernel<float><<<blocks, 256, 0, s->stream>>>(s->rows, s->row_stride, s->count, s->type, s->plan,
+                                                              (const uint8_t *)q_dev, q_stride, nq, ids, ids_ld,
+                                                              (float *)scores, ld, per_q);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
+}
+
+template <typename F> static int dispatch_chain(const vsgpu_store *s, F &&f) {
+    const ChainPlan &p = s->plan;
+    const bool l2 = p.is_l2;
+    if (s->type == VSGPU_FLOAT64) return l2 ? f.template operator()<double, 16, false, true>() : f.template operator()<double, 16, false, false>();
+    if (p.kind == CK_BF16_DP) return f.template operator()<float, 16, true, false>();
+    if (p.kind == CK_BF16_VBMI2) return f.template operator()<float, 16, false, true>();
+    return l2 ? f.template operator()<float, 32, false, true>() : f.template operator()<float, 32, false, false>();
+}
+
+int launch_exact_scan(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, void *scores,
+                      size_t ld) {
+    if (s->count == 0 || nq == 0) return VSGPU_OK;
+    const ChainPlan &p = s->plan;
+    if (p.kind == CK_INT) return launch_int(s, q_dev, nq, q_stride, q_norms, scores, ld, nullptr, 0, nullptr, 0);
+    if (p.kind == CK_SEQ) return launch_seq(s, q_dev, nq, q_stride, scores, ld, nullptr, 0, s->count);
+    const void *qchain = nullptr;
+    VS_TRY(prep_queries(s, q_dev, nq, q_stride, &qchain));
+    ScanArgs a{};
+    a.rows = s->rows;
+    a.row_stride = s->row_stride;
+    a.n = s->count;
+    a.type = s->type;
+    a.plan = p;
+    a.qchain = qchain;
+    a.nq = nq;
+    a.scores = scores;
+    a.ld = ld;
+    return dispatch_chain(s, [&]<typename CT, int G, bool FTZ, bool L2>() { return launch_scan_t<CT, G, FTZ, L2>(s, a); });
+}
+
+int launch_exact_gather(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms,
+                        const uint32_t *ids, size_t ids_ld, const uint32_t *counts, size_t max_count, void *out,
+                        size_t ld) {
+    if (nq == 0 || max_count == 0) return VSGPU_OK;
+    const ChainPlan &p = s->plan;
+    if (p.kind == CK_INT) return launch_int(s, q_dev, nq, q_stride, q_norms, out, ld, ids, ids_ld, counts, max_count);
+    if (p.kind == CK_SEQ) {
+        if (counts) {
+            set_error("sequential tier gather does not take per-query counts");
+            return VSGPU_ERR_ARG;
+        }
+        return launch_seq(s, q_dev, nq, q_stride, out, ld, ids, ids_ld, max_count);
+    }
+    const void *qchain = nullptr;
+    VS_TRY(prep_queries(s, q_dev, nq, q_stride, &qchain));
+    ScanArgs a{};
+    a.rows = s->rows;
+    a.row_stride = s->row_stride;
+    a.n = s->count;
+    a.type = s->type;
+    a.plan = p;
+    a.qchain = qchain;
+    a.nq = nq;
+    a.scores = out;
+    a.ld = ld;
+    return dispatch_chain(s, [&]<typename CT, int G, bool FTZ, bool L2>() {
+        return launch_gather_t<CT, G, FTZ, L2>(s, a, ids, ids_ld, counts, max_count);
+    });
+}
+
+} // namespace vsgpu
