@@ -188,6 +188,11 @@ int VecSimIndex_TopKQueryBatchRaw(VecSimIndex *index, const void *queries, size_
 /* Bulk ingest: n blobs back to back, labels[i] (NULL: first_label + i). Returns #new vectors or -1. */
 long VecSimIndex_AddVectorBatch(VecSimIndex *index, const void *blobs, size_t n, const size_t *labels, size_t first_label);
 
+/* Bulk ingest of rows that already sit in DEVICE memory of the index's GPU, in processed form
+ * (normalised for Cosine; int8/uint8 Cosine: dim bytes per row, the norm is computed on the device).
+ * Row i gets label first_label + i. Returns #rows added or -1. */
+long VecSimGPU_AppendDeviceRows(VecSimIndex *index, const void *device_rows, size_t stride_bytes, size_t n, size_t first_label);
+
 /* Device placement for indexes created afterwards (process-wide; default device 0). */
 int VecSimGPU_SetDevice(int device);
 int VecSimGPU_GetDevice(void);

@@ -66,10 +66,11 @@ size_t vsgpu_store_device_bytes(const vsgpu_store *s);
 
 /* Append n processed rows from HOST memory (`stride` bytes apart) with their labels. */
 int vsgpu_store_append(vsgpu_store *s, const void *rows, size_t stride, const uint64_t *labels, size_t n);
-/* Same, rows and labels already in DEVICE memory of the store's device (bulk loaders). For
- * int8/uint8 cosine `norms` (device, fp32) replaces the appended norm; NULL = compute on device. */
+/* Same, rows and labels already in DEVICE memory of the store's device (bulk loaders).
+ * labels == NULL: row i gets first_label + i. For int8/uint8 cosine `norms` (device, fp32) replaces
+ * the appended norm; NULL = compute on device. */
 int vsgpu_store_append_device(vsgpu_store *s, const void *rows, size_t stride, const uint64_t *labels,
-                              const float *norms, size_t n);
+                              uint64_t first_label, const float *norms, size_t n);
 /* Overwrite row `id` (label update in place). */
 int vsgpu_store_update(vsgpu_store *s, size_t id, const void *row, uint64_t label);
 /* Delete-by-swap (brute_force.h:195-224): row `src` (the last one) moves to `dst`; count -= 1. */

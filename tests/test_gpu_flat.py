@@ -54,6 +54,10 @@ def test_scores_bit_exact_all_dims(capi, port, vtype, metric):
     for dim in DIMS:
         X = make_vectors(vtype, n, dim, seed=dim * 31 + vtype)
         Q = make_vectors(vtype, nq, dim, seed=dim * 17 + metric + 5)
+        if metric == 2:
+            # a zero vector has no cosine (0/0 = NaN) and the reference's heap order is then unspecified
+            X[(X == 0).all(1), 0] = 1
+            Q[(Q == 0).all(1), 0] = 1
         G, P = make_pair(capi, port, vtype, dim, metric, X)
         gl, gs = G.knn_batch(Q, n)
         for i in range(nq):

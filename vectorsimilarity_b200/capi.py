@@ -89,7 +89,7 @@ EXPORTS = [
     "VecSimBatchIterator_Next", "VecSimBatchIterator_HasNext", "VecSimBatchIterator_Free", "VecSimBatchIterator_Reset",
     "VecSimIndex_TopKQueryBatch", "VecSimIndex_TopKQueryBatchRaw", "VecSimIndex_AddVectorBatch",
     "VecSimGPU_SetDevice", "VecSimGPU_GetDevice", "VecSimGPU_DeviceCount", "VecSimGPU_SetTopKMode",
-    "VecSimGPU_LastQueryStats", "VecSimGPU_GetStore", "VecSimGPU_LastError",
+    "VecSimGPU_LastQueryStats", "VecSimGPU_GetStore", "VecSimGPU_LastError", "VecSimGPU_AppendDeviceRows",
 ]
 
 
@@ -168,6 +168,8 @@ def lib():
     L.VecSimGPU_SetTopKMode.argtypes = [i32]
     L.VecSimGPU_LastQueryStats.argtypes = [vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint64),
                                            C.POINTER(C.c_uint), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.VecSimGPU_AppendDeviceRows.restype = C.c_long
+    L.VecSimGPU_AppendDeviceRows.argtypes = [vp, vp, sz, sz, sz]
     L.VecSimGPU_GetStore.restype = vp
     L.VecSimGPU_GetStore.argtypes = [vp]
     L.VecSimGPU_LastError.restype = C.c_char_p
@@ -266,6 +268,13 @@ class VecSimIndex:
         if n < 0:
             raise RuntimeError("AddVectorBatch failed: " + lib().VecSimGPU_LastError().decode())
         return n
+
+    def add_device_rows(self, device_ptr, stride_bytes, n, first_label):
+        """Bulk ingest of processed rows already resident on the index's GPU (VecSimGPU_AppendDeviceRows)."""
+        r = lib().VecSimGPU_AppendDeviceRows(self._h, C.c_void_p(device_ptr), stride_bytes, n, first_label)
+        if r < 0:
+            raise RuntimeError("AppendDeviceRows failed: " + lib().VecSimGPU_LastError().decode())
+        return r
 
     def delete_vector(self, label):
         return lib().VecSimIndex_DeleteVector(self._h, int(label))

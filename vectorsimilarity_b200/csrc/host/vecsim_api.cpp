@@ -256,6 +256,12 @@ long VecSimIndex_AddVectorBatch(VecSimIndex *index, const void *blobs, size_t n,
     return index->addVectorBatch(blobs, n, labels, first_label);
 }
 
+long VecSimGPU_AppendDeviceRows(VecSimIndex *index, const void *device_rows, size_t stride_bytes, size_t n, size_t first_label) {
+    auto *flat = dynamic_cast<FlatIndex *>(index);
+    if (!flat) return -1;
+    return flat->appendDeviceRows(device_rows, stride_bytes, n, first_label);
+}
+
 int VecSimGPU_SetDevice(int device) {
     if (device < 0 || device >= vsgpu_device_count()) return -1;
     globals().device = device;

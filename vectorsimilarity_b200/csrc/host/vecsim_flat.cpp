@@ -91,24 +91,74 @@ vsgpu_store *FlatIndex::deviceStore() {
 
 void FlatIndex::lastStats(vsgpu_stats *out) { vsgpu_last_stats(store_, out); }
 
+bool FlatIndex::findId(size_t label, idType *id) const {
+    if (identity_) {
+        if (label >= count_) return false;
+        *id = (idType)label;
+        return true;
+    }
+    auto it = label_to_id_.find(label);
+    if (it == label_to_id_.end()) return false;
+    *id = it->second;
+    return true;
+}
+
+void FlatIndex::materialize() {
+    if (!identity_) return;
+    id_to_label_.resize(count_);
+    label_to_id_.reserve(count_ * 2 + 16);
+    for (size_t i = 0; i < count_; i++) {
+        id_to_label_[i] = i;
+        label_to_id_.emplace(i, (idType)i);
+    }
+    identity_ = false;
+}
+
+long FlatIndex::appendDeviceRows(const void *dev_rows, size_t stride, size_t n, size_t first_label) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (n == 0) return 0;
+    if (flush() != 0) return -1;
+    if (count_ + n >= 0xfffffffeull) return -1;
+    for (size_t i = 0; i < n && !(identity_ && first_label >= count_); i++) {
+        idType tmp;
+        if (findId(first_label + i, &tmp)) return -1; // bulk ingest never overwrites
+    }
+    if (vsgpu_store_append_device(store_, dev_rows, stride, nullptr, first_label, nullptr, n) != VSGPU_OK) return -1;
+    if (count_ > 0 && first_label <= max_label_) labels_monotone_ = false;
+    if (!(identity_ && first_label == count_)) {
+        materialize();
+        for (size_t i = 0; i < n; i++) {
+            id_to_label_.push_back(first_label + i);
+            label_to_id_.emplace(first_label + i, (idType)(count_ + i));
+        }
+    }
+    max_label_ = count_ == 0 ? first_label + n - 1 : std::max(max_label_, first_label + n - 1);
+    count_ += n;
+    return (long)n;
+}
+
 int FlatIndex::addVector(const void *blob, size_t label) {
     std::lock_guard<std::mutex> g(mu_);
-    auto it = label_to_id_.find(label);
-    if (it != label_to_id_.end()) {
+    idType existing;
+    if (findId(label, &existing)) {
         // Overwrite in place. The reference copies the caller's raw bytes here
         // (brute_force_single.h:138-144), skipping cosine preprocessing; we preprocess.
         if (flush() != 0) return -1;
         std::vector<uint8_t> row(stored_size_);
         preprocess(blob, row.data());
-        if (vsgpu_store_update(store_, it->second, row.data(), label) != VSGPU_OK) return -1;
+        if (vsgpu_store_update(store_, existing, row.data(), label) != VSGPU_OK) return -1;
         return 0;
     }
-    const size_t id = id_to_label_.size();
+    const size_t id = count_;
     if (id >= 0xfffffffeull) return -1;
     if (id > 0 && label <= max_label_) labels_monotone_ = false;
     max_label_ = id == 0 ? label : std::max(max_label_, label);
-    id_to_label_.push_back(label);
-    label_to_id_.emplace(label, (idType)id);
+    if (!(identity_ && label == id)) {
+        materialize();
+        id_to_label_.push_back(label);
+        label_to_id_.emplace(label, (idType)id);
+    }
+    count_++;
     const size_t off = pending_rows_.size();
     pending_rows_.resize(off + stored_size_);
     preprocess(blob, pending_rows_.data() + off);
@@ -130,13 +180,18 @@ long FlatIndex::addVectorBatch(const void *blobs, size_t n, const size_t *labels
 
 int FlatIndex::deleteVector(size_t label) {
     std::lock_guard<std::mutex> g(mu_);
-    auto it = label_to_id_.find(label);
-    if (it == label_to_id_.end()) return 0;
+    idType id;
+    if (!findId(label, &id)) return 0;
     if (flush() != 0) return 0;
-    const idType id = it->second;
-    const size_t last = id_to_label_.size() - 1;
+    const size_t last = count_ - 1;
     if (vsgpu_store_remove_swap(store_, id) != VSGPU_OK) return 0;
-    label_to_id_.erase(it);
+    if (identity_ && id == last) {
+        count_--;
+        if (count_ == 0) max_label_ = 0;
+        return 1;
+    }
+    materialize();
+    label_to_id_.erase(label);
     if (id != last) {
         // the last row moved into the hole (brute_force.h:204-218)
         const size_t moved = id_to_label_[last];
@@ -145,8 +200,11 @@ int FlatIndex::deleteVector(size_t label) {
         labels_monotone_ = false;
     }
     id_to_label_.pop_back();
-    if (id_to_label_.empty()) {
+    count_--;
+    if (count_ == 0) {
         labels_monotone_ = true;
+        identity_ = true;
+        label_to_id_.clear();
         max_label_ = 0;
     }
     return 1;
@@ -154,10 +212,10 @@ int FlatIndex::deleteVector(size_t label) {
 
 double FlatIndex::getDistanceFrom(size_t label, const void *blob) {
     std::lock_guard<std::mutex> g(mu_);
-    auto it = label_to_id_.find(label);
-    if (it == label_to_id_.end()) return std::numeric_limits<double>::quiet_NaN();
+    idType found;
+    if (!findId(label, &found)) return std::numeric_limits<double>::quiet_NaN();
     if (flush() != 0) return std::numeric_limits<double>::quiet_NaN();
-    const uint32_t id = it->second;
+    const uint32_t id = found;
     double out = std::numeric_limits<double>::quiet_NaN();
     // the caller's blob is used as is (brute_force_single.h:200-212)
     if (vsgpu_distances(store_, blob, &id, 1, &out) != VSGPU_OK) return std::numeric_limits<double>::quiet_NaN();
@@ -172,9 +230,9 @@ void FlatIndex::exactDistances(const void *processed_query, const size_t *labels
     std::vector<uint32_t> ids;
     std::vector<size_t> pos;
     for (size_t i = 0; i < n; i++) {
-        auto it = label_to_id_.find(labels[i]);
-        if (it == label_to_id_.end()) continue;
-        ids.push_back(it->second);
+        idType id;
+        if (!findId(labels[i], &id)) continue;
+        ids.push_back(id);
         pos.push_back(i);
     }
     if (ids.empty()) return;
@@ -230,7 +288,7 @@ int FlatIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryPa
             for (size_t q = 0; q < nq; q++) out_counts[q] = 0;
     };
     if (nq == 0) return 0;
-    if (k == 0 || id_to_label_.empty()) {
+    if (k == 0 || count_ == 0) {
         pad_all();
         return 0;
     }
@@ -239,7 +297,7 @@ int FlatIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryPa
         return 1;
     }
     if (flush() != 0) return -1;
-    const size_t n = id_to_label_.size();
+    const size_t n = count_;
     std::vector<uint8_t> qbuf(nq * stored_size_);
     for (size_t q = 0; q < nq; q++) preprocess((const uint8_t *)queries + q * data_size_, qbuf.data() + q * stored_size_);
     const bool fast = labels_monotone_;
@@ -324,7 +382,7 @@ VecSimQueryReply *FlatIndex::rangeQuery(const void *blob, double radius, VecSimQ
     auto *rep = new VecSimQueryReply();
     void *tctx = qp ? qp->timeoutCtx : nullptr;
     last_mode_ = RANGE_QUERY;
-    if (id_to_label_.empty()) return rep;
+    if (count_ == 0) return rep;
     if (timed_out(tctx)) {
         rep->code = VecSim_QueryReply_TimedOut; // partial (here: empty) results, brute_force.h:311-314
         return rep;
@@ -366,12 +424,12 @@ int FlatIndex::allScores(const void *processed_query, std::vector<std::pair<doub
     std::lock_guard<std::mutex> g(mu_);
     out.clear();
     if (flush() != 0) return -1;
-    const size_t n = id_to_label_.size();
+    const size_t n = count_;
     if (n == 0) return 0;
     std::vector<double> sc(n);
     if (vsgpu_scores(store_, processed_query, sc.data()) != VSGPU_OK) return -1;
     out.resize(n);
-    for (size_t i = 0; i < n; i++) out[i] = {sc[i], id_to_label_[i]};
+    for (size_t i = 0; i < n; i++) out[i] = {sc[i], labelOf(i)};
     return 0;
 }
 

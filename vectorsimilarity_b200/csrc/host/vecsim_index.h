@@ -86,8 +86,9 @@ class FlatIndex final : public VecSimIndexInterface {
     long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) override;
     int deleteVector(size_t label) override;
     double getDistanceFrom(size_t label, const void *blob) override;
-    size_t indexSize() override { return id_to_label_.size(); }
-    size_t indexLabelCount() override { return id_to_label_.size(); }
+    size_t indexSize() override { return count_; }
+    size_t indexLabelCount() override { return count_; }
+    long appendDeviceRows(const void *dev_rows, size_t stride, size_t n, size_t first_label);
     VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) override;
     int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels, double *scores,
                   uint32_t *counts) override;
@@ -114,12 +115,19 @@ class FlatIndex final : public VecSimIndexInterface {
   private:
     void preprocess(const void *blob, uint8_t *out) const;
     int flush();
+    // label <-> internal id. While every label equals its internal id (the common bulk-ingest case)
+    // no per-row host state is kept at all; the maps are materialised on the first exception.
+    bool findId(size_t label, idType *id) const;
+    size_t labelOf(size_t id) const { return identity_ ? id : id_to_label_[id]; }
+    void materialize();
 
     VecSimType type_;
     VecSimMetric metric_;
     size_t dim_, block_size_, data_size_, stored_size_;
     void *log_ctx_;
     vsgpu_store *store_ = nullptr;
+    size_t count_ = 0;
+    bool identity_ = true;
     std::unordered_map<size_t, idType> label_to_id_;
     std::vector<size_t> id_to_label_;
     bool labels_monotone_ = true;

@@ -118,6 +118,10 @@ __global__ void int_norm_kernel(const uint8_t *__restrict__ rows, size_t row_str
     }
 }
 
+__global__ void iota_kernel(uint64_t *p, uint64_t first, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = first + i;
+}
+
 template <typename T> __global__ void fill_kernel(T *p, T v, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -186,9 +190,9 @@ static int topk_core(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stri
     s->stats.path = 0;
     // exact path: chunks of queries sized so the score matrix stays within ~1/16 of HBM or 2 GB
     const size_t ld = (n + 63) / 64 * 64;
+    // one launch = one pass over the store for up to 16 queries (the kernel's register tile)
     size_t budget = (size_t)2 << 30;
-    size_t qc = std::max<size_t>(1, std::min<size_t>(nq, budget / (ld * ssz)));
-    if (qc > 16) qc = qc / 16 * 16;
+    size_t qc = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(nq, 16), budget / (ld * ssz)));
     VS_TRY(ensure_scratch(s, s->scores, qc * ld * ssz));
     for (size_t q0 = 0; q0 < nq; q0 += qc) {
         const size_t nqc = std::min(qc, nq - q0);
@@ -317,10 +321,10 @@ int vsgpu_store_append(vsgpu_store *s, const void *rows, size_t stride, const ui
     return VSGPU_OK;
 }
 
-int vsgpu_store_append_device(vsgpu_store *s, const void *rows, size_t stride, const uint64_t *labels, const float *norms,
-                              size_t n) {
+int vsgpu_store_append_device(vsgpu_store *s, const void *rows, size_t stride, const uint64_t *labels,
+                              uint64_t first_label, const float *norms, size_t n) {
     if (n == 0) return VSGPU_OK;
-    if (!rows || !labels || stride < s->row_bytes) {
+    if (!rows || stride < s->row_bytes) {
         set_error("vsgpu_store_append_device: bad arguments");
         return VSGPU_ERR_ARG;
     }
@@ -329,7 +333,12 @@ int vsgpu_store_append_device(vsgpu_store *s, const void *rows, size_t stride, c
     uint8_t *dst = s->rows + s->count * s->row_stride;
     if (s->row_stride != s->row_bytes) VS_CUDA(cudaMemsetAsync(dst, 0, n * s->row_stride, s->stream));
     VS_CUDA(cudaMemcpy2DAsync(dst, s->row_stride, rows, stride, s->row_bytes, n, cudaMemcpyDeviceToDevice, s->stream));
-    VS_CUDA(cudaMemcpyAsync(s->labels + s->count, labels, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s->stream));
+    if (labels) {
+        VS_CUDA(cudaMemcpyAsync(s->labels + s->count, labels, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s->stream));
+    } else {
+        iota_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, s->stream>>>(s->labels + s->count, first_label, n);
+        VS_CUDA(cudaGetLastError());
+    }
     if (s->has_norm) {
         if (norms) {
             VS_CUDA(cudaMemcpyAsync(s->norms + s->count, norms, n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
@@ -631,6 +640,15 @@ int vsgpu_distances(vsgpu_store *s, const void *query, const uint32_t *ids, size
 int vsgpu_last_stats(const vsgpu_store *s, vsgpu_stats *out) {
     if (!s || !out) return VSGPU_ERR_ARG;
     *out = s->stats;
+    // device-side timings become available once the call's last event has completed
+    float ms = 0;
+    if (out->total_ms == 0 && s->ev1 && cudaEventQuery(s->ev1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess)
+        out->total_ms = ms;
+    if (out->scan_ms == 0 && s->ev3 && cudaEventQuery(s->ev3) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, s->ev2, s->ev3) == cudaSuccess)
+        out->scan_ms = ms;
+    cudaGetLastError();
     return VSGPU_OK;
 }
 

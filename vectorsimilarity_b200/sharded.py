@@ -1,0 +1,166 @@
+"""Sharded flat index: one process per GPU (torch.distributed), rows partitioned by contiguous label
+ranges, queries replicated, one all-gather of the per-shard top-k (score, label) lists and a k-way
+merge on every rank. The reference has no counterpart — its flat index is a single
+in-process scan (algorithms/brute_force/brute_force.h:242-291); the merge order is the reference's
+reply order, ascending (score, label).
+
+torch is plumbing here: device buffers for the collective and NCCL itself. The scan and the merge are
+libvsgpu kernels reached through the C-ABI (vsgpu_topk_device / vsgpu_merge_topk_device).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+_gpu_lib = None
+
+
+def _vsgpu():
+    global _gpu_lib
+    if _gpu_lib is None:
+        capi.lib()
+        G = C.CDLL(os.path.join(capi.HERE, "libvsgpu.so"))
+        vp, sz = C.c_void_p, C.c_size_t
+        G.vsgpu_topk_device.argtypes = [vp, vp, sz, sz, sz, C.c_uint, vp, vp, vp]
+        G.vsgpu_store_sync.argtypes = [vp]
+        G.vsgpu_store_stream.restype = vp
+        G.vsgpu_store_stream.argtypes = [vp]
+        G.vsgpu_merge_topk_device.argtypes = [C.c_int, vp, C.c_int, sz, sz, sz, vp, vp, vp, vp]
+        G.vsgpu_last_error.restype = C.c_char_p
+        G.vsgpu_last_stats.argtypes = [vp, vp]
+        _gpu_lib = G
+    return _gpu_lib
+
+
+class Stats(C.Structure):
+    _fields_ = [("path", C.c_uint32), ("kernel_launches", C.c_uint32), ("candidates", C.c_uint64),
+                ("fallback_queries", C.c_uint32), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
+
+
+def shard_bounds(n_total, world_size, rank):
+    """Contiguous, balanced row range [lo, hi) of `rank`."""
+    base, rem = divmod(n_total, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def merge_topk_host(scores, labels, k):
+    """Reference merge semantics on the host (numpy): scores/labels [parts, nq, k] -> [nq, k] by
+    ascending (score, label); padded entries carry label -1 / UINT64_MAX. Used by the CPU (gloo)
+    tests of the collective plumbing and as the checker of the device merge kernel."""
+    parts, nq, kk = scores.shape
+    s = np.transpose(scores, (1, 0, 2)).reshape(nq, parts * kk)
+    l = np.transpose(labels, (1, 0, 2)).reshape(nq, parts * kk).astype(np.uint64)
+    out_s = np.full((nq, k), np.nan, dtype=scores.dtype)
+    out_l = np.full((nq, k), np.iinfo(np.uint64).max, dtype=np.uint64)
+    for q in range(nq):
+        valid = l[q] != np.iinfo(np.uint64).max
+        order = np.lexsort((l[q][valid], s[q][valid]))[:k]
+        out_s[q, :len(order)] = s[q][valid][order]
+        out_l[q, :len(order)] = l[q][valid][order]
+    return out_s, out_l
+
+
+class ShardedFlatIndex:
+    """Rank-local shard + collective. Every rank calls every method (SPMD)."""
+
+    def __init__(self, params, n_total=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = params
+        self.f64 = params.type == capi.VecSimType_FLOAT64
+        self.local = capi.BFIndex(params)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._store = None
+        self._bufs = {}
+
+    def close(self):
+        self.local.close()
+
+    # ---- ingest: the caller hands each rank its own rows (already sharded) ----
+    def add_vectors(self, blobs, labels):
+        return self.local.add_vectors(blobs, labels=labels)
+
+    def add_device_rows(self, tensor, first_label):
+        assert tensor.is_cuda and tensor.is_contiguous()
+        return self.local.add_device_rows(tensor.data_ptr(), tensor.stride(0) * tensor.element_size(), tensor.shape[0],
+                                          first_label)
+
+    def store(self):
+        if self._store is None:
+            self._store = self.local.device_store()
+        return self._store
+
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty(shape, dtype=dtype, device=self.device)
+        return self._bufs[key]
+
+    def local_topk_device(self, q_dev, k, flags=0):
+        """q_dev: [nq, blob] processed queries on this GPU -> (scores [nq,k], labels [nq,k]) device tensors."""
+        G = _vsgpu()
+        nq = q_dev.shape[0]
+        sdt = torch.float64 if self.f64 else torch.float32
+        scores = self._buf("ls", (nq, k), sdt)
+        labels = self._buf("ll", (nq, k), torch.int64)
+        rc = G.vsgpu_topk_device(self.store(), q_dev.data_ptr(), nq, q_dev.stride(0) * q_dev.element_size(), k, flags,
+                                 labels.data_ptr(), scores.data_ptr(), None)
+        if rc != 0:
+            raise RuntimeError("vsgpu_topk_device: " + G.vsgpu_last_error().decode())
+        return scores, labels
+
+    def topk_device(self, q_dev, k, flags=0):
+        """Global top-k on every rank: local scan -> all-gather -> device merge."""
+        G = _vsgpu()
+        scores, labels = self.local_topk_device(q_dev, k, flags)
+        if self.world == 1:
+            G.vsgpu_store_sync(self.store())
+            return scores, labels
+        nq = q_dev.shape[0]
+        G.vsgpu_store_sync(self.store())          # NCCL runs on torch's stream
+        all_s = self._buf("as", (self.world, nq, k), scores.dtype)
+        all_l = self._buf("al", (self.world, nq, k), torch.int64)
+        dist.all_gather_into_tensor(all_s, scores, group=self.group)
+        dist.all_gather_into_tensor(all_l, labels, group=self.group)
+        out_s = self._buf("os", (nq, k), scores.dtype)
+        out_l = self._buf("ol", (nq, k), torch.int64)
+        stream = torch.cuda.current_stream(self.device)
+        rc = G.vsgpu_merge_topk_device(self.device.index, C.c_void_p(stream.cuda_stream), int(self.f64), self.world, nq, k,
+                                       all_s.data_ptr(), all_l.data_ptr(), out_s.data_ptr(), out_l.data_ptr())
+        if rc != 0:
+            raise RuntimeError("vsgpu_merge_topk_device: " + G.vsgpu_last_error().decode())
+        return out_s, out_l
+
+    def knn_batch(self, queries, k, flags=0):
+        """Host queries (processed blobs, numpy [nq, blob]) -> host (labels int64 [nq,k], scores float64 [nq,k])."""
+        q = torch.from_numpy(np.ascontiguousarray(queries).view(np.uint8).reshape(queries.shape[0], -1))
+        q_dev = q.to(self.device, non_blocking=True)
+        out_s, out_l = self.topk_device(q_dev, k, flags)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_l.cpu().numpy(), out_s.double().cpu().numpy()
+
+    def last_stats(self):
+        st = Stats()
+        _vsgpu().vsgpu_last_stats(self.store(), C.byref(st))
+        return {f[0]: getattr(st, f[0]) for f in Stats._fields_}
+
+
+def gather_merge_host(local_scores, local_labels, k, group=None):
+    """The collective step with host tensors (gloo): all-gather per-shard lists, merge with the
+    reference order. Mirrors ShardedFlatIndex.topk_device for CPU tests of the N>1 plumbing."""
+    world = dist.get_world_size(group)
+    s = torch.from_numpy(np.ascontiguousarray(local_scores))
+    l = torch.from_numpy(np.ascontiguousarray(local_labels).view(np.int64))
+    all_s = [torch.empty_like(s) for _ in range(world)]
+    all_l = [torch.empty_like(l) for _ in range(world)]
+    dist.all_gather(all_s, s, group=group)
+    dist.all_gather(all_l, l, group=group)
+    S = np.stack([t.numpy() for t in all_s])
+    L = np.stack([t.numpy().view(np.uint64) for t in all_l])
+    return merge_topk_host(S, L, k)
