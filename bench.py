@@ -167,15 +167,16 @@ def cpu_reference_qps(tname, mname, n_full, dim, k, batch, seconds, threads=None
     vtype, metric = TYPE_ID[tname], METRIC_ID[mname]
     # size the sample: assume ~8 GB/s/core scanned; aim at `seconds` of wall time
     row_bytes = dim * ELEM[tname]
-    n_s = int(min(n_full, max(20_000, 400e6 // row_bytes)))     # <= 400 MB of rows
+    n_s = int(min(n_full, max(20_000, 1.2e9 // row_bytes)))     # ~1.2 GB of rows: larger than the host's L3
     X = gen_rows_numpy(tname, n_s, dim)
     Q = gen_queries_numpy(tname, max(threads * 4, 16), dim)
     if ref is not None:
         idx = ref.RefIndex(vtype, dim, metric)
         idx.add_many(X)
         # calibrate then run
+        idx.topk_many(Q[:threads], k, n_threads=threads, want_results=False)          # warm-up
         _, _, t1 = idx.topk_many(Q[:threads], k, n_threads=threads, want_results=False)
-        per_q = max(t1 / 1.0, 1e-4)  # seconds per `threads` queries
+        per_q = max(t1, 1e-4)  # seconds per round of `threads` queries
         nq = int(max(threads, min(len(Q) * 64, seconds / per_q * threads)))
         Qrun = np.concatenate([Q] * (nq // len(Q) + 1))[:nq]
         _, _, secs = idx.topk_many(Qrun, k, n_threads=threads, want_results=False)

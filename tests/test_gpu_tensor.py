@@ -1,0 +1,130 @@
+"""Tensor-core path (tcgen05 coarse pass + exact re-rank): (1) the raw TMA/MMA/TMEM pipeline against a
+float64 matmul of the bf16-rounded operands, (2) end-to-end parity — the path must return exactly what
+the exact path and the oracle return (ids, order, and the fp32 scores bit for bit)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from datagen import from_bf16, make_vectors, to_bf16
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from vectorsimilarity_b200 import build, capi as c
+    build.build()
+    c.lib()
+    yield c
+    c.set_topk_mode(0)
+
+
+@pytest.fixture(scope="module")
+def gpulib(capi):
+    G = C.CDLL(os.path.join(ROOT, "vectorsimilarity_b200", "libvsgpu.so"))
+    G.vsgpu_debug_coarse.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    G.vsgpu_last_error.restype = C.c_char_p
+    return G
+
+
+def _index(capi, vtype, dim, metric, X):
+    G = capi.BFIndex(capi.BFParams(type=vtype, dim=dim, metric=metric, multi=False, initialCapacity=len(X), blockSize=1024))
+    G.add_vectors(X)
+    return G
+
+
+@pytest.mark.parametrize("vtype,dim", [(0, 768), (0, 128), (0, 100), (2, 1024), (2, 72), (0, 64)])
+def test_coarse_pipeline_matches_matmul(capi, gpulib, vtype, dim):
+    n, nq = 1000, 300                       # ragged: last row tile and last query tile partly empty
+    X = make_vectors(vtype, n, dim, seed=dim, dist="normal")
+    Q = make_vectors(vtype, nq, dim, seed=dim + 1, dist="normal")
+    G = _index(capi, vtype, dim, 1, X)
+    out = np.zeros((n - 128, nq), dtype=np.float32)
+    rc = gpulib.vsgpu_debug_coarse(G.device_store(), Q.ctypes.data, nq, Q.strides[0], 128, n - 128, out.ctypes.data)
+    assert rc == 0, gpulib.vsgpu_last_error()
+    if vtype == 0:
+        xb, qb = from_bf16(to_bf16(X)).astype(np.float64), from_bf16(to_bf16(Q)).astype(np.float64)
+    else:
+        xb, qb = from_bf16(X).astype(np.float64), from_bf16(Q).astype(np.float64)
+    want = xb[128:] @ qb.T
+    err = np.abs(out - want).max()
+    assert err < 2e-6 * max(1.0, dim / 256), err     # fp32 accumulation of exact bf16 products
+    G.close()
+
+
+def _check_against(capi, G, P, Q, k, mode):
+    capi.set_topk_mode(mode)
+    gl, gs = G.knn_batch(Q, k)
+    st = G.last_query_stats()
+    for i in range(Q.shape[0]):
+        pl, ps, _ = P.topk(Q[i], k)
+        assert np.array_equal(gl[i], pl.astype(np.int64)), (i, st)
+        assert np.array_equal(gs[i], ps), (i, st)
+    return st
+
+
+@pytest.mark.parametrize("vtype,metric,dim,n,k,nq", [
+    (0, 1, 128, 40000, 10, 40),
+    (0, 1, 256, 50000, 100, 33),
+    (0, 2, 96, 40000, 50, 64),       # cosine: rows and queries normalised by the index
+    (2, 1, 128, 40000, 100, 70),     # bf16 store, no mirror
+    (2, 2, 200, 36000, 10, 32),
+])
+def test_tensor_path_equals_oracle(capi, port, vtype, metric, dim, n, k, nq):
+    dist = "normal" if metric == 1 else "uniform"
+    X = make_vectors(vtype, n, dim, seed=n + dim, dist=dist)
+    Q = make_vectors(vtype, nq, dim, seed=n + dim + 1, dist=dist)
+    G = _index(capi, vtype, dim, metric, X)
+    P = port.PortIndex(vtype, dim, metric)
+    P.add_many(X)
+    st = _check_against(capi, G, P, Q, k, mode=2)
+    assert st["path"] == 1 and st["candidates"] > 0
+    # appending after the mirrors were built extends them
+    X2 = make_vectors(vtype, 700, dim, seed=5, dist=dist)
+    G.add_vectors(X2, first_label=n)
+    P.add_many(X2, first_label=n)
+    _check_against(capi, G, P, Q[:32], k, mode=2)
+    # a delete invalidates and rebuilds them
+    assert G.delete_vector(5) == P.delete(5) == 1
+    _check_against(capi, G, P, Q[:32], k, mode=2)
+    G.close()
+    P.close()
+
+
+def test_tensor_path_equals_exact_path_large(capi):
+    """Config-2 shape at reduced N: fp32 IP d=768 K=100, 256 queries; tensor path vs exact scan."""
+    n, dim, k, nq = 200_000, 768, 100, 256
+    X = make_vectors(0, n, dim, seed=1, dist="normal")
+    Q = make_vectors(0, nq, dim, seed=2, dist="normal")
+    G = _index(capi, 0, dim, 1, X)
+    capi.set_topk_mode(1)
+    el, es = G.knn_batch(Q, k)
+    capi.set_topk_mode(2)
+    tl, ts = G.knn_batch(Q, k)
+    st = G.last_query_stats()
+    assert st["path"] == 1
+    assert np.array_equal(el, tl)
+    assert np.array_equal(es, ts)
+    assert st["candidates"] / nq < 6000, st          # the filter is selective (2048 unfiltered rows + ~k*ln growth per phase)
+    G.close()
+
+
+def test_candidate_overflow_falls_back_to_exact(capi, port):
+    """Near-duplicate rows: every row is within the coarse error bound of the k-th score, the
+    candidate buffers overflow, and the affected queries are redone on the exact path."""
+    n, dim, k, nq = 40000, 64, 10, 32
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal(dim).astype(np.float32)
+    base /= np.linalg.norm(base)
+    X = (base[None, :] + 1e-4 * rng.standard_normal((n, dim))).astype(np.float32)
+    Q = (base[None, :] + 1e-2 * rng.standard_normal((nq, dim))).astype(np.float32)
+    G = _index(capi, 0, dim, 1, X)
+    P = port.PortIndex(0, dim, 1)
+    P.add_many(X)
+    st = _check_against(capi, G, P, Q, k, mode=2)
+    assert st["fallback_queries"] > 0
+    G.close()
+    P.close()

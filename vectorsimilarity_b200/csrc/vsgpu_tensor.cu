@@ -1,13 +1,767 @@
-// Tensor-core coarse pass + exact re-rank. Placeholder until the tcgen05 kernel lands:
-// reports "not supported" so every query takes the exact path.
+// Tensor-core coarse pass + exact re-rank for large query batches.
+//
+// Batched IP / Cosine over contiguous rows is a dense Q x V^T contraction (north star), so for
+// nq >= 32 the scan runs on the 5th-gen tensor cores:
+//   * rows are the MMA "A" operand (128 rows per tile), streamed HBM -> smem by TMA as 128B-swizzled
+//     [128 x 64] bf16 boxes; queries are the "B" operand ([256 x 64] boxes, L2 resident);
+//     tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulates a 128 x 256 tile in TMEM, double
+//     buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * the epilogue reads the accumulators with tcgen05.ld and keeps only rows whose coarse score can
+//     still beat the query's current k-th exact score (+ a proven error bound): a handful per tile.
+//     Nothing but those candidate ids ever leaves the SM;
+//   * candidates are re-scored by the exact kernels (vsgpu_exact.cu: bit-identical to the CPU
+//     reference) and merged into the running top-k, which tightens the bound for the next phase.
+// fp32 stores keep a bf16 (RNE) mirror of the rows for the coarse pass; bf16 stores are used as is.
+// The result is exactly the exact path's result: the bound makes the candidate set a superset of
+// the true top-k (proof in DESIGN.md §5.3), and a query whose candidate buffer overflows is redone
+// on the exact path.
 #include "vsgpu_internal.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <cmath>
+#include <vector>
 
 namespace vsgpu {
-bool tensor_path_supported(const vsgpu_store *, size_t, size_t) { return false; }
-int tensor_topk(vsgpu_store *, const void *, size_t, size_t, const float *, size_t, uint32_t *, void *, uint64_t *) {
-    set_error("tensor path not built");
-    return VSGPU_ERR_ARG;
+
+// ------------------------------------------------------------------------------------------------
+// tile configuration
+constexpr int BM = 128;          // rows per tile (UMMA M, cta_group::1)
+constexpr int BN = 256;          // queries per tile (UMMA N)
+constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UK = 16;           // UMMA K for 16-bit inputs
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KB
+constexpr int MAX_NQ = 4096;          // thresholds of the whole batch sit in smem
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+constexpr uint32_t CAND_CAP = 3072;   // candidate ids per query and phase
+
+struct GemmSmem {
+    // operand ring (1024-byte aligned for SWIZZLE_128B)
+    uint8_t a[STAGES][A_BYTES];
+    uint8_t b[STAGES][B_BYTES];
+    float athr[MAX_NQ];
+    uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int tensor_sync_mirrors(vsgpu_store *) { return VSGPU_OK; }
-void tensor_release(vsgpu_store *) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B operand descriptor: rows at a 128-byte pitch, 8-row groups 1024 bytes apart
+// (SBO = 64 x 16 B), LBO unused (1), descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fff) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), both
+// K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct GemmArgs {
+    uint32_t row0;       // first row of this phase (multiple of BM)
+    uint32_t row_end;    // one past the last row
+    uint32_t nq;         // valid queries
+    uint32_t n_qtiles;   // ceil(nq / BN)
+    uint32_t k_blocks;   // ceil(dim / BK)
+    const float *athr;   // [nq] admit when acc >= athr[q]
+    uint32_t *cnt;       // [nq] candidate counters
+    uint32_t *cand;      // [nq][CAND_CAP] candidate row ids
+    float *dump;         // debug: [rows][dump_ld] raw accumulators (else NULL)
+    uint32_t dump_ld;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    GemmSmem &sm = *reinterpret_cast<GemmSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t m_tiles = (g.row_end - g.row0 + BM - 1) / BM;
+    const uint32_t items = m_tiles * g.n_qtiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.tfull[i], 1);
+            mbar_init(&sm.tempty[i], EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x)
+        sm.athr[i] = i < g.nq ? g.athr[i] : __int_as_float(0x7f800000);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
+                const int row = (int)(g.row0 + mt * BM), qrow = (int)(nt * BN);
+                for (uint32_t kb = 0; kb < g.k_blocks; kb++) {
+                    mbar_wait(&sm.empty[stage], phase ^ 1);
+                    mbar_expect_tx(&sm.full[stage], A_BYTES + B_BYTES);
+                    tma_load_2d(sm.a[stage], &map_a, &sm.full[stage], (int)(kb * BK), row);
+                    tma_load_2d(sm.b[stage], &map_b, &sm.full[stage], (int)(kb * BK), qrow);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                mbar_wait(&sm.tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + as * BN;
+                for (uint32_t kb = 0; kb < g.k_blocks; kb++) {
+                    mbar_wait(&sm.full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc(smem_u32(sm.a[stage]));
+                    const uint64_t bdesc = make_desc(smem_u32(sm.b[stage]));
+#pragma unroll
+                    for (int k = 0; k < BK / UK; k++) {
+                        // advance 32 bytes (2 x 16 B) along K inside the swizzled row
+                        tc_mma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16, (kb | (uint32_t)k) != 0);
+                    }
+                    tc_commit(&sm.empty[stage]);   // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&sm.tfull[as]);          // accumulator complete
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> threshold filter -> candidate ids =====
+        const int ew = warp - 4;
+        const uint32_t quad = (uint32_t)(warp & 3);       // TMEM lane quadrant this warp may read
+        const uint32_t half = (uint32_t)(ew >> 2);         // which 128 of the 256 columns
+        uint32_t as = 0, aphase = 0;
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
+            const uint32_t row = g.row0 + mt * BM + quad * 32 + (uint32_t)lane;
+            const bool row_ok = row < g.row_end;
+            mbar_wait(&sm.tfull[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t col = half * 128 + c * 32;
+                uint32_t r[32];
+                tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
+                tc_wait_ld();
+                const float *thr = &sm.athr[nt * BN + col];
+                if (g.dump) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const uint32_t q = nt * BN + col + j;
+                            if (q < g.nq) g.dump[(size_t)(row - g.row0) * g.dump_ld + q] = __uint_as_float(r[j]);
+                        }
+                    }
+                } else if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        if (__uint_as_float(r[j]) >= thr[j]) {
+                            const uint32_t q = nt * BN + col + j;
+                            const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
+                            if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = row;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&sm.tempty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mirrors and query preparation
+__global__ void shadow_rows_kernel(const float *__restrict__ rows, size_t row_stride_f, size_t dim, size_t first, size_t n,
+                                   __nv_bfloat16 *__restrict__ shadow, size_t shadow_stride, float *__restrict__ row_l2,
+                                   unsigned *__restrict__ max_l2_bits) {
+    // one warp per row: bf16 (RNE) copy + ||row||_2 rounded up
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (size_t i = warp; i < n; i += nwarps) {
+        const float *src = rows + (first + i) * row_stride_f;
+        __nv_bfloat16 *dst = shadow + (first + i) * shadow_stride;
+        float ss = 0.f;
+        for (size_t e = lane; e < shadow_stride; e += 32) {
+            const float v = e < dim ? src[e] : 0.f;
+            ss = fmaf(v, v, ss);
+            dst[e] = __float2bfloat16_rn(v);
+        }
+        for (int w = 16; w >= 1; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
+        if (lane == 0) {
+            const float nrm = sqrtf(ss) * 1.000001f;
+            row_l2[first + i] = nrm;
+            atomicMax(max_l2_bits, __float_as_uint(nrm));
+        }
+    }
+}
+
+__global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t row_stride_e, size_t dim, size_t first, size_t n,
+                                  float *__restrict__ row_l2, unsigned *__restrict__ max_l2_bits) {
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (size_t i = warp; i < n; i += nwarps) {
+        const __nv_bfloat16 *src = rows + (first + i) * row_stride_e;
+        float ss = 0.f;
+        for (size_t e = lane; e < dim; e += 32) {
+            const float v = __bfloat162float(src[e]);
+            ss = fmaf(v, v, ss);
+        }
+        for (int w = 16; w >= 1; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
+        if (lane == 0) {
+            const float nrm = sqrtf(ss) * 1.000001f;
+            if (row_l2) row_l2[first + i] = nrm;
+            atomicMax(max_l2_bits, __float_as_uint(nrm));
+        }
+    }
+}
+
+// queries -> bf16 operand matrix [nq][qb_stride] (zero padded) + per-query error bound
+// eps[q] = c * ||q|| * max||row||, c from DESIGN.md §5.3
+__global__ void prep_coarse_queries_kernel(const uint8_t *__restrict__ q, size_t q_stride, int is_f32, size_t dim, size_t nq,
+                                           __nv_bfloat16 *__restrict__ qb, size_t qb_stride, float c_rel,
+                                           const unsigned *__restrict__ max_l2_bits, float *__restrict__ eps) {
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (size_t i = warp; i < nq; i += nwarps) {
+        const uint8_t *src = q + i * q_stride;
+        float ss = 0.f;
+        for (size_t e = lane; e < qb_stride; e += 32) {
+            float v = 0.f;
+            __nv_bfloat16 b = __float2bfloat16_rn(0.f);
+            if (e < dim) {
+                if (is_f32) {
+                    v = reinterpret_cast<const float *>(src)[e];
+                    b = __float2bfloat16_rn(v);
+                } else {
+                    b = reinterpret_cast<const __nv_bfloat16 *>(src)[e];
+                    v = __bfloat162float(b);
+                }
+            }
+            ss = fmaf(v, v, ss);
+            qb[i * qb_stride + e] = b;
+        }
+        for (int w = 16; w >= 1; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
+        if (lane == 0) eps[i] = c_rel * (sqrtf(ss) * 1.000001f) * __uint_as_float(*max_l2_bits);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-query running top-k state and the merge of a phase's (exactly re-scored) candidates
+__device__ __forceinline__ uint32_t f2key(float v) {
+    uint32_t u = __float_as_uint(v);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    if (k == 0xffffffffu) return __uint_as_float(0x7fc00000u);
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct MergeArgs {
+    uint32_t nq, k;
+    uint32_t *run_ids;       // [nq][k] sorted ascending (score, id); UINT32_MAX = empty
+    float *run_scores;       // [nq][k] exact scores
+    uint32_t *cnt;           // [nq] candidates appended this phase (reset to 0 here)
+    const uint32_t *cand;    // [nq][CAND_CAP]
+    const float *cand_scores;// [nq][CAND_CAP] exact scores of the candidates
+    const float *eps;        // [nq]
+    float *athr;             // [nq] next phase's admission bound in accumulator space
+    uint32_t *overflow;      // [nq] set when a phase produced more than CAND_CAP candidates
+    unsigned long long *total_cand;
+};
+
+__global__ void __launch_bounds__(1024) merge_phase_kernel(MergeArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t q = blockIdx.x;
+    uint32_t cnt = a.cnt[q];
+    if (threadIdx.x == 0 && cnt) atomicAdd(a.total_cand, (unsigned long long)min(cnt, CAND_CAP));
+    if (cnt > CAND_CAP) {
+        if (threadIdx.x == 0) a.overflow[q] = 1;
+        cnt = CAND_CAP;
+    }
+    const uint32_t total = a.k + cnt;
+    uint32_t P = 1;
+    while (P < total) P <<= 1;
+    uint32_t *sk = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *si = sk + P;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        uint32_t key = 0xffffffffu, id = 0xffffffffu;
+        if (i < a.k) {
+            id = a.run_ids[(size_t)q * a.k + i];
+            if (id != 0xffffffffu) key = f2key(a.run_scores[(size_t)q * a.k + i]);
+        } else if (i < total) {
+            id = a.cand[(size_t)q * CAND_CAP + (i - a.k)];
+            key = f2key(a.cand_scores[(size_t)q * CAND_CAP + (i - a.k)]);
+        }
+        sk[i] = key;
+        si[i] = id;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const uint32_t ka = sk[lo], kb = sk[hi], ia = si[lo], ib = si[hi];
+                const bool gt = ka > kb || (ka == kb && ia > ib);
+                if (gt == asc) { sk[lo] = kb; sk[hi] = ka; si[lo] = ib; si[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < a.k; i += blockDim.x) {
+        a.run_ids[(size_t)q * a.k + i] = si[i];
+        a.run_scores[(size_t)q * a.k + i] = key2f(sk[i]);
+    }
+    if (threadIdx.x == 0) {
+        a.cnt[q] = 0;
+        // k-th exact score so far (T): a row can still enter the top-k only if exact <= T, and
+        // coarse <= exact + eps, i.e. acc = 1 - coarse >= 1 - T - eps. Rounded down to stay safe.
+        float bound = -__int_as_float(0x7f800000);
+        if (si[a.k - 1] != 0xffffffffu) {
+            const float T = key2f(sk[a.k - 1]);
+            bound = __fsub_rd(__fsub_rd(1.0f, T), a.eps[q]);
+            bound = __fsub_rd(bound, fabsf(bound) * 1e-6f);
+        }
+        a.athr[q] = bound;
+    }
+}
+
+template <typename T> __global__ void fill_t(T *p, T v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void finalize_kernel(const uint32_t *__restrict__ run_ids, const float *__restrict__ run_scores, size_t total,
+                                const uint64_t *__restrict__ labels, uint32_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                                uint64_t *__restrict__ out_labels) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t id = run_ids[i];
+        if (out_ids) out_ids[i] = id;
+        if (out_scores) out_scores[i] = run_scores[i];
+        if (out_labels) out_labels[i] = id == 0xffffffffu ? ~0ull : labels[id];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, const void *base, size_t rows, size_t dim_elems, size_t stride_bytes, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available");
+        return VSGPU_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)dim_elems, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+        return VSGPU_ERR_CUDA;
+    }
+    return VSGPU_OK;
+}
+
+struct TensorState {
+    size_t mirrored = 0;         // rows [0, mirrored) have a valid mirror / norm
+    size_t cap = 0;              // capacity the mirrors were sized for
+    unsigned *max_l2_bits = nullptr;
+    int sms = 0;
+    bool attr_set = false;
+};
+
+static TensorState *state(vsgpu_store *s) {
+    if (!s->tmap_cache) s->tmap_cache = new TensorState();
+    return (TensorState *)s->tmap_cache;
+}
+
+void tensor_release(vsgpu_store *s) {
+    auto *t = (TensorState *)s->tmap_cache;
+    if (t) {
+        if (t->max_l2_bits) cudaFree(t->max_l2_bits);
+        delete t;
+        s->tmap_cache = nullptr;
+    }
+    if (s->shadow) cudaFree(s->shadow);
+    if (s->row_l2) cudaFree(s->row_l2);
+    s->shadow = nullptr;
+    s->row_l2 = nullptr;
+    s->shadow_stride = 0;
+}
+
+static bool g_tensor_disabled = false;
+
+bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k) {
+    if (g_tensor_disabled) return false;
+    if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16) return false;
+    if (s->metric != VSGPU_IP && s->metric != VSGPU_COSINE) return false;
+    if (s->plan.kind == CK_SEQ) return false;
+    if (nq < 32 || k > 512 || k == 0) return false;
+    if (s->dim < 64 || s->dim > 8192) return false;
+    if (s->count < 32768 || s->count < 16 * k) return false;
+    if (!encode_fn()) return false;
+    static int cc_major[64] = {0};
+    if (s->device < 64 && !cc_major[s->device]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, s->device);
+        cc_major[s->device] = v ? v : -1;
+    }
+    return s->device < 64 && cc_major[s->device] == 10;
+}
+
+// bring the bf16 mirror (fp32 stores) and the row norms up to date with the store
+int tensor_sync_mirrors(vsgpu_store *s) {
+    TensorState *t = state(s);
+    if (!t->sms) {
+        cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, s->device);
+        if (t->sms <= 0) t->sms = 148;
+    }
+    if (!t->max_l2_bits) {
+        VS_CUDA(cudaMalloc(&t->max_l2_bits, sizeof(unsigned)));
+        VS_CUDA(cudaMemsetAsync(t->max_l2_bits, 0, sizeof(unsigned), s->stream));
+    }
+    if (s->type == VSGPU_FLOAT32) {
+        if (!s->shadow) {
+            s->shadow_stride = (s->dim + 7) / 8 * 8;
+            VS_CUDA(cudaMalloc(&s->shadow, s->capacity * s->shadow_stride * 2));
+            VS_CUDA(cudaMalloc(&s->row_l2, s->capacity * sizeof(float)));
+            t->cap = s->capacity;
+            t->mirrored = 0;
+        }
+        if (t->mirrored < s->count) {
+            const size_t n = s->count - t->mirrored;
+            const unsigned blocks = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)t->sms * 16);
+            shadow_rows_kernel<<<blocks, 256, 0, s->stream>>>((const float *)s->rows, s->row_stride / 4, s->dim, t->mirrored, n,
+                                                             (__nv_bfloat16 *)s->shadow, s->shadow_stride, s->row_l2,
+                                                             t->max_l2_bits);
+            VS_CUDA(cudaGetLastError());
+            s->stats.kernel_launches++;
+            t->mirrored = s->count;
+        }
+    } else {
+        if (t->mirrored < s->count) {
+            const size_t n = s->count - t->mirrored;
+            const unsigned blocks = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)t->sms * 16);
+            bf16_norms_kernel<<<blocks, 256, 0, s->stream>>>((const __nv_bfloat16 *)s->rows, s->row_stride / 2, s->dim, t->mirrored,
+                                                            n, nullptr, t->max_l2_bits);
+            VS_CUDA(cudaGetLastError());
+            s->stats.kernel_launches++;
+            t->mirrored = s->count;
+        }
+    }
+    return VSGPU_OK;
+}
+
+static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+static int launch_gemm(vsgpu_store *s, TensorState *t, const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs &g) {
+    const size_t smem = sizeof(GemmSmem) + 1024;
+    if (!t->attr_set) {
+        VS_CUDA(cudaFuncSetAttribute(coarse_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        t->attr_set = true;
+    }
+    const uint32_t m_tiles = (g.row_end - g.row0 + BM - 1) / BM;
+    const uint32_t items = m_tiles * g.n_qtiles;
+    const unsigned grid = (unsigned)std::min<uint32_t>(items, (uint32_t)t->sms);
+    coarse_gemm_filter_kernel<<<grid, GEMM_THREADS, smem, s->stream>>>(ma, mb, g);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
+}
+
+int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_stride, const float *q_norms, size_t k,
+                uint32_t *out_ids, void *out_scores, uint64_t *out_labels) {
+    (void)q_norms;
+    TensorState *t = state(s);
+    VS_TRY(tensor_sync_mirrors(s));
+    const size_t n = s->count;
+    const bool f32 = s->type == VSGPU_FLOAT32;
+    const void *a_base = f32 ? (const void *)s->shadow : (const void *)s->rows;
+    const size_t a_stride = f32 ? s->shadow_stride * 2 : s->row_stride;
+    const size_t qb_stride = (s->dim + 7) / 8 * 8;
+    // error bound of the coarse score relative to ||q|| * ||row||
+    const float c_rel = f32 ? (float)(1.0 / 256 + 1.0 / 65536 + 4.0 * (double)s->dim / 8388608.0)
+                            : (float)(6.0 * (double)s->dim / 8388608.0);
+    CUtensorMap map_a;
+    VS_TRY(make_map(&map_a, a_base, n, s->dim, a_stride, BM));
+
+    // phases: [0,S0) unfiltered, then geometric growth so a phase admits ~ (growth-1) * k rows per query
+    std::vector<std::pair<uint32_t, uint32_t>> phases;
+    {
+        size_t s0 = std::max<size_t>(BM, std::min<size_t>(CAND_CAP, 2048) / BM * BM);
+        s0 = std::max(s0, (std::min<size_t>(2 * k, CAND_CAP) + BM - 1) / BM * BM);
+        size_t a = 0, b = std::min(n, s0);
+        const double growth = std::max(3.0, std::min(8.0, (double)CAND_CAP / (2.5 * (double)k)));
+        while (a < n) {
+            phases.emplace_back((uint32_t)a, (uint32_t)b);
+            a = b;
+            size_t nb = (size_t)((double)b * growth);
+            nb = nb / BM * BM;
+            b = std::min(n, std::max(nb, a + BM));
+        }
+    }
+
+    for (size_t q0 = 0; q0 < nq_all; q0 += MAX_NQ) {
+        const size_t nq = std::min<size_t>(MAX_NQ, nq_all - q0);
+        const uint8_t *qp = (const uint8_t *)q_dev + q0 * q_stride;
+        const size_t nq_pad = (nq + BN - 1) / BN * BN;
+        // scratch layout in s->cand
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+        const size_t o_qb = take(nq_pad * qb_stride * 2), o_eps = take(nq * 4), o_athr = take(nq * 4), o_cnt = take(nq * 4),
+                     o_ovf = take(nq * 4), o_rid = take(nq * k * 4), o_rsc = take(nq * k * 4), o_cand = take(nq * CAND_CAP * 4),
+                     o_csc = take(nq * CAND_CAP * 4), o_tot = take(8);
+        VS_TRY(ensure_scratch(s, s->cand, off));
+        uint8_t *base = (uint8_t *)s->cand.ptr;
+        auto *qb = (__nv_bfloat16 *)(base + o_qb);
+        float *eps = (float *)(base + o_eps), *athr = (float *)(base + o_athr);
+        uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = (uint32_t *)(base + o_ovf), *rid = (uint32_t *)(base + o_rid);
+        float *rsc = (float *)(base + o_rsc), *csc = (float *)(base + o_csc);
+        uint32_t *cand = (uint32_t *)(base + o_cand);
+        auto *tot = (unsigned long long *)(base + o_tot);
+
+        VS_CUDA(cudaMemsetAsync(base + o_qb, 0, nq_pad * qb_stride * 2, s->stream));
+        VS_CUDA(cudaMemsetAsync(cnt, 0, nq * 4, s->stream));
+        VS_CUDA(cudaMemsetAsync(ovf, 0, nq * 4, s->stream));
+        VS_CUDA(cudaMemsetAsync(tot, 0, 8, s->stream));
+        VS_CUDA(cudaMemsetAsync(rid, 0xff, nq * k * 4, s->stream));
+        fill_t<float><<<64, 256, 0, s->stream>>>(athr, -INFINITY, nq);
+        prep_coarse_queries_kernel<<<(unsigned)std::min<size_t>((nq + 7) / 8, 1024), 256, 0, s->stream>>>(
+            qp, q_stride, f32 ? 1 : 0, s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches += 2;
+        CUtensorMap map_b;
+        VS_TRY(make_map(&map_b, qb, nq_pad, s->dim, qb_stride * 2, BN));
+
+        float gemm_ms_total = 0;
+        for (size_t p = 0; p < phases.size(); p++) {
+            GemmArgs g{};
+            g.row0 = phases[p].first;
+            g.row_end = phases[p].second;
+            g.nq = (uint32_t)nq;
+            g.n_qtiles = (uint32_t)(nq_pad / BN);
+            g.k_blocks = (uint32_t)((s->dim + BK - 1) / BK);
+            g.athr = athr;
+            g.cnt = cnt;
+            g.cand = cand;
+            g.dump = nullptr;
+            const bool timed = p + 1 == phases.size();
+            if (timed) VS_CUDA(cudaEventRecord(s->ev2, s->stream));
+            VS_TRY(launch_gemm(s, t, map_a, map_b, g));
+            if (timed) VS_CUDA(cudaEventRecord(s->ev3, s->stream));
+            // exact re-score of this phase's candidates, then merge into the running top-k
+            VS_TRY(launch_exact_gather(s, qp, nq, q_stride, nullptr, cand, CAND_CAP, cnt, CAND_CAP, csc, CAND_CAP));
+            MergeArgs m{};
+            m.nq = (uint32_t)nq;
+            m.k = (uint32_t)k;
+            m.run_ids = rid;
+            m.run_scores = rsc;
+            m.cnt = cnt;
+            m.cand = cand;
+            m.cand_scores = csc;
+            m.eps = eps;
+            m.athr = athr;
+            m.overflow = ovf;
+            m.total_cand = tot;
+            uint32_t P = 1;
+            while (P < k + CAND_CAP) P <<= 1;
+            const size_t msmem = (size_t)P * 8;
+            merge_phase_kernel<<<(unsigned)nq, 1024, msmem, s->stream>>>(m);
+            VS_CUDA(cudaGetLastError());
+            s->stats.kernel_launches++;
+        }
+        (void)gemm_ms_total;
+        // outputs of this query chunk
+        finalize_kernel<<<256, 256, 0, s->stream>>>(rid, rsc, nq * k, s->labels, out_ids ? out_ids + q0 * k : nullptr,
+                                                   out_scores ? (float *)out_scores + q0 * k : nullptr,
+                                                   out_labels ? out_labels + q0 * k : nullptr);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+        // overflowed queries are redone on the exact path
+        std::vector<uint32_t> h_ovf(nq);
+        unsigned long long h_tot = 0;
+        VS_CUDA(cudaMemcpyAsync(h_ovf.data(), ovf, nq * 4, cudaMemcpyDeviceToHost, s->stream));
+        VS_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, s->stream));
+        VS_CUDA(cudaStreamSynchronize(s->stream));
+        s->stats.candidates += h_tot;
+        const size_t ld = (n + 63) / 64 * 64;
+        for (size_t q = 0; q < nq; q++) {
+            if (!h_ovf[q]) continue;
+            s->stats.fallback_queries++;
+            VS_TRY(ensure_scratch(s, s->scores, ld * 4));
+            VS_TRY(launch_exact_scan(s, qp + q * q_stride, 1, q_stride, nullptr, s->scores.ptr, ld));
+            VS_TRY(launch_select_topk(s, s->scores.ptr, ld, 1, n, k, k, out_ids ? out_ids + (q0 + q) * k : nullptr,
+                                      out_scores ? (float *)out_scores + (q0 + q) * k : nullptr,
+                                      out_labels ? out_labels + (q0 + q) * k : nullptr));
+        }
+    }
+    return VSGPU_OK;
+}
+
 } // namespace vsgpu
+
+// Debug / test hook: raw coarse accumulators of rows [row0, row0 + nrows) against nq queries
+// (HOST pointers; out is [nrows][nq] fp32). Exercises exactly the production TMA/MMA/TMEM pipeline.
+extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t row0, size_t nrows,
+                                  float *out) {
+    using namespace vsgpu;
+    if (!s || !queries || !out || nq == 0 || nrows == 0 || row0 % BM != 0 || row0 + nrows > s->count || nq > MAX_NQ) {
+        set_error("vsgpu_debug_coarse: bad arguments");
+        return VSGPU_ERR_ARG;
+    }
+    if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16) {
+        set_error("vsgpu_debug_coarse: fp32 / bf16 stores only");
+        return VSGPU_ERR_ARG;
+    }
+    VS_CUDA(cudaSetDevice(s->device));
+    TensorState *t = state(s);
+    VS_TRY(tensor_sync_mirrors(s));
+    const bool f32 = s->type == VSGPU_FLOAT32;
+    const size_t qb_stride = (s->dim + 7) / 8 * 8;
+    const size_t nq_pad = (nq + BN - 1) / BN * BN;
+    uint8_t *d_q = nullptr;
+    __nv_bfloat16 *qb = nullptr;
+    float *eps = nullptr, *athr = nullptr, *dump = nullptr;
+    VS_CUDA(cudaMalloc(&d_q, nq * s->row_bytes));
+    VS_CUDA(cudaMalloc(&qb, nq_pad * qb_stride * 2));
+    VS_CUDA(cudaMalloc(&eps, nq * 4));
+    VS_CUDA(cudaMalloc(&athr, nq * 4));
+    VS_CUDA(cudaMalloc(&dump, nrows * nq * 4));
+    VS_CUDA(cudaMemcpy2D(d_q, s->row_bytes, queries, qstride, s->row_bytes, nq, cudaMemcpyHostToDevice));
+    VS_CUDA(cudaMemsetAsync(qb, 0, nq_pad * qb_stride * 2, s->stream));
+    VS_CUDA(cudaMemsetAsync(dump, 0, nrows * nq * 4, s->stream));
+    prep_coarse_queries_kernel<<<64, 256, 0, s->stream>>>(d_q, s->row_bytes, f32 ? 1 : 0, s->dim, nq, qb, qb_stride, 0.f,
+                                                         t->max_l2_bits, eps);
+    CUtensorMap map_a, map_b;
+    VS_TRY(make_map(&map_a, f32 ? (const void *)s->shadow : (const void *)s->rows, s->count, s->dim,
+                    f32 ? s->shadow_stride * 2 : s->row_stride, BM));
+    VS_TRY(make_map(&map_b, qb, nq_pad, s->dim, qb_stride * 2, BN));
+    GemmArgs g{};
+    g.row0 = (uint32_t)row0;
+    g.row_end = (uint32_t)(row0 + nrows);
+    g.nq = (uint32_t)nq;
+    g.n_qtiles = (uint32_t)(nq_pad / BN);
+    g.k_blocks = (uint32_t)((s->dim + BK - 1) / BK);
+    g.athr = athr;
+    g.cnt = nullptr;
+    g.cand = nullptr;
+    g.dump = dump;
+    g.dump_ld = (uint32_t)nq;
+    VS_TRY(launch_gemm(s, t, map_a, map_b, g));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    VS_CUDA(cudaMemcpy(out, dump, nrows * nq * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_q);
+    cudaFree(qb);
+    cudaFree(eps);
+    cudaFree(athr);
+    cudaFree(dump);
+    return VSGPU_OK;
+}
