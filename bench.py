@@ -376,7 +376,8 @@ def main():
             ach = flops / (stl["scan_ms"] / 1e3) / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                    "kernel": "coarse_gemm_filter", "kernel_ms": stl["scan_ms"], "peak_source": peak_src + " (sustained bf16)"}
+                    "kernel": "coarse_gemm_filter_kernel", "kernel_ms": stl["scan_ms"], "peak_source": peak_src + " (sustained bf16)",
+                    "note": "2*B*N*d flops over the summed CUDA-event time of the step's coarse GEMM launches (one per phase)"}
         elif stl["scan_ms"] > 0:
             # exact path: one scan launch streams the shard once for a chunk of <=16 queries
             qc = min(batch, 16)

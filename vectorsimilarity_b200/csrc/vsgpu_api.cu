@@ -645,7 +645,7 @@ int vsgpu_last_stats(const vsgpu_store *s, vsgpu_stats *out) {
     if (out->total_ms == 0 && s->ev1 && cudaEventQuery(s->ev1) == cudaSuccess &&
         cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess)
         out->total_ms = ms;
-    if (out->scan_ms == 0 && s->ev3 && cudaEventQuery(s->ev3) == cudaSuccess &&
+    if (out->path == 0 && out->scan_ms == 0 && s->ev3 && cudaEventQuery(s->ev3) == cudaSuccess &&
         cudaEventElapsedTime(&ms, s->ev2, s->ev3) == cudaSuccess)
         out->scan_ms = ms;
     cudaGetLastError();

@@ -124,7 +124,7 @@ struct GemmArgs {
     uint32_t k_blocks;   // ceil(dim / BK)
     const float *athr;   // [nq] admit when acc >= athr[q]
     uint32_t *cnt;       // [nq] candidate counters
-    uint32_t *cand;      // [nq][CAND_CAP] candidate row ids
+    uint2 *cand;         // [nq][CAND_CAP] (row id, coarse accumulator bits)
     float *dump;         // debug: [rows][dump_ld] raw accumulators (else NULL)
     uint32_t dump_ld;
 };
@@ -235,7 +235,7 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                         if (__uint_as_float(r[j]) >= thr[j]) {
                             const uint32_t q = nt * BN + col + j;
                             const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
-                            if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = row;
+                            if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = make_uint2(row, r[j]);
                         }
                     }
                 }
@@ -344,45 +344,52 @@ __device__ __forceinline__ float key2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+constexpr uint32_t RUN_CAP = 1024;   // survivors kept per query between phases
+
 struct MergeArgs {
     uint32_t nq, k;
-    uint32_t *run_ids;       // [nq][k] sorted ascending (score, id); UINT32_MAX = empty
-    float *run_scores;       // [nq][k] exact scores
+    uint2 *run;              // [nq][RUN_CAP] (row id, coarse acc bits) of rows that can still make the top-k
+    uint32_t *run_cnt;       // [nq]
     uint32_t *cnt;           // [nq] candidates appended this phase (reset to 0 here)
-    const uint32_t *cand;    // [nq][CAND_CAP]
-    const float *cand_scores;// [nq][CAND_CAP] exact scores of the candidates
-    const float *eps;        // [nq]
-    float *athr;             // [nq] next phase's admission bound in accumulator space
-    uint32_t *overflow;      // [nq] set when a phase produced more than CAND_CAP candidates
+    const uint2 *cand;       // [nq][CAND_CAP]
+    const float *eps;        // [nq] bound on |coarse acc - exact sum|
+    float *athr;             // [nq] admission bound for the next phase (accumulator space)
+    uint32_t *overflow;      // [nq] set when a buffer overflowed: the query is redone exactly
     unsigned long long *total_cand;
 };
 
+// One block per query. Sort (survivors U this phase's candidates) by coarse accumulator, descending.
+// With A_K the k-th largest accumulator seen so far, every row of the exact top-k — including every
+// row tied with the k-th exact score — has acc >= A_K - 2*eps, so that is both the
+// survivor cut and the next phase's admission bound.
 __global__ void __launch_bounds__(1024) merge_phase_kernel(MergeArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint32_t s_keep;
     const uint32_t q = blockIdx.x;
     uint32_t cnt = a.cnt[q];
+    const uint32_t rcnt = a.run_cnt[q];
     if (threadIdx.x == 0 && cnt) atomicAdd(a.total_cand, (unsigned long long)min(cnt, CAND_CAP));
     if (cnt > CAND_CAP) {
         if (threadIdx.x == 0) a.overflow[q] = 1;
         cnt = CAND_CAP;
     }
-    const uint32_t total = a.k + cnt;
-    uint32_t P = 1;
+    const uint32_t total = rcnt + cnt;
+    uint32_t P = 32;
     while (P < total) P <<= 1;
-    uint32_t *sk = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *sk = reinterpret_cast<uint32_t *>(smem_raw); // ~key(acc): ascending key = descending acc
     uint32_t *si = sk + P;
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
         uint32_t key = 0xffffffffu, id = 0xffffffffu;
-        if (i < a.k) {
-            id = a.run_ids[(size_t)q * a.k + i];
-            if (id != 0xffffffffu) key = f2key(a.run_scores[(size_t)q * a.k + i]);
-        } else if (i < total) {
-            id = a.cand[(size_t)q * CAND_CAP + (i - a.k)];
-            key = f2key(a.cand_scores[(size_t)q * CAND_CAP + (i - a.k)]);
+        if (i < total) {
+            const uint2 e = i < rcnt ? a.run[(size_t)q * RUN_CAP + i] : a.cand[(size_t)q * CAND_CAP + (i - rcnt)];
+            id = e.x;
+            key = ~f2key(__uint_as_float(e.y));
+            if (key == 0xffffffffu) key = 0xfffffffeu; // keep real entries ahead of padding
         }
         sk[i] = key;
         si[i] = id;
     }
+    if (threadIdx.x == 0) s_keep = 0;
     __syncthreads();
     for (uint32_t size = 2; size <= P; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -396,37 +403,37 @@ __global__ void __launch_bounds__(1024) merge_phase_kernel(MergeArgs a) {
             __syncthreads();
         }
     }
-    for (uint32_t i = threadIdx.x; i < a.k; i += blockDim.x) {
-        a.run_ids[(size_t)q * a.k + i] = si[i];
-        a.run_scores[(size_t)q * a.k + i] = key2f(sk[i]);
+    float bound = -__int_as_float(0x7f800000);
+    if (total >= a.k) {
+        const float ak = key2f(~sk[a.k - 1]);
+        bound = __fsub_rd(ak, __fmul_ru(2.0f, a.eps[q]));
+        bound = __fsub_rd(bound, fabsf(bound) * 1e-6f);
     }
+    // survivors: a prefix of the sorted list
+    uint32_t local = 0;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) local += key2f(~sk[i]) >= bound ? 1u : 0u;
+    if (local) atomicAdd(&s_keep, local);
+    __syncthreads();
+    uint32_t keep = s_keep;
+    if (keep > RUN_CAP) {
+        if (threadIdx.x == 0) a.overflow[q] = 1;
+        keep = RUN_CAP;
+    }
+    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x)
+        a.run[(size_t)q * RUN_CAP + i] = make_uint2(si[i], __float_as_uint(key2f(~sk[i])));
     if (threadIdx.x == 0) {
+        a.run_cnt[q] = keep;
         a.cnt[q] = 0;
-        // k-th exact score so far (T): a row can still enter the top-k only if exact <= T, and
-        // coarse <= exact + eps, i.e. acc = 1 - coarse >= 1 - T - eps. Rounded down to stay safe.
-        float bound = -__int_as_float(0x7f800000);
-        if (si[a.k - 1] != 0xffffffffu) {
-            const float T = key2f(sk[a.k - 1]);
-            bound = __fsub_rd(__fsub_rd(1.0f, T), a.eps[q]);
-            bound = __fsub_rd(bound, fabsf(bound) * 1e-6f);
-        }
         a.athr[q] = bound;
     }
 }
 
-template <typename T> __global__ void fill_t(T *p, T v, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+__global__ void unpack_ids_kernel(const uint2 *__restrict__ run, size_t total, uint32_t *__restrict__ ids) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) ids[i] = run[i].x;
 }
 
-__global__ void finalize_kernel(const uint32_t *__restrict__ run_ids, const float *__restrict__ run_scores, size_t total,
-                                const uint64_t *__restrict__ labels, uint32_t *__restrict__ out_ids, float *__restrict__ out_scores,
-                                uint64_t *__restrict__ out_labels) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t id = run_ids[i];
-        if (out_ids) out_ids[i] = id;
-        if (out_scores) out_scores[i] = run_scores[i];
-        if (out_labels) out_labels[i] = id == 0xffffffffu ? ~0ull : labels[id];
-    }
+template <typename T> __global__ void fill_t(T *p, T v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -476,6 +483,7 @@ struct TensorState {
     unsigned *max_l2_bits = nullptr;
     int sms = 0;
     bool attr_set = false;
+    std::vector<cudaEvent_t> evs; // per-phase (start, stop) pairs around the coarse GEMM launches
 };
 
 static TensorState *state(vsgpu_store *s) {
@@ -487,6 +495,7 @@ void tensor_release(vsgpu_store *s) {
     auto *t = (TensorState *)s->tmap_cache;
     if (t) {
         if (t->max_l2_bits) cudaFree(t->max_l2_bits);
+        for (cudaEvent_t e : t->evs) cudaEventDestroy(e);
         delete t;
         s->tmap_cache = nullptr;
     }
@@ -504,7 +513,7 @@ bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k) {
     if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16) return false;
     if (s->metric != VSGPU_IP && s->metric != VSGPU_COSINE) return false;
     if (s->plan.kind == CK_SEQ) return false;
-    if (nq < 32 || k > 512 || k == 0) return false;
+    if (nq < 32 || k > 384 || k == 0) return false;
     if (s->dim < 64 || s->dim > 8192) return false;
     if (s->count < 32768 || s->count < 16 * k) return false;
     if (!encode_fn()) return false;
@@ -617,22 +626,22 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
         const size_t o_qb = take(nq_pad * qb_stride * 2), o_eps = take(nq * 4), o_athr = take(nq * 4), o_cnt = take(nq * 4),
-                     o_ovf = take(nq * 4), o_rid = take(nq * k * 4), o_rsc = take(nq * k * 4), o_cand = take(nq * CAND_CAP * 4),
-                     o_csc = take(nq * CAND_CAP * 4), o_tot = take(8);
+                     o_ovf = take(nq * 4), o_rcnt = take(nq * 4), o_run = take(nq * RUN_CAP * 8), o_cand = take(nq * CAND_CAP * 8),
+                     o_rid = take(nq * RUN_CAP * 4), o_rsc = take(nq * RUN_CAP * 4), o_tot = take(8);
         VS_TRY(ensure_scratch(s, s->cand, off));
         uint8_t *base = (uint8_t *)s->cand.ptr;
         auto *qb = (__nv_bfloat16 *)(base + o_qb);
         float *eps = (float *)(base + o_eps), *athr = (float *)(base + o_athr);
-        uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = (uint32_t *)(base + o_ovf), *rid = (uint32_t *)(base + o_rid);
-        float *rsc = (float *)(base + o_rsc), *csc = (float *)(base + o_csc);
-        uint32_t *cand = (uint32_t *)(base + o_cand);
+        uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = (uint32_t *)(base + o_ovf), *rcnt = (uint32_t *)(base + o_rcnt);
+        uint2 *run = (uint2 *)(base + o_run), *cand = (uint2 *)(base + o_cand);
+        uint32_t *rid = (uint32_t *)(base + o_rid);
+        float *rsc = (float *)(base + o_rsc);
         auto *tot = (unsigned long long *)(base + o_tot);
 
         VS_CUDA(cudaMemsetAsync(base + o_qb, 0, nq_pad * qb_stride * 2, s->stream));
-        VS_CUDA(cudaMemsetAsync(cnt, 0, nq * 4, s->stream));
-        VS_CUDA(cudaMemsetAsync(ovf, 0, nq * 4, s->stream));
+        // cnt, ovf, rcnt are adjacent 256-byte-aligned blocks: clear them and the counter in one go
+        VS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)((uint8_t *)run - (uint8_t *)cnt), s->stream));
         VS_CUDA(cudaMemsetAsync(tot, 0, 8, s->stream));
-        VS_CUDA(cudaMemsetAsync(rid, 0xff, nq * k * 4, s->stream));
         fill_t<float><<<64, 256, 0, s->stream>>>(athr, -INFINITY, nq);
         prep_coarse_queries_kernel<<<(unsigned)std::min<size_t>((nq + 7) / 8, 1024), 256, 0, s->stream>>>(
             qp, q_stride, f32 ? 1 : 0, s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps);
@@ -641,7 +650,6 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         CUtensorMap map_b;
         VS_TRY(make_map(&map_b, qb, nq_pad, s->dim, qb_stride * 2, BN));
 
-        float gemm_ms_total = 0;
         for (size_t p = 0; p < phases.size(); p++) {
             GemmArgs g{};
             g.row0 = phases[p].first;
@@ -653,38 +661,38 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             g.cnt = cnt;
             g.cand = cand;
             g.dump = nullptr;
-            const bool timed = p + 1 == phases.size();
-            if (timed) VS_CUDA(cudaEventRecord(s->ev2, s->stream));
+            while (t->evs.size() < 2 * (p + 1)) {
+                cudaEvent_t e;
+                VS_CUDA(cudaEventCreate(&e));
+                t->evs.push_back(e);
+            }
+            VS_CUDA(cudaEventRecord(t->evs[2 * p], s->stream));
             VS_TRY(launch_gemm(s, t, map_a, map_b, g));
-            if (timed) VS_CUDA(cudaEventRecord(s->ev3, s->stream));
-            // exact re-score of this phase's candidates, then merge into the running top-k
-            VS_TRY(launch_exact_gather(s, qp, nq, q_stride, nullptr, cand, CAND_CAP, cnt, CAND_CAP, csc, CAND_CAP));
+            VS_CUDA(cudaEventRecord(t->evs[2 * p + 1], s->stream));
             MergeArgs m{};
             m.nq = (uint32_t)nq;
             m.k = (uint32_t)k;
-            m.run_ids = rid;
-            m.run_scores = rsc;
+            m.run = run;
+            m.run_cnt = rcnt;
             m.cnt = cnt;
             m.cand = cand;
-            m.cand_scores = csc;
             m.eps = eps;
             m.athr = athr;
             m.overflow = ovf;
             m.total_cand = tot;
-            uint32_t P = 1;
-            while (P < k + CAND_CAP) P <<= 1;
-            const size_t msmem = (size_t)P * 8;
+            const size_t msmem = (size_t)4096 * 8;
             merge_phase_kernel<<<(unsigned)nq, 1024, msmem, s->stream>>>(m);
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
         }
-        (void)gemm_ms_total;
-        // outputs of this query chunk
-        finalize_kernel<<<256, 256, 0, s->stream>>>(rid, rsc, nq * k, s->labels, out_ids ? out_ids + q0 * k : nullptr,
-                                                   out_scores ? (float *)out_scores + q0 * k : nullptr,
-                                                   out_labels ? out_labels + q0 * k : nullptr);
+        // exact scores of the survivors (bit-identical to the CPU reference), then the final order
+        unpack_ids_kernel<<<256, 256, 0, s->stream>>>(run, nq * RUN_CAP, rid);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches++;
+        VS_TRY(launch_exact_gather(s, qp, nq, q_stride, nullptr, rid, RUN_CAP, rcnt, RUN_CAP, rsc, RUN_CAP));
+        VS_TRY(launch_sort_candidates(s, nq, k, rid, rsc, RUN_CAP, rcnt, k, out_ids ? out_ids + q0 * k : nullptr,
+                                      out_scores ? (float *)out_scores + q0 * k : nullptr,
+                                      out_labels ? out_labels + q0 * k : nullptr));
         // overflowed queries are redone on the exact path
         std::vector<uint32_t> h_ovf(nq);
         unsigned long long h_tot = 0;
@@ -692,6 +700,10 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         VS_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, s->stream));
         VS_CUDA(cudaStreamSynchronize(s->stream));
         s->stats.candidates += h_tot;
+        for (size_t p = 0; p < phases.size(); p++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, t->evs[2 * p], t->evs[2 * p + 1]) == cudaSuccess) s->stats.scan_ms += ms;
+        }
         const size_t ld = (n + 63) / 64 * 64;
         for (size_t q = 0; q < nq; q++) {
             if (!h_ovf[q]) continue;
