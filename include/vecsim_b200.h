@@ -206,6 +206,16 @@ void VecSimGPU_LastQueryStats(VecSimIndex *index, unsigned *path, unsigned *laun
 /* The device store behind a flat index (vsgpu_store*, include/vsgpu.h) for callers that keep queries
  * and results on the device (sharded multi-GPU front-end). Flushes pending appends first. */
 void *VecSimGPU_GetStore(VecSimIndex *index);
+/* HNSW indexes: the device graph (vsgpu_hnsw*), bulk load of a graph built elsewhere over rows in
+ * insertion order (`processed` != 0: blobs are stored rows, e.g. already normalised; layout of
+ * levels / l0 / upper as vsgpu_hnsw_import), read-back, and counters of the last traversal. */
+void *VecSimGPU_GetGraph(VecSimIndex *index);
+int VecSimGPU_HNSWImportGraph(VecSimIndex *index, const void *blobs, int processed, size_t n, const size_t *labels,
+                              const uint32_t *levels, const uint32_t *l0, const uint32_t *upper, size_t upper_records,
+                              long entry, long max_level);
+int VecSimGPU_HNSWExportGraph(VecSimIndex *index, uint32_t *levels, uint32_t *l0, uint32_t *upper, size_t upper_cap_records,
+                              size_t *upper_records, long *entry, long *max_level);
+int VecSimGPU_HNSWLastStats(VecSimIndex *index, unsigned long long *dist_evals, unsigned long long *hops, float *ms);
 const char *VecSimGPU_LastError(void);
 
 #ifdef __cplusplus

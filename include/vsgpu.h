@@ -121,6 +121,42 @@ int vsgpu_merge_topk_device(int device, void *stream, int dtype_f64, size_t part
                             const void *scores, const uint64_t *labels, void *out_scores,
                             uint64_t *out_labels);
 
+/* ---- HNSW (algorithms/hnsw/hnsw.h) -----------------------------------------------------------
+ * A graph over the rows of a store (internal id = row index). Level-0 records hold up to 2M links,
+ * upper levels M. Traversal results are identical to HNSWIndex::topKQuery / rangeQuery on the same
+ * graph (same admission order, same heaps' total order, bit-exact distances); the builder inserts
+ * sequentially in id order and reproduces the reference's single-threaded graph. */
+typedef struct vsgpu_hnsw vsgpu_hnsw;
+/* M in [2,256]; ef_construction is raised to M like hnsw.h:1632-1633. */
+vsgpu_hnsw *vsgpu_hnsw_create(vsgpu_store *s, size_t M, size_t ef_construction);
+void vsgpu_hnsw_destroy(vsgpu_hnsw *g);
+size_t vsgpu_hnsw_size(const vsgpu_hnsw *g);
+size_t vsgpu_hnsw_device_bytes(const vsgpu_hnsw *g);
+int vsgpu_hnsw_entry(const vsgpu_hnsw *g, long *entry, long *max_level); /* -1/-1 when empty */
+/* Index the next n rows of the store (ids size()..size()+n-1, appended beforehand) with the given
+ * top levels (HOST; drawn by the caller as hnsw.h:418-422 does). insertElementToGraph :1567-1602. */
+int vsgpu_hnsw_insert(vsgpu_hnsw *g, size_t n, const uint32_t *levels);
+/* Bulk load / read back a graph (HOST buffers). l0: n x (2M+1) u32 = count then links; upper: one
+ * (M+1)-u32 record per (node, level>=1), nodes in id order, levels ascending. */
+int vsgpu_hnsw_import(vsgpu_hnsw *g, size_t n, const uint32_t *levels, const uint32_t *l0, const uint32_t *upper,
+                      size_t upper_records, long entry, long max_level);
+int vsgpu_hnsw_export(const vsgpu_hnsw *g, uint32_t *levels, uint32_t *l0, uint32_t *upper, size_t upper_cap_records,
+                      size_t *upper_records);
+/* markDelete / unmark (VecSimIndexTombstone): deleted nodes are traversed but never returned. */
+int vsgpu_hnsw_set_deleted(vsgpu_hnsw *g, size_t id, int deleted);
+/* Batched top-k, ef = max(ef, k) (hnsw.h:2072). Layout and padding as vsgpu_topk; results ascending
+ * (score, label). out_counts[q] <= k. */
+int vsgpu_hnsw_topk(vsgpu_hnsw *g, const void *queries, size_t nq, size_t qstride, size_t k, size_t ef,
+                    uint64_t *out_labels, double *out_scores, uint32_t *out_ids, uint32_t *out_counts);
+/* DEVICE queries/outputs (scores in the DistType); synchronises the store's stream before returning. */
+int vsgpu_hnsw_topk_device(vsgpu_hnsw *g, const void *queries, size_t nq, size_t qstride, size_t k, size_t ef,
+                           uint64_t *out_labels, void *out_scores, uint32_t *out_ids, uint32_t *out_counts);
+/* Range search for ONE query (hnsw.h:2086-2200). Unordered; VSGPU_ERR_OVERFLOW + needed count as vsgpu_range. */
+int vsgpu_hnsw_range(vsgpu_hnsw *g, const void *query, double radius, double epsilon, size_t cap, uint64_t *out_labels,
+                     double *out_scores, uint32_t *out_ids, size_t *out_count);
+/* Counters of the last traversal / insert call: distance evaluations, expanded nodes, device ms. */
+int vsgpu_hnsw_last_stats(const vsgpu_hnsw *g, unsigned long long *dist_evals, unsigned long long *hops, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,2 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_hnsw.py -x -q 2>&1 | tail -40

@@ -1,0 +1,197 @@
+"""HNSW parity on the device, through the C-ABI (libvecsim_b200.so): traversal results on the
+reference's own graph, and the device builder against the graph the reference builds
+(SURVEY §8 rows a13-a15). Everything is compared bit-exact: labels, order, fp scores, link lists."""
+import os
+
+import numpy as np
+import pytest
+
+from datagen import METRIC_NAMES, TYPE_NAMES, make_vectors
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "hnsw_case.npz"))
+N, DIM, M, EFC, NQ, K = 1500, 24, 8, 48, 16, 10  # tests/golden/make_hnsw_golden.py
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from vectorsimilarity_b200 import build, capi as c
+    build.build()
+    c.lib()
+    return c
+
+
+def new_index(capi, vtype, dim, metric, M=16, efc=200, ef=10):
+    return capi.HNSWIndex(capi.HNSWParams(type=vtype, dim=dim, metric=metric, multi=False, initialCapacity=0,
+                                          blockSize=1024, M=M, efConstruction=efc, efRuntime=ef, epsilon=0.01))
+
+
+def gold_graph(name):
+    levels = GOLD[name + "_levels"]
+    nl = int(GOLD[name + "_entry"][1]) + 1
+    links = [GOLD[f"{name}_links{l}"] for l in range(nl)]
+    counts = [GOLD[f"{name}_counts{l}"] for l in range(nl)]
+    return levels, links, counts, int(GOLD[name + "_entry"][0]), int(GOLD[name + "_entry"][1])
+
+
+def graph_records(levels, links, counts, M):
+    """(l0 [n, 2M+1], upper [records, M+1]) in the export layout of include/vsgpu.h."""
+    n = len(levels)
+    l0 = np.zeros((n, 2 * M + 1), dtype=np.uint32)
+    l0[:, 0] = counts[0]
+    l0[:, 1:] = np.where(np.arange(2 * M)[None, :] < counts[0][:, None], links[0], 0)
+    recs = []
+    for i in np.nonzero(levels)[0]:
+        for lvl in range(1, int(levels[i]) + 1):
+            r = np.zeros(M + 1, dtype=np.uint32)
+            c = int(counts[lvl][i])
+            r[0] = c
+            r[1:1 + c] = links[lvl][i][:c]
+            recs.append(r)
+    return l0, (np.stack(recs) if recs else np.zeros((0, M + 1), dtype=np.uint32))
+
+
+def masked(rec):
+    """zero the unused tail of each link record so records compare as arrays"""
+    rec = rec.copy()
+    w = rec.shape[1] - 1
+    rec[:, 1:] = np.where(np.arange(w)[None, :] < rec[:, :1], rec[:, 1:], 0)
+    return rec
+
+
+@pytest.mark.parametrize("name,metric", [("l2", 0), ("cos", 2)])
+def test_traversal_on_reference_graph_matches_golden(capi, name, metric):
+    """Import the graph the reference built, search it on the device: top-k and range results are the
+    reference's, bit for bit."""
+    levels, links, counts, entry, maxl = gold_graph(name)
+    G = new_index(capi, 0, DIM, metric, M=M, efc=EFC)
+    G.import_graph(GOLD[name + "_stored"], levels, links, counts, entry, maxl, processed=True)
+    assert G.index_size() == N
+    Q = GOLD[name + "_Q"]
+    for ef in (10, 40):
+        G.set_ef(ef)
+        labels, scores = G.knn_batch(Q, K)
+        assert np.array_equal(labels, GOLD[f"{name}_labels_ef{ef}"]), ef
+        assert np.array_equal(scores, GOLD[f"{name}_scores_ef{ef}"]), ef
+        # single-query API gives the same as the batch
+        l1, s1 = G.knn_query(Q[3], K)
+        assert np.array_equal(l1[0], labels[3]) and np.array_equal(s1[0], scores[3])
+    off = 0
+    for i in range(NQ):
+        n = int(GOLD[name + "_range_n"][i])
+        l, s = G.range_query(Q[i], float(GOLD[name + "_radius"][i]))
+        assert l.shape[1] == n
+        assert np.array_equal(l[0], GOLD[name + "_range_labels"][off:off + n])
+        assert np.array_equal(s[0], GOLD[name + "_range_scores"][off:off + n])
+        off += n
+    st = G.hnsw_stats()
+    assert st["dist_evals"] > 0 and st["hops"] > 0
+    G.close()
+
+
+@pytest.mark.parametrize("name,metric", [("l2", 0), ("cos", 2)])
+def test_builder_reproduces_reference_graph(capi, name, metric):
+    """VecSimIndex_AddVector on the device: same levels, entry point and link lists (in order) as the
+    reference's single-threaded build over the same vectors."""
+    levels, links, counts, entry, maxl = gold_graph(name)
+    G = new_index(capi, 0, DIM, metric, M=M, efc=EFC)
+    X = GOLD[name + "_X"]
+    assert G.add_vectors(X[:700]) == 700
+    for i in range(700, 720):  # one at a time through VecSimIndex_AddVector
+        assert G.add_vector(X[i], i) == 1
+    assert G.add_vectors(X[720:], first_label=720) == N - 720
+    g = G.export_graph(N)
+    assert np.array_equal(g["levels"], levels)
+    assert (g["entry"], g["max_level"]) == (entry, maxl)
+    l0, upper = graph_records(levels, links, counts, M)
+    assert np.array_equal(masked(g["l0"])[:, 0], l0[:, 0]), "level-0 degrees differ"
+    assert np.array_equal(masked(g["l0"]), l0), "level-0 links differ"
+    assert np.array_equal(masked(g["upper"]), upper), "upper-level links differ"
+    Q = GOLD[name + "_Q"]
+    G.set_ef(40)
+    labels, scores = G.knn_batch(Q, K)
+    assert np.array_equal(labels, GOLD[f"{name}_labels_ef40"])
+    assert np.array_equal(scores, GOLD[f"{name}_scores_ef40"])
+    G.close()
+
+
+@pytest.mark.parametrize("vtype,metric,dim", [(0, 1, 128), (1, 0, 20), (2, 1, 64), (2, 0, 40), (3, 2, 48), (4, 2, 64),
+                                              (4, 0, 33), (5, 1, 100), (0, 0, 5), (3, 0, 12)],
+                         ids=lambda v: str(v))
+def test_build_and_search_match_live_reference(capi, ref, vtype, metric, dim):
+    """Every distance policy (chain fp32/fp64/bf16/fp16, integer, scalar tiers): build on the device and in
+    the unmodified reference from the same vectors, then compare query results."""
+    feats = ref.host_features()
+    if vtype == 2 and metric != 0 and "avx512_bf16" not in feats:
+        pytest.skip("host lacks avx512_bf16: the reference dispatches a different bf16 IP tier here")
+    if "avx512f" not in feats:
+        pytest.skip("host lacks avx512f")
+    ref.set_disabled_features("avx512_fp16")
+    n, nq, k = 1200, 12, 8
+    X = make_vectors(vtype, n, dim, seed=900 + vtype * 7 + metric)
+    Q = make_vectors(vtype, nq, dim, seed=901 + vtype * 7 + metric)
+    if metric == 2:
+        X[(X == 0).all(1), 0] = 1
+        Q[(Q == 0).all(1), 0] = 1
+    R = ref.RefIndex(vtype, dim, metric, algo="hnsw", M=6, ef_construction=40, ef_runtime=10)
+    R.add_many(X)
+    G = new_index(capi, vtype, dim, metric, M=6, efc=40)
+    assert G.add_vectors(X) == n
+    for ef in (10, 64):
+        G.set_ef(ef)
+        labels, scores = G.knn_batch(Q, k)
+        for i in range(nq):
+            rl, rs, code = R.topk(Q[i], k, ef_runtime=ef)
+            assert code == 0
+            assert np.array_equal(labels[i], rl.astype(np.int64)), (TYPE_NAMES[vtype], METRIC_NAMES[metric], ef, i)
+            assert np.array_equal(scores[i], rs), (TYPE_NAMES[vtype], METRIC_NAMES[metric], ef, i)
+    G.close()
+    R.close()
+    ref.set_disabled_features("")
+
+
+def test_deleted_nodes_are_traversed_not_returned(capi):
+    n, dim = 600, 16
+    X = make_vectors(0, n, dim, seed=5)
+    G = new_index(capi, 0, dim, 0, M=8, efc=40)
+    G.add_vectors(X)
+    G.set_ef(50)
+    l0, s0 = G.knn_query(X[17], 5)
+    assert l0[0][0] == 17 and s0[0][0] == 0.0
+    assert G.delete_vector(17) == 1 and G.delete_vector(17) == 0
+    assert G.index_size() == n - 1
+    l1, _ = G.knn_query(X[17], 5)
+    assert 17 not in l1[0]
+    assert list(l1[0][:4]) == list(l0[0][1:5])
+    # overwrite = tombstone + append
+    assert G.add_vector(X[18] * 0.5, 18) == 0
+    l2, _ = G.knn_query(X[18] * 0.5, 1)
+    assert l2[0][0] == 18
+    G.close()
+
+
+def test_empty_and_small(capi):
+    G = new_index(capi, 0, 8, 0, M=4, efc=10)
+    q = np.ones(8, dtype=np.float32)
+    l, s = G.knn_query(q, 5)
+    assert l.shape == (1, 0)
+    l, s = G.range_query(q, 10.0)
+    assert l.shape == (1, 0)
+    G.add_vector(q * 2, 42)
+    l, s = G.knn_query(q, 5)
+    assert list(l[0]) == [42] and s[0][0] == 8.0
+    G.add_vector(q * 3, 7)
+    l, s = G.knn_query(q, 5)
+    assert list(l[0]) == [42, 7]
+    l, s = G.range_query(q, 8.0)
+    assert list(l[0]) == [42]
+    it = G.create_batch_iterator(q)
+    assert it.has_next()
+    l, _ = it.get_next_results(1)
+    assert list(l[0]) == [42]
+    l, _ = it.get_next_results(5)
+    assert list(l[0]) == [7]
+    assert not it.has_next()
+    it.close()
+    G.close()

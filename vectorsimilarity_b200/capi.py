@@ -90,6 +90,7 @@ EXPORTS = [
     "VecSimIndex_TopKQueryBatch", "VecSimIndex_TopKQueryBatchRaw", "VecSimIndex_AddVectorBatch",
     "VecSimGPU_SetDevice", "VecSimGPU_GetDevice", "VecSimGPU_DeviceCount", "VecSimGPU_SetTopKMode",
     "VecSimGPU_LastQueryStats", "VecSimGPU_GetStore", "VecSimGPU_LastError", "VecSimGPU_AppendDeviceRows",
+    "VecSimGPU_GetGraph", "VecSimGPU_HNSWImportGraph", "VecSimGPU_HNSWExportGraph", "VecSimGPU_HNSWLastStats",
 ]
 
 
@@ -173,6 +174,11 @@ def lib():
     L.VecSimGPU_GetStore.restype = vp
     L.VecSimGPU_GetStore.argtypes = [vp]
     L.VecSimGPU_LastError.restype = C.c_char_p
+    L.VecSimGPU_GetGraph.restype = vp
+    L.VecSimGPU_GetGraph.argtypes = [vp]
+    L.VecSimGPU_HNSWImportGraph.argtypes = [vp, vp, i32, sz, vp, vp, vp, vp, sz, C.c_long, C.c_long]
+    L.VecSimGPU_HNSWExportGraph.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz), C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    L.VecSimGPU_HNSWLastStats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -366,6 +372,83 @@ class BFIndex(VecSimIndex):
         p.algo = VecSimAlgo_BF
         p.algoParams.bfParams = params
         super().__init__(p)
+
+
+class HNSWIndex(VecSimIndex):
+    """Mirror of the reference binding's HNSWIndex (src/python_bindings/bindings.cpp:286-420): add_vector,
+    knn_query, range_query, set_ef; plus the bulk graph import / export of include/vecsim_b200.h."""
+
+    def __init__(self, params):
+        p = VecSimParams()
+        p.algo = VecSimAlgo_HNSWLIB
+        p.algoParams.hnswParams = params
+        super().__init__(p)
+        self.M = params.M or 16
+        self._ef = 0
+
+    def set_ef(self, ef):
+        self._ef = int(ef)
+
+    def _qp(self, query_param):
+        if query_param is not None or not self._ef:
+            return query_param
+        qp = VecSimQueryParams()
+        qp.hnswRuntimeParams.efRuntime = self._ef
+        return qp
+
+    def knn_query(self, vector, k, query_param=None, order=BY_SCORE):
+        return super().knn_query(vector, k, self._qp(query_param), order)
+
+    def knn_batch(self, queries, k, query_param=None):
+        return super().knn_batch(queries, k, self._qp(query_param))
+
+    def import_graph(self, vectors, levels, links, counts, entry, max_level, labels=None, processed=True):
+        """Adopt a graph over `vectors` (rows in internal-id order). links[l]: [n, width_l] u32, counts[l]: [n]
+        (the layout oracle.ref.RefIndex.hnsw_export produces)."""
+        vectors = np.ascontiguousarray(vectors)
+        n = vectors.shape[0]
+        levels = np.ascontiguousarray(levels, dtype=np.uint32)
+        M, M0 = self.M, 2 * self.M
+        l0 = np.zeros((n, M0 + 1), dtype=np.uint32)
+        l0[:, 0] = counts[0]
+        l0[:, 1:] = np.where(np.arange(M0)[None, :] < np.asarray(counts[0])[:, None], links[0], 0)
+        recs = []
+        for i in np.nonzero(levels)[0]:
+            for lvl in range(1, int(levels[i]) + 1):
+                r = np.zeros(M + 1, dtype=np.uint32)
+                c = int(counts[lvl][i])
+                r[0] = c
+                r[1:1 + c] = links[lvl][i][:c]
+                recs.append(r)
+        upper = np.ascontiguousarray(np.stack(recs)) if recs else np.zeros((0, M + 1), dtype=np.uint32)
+        lab = None if labels is None else np.ascontiguousarray(labels, dtype=np.uint64)
+        rc = lib().VecSimGPU_HNSWImportGraph(self._h, _ptr(vectors), int(processed), n, _ptr(lab) if lab is not None else None,
+                                             _ptr(levels), _ptr(l0), _ptr(upper) if len(recs) else None, len(recs),
+                                             int(entry), int(max_level))
+        if rc != 0:
+            raise RuntimeError("HNSWImportGraph failed: " + lib().VecSimGPU_LastError().decode())
+
+    def export_graph(self, n):
+        """-> dict(levels[n], l0[n, 2M+1], upper[records, M+1], entry, max_level)."""
+        M, M0 = self.M, 2 * self.M
+        levels = np.zeros(n, dtype=np.uint32)
+        l0 = np.zeros((n, M0 + 1), dtype=np.uint32)
+        recs = C.c_size_t()
+        entry, maxl = C.c_long(), C.c_long()
+        rc = lib().VecSimGPU_HNSWExportGraph(self._h, _ptr(levels), _ptr(l0), None, 0, C.byref(recs), C.byref(entry),
+                                             C.byref(maxl))
+        assert rc == 0, lib().VecSimGPU_LastError()
+        upper = np.zeros((recs.value, M + 1), dtype=np.uint32)
+        if recs.value:
+            rc = lib().VecSimGPU_HNSWExportGraph(self._h, None, None, _ptr(upper), recs.value, C.byref(recs),
+                                                 C.byref(entry), C.byref(maxl))
+            assert rc == 0, lib().VecSimGPU_LastError()
+        return dict(levels=levels, l0=l0, upper=upper, entry=entry.value, max_level=maxl.value)
+
+    def hnsw_stats(self):
+        ev, hops, ms = C.c_ulonglong(), C.c_ulonglong(), C.c_float()
+        lib().VecSimGPU_HNSWLastStats(self._h, C.byref(ev), C.byref(hops), C.byref(ms))
+        return dict(dist_evals=ev.value, hops=hops.value, ms=ms.value)
 
 
 class BatchIterator:

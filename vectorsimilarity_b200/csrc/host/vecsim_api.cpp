@@ -80,7 +80,22 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
             }
             return idx;
         }
-        g_api_err = "only VecSimAlgo_BF is served by this library (HNSW search: vsgpu_hnsw_*)";
+        if (params->algo == VecSimAlgo_HNSWLIB) {
+            const HNSWParams &p = params->algoParams.hnswParams;
+            if (p.dim == 0 || p.type > VecSimType_UINT8 || p.metric > VecSimMetric_Cosine) return nullptr;
+            if (p.multi) {
+                g_api_err = "multi-value HNSW indexes are not built yet (SURVEY §8 row f2)";
+                return nullptr;
+            }
+            auto *idx = new HnswIndex(p, params->logCtx);
+            if (!idx->ok()) {
+                g_api_err = std::string("HNSW index: ") + vsgpu_last_error();
+                delete idx;
+                return nullptr;
+            }
+            return idx;
+        }
+        g_api_err = "VecSimAlgo_BF and VecSimAlgo_HNSWLIB are served by this library (tiered / SVS: SURVEY §8 row f1)";
         return nullptr;
     } catch (...) {
         return nullptr;
@@ -88,6 +103,12 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
 }
 size_t VecSimIndex_EstimateInitialSize(const VecSimParams *) { return sizeof(FlatIndex); }
 size_t VecSimIndex_EstimateElementSize(const VecSimParams *params) {
+    if (params && params->algo == VecSimAlgo_HNSWLIB) {
+        // index_factories/hnsw_factory.cpp:123-148: level-0 record + expected upper levels + vector + metadata
+        const HNSWParams &p = params->algoParams.hnswParams;
+        const size_t M = p.M ? p.M : 16;
+        return stored_size(p.type, p.dim, p.metric) + (2 * M + 1) * sizeof(idType) + sizeof(size_t) + 2 * sizeof(idType) + 5;
+    }
     if (!params || params->algo != VecSimAlgo_BF) return 0;
     const BFParams &p = params->algoParams.bfParams;
     return stored_size(p.type, p.dim, p.metric) + sizeof(size_t) + sizeof(idType);
@@ -282,6 +303,32 @@ void VecSimGPU_LastQueryStats(VecSimIndex *index, unsigned *path, unsigned *laun
     if (total_ms) *total_ms = st.total_ms;
 }
 void *VecSimGPU_GetStore(VecSimIndex *index) { return index->deviceStore(); }
+void *VecSimGPU_GetGraph(VecSimIndex *index) {
+    auto *h = dynamic_cast<HnswIndex *>(index);
+    return h ? (void *)h->deviceGraph() : nullptr;
+}
+int VecSimGPU_HNSWImportGraph(VecSimIndex *index, const void *blobs, int processed, size_t n, const size_t *labels,
+                              const uint32_t *levels, const uint32_t *l0, const uint32_t *upper, size_t upper_records,
+                              long entry, long max_level) {
+    auto *h = dynamic_cast<HnswIndex *>(index);
+    if (!h) return -1;
+    return h->importGraph(blobs, processed, n, labels, levels, l0, upper, upper_records, entry, max_level);
+}
+int VecSimGPU_HNSWExportGraph(VecSimIndex *index, uint32_t *levels, uint32_t *l0, uint32_t *upper, size_t upper_cap_records,
+                              size_t *upper_records, long *entry, long *max_level) {
+    auto *h = dynamic_cast<HnswIndex *>(index);
+    if (!h) return -1;
+    vsgpu_hnsw *g = h->deviceGraph();
+    if (!g) return -1;
+    if (vsgpu_hnsw_export(g, levels, l0, upper, upper_cap_records, upper_records) != VSGPU_OK) return -1;
+    vsgpu_hnsw_entry(g, entry, max_level);
+    return 0;
+}
+int VecSimGPU_HNSWLastStats(VecSimIndex *index, unsigned long long *dist_evals, unsigned long long *hops, float *ms) {
+    auto *h = dynamic_cast<HnswIndex *>(index);
+    if (!h) return -1;
+    return vsgpu_hnsw_last_stats(h->deviceGraph(), dist_evals, hops, ms);
+}
 const char *VecSimGPU_LastError(void) {
     if (!g_api_err.empty()) return g_api_err.c_str();
     return vsgpu_last_error();

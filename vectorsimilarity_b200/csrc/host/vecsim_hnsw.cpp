@@ -1,0 +1,406 @@
+// HNSW index: host bookkeeping of the reference's HNSWIndex_Single
+// (/root/reference/src/VecSim/algorithms/hnsw/hnsw.h:1616-1650 ctor, :418-422 level draw, :1860-1960
+// store + index a vector, :2037-2084 topKQuery, :2152-2186 rangeQuery; hnsw_single.h:134-170 add /
+// delete) over a device-resident row store and graph. Every distance, the traversals and the graph
+// construction run in libvsgpu.so (vsgpu_hnsw_*); there is no CPU fallback.
+#include "vecsim_index.h"
+#include "vecsim_numeric.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <random>
+#include <unordered_set>
+
+namespace vsb {
+
+static constexpr size_t HNSW_FLUSH_ROWS = 4096;
+
+HnswIndex::HnswIndex(const HNSWParams &p, void *logCtx)
+    : type_(p.type), metric_(p.metric), dim_(p.dim), block_size_(p.blockSize ? p.blockSize : 1024),
+      data_size_(type_size(p.type) * p.dim), stored_size_(stored_size(p.type, p.dim, p.metric)), log_ctx_(logCtx) {
+    M_ = p.M ? p.M : 16;                                              // HNSW_DEFAULT_M
+    efc_ = std::max<size_t>(p.efConstruction ? p.efConstruction : 200, M_); // hnsw.h:1632-1633
+    ef_ = p.efRuntime ? p.efRuntime : 10;
+    epsilon_ = p.epsilon > 0.0 ? p.epsilon : 0.01;
+    if (M_ <= 1 || 2 * M_ > 512) return; // the reference throws for M<=1 (hnsw.h:1644); >256 is a device limit
+    mult_ = 1.0 / std::log(1.0 * (double)M_);
+    level_gen_.seed(100); // hnsw.h:230 default random_seed
+    store_ = vsgpu_store_create(globals().device, (int)type_, (int)metric_, dim_, p.initialCapacity);
+    if (store_) graph_ = vsgpu_hnsw_create(store_, M_, efc_);
+}
+
+HnswIndex::~HnswIndex() {
+    if (graph_) vsgpu_hnsw_destroy(graph_);
+    if (store_) vsgpu_store_destroy(store_);
+}
+
+void HnswIndex::preprocess(const void *blob, uint8_t *out) const {
+    std::memcpy(out, blob, data_size_);
+    if (metric_ == VecSimMetric_Cosine) normalize_blob(out, dim_, type_);
+}
+
+std::vector<uint8_t> HnswIndex::preprocessQuery(const void *blob) {
+    std::vector<uint8_t> q(stored_size_);
+    preprocess(blob, q.data());
+    return q;
+}
+
+// getRandomLevel (hnsw.h:418-422): the same engine and distribution objects as the reference, so
+// the level sequence is the reference's for the same insertion order.
+uint32_t HnswIndex::drawLevel() {
+    std::uniform_real_distribution<double> distribution(0.0, 1.0);
+    const double r = -std::log(distribution(level_gen_)) * mult_;
+    return (uint32_t)(size_t)r;
+}
+
+int HnswIndex::flush() {
+    if (pending_labels_.empty()) return 0;
+    const size_t n = pending_labels_.size();
+    int rc = vsgpu_store_append(store_, pending_rows_.data(), stored_size_, pending_labels_.data(), n);
+    if (rc != VSGPU_OK) return rc;
+    rc = vsgpu_hnsw_insert(graph_, n, pending_levels_.data());
+    pending_rows_.clear();
+    pending_labels_.clear();
+    pending_levels_.clear();
+    return rc;
+}
+
+int HnswIndex::addVector(const void *blob, size_t label) {
+    std::lock_guard<std::mutex> g(mu_);
+    int ret = 1;
+    auto it = label_to_id_.find(label);
+    if (it != label_to_id_.end()) {
+        // hnsw_single.h:153-163 deletes the old vector and appends the new one. The old node is
+        // tombstoned here instead of being cut out of the graph.
+        if (markDeletedLocked(it->second) != 0) return -1;
+        label_to_id_.erase(it);
+        ret = 0;
+    }
+    const size_t id = id_to_label_.size();
+    if (id >= 0xfffffffeull) return -1;
+    id_to_label_.push_back(label);
+    label_to_id_[label] = (idType)id;
+    const size_t off = pending_rows_.size();
+    pending_rows_.resize(off + stored_size_);
+    preprocess(blob, pending_rows_.data() + off);
+    pending_labels_.push_back(label);
+    pending_levels_.push_back(drawLevel());
+    if (pending_labels_.size() >= HNSW_FLUSH_ROWS)
+        if (flush() != 0) return -1;
+    return ret;
+}
+
+long HnswIndex::addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) {
+    long added = 0;
+    for (size_t i = 0; i < n; i++) {
+        const int rc = addVector((const uint8_t *)blobs + i * data_size_, labels ? labels[i] : first_label + i);
+        if (rc < 0) return -1;
+        added += rc;
+    }
+    return added;
+}
+
+int HnswIndex::markDeletedLocked(idType id) {
+    if (flush() != 0) return -1;
+    if (vsgpu_hnsw_set_deleted(graph_, id, 1) != VSGPU_OK) return -1;
+    num_deleted_++;
+    return 0;
+}
+
+int HnswIndex::deleteVector(size_t label) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = label_to_id_.find(label);
+    if (it == label_to_id_.end()) return 0;
+    if (markDeletedLocked(it->second) != 0) return 0;
+    label_to_id_.erase(it);
+    return 1;
+}
+
+double HnswIndex::getDistanceFrom(size_t label, const void *blob) {
+    std::lock_guard<std::mutex> g(mu_);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    auto it = label_to_id_.find(label);
+    if (it == label_to_id_.end()) return nan;
+    if (flush() != 0) return nan;
+    const uint32_t id = it->second;
+    double out = nan;
+    if (vsgpu_distances(store_, blob, &id, 1, &out) != VSGPU_OK) return nan;
+    return out;
+}
+
+void HnswIndex::exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) {
+    std::lock_guard<std::mutex> g(mu_);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (size_t i = 0; i < n; i++) out[i] = nan;
+    if (flush() != 0) return;
+    std::vector<uint32_t> ids;
+    std::vector<size_t> pos;
+    for (size_t i = 0; i < n; i++) {
+        auto it = label_to_id_.find(labels[i]);
+        if (it == label_to_id_.end()) continue;
+        ids.push_back(it->second);
+        pos.push_back(i);
+    }
+    if (ids.empty()) return;
+    std::vector<double> d(ids.size());
+    if (vsgpu_distances(store_, processed_query, ids.data(), ids.size(), d.data()) != VSGPU_OK) return;
+    for (size_t j = 0; j < ids.size(); j++) out[pos[j]] = d[j];
+}
+
+int HnswIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *out_labels,
+                         double *out_scores, uint32_t *out_counts) {
+    std::lock_guard<std::mutex> g(mu_);
+    void *tctx = qp ? qp->timeoutCtx : nullptr;
+    last_mode_ = STANDARD_KNN;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    auto pad_all = [&]() {
+        for (size_t i = 0; i < nq * k; i++) {
+            if (out_labels) out_labels[i] = (size_t)-1;
+            if (out_scores) out_scores[i] = nan;
+        }
+        if (out_counts)
+            for (size_t q = 0; q < nq; q++) out_counts[q] = 0;
+    };
+    if (nq == 0) return 0;
+    if (k == 0 || id_to_label_.empty()) {
+        pad_all();
+        return 0;
+    }
+    if (timed_out(tctx)) {
+        pad_all();
+        return 1;
+    }
+    if (flush() != 0) return -1;
+    size_t ef = ef_;
+    if (qp && qp->hnswRuntimeParams.efRuntime != 0) ef = qp->hnswRuntimeParams.efRuntime;
+    std::vector<uint8_t> qbuf(nq * stored_size_);
+    for (size_t q = 0; q < nq; q++) preprocess((const uint8_t *)queries + q * data_size_, qbuf.data() + q * stored_size_);
+    static_assert(sizeof(size_t) == sizeof(uint64_t), "labelType is 64-bit");
+    std::vector<uint32_t> counts(nq);
+    const int rc = vsgpu_hnsw_topk(graph_, qbuf.data(), nq, stored_size_, k, ef, (uint64_t *)out_labels, out_scores, nullptr,
+                                   counts.data());
+    if (rc != VSGPU_OK) return -1;
+    if (timed_out(tctx)) {
+        pad_all();
+        return 1;
+    }
+    if (out_counts) std::copy(counts.begin(), counts.end(), out_counts);
+    return 0;
+}
+
+VecSimQueryReply *HnswIndex::topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) {
+    auto *rep = new VecSimQueryReply();
+    if (k == 0 || indexSize() == 0) {
+        last_mode_ = STANDARD_KNN;
+        return rep;
+    }
+    const size_t cap = std::min(k, id_to_label_.size());
+    std::vector<size_t> labels(cap);
+    std::vector<double> scores(cap);
+    uint32_t cnt = 0;
+    const int rc = topKBatch(blob, 1, cap, qp, labels.data(), scores.data(), &cnt);
+    if (rc == 1) rep->code = VecSim_QueryReply_TimedOut;
+    if (rc != 0) return rep;
+    rep->results.resize(cnt);
+    for (uint32_t i = 0; i < cnt; i++) rep->results[i] = {labels[i], scores[i]};
+    return rep;
+}
+
+VecSimQueryReply *HnswIndex::rangeQuery(const void *blob, double radius, VecSimQueryParams *qp, VecSimQueryReply_Order order) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto *rep = new VecSimQueryReply();
+    void *tctx = qp ? qp->timeoutCtx : nullptr;
+    last_mode_ = RANGE_QUERY;
+    if (id_to_label_.empty()) return rep;
+    if (timed_out(tctx)) {
+        rep->code = VecSim_QueryReply_TimedOut;
+        return rep;
+    }
+    if (flush() != 0) return rep;
+    double eps = epsilon_;
+    if (qp && qp->hnswRuntimeParams.epsilon != 0.0) eps = qp->hnswRuntimeParams.epsilon;
+    std::vector<uint8_t> q(stored_size_);
+    preprocess(blob, q.data());
+    size_t cap = 4096, count = 0;
+    std::vector<uint64_t> lab;
+    std::vector<double> sc;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        lab.resize(cap);
+        sc.resize(cap);
+        const int rc = vsgpu_hnsw_range(graph_, q.data(), radius, eps, cap, lab.data(), sc.data(), nullptr, &count);
+        if (rc == VSGPU_OK) break;
+        if (rc != VSGPU_ERR_OVERFLOW) return rep;
+        cap = count;
+    }
+    if (timed_out(tctx)) {
+        rep->code = VecSim_QueryReply_TimedOut;
+        return rep;
+    }
+    rep->results.resize(count);
+    for (size_t i = 0; i < count; i++) rep->results[i] = {(size_t)lab[i], sc[i]};
+    if (order == BY_ID)
+        std::sort(rep->results.begin(), rep->results.end(),
+                  [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id < b.id; });
+    else
+        std::sort(rep->results.begin(), rep->results.end(), [](const VecSimQueryResult &a, const VecSimQueryResult &b) {
+            if (a.score < b.score) return true;
+            if (b.score < a.score) return false;
+            return a.id < b.id;
+        });
+    return rep;
+}
+
+namespace {
+// Batches through repeated top-k with a growing k: results already returned are skipped. This keeps
+// the contract of VecSimBatchIterator_Next (n best not yet returned, hnsw_batch_iterator.h:206-249)
+// on top of the batched traversal; the resumable single-traversal form is SURVEY §8 row a15.
+class HnswBatchIterator final : public VecSimBatchIterator {
+  public:
+    HnswBatchIterator(HnswIndex *idx, const void *raw_query, size_t bytes, VecSimQueryParams *qp)
+        : idx_(idx), query_((const uint8_t *)raw_query, (const uint8_t *)raw_query + bytes) {
+        if (qp) qp_ = *qp;
+        has_qp_ = qp != nullptr;
+    }
+    VecSimQueryReply *next(size_t n, VecSimQueryReply_Order order) override {
+        auto *rep = new VecSimQueryReply();
+        const size_t total = idx_->indexLabelCount();
+        const size_t want = std::min(returned_.size() + n, total);
+        if (want == returned_.size()) {
+            depleted_ = true;
+            return rep;
+        }
+        VecSimQueryParams qp = qp_;
+        if (qp.hnswRuntimeParams.efRuntime < want) qp.hnswRuntimeParams.efRuntime = std::max(want, idx_->efRuntime());
+        VecSimQueryReply *all = idx_->topKQuery(query_.data(), want, &qp);
+        rep->code = all->code;
+        for (auto &r : all->results) {
+            if (rep->results.size() == n) break;
+            if (returned_.insert(r.id).second) rep->results.push_back(r);
+        }
+        delete all;
+        if (rep->results.size() < n || returned_.size() == total) depleted_ = true;
+        if (order == BY_ID)
+            std::sort(rep->results.begin(), rep->results.end(),
+                      [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id < b.id; });
+        return rep;
+    }
+    bool hasNext() override { return !depleted_ && returned_.size() < idx_->indexLabelCount(); }
+    void reset() override {
+        returned_.clear();
+        depleted_ = false;
+    }
+
+  private:
+    HnswIndex *idx_;
+    std::vector<uint8_t> query_;
+    VecSimQueryParams qp_{};
+    bool has_qp_ = false;
+    std::unordered_set<size_t> returned_;
+    bool depleted_ = false;
+};
+} // namespace
+
+VecSimBatchIterator *HnswIndex::newBatchIterator(const void *blob, VecSimQueryParams *qp) {
+    return new HnswBatchIterator(this, blob, data_size_, qp);
+}
+
+VecSimIndexBasicInfo HnswIndex::basicInfo() {
+    VecSimIndexBasicInfo b{};
+    b.algo = VecSimAlgo_HNSWLIB;
+    b.metric = metric_;
+    b.type = type_;
+    b.isMulti = false;
+    b.isTiered = false;
+    b.isDisk = false;
+    b.blockSize = block_size_;
+    b.dim = dim_;
+    return b;
+}
+
+VecSimIndexStatsInfo HnswIndex::statsInfo() {
+    VecSimIndexStatsInfo s{};
+    s.memory = sizeof(*this) + id_to_label_.capacity() * sizeof(size_t) + label_to_id_.size() * 32 + pending_rows_.capacity() +
+               (store_ ? vsgpu_store_device_bytes(store_) : 0) + (graph_ ? vsgpu_hnsw_device_bytes(graph_) : 0);
+    s.numberOfMarkedDeleted = num_deleted_;
+    return s;
+}
+
+VecSimIndexDebugInfo HnswIndex::debugInfo() {
+    std::lock_guard<std::mutex> g(mu_);
+    flush();
+    VecSimIndexDebugInfo d{};
+    d.commonInfo.basicInfo = basicInfo();
+    d.commonInfo.indexSize = id_to_label_.size() - num_deleted_;
+    d.commonInfo.indexLabelCount = label_to_id_.size();
+    d.commonInfo.memory = statsInfo().memory;
+    d.commonInfo.lastMode = last_mode_;
+    long ep = -1, ml = -1;
+    vsgpu_hnsw_entry(graph_, &ep, &ml);
+    d.hnswInfo.M = M_;
+    d.hnswInfo.efConstruction = efc_;
+    d.hnswInfo.efRuntime = ef_;
+    d.hnswInfo.epsilon = epsilon_;
+    d.hnswInfo.max_level = (size_t)ml; // HNSW_INVALID_LEVEL == SIZE_MAX when empty
+    d.hnswInfo.entrypoint = ep < 0 ? (size_t)-1 : id_to_label_[(size_t)ep];
+    d.hnswInfo.visitedNodesPoolSize = 1;
+    d.hnswInfo.numberOfMarkedDeletedNodes = num_deleted_;
+    return d;
+}
+
+// hnsw.h:2340-2400 uses a CPU-fitted tree; on the device graph traversal is latency-bound per query
+// while ad-hoc scoring is a gather, so ad-hoc wins for small subsets (re-tuning: SURVEY §8 row f4).
+bool HnswIndex::preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) {
+    const size_t n = indexSize();
+    subsetSize = std::min(subsetSize, n);
+    const float r = n == 0 ? 0.0f : (float)subsetSize / (float)n;
+    const bool res = n <= 1000 || r <= 0.05f || (float)k / std::max<float>(1.f, (float)subsetSize) > 0.1f;
+    last_mode_ = res ? (initial_check ? HYBRID_ADHOC_BF : HYBRID_BATCHES_TO_ADHOC_BF) : HYBRID_BATCHES;
+    return res;
+}
+
+vsgpu_store *HnswIndex::deviceStore() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (flush() != 0) return nullptr;
+    return store_;
+}
+
+vsgpu_hnsw *HnswIndex::deviceGraph() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (flush() != 0) return nullptr;
+    return graph_;
+}
+
+void HnswIndex::lastStats(vsgpu_stats *out) {
+    *out = vsgpu_stats{};
+    unsigned long long ev = 0, hops = 0;
+    float ms = 0;
+    vsgpu_hnsw_last_stats(graph_, &ev, &hops, &ms);
+    out->path = 2;
+    out->kernel_launches = 1;
+    out->candidates = ev;
+    out->scan_ms = ms;
+    out->total_ms = ms;
+}
+
+// Adopt a graph built elsewhere over rows in insertion order (bulk load; the serialized-file reader of
+// SURVEY §8 row f3 lands on this).
+int HnswIndex::importGraph(const void *blobs, int processed, size_t n, const size_t *labels, const uint32_t *levels,
+                           const uint32_t *l0, const uint32_t *upper, size_t upper_records, long entry, long max_level) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!id_to_label_.empty()) return -1;
+    std::vector<uint8_t> rows(n * stored_size_);
+    std::vector<uint64_t> lab(n);
+    for (size_t i = 0; i < n; i++) {
+        if (processed) std::memcpy(rows.data() + i * stored_size_, (const uint8_t *)blobs + i * stored_size_, stored_size_);
+        else preprocess((const uint8_t *)blobs + i * data_size_, rows.data() + i * stored_size_);
+        lab[i] = labels ? labels[i] : i;
+    }
+    if (vsgpu_store_append(store_, rows.data(), stored_size_, lab.data(), n) != VSGPU_OK) return -1;
+    if (vsgpu_hnsw_import(graph_, n, levels, l0, upper, upper_records, entry, max_level) != VSGPU_OK) return -1;
+    id_to_label_.assign(lab.begin(), lab.end());
+    for (size_t i = 0; i < n; i++) label_to_id_[lab[i]] = (idType)i;
+    return 0;
+}
+
+} // namespace vsb

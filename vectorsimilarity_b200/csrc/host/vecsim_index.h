@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -40,6 +41,7 @@ inline bool timed_out(void *ctx) { return globals().timeout_cb && globals().time
 size_t type_size(VecSimType t);
 size_t stored_size(VecSimType t, size_t dim, VecSimMetric m);
 void normalize_blob(void *blob, size_t dim, VecSimType type); // VecSim_Normalize
+
 } // namespace vsb
 
 struct VecSimBatchIterator {
@@ -134,6 +136,67 @@ class FlatIndex final : public VecSimIndexInterface {
     size_t max_label_ = 0;
     std::vector<uint8_t> pending_rows_;
     std::vector<uint64_t> pending_labels_;
+    VecSearchMode last_mode_ = EMPTY_MODE;
+    std::mutex mu_;
+};
+
+
+// HNSW (single value per label): vecsim_hnsw.cpp
+class HnswIndex final : public VecSimIndexInterface {
+  public:
+    HnswIndex(const HNSWParams &p, void *logCtx);
+    ~HnswIndex() override;
+    bool ok() const { return store_ != nullptr && graph_ != nullptr; }
+
+    int addVector(const void *blob, size_t label) override;
+    long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) override;
+    int deleteVector(size_t label) override;
+    double getDistanceFrom(size_t label, const void *blob) override;
+    size_t indexSize() override { return id_to_label_.size() - num_deleted_; }
+    size_t indexLabelCount() override { return label_to_id_.size(); }
+    VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) override;
+    int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels, double *scores,
+                  uint32_t *counts) override;
+    VecSimQueryReply *rangeQuery(const void *blob, double radius, VecSimQueryParams *qp,
+                                 VecSimQueryReply_Order order) override;
+    VecSimBatchIterator *newBatchIterator(const void *blob, VecSimQueryParams *qp) override;
+    VecSimIndexBasicInfo basicInfo() override;
+    VecSimIndexDebugInfo debugInfo() override;
+    VecSimIndexStatsInfo statsInfo() override;
+    bool preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) override;
+    void setLastSearchMode(VecSearchMode m) override { last_mode_ = m; }
+    void exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) override;
+    std::vector<uint8_t> preprocessQuery(const void *blob) override;
+    vsgpu_store *deviceStore() override;
+    void lastStats(vsgpu_stats *out) override;
+
+    vsgpu_hnsw *deviceGraph();
+    size_t efRuntime() const { return ef_; }
+    size_t M() const { return M_; }
+    int importGraph(const void *blobs, int processed, size_t n, const size_t *labels, const uint32_t *levels,
+                    const uint32_t *l0, const uint32_t *upper, size_t upper_records, long entry, long max_level);
+
+  private:
+    void preprocess(const void *blob, uint8_t *out) const;
+    int flush();
+    uint32_t drawLevel();
+    int markDeletedLocked(idType id);
+
+    VecSimType type_;
+    VecSimMetric metric_;
+    size_t dim_, block_size_, data_size_, stored_size_;
+    void *log_ctx_;
+    size_t M_ = 0, efc_ = 0, ef_ = 0;
+    double epsilon_ = 0.01, mult_ = 0;
+    std::default_random_engine level_gen_;
+    vsgpu_store *store_ = nullptr;
+    vsgpu_hnsw *graph_ = nullptr;
+    std::unordered_map<size_t, idType> label_to_id_;
+    std::vector<size_t> id_to_label_;
+    size_t num_deleted_ = 0;
+    std::vector<uint8_t> pending_rows_;
+    std::vector<uint64_t> pending_labels_;
+    std::vector<uint32_t> pending_levels_;
     VecSearchMode last_mode_ = EMPTY_MODE;
     std::mutex mu_;
 };

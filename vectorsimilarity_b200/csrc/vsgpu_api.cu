@@ -126,7 +126,7 @@ template <typename T> __global__ void fill_kernel(T *p, T v, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-static int stage_queries_device(vsgpu_store *s, const void *q_dev_raw, size_t nq, size_t qstride, const void **q_out,
+int stage_queries_device(vsgpu_store *s, const void *q_dev_raw, size_t nq, size_t qstride, const void **q_out,
                                 size_t *q_stride_out, const float **q_norms_out) {
     const bool need_repack = s->plan.kind == CK_INT || s->has_norm;
     if (!need_repack) {

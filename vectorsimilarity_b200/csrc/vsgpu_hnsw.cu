@@ -1,0 +1,1589 @@
+// HNSW on the device: batched graph traversal (one CTA per query) and a sequential, reference-order
+// graph builder (one CTA per insertion). What each kernel re-states (paths relative to
+// /root/reference/src/VecSim/algorithms/hnsw):
+//   hnsw_search_kernel   HNSWIndex::topKQuery hnsw.h:2037-2084 = searchBottomLayerEP :1967-1981 +
+//                        greedySearchLevel :1210-1258 + searchBottomLayer_WithTimeout :1983-2035 +
+//                        processCandidate :530-613
+//   hnsw_range_kernel    rangeQuery :2152-2200, searchRangeBottomLayer_WithTimeout :2086-2150,
+//                        processCandidate_RangeSearch :615-680
+//   hnsw_insert_kernel   appendVector/indexVector :1930-1960, insertElementToGraph :1567-1602,
+//                        searchLayer :682-721, mutuallyConnectNewElement :870-941,
+//                        getNeighborsByHeuristic2 :725-799, revisitNeighborConnections :801-868
+//
+// B200 mapping. A traversal is a chain of dependent random reads, so the unit of parallelism is the
+// query: one CTA owns one query, its heaps live in shared memory, and each hop fans the <= M0
+// neighbour distance evaluations out over the CTA's warps (all row loads of a hop in flight at
+// once), with the reference's bit-exact operation order per distance (vsgpu_dist.cuh). Heap
+// admission runs in link order on one thread, which is exactly the reference's sequential rule, so
+// ids/scores are identical, not just close. Hundreds of queries are resident at once; visited sets
+// are per-query bitmaps in HBM/L2.
+#include "vsgpu_dist.cuh"
+#include <algorithm>
+#include <limits>
+#include <vector>
+
+namespace vsgpu {
+
+static constexpr uint32_t INV = 0xffffffffu;
+template <typename DT> __device__ __forceinline__ DT dt_max();
+template <> __device__ __forceinline__ float dt_max<float>() { return 3.402823466e+38f; }
+template <> __device__ __forceinline__ double dt_max<double>() { return 1.7976931348623157e+308; }
+template <typename DT> __device__ __forceinline__ DT dt_nan();
+template <> __device__ __forceinline__ float dt_nan<float>() { return __int_as_float(0x7fc00000); }
+template <> __device__ __forceinline__ double dt_nan<double>() { return __longlong_as_double(0x7ff8000000000000ll); }
+static constexpr int HNSW_THREADS = 256;
+static constexpr int HEUR_CHUNK = 16; // candidates examined per speculative round of the heuristic
+
+struct KCtx {
+    const uint8_t *rows;
+    size_t row_stride;
+    int type, metric;
+    ChainPlan plan;
+    const float *norms;
+    int chunks; // row_stride / 16 (integer types)
+};
+
+struct GraphDev {
+    uint32_t *l0;           // [capacity][M0 + 1]: count, links
+    uint32_t *up;           // [records][M + 1]
+    const uint32_t *up_off; // [capacity]: first upper record of a node
+    const uint32_t *levels; // [capacity]: top level
+    const uint8_t *flags;   // [capacity]: bit0 = marked deleted
+    int *state;             // [0] entry point (-1 = none), [1] max level
+    int M, M0;
+};
+
+__device__ __forceinline__ uint32_t *links_of(const GraphDev &g, uint32_t node, int level) {
+    return level == 0 ? g.l0 + (size_t)node * (g.M0 + 1) : g.up + ((size_t)g.up_off[node] + (level - 1)) * (g.M + 1);
+}
+__device__ __forceinline__ bool is_deleted(const GraphDev &g, uint32_t node) { return g.flags[node] & 1; }
+
+// ------------------------------------------------------------------------------------------------
+// Distance policies: P::dists<PIVOT> evaluates RU (row, other) pairs per thread group of G lanes;
+// `other` is the pivot staged in shared memory (the query) or a second stored row.
+template <typename CT_, int G_, bool FTZ, bool L2> struct PolChain {
+    using DT = CT_;
+    static constexpr int G = G_;
+    static constexpr int RU = sizeof(CT_) == 8 ? 2 : 4;
+    static size_t pivot_bytes(const vsgpu_store *s) { return (size_t)s->plan.S * G * sizeof(DT); }
+    __device__ static void load_pivot(const KCtx &k, void *pv_, const uint8_t *src, float) {
+        DT *pv = (DT *)pv_;
+        const int total = k.plan.S * G;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int e = chain_elem(k.plan, i % G, i / G);
+            pv[i] = e < 0 ? DT(0) : Loader<DT>::load(src, k.type, e);
+        }
+    }
+    template <bool PIVOT>
+    __device__ static void dists(const KCtx &k, const void *pv_, const uint32_t (&a)[RU], const uint32_t (&b)[RU], int c,
+                                 DT (&out)[RU]) {
+        const DT *pv = (const DT *)pv_ + c;
+        const uint8_t *ra[RU], *rb[RU];
+#pragma unroll
+        for (int r = 0; r < RU; r++) {
+            ra[r] = k.rows + (size_t)(a[r] == INV ? 0 : a[r]) * k.row_stride;
+            rb[r] = k.rows + (size_t)(b[r] == INV ? 0 : b[r]) * k.row_stride;
+        }
+        DT acc[RU];
+#pragma unroll
+        for (int r = 0; r < RU; r++) acc[r] = DT(0);
+        const bool fast = k.plan.kind == CK_LANES && k.plan.prefix == 0;
+        const int S = k.plan.S;
+#pragma unroll 4
+        for (int s = 0; s < S; s++) {
+            const int e = fast ? G * s + c : chain_elem(k.plan, c, s);
+#pragma unroll
+            for (int r = 0; r < RU; r++) {
+                const DT x = e < 0 ? DT(0) : Loader<DT>::load(ra[r], k.type, e);
+                DT y;
+                if constexpr (PIVOT) y = pv[s * G];
+                else y = e < 0 ? DT(0) : Loader<DT>::load(rb[r], k.type, e);
+                if constexpr (L2) {
+                    const DT d = sub_rn(x, y);
+                    acc[r] = fma_step<FTZ>(d, d, acc[r]);
+                } else {
+                    acc[r] = fma_step<FTZ>(x, y, acc[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RU; r++) {
+            DT v = butterfly<DT, G>(acc[r]);
+            if (!L2) v = sub_rn(DT(1), v);
+            out[r] = v;
+        }
+    }
+};
+
+struct IntPivotTail {
+    long long qq;
+    float qn;
+    int pad;
+};
+template <bool U> struct PolInt {
+    using DT = float;
+    static constexpr int G = 8;
+    static constexpr int RU = 2;
+    static size_t pivot_bytes(const vsgpu_store *s) { return s->row_stride + sizeof(IntPivotTail); }
+    // src: dim bytes zero padded to row_stride (a stored row, or a staged query)
+    __device__ static void load_pivot(const KCtx &k, void *pv_, const uint8_t *src, float norm) {
+        uint4 *pv = (uint4 *)pv_;
+        for (int i = threadIdx.x; i < k.chunks; i += blockDim.x) pv[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+        if (threadIdx.x == 0) {
+            long long t = 0;
+            for (int i = 0; i < k.chunks; i++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+                t += dot4<U>(v.x, v.x, 0) + dot4<U>(v.y, v.y, 0) + dot4<U>(v.z, v.z, 0) + dot4<U>(v.w, v.w, 0);
+            }
+            IntPivotTail *tail = reinterpret_cast<IntPivotTail *>((uint8_t *)pv_ + k.row_stride);
+            tail->qq = t;
+            tail->qn = norm;
+        }
+    }
+    template <bool PIVOT>
+    __device__ static void dists(const KCtx &k, const void *pv_, const uint32_t (&a)[RU], const uint32_t (&b)[RU], int c,
+                                 DT (&out)[RU]) {
+        const uint4 *pv = (const uint4 *)pv_;
+        const IntPivotTail *tail = reinterpret_cast<const IntPivotTail *>((const uint8_t *)pv_ + k.row_stride);
+#pragma unroll
+        for (int r = 0; r < RU; r++) {
+            const uint32_t ia = a[r] == INV ? 0 : a[r], ib = b[r] == INV ? 0 : b[r];
+            const uint4 *ra = reinterpret_cast<const uint4 *>(k.rows + (size_t)ia * k.row_stride);
+            const uint4 *rb = reinterpret_cast<const uint4 *>(k.rows + (size_t)ib * k.row_stride);
+            long long dot = 0, aa = 0, bb = 0;
+            for (int ch = c; ch < k.chunks; ch += G) {
+                const uint4 x = __ldg(ra + ch);
+                uint4 y;
+                if constexpr (PIVOT) y = pv[ch];
+                else y = __ldg(rb + ch);
+                dot += dot4<U>(x.x, y.x, 0) + dot4<U>(x.y, y.y, 0) + dot4<U>(x.z, y.z, 0) + dot4<U>(x.w, y.w, 0);
+                aa += dot4<U>(x.x, x.x, 0) + dot4<U>(x.y, x.y, 0) + dot4<U>(x.z, x.z, 0) + dot4<U>(x.w, x.w, 0);
+                if constexpr (!PIVOT)
+                    bb += dot4<U>(y.x, y.x, 0) + dot4<U>(y.y, y.y, 0) + dot4<U>(y.z, y.z, 0) + dot4<U>(y.w, y.w, 0);
+            }
+#pragma unroll
+            for (int w = G / 2; w >= 1; w >>= 1) {
+                dot += __shfl_xor_sync(0xffffffffu, dot, w);
+                aa += __shfl_xor_sync(0xffffffffu, aa, w);
+                if constexpr (!PIVOT) bb += __shfl_xor_sync(0xffffffffu, bb, w);
+            }
+            const float rn = k.norms ? k.norms[ia] : 0.f;
+            const float qn = PIVOT ? tail->qn : (k.norms ? k.norms[ib] : 0.f);
+            out[r] = int_score(k.metric, dot, aa, PIVOT ? tail->qq : bb, rn, qn);
+        }
+    }
+};
+
+template <typename CT_> struct PolSeq {
+    using DT = CT_;
+    static constexpr int G = 1;
+    static constexpr int RU = 1;
+    static size_t pivot_bytes(const vsgpu_store *s) { return s->dim * sizeof(DT); }
+    __device__ static void load_pivot(const KCtx &k, void *pv_, const uint8_t *src, float) {
+        DT *pv = (DT *)pv_;
+        for (int i = threadIdx.x; i < k.plan.dim; i += blockDim.x) pv[i] = Loader<DT>::load(src, k.type, i);
+    }
+    template <bool PIVOT>
+    __device__ static void dists(const KCtx &k, const void *pv_, const uint32_t (&a)[RU], const uint32_t (&b)[RU], int,
+                                 DT (&out)[RU]) {
+        const DT *pv = (const DT *)pv_;
+        const uint8_t *ra = k.rows + (size_t)(a[0] == INV ? 0 : a[0]) * k.row_stride;
+        const uint8_t *rb = k.rows + (size_t)(b[0] == INV ? 0 : b[0]) * k.row_stride;
+        if constexpr (PIVOT) out[0] = seq_dist<DT>(ra, k.type, k.plan, [&](int e) { return pv[e]; });
+        else out[0] = seq_dist<DT>(ra, k.type, k.plan, [&](int e) { return Loader<DT>::load(rb, k.type, e); });
+    }
+};
+
+// out[j] = dist(pair j) for j < n; pair(j, &a, &b) names the rows (a == INV: skip). PIVOT: `b` is
+// ignored and the staged pivot is the other operand. Called by every thread of the CTA.
+template <class P, bool PIVOT, typename PairFn>
+__device__ __forceinline__ void eval_dists(const KCtx &k, const void *pv, int n, typename P::DT *out, PairFn pair) {
+    constexpr int GPW = 32 / P::G, RU = P::RU;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int c = lane % P::G, grp = lane / P::G;
+    const int per_round = nw * GPW * RU;
+    for (int base = 0; base < n; base += per_round) {
+        if (base + warp * GPW * RU >= n) continue; // warp-uniform
+        const int j0 = base + (warp * GPW + grp) * RU;
+        uint32_t a[RU], b[RU];
+#pragma unroll
+        for (int r = 0; r < RU; r++) {
+            a[r] = INV;
+            b[r] = INV;
+            if (j0 + r < n) pair(j0 + r, a[r], b[r]);
+        }
+        typename P::DT o[RU];
+        P::template dists<PIVOT>(k, pv, a, b, c, o);
+        if (c == 0) {
+#pragma unroll
+            for (int r = 0; r < RU; r++)
+                if (a[r] != INV) out[j0 + r] = o[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// binary heaps driven by one thread; Less(a_d, a_id, b_d, b_id) is the reference's pair ordering
+template <typename DT, typename Less>
+__device__ __forceinline__ void heap_push(DT *hd, uint32_t *hid, int &n, DT d, uint32_t id, Less less) {
+    int i = n++;
+    while (i > 0) {
+        const int p = (i - 1) >> 1;
+        if (!less(hd[p], hid[p], d, id)) break;
+        hd[i] = hd[p];
+        hid[i] = hid[p];
+        i = p;
+    }
+    hd[i] = d;
+    hid[i] = id;
+}
+template <typename DT, typename Less> __device__ __forceinline__ void heap_pop(DT *hd, uint32_t *hid, int &n, Less less) {
+    n--;
+    if (n == 0) return;
+    const DT d = hd[n];
+    const uint32_t id = hid[n];
+    int i = 0;
+    for (;;) {
+        int ch = 2 * i + 1;
+        if (ch >= n) break;
+        if (ch + 1 < n && less(hd[ch], hid[ch], hd[ch + 1], hid[ch + 1])) ch++;
+        if (!less(d, id, hd[ch], hid[ch])) break;
+        hd[i] = hd[ch];
+        hid[i] = hid[ch];
+        i = ch;
+    }
+    hd[i] = d;
+    hid[i] = id;
+}
+
+// std::pair<DistType, key> operator< (top candidates: key = label for queries, id for the builder)
+template <typename DT> struct TopLess {
+    const uint64_t *labels; // nullptr: key = id
+    __device__ __forceinline__ bool operator()(DT ad, uint32_t ai, DT bd, uint32_t bi) const {
+        if (ad < bd) return true;
+        if (bd < ad) return false;
+        if (labels) return labels[ai] < labels[bi];
+        return ai < bi;
+    }
+};
+// candidate set: std::pair<DistType, idType>(-dist, id) under operator<
+template <typename DT> struct CandLess {
+    __device__ __forceinline__ bool operator()(DT ad, uint32_t ai, DT bd, uint32_t bi) const {
+        if (-ad < -bd) return true;
+        if (-bd < -ad) return false;
+        return ai < bi;
+    }
+};
+
+struct Visited {
+    uint32_t *p;
+    uint32_t tag; // 0: p is a bitmap (atomic), else p is a tag array
+};
+__device__ __forceinline__ bool test_and_set(const Visited &v, uint32_t id) {
+    if (v.tag) {
+        if (v.p[id] == v.tag) return true;
+        v.p[id] = v.tag;
+        return false;
+    }
+    const uint32_t bit = 1u << (id & 31);
+    return (atomicOr(&v.p[id >> 5], bit) & bit) != 0;
+}
+
+// Per-CTA working set (pointers into shared memory, cand_* may be re-pointed to the HBM spill area)
+template <typename DT> struct Work {
+    void *pivot;
+    uint32_t *nb_ids;
+    DT *nb_dist;
+    DT *top_d;
+    uint32_t *top_id;
+    DT *cand_d;
+    uint32_t *cand_id;
+    int cand_cap;
+    DT *spill_d; // HBM spill for the candidate set (capacity = element count) or nullptr
+    uint32_t *spill_id;
+    int spill_cap;
+    int *sc; // shared scalars
+    DT *sdt; // shared DT scalars: [0] lowerBound / curDist
+    // admission log (builder): the first `adm_cap` pushes to the top heap, in order
+    DT *adm_d;
+    uint32_t *adm_id;
+    int adm_cap;
+};
+enum { SC_TOPN = 0, SC_CANDN, SC_NBN, SC_STOP, SC_CUR, SC_STATUS, SC_ADMN, SC_AUX0, SC_AUX1, SC_AUX2, SC_AUX3, SC_COUNT = 16 };
+
+// warp 0: links of `node` at `level` that were not visited yet, in link order -> w.nb_ids, SC_NBN
+template <typename DT>
+__device__ __forceinline__ void gather_unvisited(const GraphDev &g, const Work<DT> &w, uint32_t node, int level,
+                                                 const Visited *vis) {
+    if (threadIdx.x >= 32) return;
+    const uint32_t *rec = links_of(g, node, level);
+    const int cnt = (int)rec[0];
+    int base = 0;
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+        const int i = i0 + threadIdx.x;
+        uint32_t id = INV;
+        bool take = false;
+        if (i < cnt) {
+            id = rec[1 + i];
+            take = vis ? !test_and_set(*vis, id) : true;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (take) w.nb_ids[base + __popc(m & ((1u << threadIdx.x) - 1))] = id;
+        base += __popc(m);
+    }
+    if (threadIdx.x == 0) w.sc[SC_NBN] = base;
+}
+
+// greedySearchLevel (hnsw.h:1210-1258). cur/curDist in w.sc[SC_CUR]/w.sdt[0]. `track_deleted`: the
+// builder's variant that hands the best non-deleted node to the next level.
+template <class P>
+__device__ void greedy_level(const KCtx &k, const GraphDev &g, const Work<typename P::DT> &w, int level, bool track_deleted,
+                             unsigned long long &evals) {
+    using DT = typename P::DT;
+    if (threadIdx.x == 0) w.sc[SC_AUX0] = w.sc[SC_CUR]; // bestNonDeletedCand
+    for (;;) {
+        __syncthreads();
+        const uint32_t cur = (uint32_t)w.sc[SC_CUR];
+        gather_unvisited<DT>(g, w, cur, level, nullptr);
+        __syncthreads();
+        const int n = w.sc[SC_NBN];
+        eval_dists<P, true>(k, w.pivot, n, w.nb_dist, [&](int j, uint32_t &a, uint32_t &) { a = w.nb_ids[j]; });
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bool changed = false;
+            DT best = w.sdt[0];
+            for (int j = 0; j < n; j++) {
+                if (w.nb_dist[j] < best) {
+                    best = w.nb_dist[j];
+                    w.sc[SC_CUR] = (int)w.nb_ids[j];
+                    changed = true;
+                    if (track_deleted && !is_deleted(g, w.nb_ids[j])) w.sc[SC_AUX0] = (int)w.nb_ids[j];
+                }
+            }
+            w.sdt[0] = best;
+            w.sc[SC_STOP] = changed ? 0 : 1;
+            evals += n;
+        }
+        __syncthreads();
+        if (w.sc[SC_STOP]) break;
+    }
+    if (track_deleted && threadIdx.x == 0) w.sc[SC_CUR] = w.sc[SC_AUX0];
+    __syncthreads();
+}
+
+// thread 0: push to the candidate set, pruning entries that can no longer be expanded or spilling to HBM
+template <typename DT>
+__device__ __forceinline__ bool cand_push(Work<DT> &w, int &cand_n, DT d, uint32_t id, bool top_full, DT lower) {
+    CandLess<DT> cl;
+    if (cand_n >= w.cand_cap) {
+        if (top_full) {
+            // entries farther than the current bound are never expanded: the bound only shrinks once the
+            // result heap is full, and the stop rule fires before they are reached
+            int m = 0;
+            for (int i = 0; i < cand_n; i++)
+                if (!(w.cand_d[i] > lower)) {
+                    w.cand_d[m] = w.cand_d[i];
+                    w.cand_id[m] = w.cand_id[i];
+                    m++;
+                }
+            const int kept = m;
+            cand_n = 0;
+            for (int i = 0; i < kept; i++) {
+                const DT dd = w.cand_d[i];
+                const uint32_t ii = w.cand_id[i];
+                heap_push(w.cand_d, w.cand_id, cand_n, dd, ii, cl);
+            }
+        }
+        if (cand_n >= w.cand_cap) {
+            if (!w.spill_d || w.cand_d == w.spill_d) return false;
+            for (int i = 0; i < cand_n; i++) {
+                w.spill_d[i] = w.cand_d[i];
+                w.spill_id[i] = w.cand_id[i];
+            }
+            w.cand_d = w.spill_d;
+            w.cand_id = w.spill_id;
+            w.cand_cap = w.spill_cap;
+            if (cand_n >= w.cand_cap) return false;
+        }
+    }
+    heap_push(w.cand_d, w.cand_id, cand_n, d, id, cl);
+    return true;
+}
+
+// searchLayer / searchBottomLayer (hnsw.h:682-721, 1983-2035) from entry w.sc[SC_CUR]. Result heap in
+// w.top_* (SC_TOPN entries, max-heap under TopLess). labels != nullptr: query flavour (heap keyed by
+// label); else builder flavour (keyed by id, admissions logged). Returns through w.sc[SC_STATUS].
+template <class P>
+__device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::DT> &w, int level, int ef,
+                             const uint64_t *labels, const Visited &vis, unsigned long long &evals,
+                             unsigned long long &hops) {
+    using DT = typename P::DT;
+    TopLess<DT> tl{labels};
+    CandLess<DT> cl;
+    int top_n = 0, cand_n = 0, adm_n = 0; // thread 0's copies
+    DT lower = DT(0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ep = (uint32_t)w.sc[SC_CUR];
+        w.nb_ids[0] = ep;
+        w.sc[SC_STATUS] = 0;
+    }
+    __syncthreads();
+    eval_dists<P, true>(k, w.pivot, 1, w.nb_dist, [&](int j, uint32_t &a, uint32_t &) { a = w.nb_ids[j]; });
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ep = w.nb_ids[0];
+        evals += 1;
+        if (!is_deleted(g, ep)) {
+            lower = w.nb_dist[0];
+            heap_push(w.top_d, w.top_id, top_n, lower, ep, tl);
+            if (w.adm_cap > 0) {
+                w.adm_d[0] = lower;
+                w.adm_id[0] = ep;
+            }
+            adm_n = 1;
+            heap_push(w.cand_d, w.cand_id, cand_n, lower, ep, cl);
+        } else {
+            lower = dt_max<DT>();
+            heap_push(w.cand_d, w.cand_id, cand_n, lower, ep, cl);
+        }
+        test_and_set(vis, ep);
+    }
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int stop = 0;
+            if (cand_n == 0) stop = 1;
+            else if (w.cand_d[0] > lower && top_n >= ef) stop = 1;
+            else {
+                w.sc[SC_CUR] = (int)w.cand_id[0];
+                heap_pop(w.cand_d, w.cand_id, cand_n, cl);
+                hops++;
+            }
+            w.sc[SC_STOP] = stop;
+        }
+        __syncthreads();
+        if (w.sc[SC_STOP]) break;
+        gather_unvisited<DT>(g, w, (uint32_t)w.sc[SC_CUR], level, &vis);
+        __syncthreads();
+        const int n = w.sc[SC_NBN];
+        eval_dists<P, true>(k, w.pivot, n, w.nb_dist, [&](int j, uint32_t &a, uint32_t &) { a = w.nb_ids[j]; });
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            evals += n;
+            for (int j = 0; j < n; j++) {
+                const DT d = w.nb_dist[j];
+                const uint32_t id = w.nb_ids[j];
+                if (lower > d || top_n < ef) {
+                    if (!cand_push(w, cand_n, d, id, top_n >= ef, lower)) {
+                        w.sc[SC_STATUS] = 1;
+                        cand_n = 0; // abandon: the caller reruns with a spill area
+                        break;
+                    }
+                    if (!is_deleted(g, id)) {
+                        heap_push(w.top_d, w.top_id, top_n, d, id, tl);
+                        if (adm_n < w.adm_cap) {
+                            w.adm_d[adm_n] = d;
+                            w.adm_id[adm_n] = id;
+                        }
+                        adm_n++;
+                    }
+                    if (top_n > ef) heap_pop(w.top_d, w.top_id, top_n, tl);
+                    if (top_n > 0) lower = w.top_d[0];
+                }
+            }
+        }
+        // nb_* are rewritten only after the next __syncthreads (top of the loop)
+    }
+    if (threadIdx.x == 0) {
+        w.sc[SC_TOPN] = top_n;
+        w.sc[SC_ADMN] = adm_n;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SearchArgs {
+    KCtx k;
+    GraphDev g;
+    const uint8_t *q;
+    size_t q_stride;
+    const float *q_norms;
+    const uint64_t *labels;
+    uint32_t *visited; // [nq][vis_words]
+    size_t vis_words;
+    int ef, k_out, cand_cap, max_links;
+    void *spill; // per query: spill_cap x (DT, u32) or nullptr
+    int spill_cap;
+    uint32_t *out_ids;
+    void *out_scores;
+    uint64_t *out_labels;
+    uint32_t *out_counts;
+    size_t out_ld;
+    uint32_t *status;             // per query
+    unsigned long long *counters; // [0] distance evaluations, [1] hops
+    size_t pivot_bytes;
+    // range flavour
+    double radius, epsilon;
+    unsigned long long *range_counts; // per query
+    size_t range_cap;
+};
+
+template <typename DT> __device__ __forceinline__ Work<DT> carve(unsigned char *smem, size_t pivot_bytes, int max_links,
+                                                                int top_cap, int cand_cap, int adm_cap) {
+    Work<DT> w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        unsigned char *p = smem + off;
+        off += (bytes + 15) / 16 * 16;
+        return p;
+    };
+    w.pivot = take(pivot_bytes);
+    w.sc = (int *)take(SC_COUNT * sizeof(int));
+    w.sdt = (DT *)take(4 * sizeof(DT));
+    w.nb_dist = (DT *)take((size_t)max_links * sizeof(DT));
+    w.nb_ids = (uint32_t *)take((size_t)max_links * 4);
+    w.top_d = (DT *)take((size_t)top_cap * sizeof(DT));
+    w.top_id = (uint32_t *)take((size_t)top_cap * 4);
+    w.cand_d = (DT *)take((size_t)cand_cap * sizeof(DT));
+    w.cand_id = (uint32_t *)take((size_t)cand_cap * 4);
+    w.cand_cap = cand_cap;
+    w.adm_d = (DT *)take((size_t)adm_cap * sizeof(DT));
+    w.adm_id = (uint32_t *)take((size_t)adm_cap * 4);
+    w.adm_cap = adm_cap;
+    return w;
+}
+__host__ __device__ static size_t carve_bytes(size_t dt, size_t pivot_bytes, int max_links, int top_cap, int cand_cap, int adm_cap) {
+    auto al = [](size_t b) { return (b + 15) / 16 * 16; };
+    return al(pivot_bytes) + al(SC_COUNT * sizeof(int)) + al(4 * dt) + al((size_t)max_links * dt) + al((size_t)max_links * 4) +
+           al((size_t)top_cap * dt) + al((size_t)top_cap * 4) + al((size_t)cand_cap * dt) + al((size_t)cand_cap * 4) +
+           al((size_t)adm_cap * dt) + al((size_t)adm_cap * 4);
+}
+
+// entry point + greedy descent to level 1 (searchBottomLayerEP, hnsw.h:1967-1981). Returns false
+// for an empty graph. Leaves cur in SC_CUR.
+template <class P>
+__device__ bool descend(const KCtx &k, const GraphDev &g, Work<typename P::DT> &w, unsigned long long &evals) {
+    const int ep = g.state[0], maxl = g.state[1];
+    if (ep < 0) return false;
+    if (threadIdx.x == 0) {
+        w.sc[SC_CUR] = ep;
+        w.nb_ids[0] = (uint32_t)ep;
+    }
+    __syncthreads();
+    eval_dists<P, true>(k, w.pivot, 1, w.nb_dist, [&](int j, uint32_t &a, uint32_t &) { a = w.nb_ids[j]; });
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        w.sdt[0] = w.nb_dist[0];
+        evals += 1;
+    }
+    __syncthreads();
+    for (int level = maxl; level > 0; level--) greedy_level<P>(k, g, w, level, false, evals);
+    return true;
+}
+
+template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(SearchArgs a) {
+    using DT = typename P::DT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Work<DT> w = carve<DT>(smem_raw, a.pivot_bytes, a.max_links, a.ef + 1, a.cand_cap, 0);
+    const size_t q = blockIdx.x;
+    if (a.spill) {
+        unsigned char *sp = (unsigned char *)a.spill + q * (size_t)a.spill_cap * (sizeof(DT) + 4);
+        w.spill_d = (DT *)sp;
+        w.spill_id = (uint32_t *)(sp + (size_t)a.spill_cap * sizeof(DT));
+        w.spill_cap = a.spill_cap;
+    }
+    P::load_pivot(a.k, w.pivot, a.q + q * a.q_stride, a.q_norms ? a.q_norms[q] : 0.f);
+    __syncthreads();
+    unsigned long long evals = 0, hops = 0;
+    int count = 0;
+    if (descend<P>(a.k, a.g, w, evals)) {
+        Visited vis{a.visited + q * a.vis_words, 0};
+        search_layer<P>(a.k, a.g, w, 0, a.ef, a.labels, vis, evals, hops);
+        if (threadIdx.x == 0) {
+            TopLess<DT> tl{a.labels};
+            int top_n = w.sc[SC_TOPN];
+            while (top_n > a.k_out) heap_pop(w.top_d, w.top_id, top_n, tl);
+            count = top_n;
+            for (int i = count - 1; i >= 0; i--) {
+                const size_t o = q * a.out_ld + i;
+                const uint32_t id = w.top_id[0];
+                if (a.out_ids) a.out_ids[o] = id;
+                if (a.out_scores) ((DT *)a.out_scores)[o] = w.top_d[0];
+                if (a.out_labels) a.out_labels[o] = a.labels[id];
+                heap_pop(w.top_d, w.top_id, top_n, tl);
+            }
+            w.sc[SC_AUX1] = count;
+            if (a.status) a.status[q] = (uint32_t)w.sc[SC_STATUS];
+        }
+        __syncthreads();
+        count = w.sc[SC_AUX1];
+    } else if (threadIdx.x == 0 && a.status) {
+        a.status[q] = 0;
+    }
+    for (int j = count + threadIdx.x; j < a.k_out; j += blockDim.x) {
+        const size_t o = q * a.out_ld + j;
+        if (a.out_ids) a.out_ids[o] = INV;
+        if (a.out_scores) ((DT *)a.out_scores)[o] = dt_nan<DT>();
+        if (a.out_labels) a.out_labels[o] = ~0ull;
+    }
+    if (threadIdx.x == 0) {
+        if (a.out_counts) a.out_counts[q] = (uint32_t)count;
+        if (a.counters) {
+            atomicAdd(&a.counters[0], evals);
+            atomicAdd(&a.counters[1], hops);
+        }
+    }
+}
+
+// Range search at level 0 (hnsw.h:2086-2150 + :615-680). Results are appended unordered to
+// out_*[q * range_cap ...]; range_counts[q] is the number found (may exceed the capacity: the host
+// retries with a larger buffer — the traversal is deterministic).
+template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_range_kernel(SearchArgs a) {
+    using DT = typename P::DT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Work<DT> w = carve<DT>(smem_raw, a.pivot_bytes, a.max_links, 1, a.cand_cap, 0);
+    const size_t q = blockIdx.x;
+    if (a.spill) {
+        unsigned char *sp = (unsigned char *)a.spill + q * (size_t)a.spill_cap * (sizeof(DT) + 4);
+        w.spill_d = (DT *)sp;
+        w.spill_id = (uint32_t *)(sp + (size_t)a.spill_cap * sizeof(DT));
+        w.spill_cap = a.spill_cap;
+    }
+    P::load_pivot(a.k, w.pivot, a.q + q * a.q_stride, a.q_norms ? a.q_norms[q] : 0.f);
+    __syncthreads();
+    unsigned long long evals = 0, hops = 0, found = 0;
+    if (!descend<P>(a.k, a.g, w, evals)) {
+        if (threadIdx.x == 0) a.range_counts[q] = 0;
+        return;
+    }
+    const DT radius = (DT)a.radius;
+    Visited vis{a.visited + q * a.vis_words, 0};
+    CandLess<DT> cl;
+    int cand_n = 0;
+    DT dyn = DT(0), bound = DT(0);
+    auto emit = [&](uint32_t id, DT d) {
+        if (found < a.range_cap) {
+            const size_t o = q * a.range_cap + found;
+            if (a.out_ids) a.out_ids[o] = id;
+            if (a.out_scores) ((DT *)a.out_scores)[o] = d;
+            if (a.out_labels) a.out_labels[o] = a.labels[id];
+        }
+        found++;
+    };
+    if (threadIdx.x == 0) {
+        const uint32_t ep = (uint32_t)w.sc[SC_CUR];
+        DT ep_dist;
+        w.sc[SC_STATUS] = 0;
+        if (is_deleted(a.g, ep)) {
+            ep_dist = dt_max<DT>();
+            bound = dyn = ep_dist;
+        } else {
+            ep_dist = w.sdt[0]; // distance of the greedy descent's final node
+            dyn = ep_dist;
+            if (ep_dist <= radius) {
+                emit(ep, ep_dist);
+                dyn = radius;
+            }
+            bound = (DT)((double)dyn * (1.0 + a.epsilon));
+        }
+        heap_push(w.cand_d, w.cand_id, cand_n, ep_dist, ep, cl);
+        test_and_set(vis, ep);
+    }
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int stop = 0;
+            if (cand_n == 0 || w.cand_d[0] > bound) stop = 1;
+            else {
+                const DT cd = w.cand_d[0];
+                w.sc[SC_CUR] = (int)w.cand_id[0];
+                heap_pop(w.cand_d, w.cand_id, cand_n, cl);
+                hops++;
+                if (cd < dyn && cd >= radius) {
+                    dyn = cd;
+                    bound = (DT)((double)dyn * (1.0 + a.epsilon));
+                }
+            }
+            w.sc[SC_STOP] = stop;
+        }
+        __syncthreads();
+        if (w.sc[SC_STOP]) break;
+        gather_unvisited<DT>(a.g, w, (uint32_t)w.sc[SC_CUR], 0, &vis);
+        __syncthreads();
+        const int n = w.sc[SC_NBN];
+        eval_dists<P, true>(a.k, w.pivot, n, w.nb_dist, [&](int j, uint32_t &x, uint32_t &) { x = w.nb_ids[j]; });
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            evals += n;
+            for (int j = 0; j < n; j++) {
+                const DT d = w.nb_dist[j];
+                const uint32_t id = w.nb_ids[j];
+                if (d < bound) {
+                    if (!cand_push(w, cand_n, d, id, true, bound)) {
+                        w.sc[SC_STATUS] = 1;
+                        cand_n = 0;
+                        break;
+                    }
+                    if (d <= radius && !is_deleted(a.g, id)) emit(id, d);
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        a.range_counts[q] = found;
+        if (a.status) a.status[q] = (uint32_t)w.sc[SC_STATUS];
+        if (a.counters) {
+            atomicAdd(&a.counters[0], evals);
+            atomicAdd(&a.counters[1], hops);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Builder
+struct InsertArgs {
+    KCtx k;
+    GraphDev g;
+    uint32_t first, n; // elements [first, first + n) are already in the store
+    uint32_t *tags;    // [capacity] visited tags
+    uint32_t *tag_counter;
+    int efc, cand_cap, max_links;
+    void *spill;
+    int spill_cap;
+    size_t pivot_bytes;
+    unsigned long long *counters;
+    uint32_t *status;
+};
+
+// Scratch of the neighbour-selection heuristic, carved after the Work arrays
+template <typename DT> struct Heur {
+    DT *sd;        // sorted candidate distances [cap]
+    uint32_t *sid; // ids
+    uint32_t *spos; // original position of each sorted candidate
+    uint8_t *keep; // per sorted candidate: selected
+    uint32_t *sel; // selected sorted positions [maxM]
+    DT *pd;        // [HEUR_CHUNK][maxM + HEUR_CHUNK]
+    DT *in_d;      // unsorted input [cap]
+    uint32_t *in_id;
+    int cap, maxM;
+};
+static size_t heur_bytes(size_t dt, int cap, int maxM) {
+    auto al = [](size_t b) { return (b + 15) / 16 * 16; };
+    return al(cap * dt) + 2 * al((size_t)cap * 4) + al(cap) + al((size_t)maxM * 4) +
+           al((size_t)HEUR_CHUNK * (maxM + HEUR_CHUNK) * dt) + al(cap * dt) + al((size_t)cap * 4);
+}
+template <typename DT> __device__ __forceinline__ Heur<DT> carve_heur(unsigned char *p, int cap, int maxM) {
+    Heur<DT> h{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        unsigned char *r = p + off;
+        off += (bytes + 15) / 16 * 16;
+        return r;
+    };
+    h.sd = (DT *)take(cap * sizeof(DT));
+    h.sid = (uint32_t *)take((size_t)cap * 4);
+    h.spos = (uint32_t *)take((size_t)cap * 4);
+    h.keep = (uint8_t *)take(cap);
+    h.sel = (uint32_t *)take((size_t)maxM * 4);
+    h.pd = (DT *)take((size_t)HEUR_CHUNK * (maxM + HEUR_CHUNK) * sizeof(DT));
+    h.in_d = (DT *)take(cap * sizeof(DT));
+    h.in_id = (uint32_t *)take((size_t)cap * 4);
+    h.cap = cap;
+    h.maxM = maxM;
+    return h;
+}
+
+// sort h.in_* [n] ascending by (dist, id) into h.sd/sid/spos (rank sort, whole CTA)
+template <typename DT> __device__ void rank_sort(const Heur<DT> &h, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const DT d = h.in_d[i];
+        const uint32_t id = h.in_id[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const DT dj = h.in_d[j];
+            rank += (dj < d || (dj == d && h.in_id[j] < id)) ? 1 : 0;
+        }
+        h.sd[rank] = d;
+        h.sid[rank] = id;
+        h.spos[rank] = (uint32_t)i;
+    }
+    __syncthreads();
+}
+
+// getNeighborsByHeuristic2 (hnsw.h:741-799) over the sorted candidates: a candidate is kept unless an
+// already kept one is closer to it than the query is. Candidates are examined HEUR_CHUNK at a time:
+// the distances of a chunk to everything it could be compared with are evaluated together
+// (speculatively, they have no side effects) and one thread then applies the sequential rule.
+// Result: h.keep[] per sorted position, h.sel[0..ns) in order; returns ns through sc[SC_AUX2].
+template <class P> __device__ void heuristic(const KCtx &k, const Heur<typename P::DT> &h, int *sc, int n, int maxM) {
+    using DT = typename P::DT;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) h.keep[i] = 0;
+    if (threadIdx.x == 0) sc[SC_AUX2] = 0;
+    __syncthreads();
+    for (int pos = 0; pos < n; pos += HEUR_CHUNK) {
+        const int ns0 = sc[SC_AUX2];
+        if (ns0 >= maxM) break;
+        const int C = min(HEUR_CHUNK, n - pos);
+        const int cols = ns0 + C;
+        eval_dists<P, false>(k, nullptr, C * cols, h.pd, [&](int j, uint32_t &a, uint32_t &b) {
+            // pd index is a * W + col; map the dense pair index back
+            const int ca = j / cols, col = j % cols;
+            if (col < ns0) {
+                a = h.sid[pos + ca];
+                b = h.sid[h.sel[col]];
+            } else if (col - ns0 < ca) {
+                a = h.sid[pos + ca];
+                b = h.sid[pos + col - ns0];
+            }
+        });
+        // eval_dists wrote out[j] densely with row length `cols`
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int ns = ns0;
+            for (int ca = 0; ca < C && ns < maxM; ca++) {
+                const DT dq = h.sd[pos + ca];
+                bool good = true;
+                for (int i = 0; i < ns && good; i++) {
+                    const int col = i < ns0 ? i : ns0 + ((int)h.sel[i] - pos);
+                    if (h.pd[ca * cols + col] < dq) good = false;
+                }
+                if (good) {
+                    h.keep[pos + ca] = 1;
+                    h.sel[ns++] = (uint32_t)(pos + ca);
+                }
+            }
+            sc[SC_AUX2] = ns;
+        }
+        __syncthreads();
+    }
+}
+
+template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_insert_kernel(InsertArgs a) {
+    using DT = typename P::DT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int M = a.g.M, M0 = a.g.M0;
+    const int top_cap = a.efc + 1;
+    Work<DT> w = carve<DT>(smem_raw, a.pivot_bytes, a.max_links, top_cap, a.cand_cap, M);
+    const size_t work_bytes = carve_bytes(sizeof(DT), a.pivot_bytes, a.max_links, top_cap, a.cand_cap, M);
+    const int hcap = max(top_cap, M0 + 1);
+    Heur<DT> h = carve_heur<DT>(smem_raw + work_bytes, hcap, M0);
+    DT *const cand_d0 = w.cand_d;
+    uint32_t *const cand_id0 = w.cand_id;
+    const int cand_cap0 = w.cand_cap;
+    if (a.spill) {
+        w.spill_d = (DT *)a.spill;
+        w.spill_id = (uint32_t *)((unsigned char *)a.spill + (size_t)a.spill_cap * sizeof(DT));
+        w.spill_cap = a.spill_cap;
+    }
+    unsigned long long evals = 0, hops = 0;
+    __shared__ uint32_t s_tag;
+
+    for (uint32_t e = a.first; e < a.first + a.n; e++) {
+        __syncthreads();
+        const int ep = a.g.state[0], maxl = a.g.state[1];
+        const int lvl = (int)a.g.levels[e];
+        if (ep < 0) { // first element: nothing to connect to
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                a.g.state[0] = (int)e;
+                a.g.state[1] = lvl;
+            }
+            continue;
+        }
+        P::load_pivot(a.k, w.pivot, a.k.rows + (size_t)e * a.k.row_stride, a.k.norms ? a.k.norms[e] : 0.f);
+        if (threadIdx.x == 0) {
+            w.sc[SC_CUR] = ep;
+            w.nb_ids[0] = (uint32_t)ep;
+        }
+        __syncthreads();
+        int max_common = maxl;
+        if (lvl < maxl) {
+            max_common = lvl;
+            eval_dists<P, true>(a.k, w.pivot, 1, w.nb_dist, [&](int j, uint32_t &x, uint32_t &) { x = w.nb_ids[j]; });
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                w.sdt[0] = w.nb_dist[0];
+                evals += 1;
+            }
+            __syncthreads();
+            for (int level = maxl; level > lvl; level--) greedy_level<P>(a.k, a.g, w, level, true, evals);
+        }
+        for (int level = max_common; level >= 0; level--) {
+            // fresh visited tag; candidate set back in shared memory
+            if (threadIdx.x == 0) {
+                uint32_t t = *a.tag_counter + 1;
+                if (t == 0) t = 1; // the host clears the tag array before the counter can wrap
+                *a.tag_counter = t;
+                s_tag = t;
+            }
+            w.cand_d = cand_d0;
+            w.cand_id = cand_id0;
+            w.cand_cap = cand_cap0;
+            __syncthreads();
+            Visited vis{a.tags, s_tag};
+            search_layer<P>(a.k, a.g, w, level, a.efc, nullptr, vis, evals, hops);
+            if (w.sc[SC_STATUS]) {
+                if (threadIdx.x == 0) *a.status = 1;
+                return;
+            }
+            const int n = w.sc[SC_TOPN];
+            if (n == 0) continue; // entry point was marked deleted and nothing else was reachable
+            const int maxMcur = level ? M : M0;
+
+            // ---- choose the new element's neighbours (mutuallyConnectNewElement :870-890) ----
+            int ns;
+            if (n < M) {
+                // fewer than M candidates: all are kept, in the order of the result heap's underlying
+                // array = the admissions replayed through push_heap (no pop ever happened)
+                if (threadIdx.x == 0) {
+                    TopLess<DT> tl{nullptr};
+                    int m = 0;
+                    for (int i = 0; i < n; i++) heap_push(h.sd, h.sid, m, w.adm_d[i], w.adm_id[i], tl);
+                    int best = 0;
+                    for (int i = 1; i < n; i++)
+                        if (h.sd[i] < h.sd[best]) best = i;
+                    w.sc[SC_AUX3] = (int)h.sid[best]; // next closest entry point
+                    for (int i = 0; i < n; i++) h.sel[i] = (uint32_t)i;
+                    w.sc[SC_AUX2] = n;
+                }
+                __syncthreads();
+                ns = n;
+            } else {
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    h.in_d[i] = w.top_d[i];
+                    h.in_id[i] = w.top_id[i];
+                }
+                __syncthreads();
+                rank_sort<DT>(h, n);
+                heuristic<P>(a.k, h, w.sc, n, M);
+                ns = w.sc[SC_AUX2];
+                if (threadIdx.x == 0) w.sc[SC_AUX3] = (int)h.sid[h.sel[0]];
+                __syncthreads();
+            }
+            // the selected list (distance, id), copied out of the heuristic scratch (revisit reuses it)
+            DT *sel_d = w.top_d; // the result heap is dead now
+            uint32_t *sel_id = w.top_id;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                // gather first (sel positions ascend, so in-place reads stay ahead of writes only via a copy)
+                for (int i = 0; i < ns; i++) {
+                    w.nb_dist[i] = h.sd[h.sel[i]];
+                    w.nb_ids[i] = h.sid[h.sel[i]];
+                }
+                for (int i = 0; i < ns; i++) {
+                    sel_d[i] = w.nb_dist[i];
+                    sel_id[i] = w.nb_ids[i];
+                }
+            }
+            __syncthreads();
+            uint32_t *new_rec = links_of(a.g, e, level);
+            for (int si = 0; si < ns; si++) {
+                __syncthreads();
+                const uint32_t nb = sel_id[si];
+                uint32_t *nb_rec = links_of(a.g, nb, level);
+                if (threadIdx.x == 0) {
+                    int action = 0; // 0 nothing/simple, 1 revisit, 2 stop
+                    if ((int)new_rec[0] == maxMcur) action = 2;
+                    else if (is_deleted(a.g, nb)) action = 0;
+                    else if ((int)nb_rec[0] < maxMcur) {
+                        new_rec[1 + new_rec[0]] = nb;
+                        new_rec[0]++;
+                        nb_rec[1 + nb_rec[0]] = e;
+                        nb_rec[0]++;
+                    } else action = 1;
+                    w.sc[SC_AUX1] = action;
+                }
+                __syncthreads();
+                const int action = w.sc[SC_AUX1];
+                if (action == 2) break;
+                if (action == 0) continue;
+                // ---- revisitNeighborConnections (:801-868) ----
+                const int cnt = (int)nb_rec[0];
+                const int nc = cnt + 1;
+                eval_dists<P, false>(a.k, nullptr, cnt, h.in_d + 1, [&](int j, uint32_t &x, uint32_t &y) {
+                    x = nb_rec[1 + j];
+                    y = nb;
+                });
+                for (int j = threadIdx.x; j < cnt; j += blockDim.x) h.in_id[1 + j] = nb_rec[1 + j];
+                if (threadIdx.x == 0) {
+                    h.in_d[0] = sel_d[si];
+                    h.in_id[0] = e;
+                    evals += cnt;
+                }
+                __syncthreads();
+                rank_sort<DT>(h, nc);
+                heuristic<P>(a.k, h, w.sc, nc, maxMcur);
+                if (threadIdx.x == 0) {
+                    // keep flags by original position: 0 = the new element, 1 + j = link j
+                    bool new_chosen = false;
+                    int kept = 0;
+                    // sorted position -> original position; mark in nb_ids scratch
+                    for (int i = 0; i < nc; i++) w.nb_ids[h.spos[i]] = h.keep[i];
+                    new_chosen = w.nb_ids[0] != 0;
+                    for (int j = 0; j < cnt; j++)
+                        if (w.nb_ids[1 + j]) nb_rec[1 + kept++] = nb_rec[1 + j];
+                    if ((int)new_rec[0] < maxMcur && !is_deleted(a.g, nb)) {
+                        new_rec[1 + new_rec[0]] = nb;
+                        new_rec[0]++;
+                        if (new_chosen && kept < maxMcur) nb_rec[1 + kept++] = e;
+                    }
+                    nb_rec[0] = (uint32_t)kept;
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) w.sc[SC_CUR] = w.sc[SC_AUX3];
+            __syncthreads();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && lvl > maxl) {
+            a.g.state[0] = (int)e;
+            a.g.state[1] = lvl;
+        }
+        __threadfence_block();
+    }
+    if (threadIdx.x == 0 && a.counters) {
+        atomicAdd(&a.counters[0], evals);
+        atomicAdd(&a.counters[1], hops);
+    }
+}
+
+} // namespace vsgpu
+
+// ================================================================================================
+// host side of the C-ABI
+using namespace vsgpu;
+
+struct vsgpu_hnsw {
+    vsgpu_store *s = nullptr;
+    int M = 0, M0 = 0, efc = 0;
+    size_t capacity = 0;   // nodes the arrays are sized for
+    size_t count = 0;      // nodes in the graph
+    uint32_t *l0 = nullptr, *up = nullptr, *up_off = nullptr, *levels = nullptr, *tags = nullptr, *tag_counter = nullptr;
+    uint8_t *flags = nullptr;
+    int *state = nullptr;
+    size_t up_records = 0, up_capacity = 0;
+    int entry = -1, max_level = -1;
+    Scratch visited, spill, out, misc;
+    unsigned long long *counters = nullptr; // [0] evals [1] hops
+    uint32_t *status = nullptr;
+    unsigned long long last_evals = 0, last_hops = 0;
+    float last_ms = 0;
+    uint32_t host_tag = 0;
+};
+
+namespace vsgpu {
+
+static KCtx make_kctx(const vsgpu_store *s) {
+    KCtx k{};
+    k.rows = s->rows;
+    k.row_stride = s->row_stride;
+    k.type = s->type;
+    k.metric = s->metric;
+    k.plan = s->plan;
+    k.norms = s->has_norm ? s->norms : nullptr;
+    k.chunks = (int)(s->row_stride / 16);
+    return k;
+}
+static GraphDev make_graph(const vsgpu_hnsw *g) {
+    GraphDev d{};
+    d.l0 = g->l0;
+    d.up = g->up;
+    d.up_off = g->up_off;
+    d.levels = g->levels;
+    d.flags = g->flags;
+    d.state = g->state;
+    d.M = g->M;
+    d.M0 = g->M0;
+    return d;
+}
+
+template <typename F> static int dispatch_policy(const vsgpu_store *s, F &&f) {
+    const ChainPlan &p = s->plan;
+    const bool l2 = p.is_l2;
+    if (p.kind == CK_INT) return s->type == VSGPU_UINT8 ? f.template operator()<PolInt<true>>() : f.template operator()<PolInt<false>>();
+    if (p.kind == CK_SEQ) return s->type == VSGPU_FLOAT64 ? f.template operator()<PolSeq<double>>() : f.template operator()<PolSeq<float>>();
+    if (s->type == VSGPU_FLOAT64)
+        return l2 ? f.template operator()<PolChain<double, 16, false, true>>() : f.template operator()<PolChain<double, 16, false, false>>();
+    if (p.kind == CK_BF16_DP) return f.template operator()<PolChain<float, 16, true, false>>();
+    if (p.kind == CK_BF16_VBMI2) return f.template operator()<PolChain<float, 16, false, true>>();
+    return l2 ? f.template operator()<PolChain<float, 32, false, true>>() : f.template operator()<PolChain<float, 32, false, false>>();
+}
+
+template <typename T> static int regrow(T *&p, size_t old_n, size_t new_n, cudaStream_t st, bool zero) {
+    T *np = nullptr;
+    VS_CUDA(cudaMalloc(&np, new_n * sizeof(T)));
+    if (zero) VS_CUDA(cudaMemsetAsync(np, 0, new_n * sizeof(T), st));
+    if (p && old_n) VS_CUDA(cudaMemcpyAsync(np, p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    VS_CUDA(cudaStreamSynchronize(st));
+    if (p) cudaFree(p);
+    p = np;
+    return VSGPU_OK;
+}
+
+static int graph_reserve(vsgpu_hnsw *g, size_t nodes, size_t up_records) {
+    vsgpu_store *s = g->s;
+    if (nodes > g->capacity) {
+        size_t cap = std::max<size_t>(nodes, g->capacity + g->capacity / 2);
+        cap = std::max<size_t>(cap, 1024);
+        VS_TRY(regrow(g->l0, g->capacity * (g->M0 + 1), cap * (g->M0 + 1), s->stream, true));
+        VS_TRY(regrow(g->up_off, g->capacity, cap, s->stream, true));
+        VS_TRY(regrow(g->levels, g->capacity, cap, s->stream, true));
+        VS_TRY(regrow(g->tags, g->capacity, cap, s->stream, true));
+        VS_TRY(regrow(g->flags, g->capacity, cap, s->stream, true));
+        g->capacity = cap;
+    }
+    if (up_records > g->up_capacity) {
+        size_t cap = std::max<size_t>(up_records, g->up_capacity + g->up_capacity / 2);
+        cap = std::max<size_t>(cap, 256);
+        VS_TRY(regrow(g->up, g->up_capacity * (g->M + 1), cap * (g->M + 1), s->stream, true));
+        g->up_capacity = cap;
+    }
+    return VSGPU_OK;
+}
+
+static int read_state(vsgpu_hnsw *g) {
+    int st[2];
+    VS_CUDA(cudaMemcpyAsync(st, g->state, sizeof(st), cudaMemcpyDeviceToHost, g->s->stream));
+    VS_CUDA(cudaStreamSynchronize(g->s->stream));
+    g->entry = st[0];
+    g->max_level = st[1];
+    return VSGPU_OK;
+}
+
+static size_t smem_limit(int device) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess || v <= 0) v = 227 * 1024;
+    return (size_t)v;
+}
+
+} // namespace vsgpu
+
+extern "C" {
+
+vsgpu_hnsw *vsgpu_hnsw_create(vsgpu_store *s, size_t M, size_t ef_construction) {
+    if (!s || M < 2 || 2 * M > 512) {
+        set_error("vsgpu_hnsw_create: M must be in [2, 256]");
+        return nullptr;
+    }
+    if (cudaSetDevice(s->device) != cudaSuccess) return nullptr;
+    auto *g = new vsgpu_hnsw();
+    g->s = s;
+    g->M = (int)M;
+    g->M0 = (int)(2 * M);
+    g->efc = (int)std::max(ef_construction, M);
+    bool ok = cudaMalloc(&g->state, 2 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&g->counters, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&g->status, sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&g->tag_counter, sizeof(uint32_t)) == cudaSuccess;
+    if (ok) {
+        const int st[2] = {-1, -1};
+        ok = cudaMemcpy(g->state, st, sizeof(st), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemset(g->tag_counter, 0, sizeof(uint32_t)) == cudaSuccess;
+    }
+    if (!ok) {
+        set_error("vsgpu_hnsw_create: device allocation failed");
+        vsgpu_hnsw_destroy(g);
+        return nullptr;
+    }
+    return g;
+}
+
+void vsgpu_hnsw_destroy(vsgpu_hnsw *g) {
+    if (!g) return;
+    cudaSetDevice(g->s->device);
+    cudaStreamSynchronize(g->s->stream);
+    for (void *p : {(void *)g->l0, (void *)g->up, (void *)g->up_off, (void *)g->levels, (void *)g->tags, (void *)g->flags,
+                    (void *)g->state, (void *)g->counters, (void *)g->status, (void *)g->tag_counter})
+        if (p) cudaFree(p);
+    for (Scratch *sc : {&g->visited, &g->spill, &g->out, &g->misc})
+        if (sc->ptr) cudaFree(sc->ptr);
+    delete g;
+}
+
+size_t vsgpu_hnsw_size(const vsgpu_hnsw *g) { return g->count; }
+size_t vsgpu_hnsw_device_bytes(const vsgpu_hnsw *g) {
+    return g->capacity * ((size_t)(g->M0 + 1) * 4 + 4 + 4 + 4 + 1) + g->up_capacity * (size_t)(g->M + 1) * 4 +
+           g->visited.bytes + g->spill.bytes + g->out.bytes + g->misc.bytes;
+}
+int vsgpu_hnsw_entry(const vsgpu_hnsw *g, long *entry, long *max_level) {
+    if (entry) *entry = g->entry;
+    if (max_level) *max_level = g->max_level;
+    return VSGPU_OK;
+}
+
+int vsgpu_hnsw_insert(vsgpu_hnsw *g, size_t n, const uint32_t *levels) {
+    vsgpu_store *s = g->s;
+    if (n == 0) return VSGPU_OK;
+    if (!levels || g->count + n > s->count) {
+        set_error("vsgpu_hnsw_insert: rows must be appended to the store first");
+        return VSGPU_ERR_ARG;
+    }
+    VS_CUDA(cudaSetDevice(s->device));
+    size_t add_records = 0;
+    std::vector<uint32_t> offs(n);
+    for (size_t i = 0; i < n; i++) {
+        offs[i] = (uint32_t)(g->up_records + add_records);
+        add_records += levels[i];
+    }
+    VS_TRY(graph_reserve(g, std::max(g->count + n, s->capacity), g->up_records + add_records));
+    VS_CUDA(cudaMemcpyAsync(g->levels + g->count, levels, n * 4, cudaMemcpyHostToDevice, s->stream));
+    VS_CUDA(cudaMemcpyAsync(g->up_off + g->count, offs.data(), n * 4, cudaMemcpyHostToDevice, s->stream));
+    // new nodes start with empty link lists (arrays are zeroed when grown, but ids may be reused after import)
+    VS_CUDA(cudaMemsetAsync(g->l0 + g->count * (g->M0 + 1), 0, n * (size_t)(g->M0 + 1) * 4, s->stream));
+    if (add_records)
+        VS_CUDA(cudaMemsetAsync(g->up + g->up_records * (g->M + 1), 0, add_records * (size_t)(g->M + 1) * 4, s->stream));
+    VS_CUDA(cudaMemsetAsync(g->flags + g->count, 0, n, s->stream));
+    // visited tags: one per search_layer call; clear before a 32-bit wrap could alias
+    if ((unsigned long long)g->host_tag + (unsigned long long)n * 64ull > 0xfffffff0ull) {
+        VS_CUDA(cudaMemsetAsync(g->tags, 0, g->capacity * 4, s->stream));
+        VS_CUDA(cudaMemsetAsync(g->tag_counter, 0, 4, s->stream));
+        g->host_tag = 0;
+    }
+    VS_CUDA(cudaMemsetAsync(g->status, 0, 4, s->stream));
+    VS_CUDA(cudaMemsetAsync(g->counters, 0, 16, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream)); // offs goes out of scope
+    const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    VS_TRY(ensure_scratch(s, g->spill, (g->capacity + 1) * (dt + 4)));
+    InsertArgs a{};
+    a.k = make_kctx(s);
+    a.g = make_graph(g);
+    a.first = (uint32_t)g->count;
+    a.n = (uint32_t)n;
+    a.tags = g->tags;
+    a.tag_counter = g->tag_counter;
+    a.efc = g->efc;
+    a.cand_cap = 2 * g->efc + 64;
+    a.max_links = g->M0 + 1;
+    a.spill = g->spill.ptr;
+    a.spill_cap = (int)std::min<size_t>(g->capacity, 0x7fffffff);
+    a.counters = g->counters;
+    a.status = g->status;
+    const int rc = dispatch_policy(s, [&]<class P>() -> int {
+        a.pivot_bytes = P::pivot_bytes(s);
+        const size_t smem = carve_bytes(dt, a.pivot_bytes, a.max_links, a.efc + 1, a.cand_cap, g->M) +
+                            heur_bytes(dt, std::max(a.efc + 1, g->M0 + 1), g->M0);
+        if (smem > smem_limit(s->device)) {
+            set_error("vsgpu_hnsw_insert: efConstruction / dim too large for the shared-memory builder");
+            return (int)VSGPU_ERR_ARG;
+        }
+        auto kern = hnsw_insert_kernel<P>;
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VS_CUDA(cudaEventRecord(s->ev0, s->stream));
+        kern<<<1, HNSW_THREADS, smem, s->stream>>>(a);
+        VS_CUDA(cudaGetLastError());
+        VS_CUDA(cudaEventRecord(s->ev1, s->stream));
+        return (int)VSGPU_OK;
+    });
+    VS_TRY(rc);
+    uint32_t st = 0;
+    unsigned long long ctr[2] = {0, 0};
+    VS_CUDA(cudaMemcpyAsync(&st, g->status, 4, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(ctr, g->counters, 16, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    cudaEventElapsedTime(&g->last_ms, s->ev0, s->ev1);
+    g->last_evals = ctr[0];
+    g->last_hops = ctr[1];
+    if (st != 0) {
+        set_error("vsgpu_hnsw_insert: candidate set overflow");
+        return VSGPU_ERR_OVERFLOW;
+    }
+    g->host_tag += (uint32_t)(n * 64);
+    g->count += n;
+    g->up_records += add_records;
+    return read_state(g);
+}
+
+int vsgpu_hnsw_import(vsgpu_hnsw *g, size_t n, const uint32_t *levels, const uint32_t *l0, const uint32_t *upper,
+                      size_t upper_records, long entry, long max_level) {
+    vsgpu_store *s = g->s;
+    if (n > s->count) {
+        set_error("vsgpu_hnsw_import: more nodes than rows in the store");
+        return VSGPU_ERR_ARG;
+    }
+    VS_CUDA(cudaSetDevice(s->device));
+    std::vector<uint32_t> offs(n);
+    size_t rec = 0;
+    for (size_t i = 0; i < n; i++) {
+        offs[i] = (uint32_t)rec;
+        rec += levels[i];
+    }
+    if (rec != upper_records) {
+        set_error("vsgpu_hnsw_import: upper_records != sum(levels)");
+        return VSGPU_ERR_ARG;
+    }
+    VS_TRY(graph_reserve(g, std::max(n, s->capacity), rec));
+    if (n) {
+        VS_CUDA(cudaMemcpyAsync(g->levels, levels, n * 4, cudaMemcpyHostToDevice, s->stream));
+        VS_CUDA(cudaMemcpyAsync(g->up_off, offs.data(), n * 4, cudaMemcpyHostToDevice, s->stream));
+        VS_CUDA(cudaMemcpyAsync(g->l0, l0, n * (size_t)(g->M0 + 1) * 4, cudaMemcpyHostToDevice, s->stream));
+        if (rec) VS_CUDA(cudaMemcpyAsync(g->up, upper, rec * (size_t)(g->M + 1) * 4, cudaMemcpyHostToDevice, s->stream));
+        VS_CUDA(cudaMemsetAsync(g->flags, 0, n, s->stream));
+    }
+    const int st[2] = {(int)entry, (int)max_level};
+    VS_CUDA(cudaMemcpyAsync(g->state, st, sizeof(st), cudaMemcpyHostToDevice, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    g->count = n;
+    g->up_records = rec;
+    g->entry = (int)entry;
+    g->max_level = (int)max_level;
+    return VSGPU_OK;
+}
+
+int vsgpu_hnsw_export(const vsgpu_hnsw *g, uint32_t *levels, uint32_t *l0, uint32_t *upper, size_t upper_cap_records,
+                      size_t *upper_records) {
+    vsgpu_store *s = g->s;
+    VS_CUDA(cudaSetDevice(s->device));
+    if (upper_records) *upper_records = g->up_records;
+    const size_t n = g->count;
+    if (n == 0) return VSGPU_OK;
+    if (levels) VS_CUDA(cudaMemcpyAsync(levels, g->levels, n * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (l0) VS_CUDA(cudaMemcpyAsync(l0, g->l0, n * (size_t)(g->M0 + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (upper && g->up_records) {
+        if (upper_cap_records < g->up_records) {
+            set_error("vsgpu_hnsw_export: upper buffer too small");
+            return VSGPU_ERR_OVERFLOW;
+        }
+        VS_CUDA(cudaMemcpyAsync(upper, g->up, g->up_records * (size_t)(g->M + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    return VSGPU_OK;
+}
+
+int vsgpu_hnsw_set_deleted(vsgpu_hnsw *g, size_t id, int deleted) {
+    if (id >= g->count) {
+        set_error("vsgpu_hnsw_set_deleted: bad id");
+        return VSGPU_ERR_ARG;
+    }
+    VS_CUDA(cudaSetDevice(g->s->device));
+    const uint8_t v = deleted ? 1 : 0;
+    VS_CUDA(cudaMemcpyAsync(g->flags + id, &v, 1, cudaMemcpyHostToDevice, g->s->stream));
+    VS_CUDA(cudaStreamSynchronize(g->s->stream));
+    return VSGPU_OK;
+}
+
+int vsgpu_hnsw_last_stats(const vsgpu_hnsw *g, unsigned long long *dist_evals, unsigned long long *hops, float *ms) {
+    if (dist_evals) *dist_evals = g->last_evals;
+    if (hops) *hops = g->last_hops;
+    if (ms) *ms = g->last_ms;
+    return VSGPU_OK;
+}
+
+} // extern "C"
+
+namespace vsgpu {
+
+// queries staged on the device (see stage_queries_device); outputs on the device
+static int hnsw_search_core(vsgpu_hnsw *g, const void *q, size_t nq, size_t q_stride, const float *q_norms, size_t k,
+                            size_t ef, bool range, double radius, double epsilon, size_t range_cap, uint32_t *out_ids,
+                            void *out_scores, uint64_t *out_labels, uint32_t *out_counts, unsigned long long *range_counts,
+                            uint32_t *status, bool with_spill) {
+    vsgpu_store *s = g->s;
+    const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    const size_t vis_words = (g->count + 31) / 32;
+    VS_TRY(ensure_scratch(s, g->visited, nq * vis_words * 4 + 256));
+    VS_CUDA(cudaMemsetAsync(g->visited.ptr, 0, nq * vis_words * 4, s->stream));
+    SearchArgs a{};
+    a.k = make_kctx(s);
+    a.g = make_graph(g);
+    a.q = (const uint8_t *)q;
+    a.q_stride = q_stride;
+    a.q_norms = q_norms;
+    a.labels = s->labels;
+    a.visited = (uint32_t *)g->visited.ptr;
+    a.vis_words = vis_words;
+    a.ef = (int)ef;
+    a.k_out = (int)k;
+    a.max_links = g->M0;
+    a.out_ids = out_ids;
+    a.out_scores = out_scores;
+    a.out_labels = out_labels;
+    a.out_counts = out_counts;
+    a.out_ld = k;
+    a.status = status;
+    a.counters = g->counters;
+    a.radius = radius;
+    a.epsilon = epsilon;
+    a.range_counts = range_counts;
+    a.range_cap = range_cap;
+    if (with_spill) {
+        VS_TRY(ensure_scratch(s, g->spill, nq * (g->count + 1) * (dt + 4)));
+        a.spill = g->spill.ptr;
+        a.spill_cap = (int)std::min<size_t>(g->count + 1, 0x7fffffff);
+    }
+    return dispatch_policy(s, [&]<class P>() -> int {
+        a.pivot_bytes = P::pivot_bytes(s);
+        const size_t limit = smem_limit(s->device);
+        const int top_cap = range ? 1 : (int)ef + 1;
+        // candidate set: room for the live frontier (<= ef + ties) plus stale entries between prunes
+        int cand_cap = range ? 4096 : (int)(2 * ef + 64);
+        size_t smem = carve_bytes(dt, a.pivot_bytes, a.max_links, top_cap, cand_cap, 0);
+        while (smem > limit && cand_cap > 64) {
+            cand_cap /= 2;
+            smem = carve_bytes(dt, a.pivot_bytes, a.max_links, top_cap, cand_cap, 0);
+        }
+        if (smem > limit) {
+            set_error("hnsw search: ef / dim too large for the shared-memory working set");
+            return (int)VSGPU_ERR_ARG;
+        }
+        a.cand_cap = cand_cap;
+        if (range) {
+            auto kern = hnsw_range_kernel<P>;
+            VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)nq, HNSW_THREADS, smem, s->stream>>>(a);
+        } else {
+            auto kern = hnsw_search_kernel<P>;
+            VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)nq, HNSW_THREADS, smem, s->stream>>>(a);
+        }
+        VS_CUDA(cudaGetLastError());
+        return (int)VSGPU_OK;
+    });
+}
+
+} // namespace vsgpu
+
+extern "C" {
+
+int vsgpu_hnsw_topk_device(vsgpu_hnsw *g, const void *queries, size_t nq, size_t qstride, size_t k, size_t ef,
+                           uint64_t *out_labels, void *out_scores, uint32_t *out_ids, uint32_t *out_counts) {
+    vsgpu_store *s = g->s;
+    if (nq == 0 || k == 0) return VSGPU_OK;
+    VS_CUDA(cudaSetDevice(s->device));
+    ef = std::max(ef, k);
+    const void *q = nullptr;
+    size_t qs = 0;
+    const float *qn = nullptr;
+    VS_TRY(stage_queries_device(s, queries, nq, qstride, &q, &qs, &qn));
+    VS_TRY(ensure_scratch(s, g->misc, nq * 4 + 256));
+    uint32_t *status = (uint32_t *)g->misc.ptr;
+    VS_CUDA(cudaMemsetAsync(g->counters, 0, 16, s->stream));
+    VS_CUDA(cudaEventRecord(s->ev0, s->stream));
+    VS_TRY(hnsw_search_core(g, q, nq, qs, qn, k, ef, false, 0, 0, 0, out_ids, out_scores, out_labels, out_counts, nullptr,
+                            status, false));
+    VS_CUDA(cudaEventRecord(s->ev1, s->stream));
+    // overflowed candidate sets (pathological ties / mostly deleted graphs): redo those queries with a spill area
+    std::vector<uint32_t> st(nq);
+    unsigned long long ctr[2];
+    VS_CUDA(cudaMemcpyAsync(st.data(), status, nq * 4, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(ctr, g->counters, 16, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    cudaEventElapsedTime(&g->last_ms, s->ev0, s->ev1);
+    g->last_evals = ctr[0];
+    g->last_hops = ctr[1];
+    const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    for (size_t i = 0; i < nq; i++) {
+        if (!st[i]) continue;
+        VS_TRY(hnsw_search_core(g, (const uint8_t *)q + i * qs, 1, qs, qn ? qn + i : nullptr, k, ef, false, 0, 0, 0,
+                                out_ids ? out_ids + i * k : nullptr, out_scores ? (uint8_t *)out_scores + i * k * dt : nullptr,
+                                out_labels ? out_labels + i * k : nullptr, out_counts ? out_counts + i : nullptr, nullptr,
+                                nullptr, true));
+        VS_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return VSGPU_OK;
+}
+
+int vsgpu_hnsw_topk(vsgpu_hnsw *g, const void *queries, size_t nq, size_t qstride, size_t k, size_t ef,
+                    uint64_t *out_labels, double *out_scores, uint32_t *out_ids, uint32_t *out_counts) {
+    vsgpu_store *s = g->s;
+    if (nq == 0) return VSGPU_OK;
+    if (!queries || qstride < s->blob_bytes) {
+        set_error("vsgpu_hnsw_topk: bad query buffer");
+        return VSGPU_ERR_ARG;
+    }
+    if (k == 0 || g->count == 0 || g->entry < 0) {
+        if (out_counts) std::fill(out_counts, out_counts + nq, 0u);
+        return VSGPU_OK;
+    }
+    VS_CUDA(cudaSetDevice(s->device));
+    const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t qbytes = nq * s->blob_bytes;
+    const size_t o_lab = al(qbytes), o_sc = o_lab + al(nq * k * 8), o_id = o_sc + al(nq * k * dt), o_cnt = o_id + al(nq * k * 4);
+    VS_TRY(ensure_pinned(s, o_cnt + al(nq * 4)));
+    uint8_t *pin = (uint8_t *)s->pinned;
+    for (size_t i = 0; i < nq; i++) memcpy(pin + i * s->blob_bytes, (const uint8_t *)queries + i * qstride, s->blob_bytes);
+    VS_TRY(ensure_scratch(s, s->q_raw, al(qbytes)));
+    VS_TRY(ensure_scratch(s, g->out, al(nq * k * 8) + al(nq * k * dt) + al(nq * k * 4) + al(nq * 4)));
+    uint64_t *d_lab = (uint64_t *)g->out.ptr;
+    uint8_t *d_sc = (uint8_t *)g->out.ptr + al(nq * k * 8);
+    uint32_t *d_id = (uint32_t *)(d_sc + al(nq * k * dt));
+    uint32_t *d_cnt = (uint32_t *)((uint8_t *)d_id + al(nq * k * 4));
+    VS_CUDA(cudaMemcpyAsync(s->q_raw.ptr, pin, qbytes, cudaMemcpyHostToDevice, s->stream));
+    VS_TRY(vsgpu_hnsw_topk_device(g, s->q_raw.ptr, nq, s->blob_bytes, k, ef, d_lab, d_sc, d_id, d_cnt));
+    VS_CUDA(cudaMemcpyAsync(pin + o_lab, d_lab, nq * k * 8, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(pin + o_sc, d_sc, nq * k * dt, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(pin + o_id, d_id, nq * k * 4, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(pin + o_cnt, d_cnt, nq * 4, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    const uint32_t *h_cnt = (const uint32_t *)(pin + o_cnt);
+    for (size_t i = 0; i < nq; i++) {
+        if (out_counts) out_counts[i] = h_cnt[i];
+        for (size_t j = 0; j < k; j++) {
+            const size_t o = i * k + j;
+            const bool valid = j < h_cnt[i];
+            if (out_labels) out_labels[o] = valid ? ((const uint64_t *)(pin + o_lab))[o] : ~0ull;
+            if (out_ids) out_ids[o] = valid ? ((const uint32_t *)(pin + o_id))[o] : INV;
+            if (out_scores)
+                out_scores[o] = !valid ? std::numeric_limits<double>::quiet_NaN()
+                                       : (dt == 8 ? ((const double *)(pin + o_sc))[o] : (double)((const float *)(pin + o_sc))[o]);
+        }
+    }
+    return VSGPU_OK;
+}
+
+int vsgpu_hnsw_range(vsgpu_hnsw *g, const void *query, double radius, double epsilon, size_t cap, uint64_t *out_labels,
+                     double *out_scores, uint32_t *out_ids, size_t *out_count) {
+    vsgpu_store *s = g->s;
+    if (!query || !out_count) {
+        set_error("vsgpu_hnsw_range: bad arguments");
+        return VSGPU_ERR_ARG;
+    }
+    *out_count = 0;
+    if (g->count == 0 || g->entry < 0) return VSGPU_OK;
+    VS_CUDA(cudaSetDevice(s->device));
+    const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    VS_TRY(ensure_pinned(s, al(s->blob_bytes)));
+    memcpy(s->pinned, query, s->blob_bytes);
+    VS_TRY(ensure_scratch(s, s->q_raw, al(s->blob_bytes)));
+    VS_CUDA(cudaMemcpyAsync(s->q_raw.ptr, s->pinned, s->blob_bytes, cudaMemcpyHostToDevice, s->stream));
+    const void *q = nullptr;
+    size_t qs = 0;
+    const float *qn = nullptr;
+    VS_TRY(stage_queries_device(s, s->q_raw.ptr, 1, s->blob_bytes, &q, &qs, &qn));
+    const size_t capd = std::max<size_t>(cap, 1);
+    VS_TRY(ensure_scratch(s, g->out, al(capd * 8) + al(capd * dt) + al(capd * 4) + 256));
+    uint64_t *d_lab = (uint64_t *)g->out.ptr;
+    uint8_t *d_sc = (uint8_t *)g->out.ptr + al(capd * 8);
+    uint32_t *d_id = (uint32_t *)(d_sc + al(capd * dt));
+    unsigned long long *d_cnt = (unsigned long long *)((uint8_t *)d_id + al(capd * 4));
+    uint32_t *d_status = (uint32_t *)(d_cnt + 1);
+    VS_CUDA(cudaMemsetAsync(g->counters, 0, 16, s->stream));
+    unsigned long long cnt = 0;
+    uint32_t st = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        VS_TRY(hnsw_search_core(g, q, 1, qs, qn, 0, 0, true, radius, epsilon, cap, d_id, d_sc, d_lab, nullptr, d_cnt,
+                                d_status, attempt == 1));
+        VS_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s->stream));
+        VS_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, s->stream));
+        VS_CUDA(cudaStreamSynchronize(s->stream));
+        if (!st) break;
+    }
+    *out_count = (size_t)cnt;
+    if (cnt > cap) return VSGPU_ERR_OVERFLOW;
+    if (cnt == 0) return VSGPU_OK;
+    if (out_labels) VS_CUDA(cudaMemcpy(out_labels, d_lab, cnt * 8, cudaMemcpyDeviceToHost));
+    if (out_ids) VS_CUDA(cudaMemcpy(out_ids, d_id, cnt * 4, cudaMemcpyDeviceToHost));
+    if (out_scores) {
+        if (dt == 8) {
+            VS_CUDA(cudaMemcpy(out_scores, d_sc, cnt * 8, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<float> tmp(cnt);
+            VS_CUDA(cudaMemcpy(tmp.data(), d_sc, cnt * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < cnt; i++) out_scores[i] = tmp[i];
+        }
+    }
+    return VSGPU_OK;
+}
+
+} // extern "C"

@@ -132,6 +132,9 @@ namespace vsgpu {
 
 int ensure_scratch(vsgpu_store *s, Scratch &sc, size_t bytes);
 int ensure_pinned(vsgpu_store *s, size_t bytes);
+// raw query blobs on the device -> what the kernels read (zero-padded rows + norms for integer types)
+int stage_queries_device(vsgpu_store *s, const void *q_dev_raw, size_t nq, size_t qstride, const void **q_out,
+                         size_t *q_stride_out, const float **q_norms_out);
 
 // ---- exact path (vsgpu_exact.cu) ----
 // scores[q * ld + id] for q < nq, id < n: DistType (float, or double for fp64 stores).
