@@ -75,6 +75,24 @@ def lib():
         L.vso_bi_has_next.argtypes = [vp]
         L.vso_bi_reset.argtypes = [vp]
         L.vso_bi_free.argtypes = [vp]
+        L.vso_hnsw_new.restype = vp
+        L.vso_hnsw_new.argtypes = [i32, sz, i32, sz, sz, sz, dbl]
+        L.vso_hnsw_free.argtypes = [vp]
+        L.vso_hnsw_add.argtypes = [vp, vp, sz]
+        L.vso_hnsw_size.restype = sz
+        L.vso_hnsw_size.argtypes = [vp]
+        L.vso_hnsw_mark_deleted.argtypes = [vp, sz, i32]
+        L.vso_hnsw_info.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        L.vso_hnsw_level.restype = C.c_uint32
+        L.vso_hnsw_level.argtypes = [vp, sz]
+        L.vso_hnsw_links.restype = sz
+        L.vso_hnsw_links.argtypes = [vp, sz, sz, vp]
+        L.vso_hnsw_dist_count.restype = sz
+        L.vso_hnsw_dist_count.argtypes = [vp]
+        L.vso_hnsw_topk.restype = sz
+        L.vso_hnsw_topk.argtypes = [vp, vp, sz, sz, vp, vp]
+        L.vso_hnsw_range.restype = sz
+        L.vso_hnsw_range.argtypes = [vp, vp, dbl, dbl, sz, vp, vp]
         _lib = L
     return _lib
 
@@ -224,3 +242,76 @@ class PortBatchIterator:
         if self.it:
             lib().vso_bi_free(self.it)
             self.it = None
+
+
+class PortHnsw:
+    """vs_oracle_hnsw.c: the reference's single-threaded HNSW build / top-k / range, restated."""
+
+    def __init__(self, vtype, dim, metric, M=16, ef_construction=200, ef_runtime=10, epsilon=0.01):
+        self.vtype, self.dim, self.metric, self.M = vtype, dim, metric, M
+        self.h = lib().vso_hnsw_new(vtype, dim, metric, M, ef_construction, ef_runtime, epsilon)
+
+    def close(self):
+        if self.h:
+            lib().vso_hnsw_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_many(self, blobs, labels=None, first_label=0):
+        blobs = np.ascontiguousarray(blobs)
+        L = lib()
+        for i in range(blobs.shape[0]):
+            L.vso_hnsw_add(self.h, blobs[i].ctypes.data, int(labels[i]) if labels is not None else first_label + i)
+        return blobs.shape[0]
+
+    def size(self):
+        return lib().vso_hnsw_size(self.h)
+
+    def mark_deleted(self, internal_id, deleted=True):
+        lib().vso_hnsw_mark_deleted(self.h, internal_id, int(deleted))
+
+    def topk(self, q, k, ef_runtime=0):
+        q = np.ascontiguousarray(q)
+        labels = np.empty(max(k, 1), dtype=np.uint64)
+        scores = np.empty(max(k, 1), dtype=np.float64)
+        n = lib().vso_hnsw_topk(self.h, _ptr(q), k, ef_runtime, _ptr(labels), _ptr(scores))
+        return labels[:n].copy(), scores[:n].copy(), 0
+
+    def range(self, q, radius, epsilon=0.0):
+        q = np.ascontiguousarray(q)
+        cap = max(self.size(), 1)
+        labels = np.empty(cap, dtype=np.uint64)
+        scores = np.empty(cap, dtype=np.float64)
+        n = lib().vso_hnsw_range(self.h, _ptr(q), float(radius), float(epsilon), cap, _ptr(labels), _ptr(scores))
+        return labels[:n].copy(), scores[:n].copy(), 0
+
+    def export(self):
+        """Same layout as oracle.ref.RefIndex.hnsw_export (levels, links[l] [n, width], counts[l] [n])."""
+        L = lib()
+        n, M = self.size(), self.M
+        entry, maxl = C.c_long(), C.c_long()
+        L.vso_hnsw_info(self.h, C.byref(entry), C.byref(maxl))
+        levels = np.array([L.vso_hnsw_level(self.h, i) for i in range(n)], dtype=np.uint32)
+        out = dict(n=n, M=M, entry=entry.value, max_level=maxl.value, levels=levels, links=[], counts=[])
+        buf = np.empty(2 * M, dtype=np.uint32)
+        for lvl in range(max(maxl.value, 0) + 1):
+            width = 2 * M if lvl == 0 else M
+            links = np.full((n, width), 0xFFFFFFFF, dtype=np.uint32)
+            counts = np.zeros(n, dtype=np.uint32)
+            for i in range(n):
+                if levels[i] < lvl:
+                    continue
+                c = L.vso_hnsw_links(self.h, i, lvl, _ptr(buf))
+                counts[i] = c
+                links[i, :c] = buf[:c]
+            out["links"].append(links)
+            out["counts"].append(counts)
+        return out
+
+    def dist_count(self):
+        return lib().vso_hnsw_dist_count(self.h)

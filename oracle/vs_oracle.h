@@ -78,20 +78,23 @@ int vso_bi_has_next(const vso_bi *it);
 void vso_bi_reset(vso_bi *it);
 void vso_bi_free(vso_bi *it);
 
-/* ---- HNSW search over an exported graph (algorithms/hnsw/hnsw.h:530-613,1210-1258,1967-2084) ---- */
-typedef struct {
-    size_t n, dim, M;
-    int metric;            /* fp32 only */
-    long entry, max_level; /* -1 if empty */
-    const float *vectors;  /* n x dim (processed) */
-    const size_t *labels;
-    const uint8_t *flags;  /* bit0 deleted, bit1 in-process */
-    const uint32_t *levels;
-    const uint32_t *const *links;  /* links[l]: n x (l==0 ? 2M : M) */
-    const uint32_t *const *counts; /* counts[l]: n */
-} vso_hnsw_graph;
-size_t vso_hnsw_topk(const vso_hnsw_graph *g, const float *query, size_t k, size_t ef,
-                     size_t *labels, double *scores, size_t *n_dist_evals);
+/* ---- HNSW (reference: algorithms/hnsw), vs_oracle_hnsw.c: single-threaded build + top-k + range ---- */
+typedef struct vso_hnsw vso_hnsw;
+vso_hnsw *vso_hnsw_new(int type, size_t dim, int metric, size_t M, size_t ef_construction, size_t ef_runtime,
+                       double epsilon);
+void vso_hnsw_free(vso_hnsw *g);
+void vso_hnsw_add(vso_hnsw *g, const void *blob, size_t label); /* raw caller blob; label must be new */
+size_t vso_hnsw_size(const vso_hnsw *g);
+void vso_hnsw_mark_deleted(vso_hnsw *g, size_t id, int deleted);
+void vso_hnsw_info(const vso_hnsw *g, long *entry, long *max_level); /* -1/-1 when empty */
+uint32_t vso_hnsw_level(const vso_hnsw *g, size_t id);
+size_t vso_hnsw_links(const vso_hnsw *g, size_t id, size_t level, uint32_t *out);
+size_t vso_hnsw_dist_count(const vso_hnsw *g);
+/* ascending (score, label); ef_runtime 0 = index default; returns the number of results (<= k) */
+size_t vso_hnsw_topk(vso_hnsw *g, const void *query, size_t k, size_t ef_runtime, size_t *labels, double *scores);
+/* sorted by (score, label); epsilon 0 = index default; returns the total found, writes <= cap */
+size_t vso_hnsw_range(vso_hnsw *g, const void *query, double radius, double epsilon, size_t cap, size_t *labels,
+                      double *scores);
 
 #ifdef __cplusplus
 }

@@ -84,3 +84,32 @@ def test_port_matches_captured_ties(port, cases):
     labels, scores, _ = idx.topk(cases["ties_q"], len(cases["ties_labels"]))
     assert np.array_equal(labels, cases["ties_labels"])
     assert np.array_equal(scores, cases["ties_scores"])
+
+
+# ---- HNSW: the oracle restatement against the committed reference outputs (tests/golden/hnsw_case.npz) ----
+@pytest.mark.parametrize("name,metric", [("l2", 0), ("cos", 2)])
+def test_hnsw_port_reproduces_golden_graph_and_results(port, name, metric):
+    G = np.load(os.path.join(HERE, "golden", "hnsw_case.npz"))
+    port.set_tier(port.TIER_AVX512)
+    P = port.PortHnsw(0, 24, metric, M=8, ef_construction=48, ef_runtime=10)
+    P.add_many(G[name + "_X"])
+    g = P.export()
+    assert np.array_equal(g["levels"], G[name + "_levels"])
+    assert [g["entry"], g["max_level"]] == list(G[name + "_entry"])
+    for lvl in range(g["max_level"] + 1):
+        assert np.array_equal(g["counts"][lvl], G[f"{name}_counts{lvl}"]), lvl
+        assert np.array_equal(g["links"][lvl], G[f"{name}_links{lvl}"]), lvl
+    Q = G[name + "_Q"]
+    for ef in (10, 40):
+        for i in range(len(Q)):
+            l, s, _ = P.topk(Q[i], 10, ef_runtime=ef)
+            assert np.array_equal(l.astype(np.int64), G[f"{name}_labels_ef{ef}"][i])
+            assert np.array_equal(s, G[f"{name}_scores_ef{ef}"][i])
+    off = 0
+    for i in range(len(Q)):
+        n = int(G[name + "_range_n"][i])
+        l, s, _ = P.range(Q[i], float(G[name + "_radius"][i]))
+        assert np.array_equal(l.astype(np.int64), G[name + "_range_labels"][off:off + n])
+        assert np.array_equal(s, G[name + "_range_scores"][off:off + n])
+        off += n
+    P.close()

@@ -116,17 +116,57 @@ def test_builder_reproduces_reference_graph(capi, name, metric):
     G.close()
 
 
-@pytest.mark.parametrize("vtype,metric,dim", [(0, 1, 128), (1, 0, 20), (2, 1, 64), (2, 0, 40), (3, 2, 48), (4, 2, 64),
-                                              (4, 0, 33), (5, 1, 100), (0, 0, 5), (3, 0, 12)],
-                         ids=lambda v: str(v))
-def test_build_and_search_match_live_reference(capi, ref, vtype, metric, dim):
+CASES = [(0, 1, 128), (1, 0, 20), (2, 1, 64), (2, 0, 40), (3, 2, 48), (4, 2, 64), (4, 0, 33), (5, 1, 100), (0, 0, 5),
+         (3, 0, 12), (0, 2, 768)]
+
+
+@pytest.mark.parametrize("vtype,metric,dim", CASES, ids=lambda v: str(v))
+def test_build_and_search_match_oracle(capi, port, vtype, metric, dim):
     """Every distance policy (chain fp32/fp64/bf16/fp16, integer, scalar tiers): build on the device and in
-    the unmodified reference from the same vectors, then compare query results."""
+    the oracle (pinned to the reference by tests/test_oracle_vs_reference.py) from the same vectors; the
+    graphs and the query results must be identical."""
+    port.set_tier(port.TIER_AVX512)
+    n, nq, k, M = 1200, 12, 8, 6
+    X = make_vectors(vtype, n, dim, seed=900 + vtype * 7 + metric)
+    Q = make_vectors(vtype, nq, dim, seed=901 + vtype * 7 + metric)
+    if metric == 2:
+        X[(X == 0).all(1), 0] = 1
+        Q[(Q == 0).all(1), 0] = 1
+    P = port.PortHnsw(vtype, dim, metric, M=M, ef_construction=40, ef_runtime=10)
+    P.add_many(X)
+    G = new_index(capi, vtype, dim, metric, M=M, efc=40)
+    assert G.add_vectors(X) == n
+    gp, gg = P.export(), G.export_graph(n)
+    assert np.array_equal(gg["levels"], gp["levels"])
+    assert (gg["entry"], gg["max_level"]) == (gp["entry"], gp["max_level"])
+    l0, upper = graph_records(gp["levels"], gp["links"], gp["counts"], M)
+    assert np.array_equal(masked(gg["l0"]), l0), "level-0 links differ"
+    assert np.array_equal(masked(gg["upper"]), upper), "upper-level links differ"
+    for ef in (10, 64):
+        G.set_ef(ef)
+        labels, scores = G.knn_batch(Q, k)
+        for i in range(nq):
+            pl, ps, _ = P.topk(Q[i], k, ef_runtime=ef)
+            assert np.array_equal(labels[i], pl.astype(np.int64)), (TYPE_NAMES[vtype], METRIC_NAMES[metric], ef, i)
+            assert np.array_equal(scores[i], ps), (TYPE_NAMES[vtype], METRIC_NAMES[metric], ef, i)
+    for i in range(nq):
+        radius = max(float(P.topk(Q[i], k, ef_runtime=64)[1][4]), 0.0)
+        pl, ps, _ = P.range(Q[i], radius)
+        gl, gs = G.range_query(Q[i], radius)
+        assert np.array_equal(gl[0], pl.astype(np.int64)) and np.array_equal(gs[0], ps), (vtype, metric, i)
+    G.close()
+    P.close()
+
+
+@pytest.mark.parametrize("vtype,metric,dim", CASES[:8], ids=lambda v: str(v))
+def test_build_and_search_match_live_reference(capi, ref, vtype, metric, dim):
+    """Same, against the unmodified reference itself (oracle/_ref) where the host CPU dispatches the tier the
+    device kernels reproduce."""
     feats = ref.host_features()
     if vtype == 2 and metric != 0 and "avx512_bf16" not in feats:
         pytest.skip("host lacks avx512_bf16: the reference dispatches a different bf16 IP tier here")
-    if "avx512f" not in feats:
-        pytest.skip("host lacks avx512f")
+    if not all(f in feats for f in ("avx512f", "avx512bw", "avx512vl", "avx512vnni", "avx512vbmi2")):
+        pytest.skip("host lacks the AVX512 tier")
     ref.set_disabled_features("avx512_fp16")
     n, nq, k = 1200, 12, 8
     X = make_vectors(vtype, n, dim, seed=900 + vtype * 7 + metric)
@@ -148,7 +188,7 @@ def test_build_and_search_match_live_reference(capi, ref, vtype, metric, dim):
             assert np.array_equal(scores[i], rs), (TYPE_NAMES[vtype], METRIC_NAMES[metric], ef, i)
     G.close()
     R.close()
-    ref.set_disabled_features("")
+    ref.set_disabled_features()
 
 
 def test_deleted_nodes_are_traversed_not_returned(capi):

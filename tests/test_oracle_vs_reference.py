@@ -186,3 +186,66 @@ def test_timeout_and_range_errors(ref, port):
         R.range(q, -1.0)
     with pytest.raises(RuntimeError):
         P.range(q, -1.0)
+
+
+# ---- HNSW: the C restatement (oracle/vs_oracle_hnsw.c) against the unmodified reference ----
+@pytest.mark.parametrize("metric", [0, 1, 2], ids=["L2", "IP", "Cosine"])
+def test_hnsw_port_builds_the_reference_graph(port, ref, metric):
+    """Same levels (the reference's std::default_random_engine stream), entry point and link lists in
+    order; same top-k and range results. fp32 (the only type the reference harness exports graphs for)."""
+    from datagen import make_vectors
+    n, dim, M, efc = 2500, 20, 6, 40
+    X = make_vectors(0, n, dim, seed=31 + metric)
+    Q = make_vectors(0, 10, dim, seed=32 + metric)
+    R = ref.RefIndex(0, dim, metric, algo="hnsw", M=M, ef_construction=efc, ef_runtime=10)
+    R.add_many(X)
+    P = port.PortHnsw(0, dim, metric, M=M, ef_construction=efc, ef_runtime=10)
+    P.add_many(X)
+    gr, gp = R.hnsw_export(), P.export()
+    assert np.array_equal(gr["levels"], gp["levels"])
+    assert (gr["entry"], gr["max_level"]) == (gp["entry"], gp["max_level"])
+    assert gr["max_level"] >= 2, "fixture should exercise upper levels"
+    for lvl in range(gr["max_level"] + 1):
+        assert np.array_equal(gr["counts"][lvl], gp["counts"][lvl]), lvl
+        assert np.array_equal(gr["links"][lvl], gp["links"][lvl]), lvl
+    for ef in (0, 10, 50):
+        for q in Q:
+            rl, rs, _ = R.topk(q, 8, ef_runtime=ef)
+            pl, ps, _ = P.topk(q, 8, ef_runtime=ef)
+            assert np.array_equal(rl, pl) and np.array_equal(rs, ps)
+    for q in Q:
+        radius = max(float(R.topk(q, 8, ef_runtime=50)[1][5]), 0.0)
+        rl, rs, _ = R.range(q, radius)
+        pl, ps, _ = P.range(q, radius)
+        o = np.lexsort((rl, rs))
+        assert np.array_equal(rl[o], pl) and np.array_equal(rs[o], ps)
+    R.close()
+    P.close()
+
+
+@pytest.mark.parametrize("vtype,metric,dim", [(1, 0, 12), (2, 1, 64), (2, 0, 40), (3, 2, 48), (4, 2, 64), (5, 0, 33),
+                                              (0, 1, 5)], ids=lambda v: str(v))
+def test_hnsw_port_queries_match_reference_all_types(port, ref, vtype, metric, dim):
+    from datagen import make_vectors
+    feats = ref.host_features()
+    if vtype == 2 and metric != 0 and "avx512_bf16" not in feats:
+        pytest.skip("host lacks avx512_bf16")
+    ref.set_disabled_features("avx512_fp16")
+    n = 1200
+    X = make_vectors(vtype, n, dim, seed=400 + vtype)
+    Q = make_vectors(vtype, 8, dim, seed=401 + vtype)
+    if metric == 2:
+        X[(X == 0).all(1), 0] = 1
+        Q[(Q == 0).all(1), 0] = 1
+    R = ref.RefIndex(vtype, dim, metric, algo="hnsw", M=5, ef_construction=30, ef_runtime=10)
+    R.add_many(X)
+    P = port.PortHnsw(vtype, dim, metric, M=5, ef_construction=30, ef_runtime=10)
+    P.add_many(X)
+    for ef in (10, 40):
+        for q in Q:
+            rl, rs, _ = R.topk(q, 6, ef_runtime=ef)
+            pl, ps, _ = P.topk(q, 6, ef_runtime=ef)
+            assert np.array_equal(rl, pl) and np.array_equal(rs, ps), (vtype, metric, ef)
+    R.close()
+    P.close()
+    ref.set_disabled_features()
