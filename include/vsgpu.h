@@ -154,6 +154,16 @@ int vsgpu_hnsw_topk_device(vsgpu_hnsw *g, const void *queries, size_t nq, size_t
 /* Range search for ONE query (hnsw.h:2086-2200). Unordered; VSGPU_ERR_OVERFLOW + needed count as vsgpu_range. */
 int vsgpu_hnsw_range(vsgpu_hnsw *g, const void *query, double radius, double epsilon, size_t cap, uint64_t *out_labels,
                      double *out_scores, uint32_t *out_ids, size_t *out_count);
+/* Resumable batch iterator (hnsw_batch_iterator.h:59-267): keeps the traversal state (visited set, candidate and
+ * spare-result heaps, lower bound) on the device between calls; every `next` returns what
+ * HNSW_BatchIterator::getNextResults(n) returns, ascending (score, label). `ef` = the query's efRuntime.
+ * `label_count` = indexLabelCount() at call time (depletion rule :243-245). */
+typedef struct vsgpu_hnsw_iter vsgpu_hnsw_iter;
+vsgpu_hnsw_iter *vsgpu_hnsw_iter_create(vsgpu_hnsw *g, const void *query, size_t ef);
+void vsgpu_hnsw_iter_destroy(vsgpu_hnsw_iter *it);
+int vsgpu_hnsw_iter_reset(vsgpu_hnsw_iter *it);
+int vsgpu_hnsw_iter_next(vsgpu_hnsw_iter *it, size_t n_res, size_t label_count, uint64_t *out_labels, double *out_scores,
+                         uint32_t *out_ids, size_t *out_count, int *depleted);
 /* Counters of the last traversal / insert call: distance evaluations, expanded nodes, device ms. */
 int vsgpu_hnsw_last_stats(const vsgpu_hnsw *g, unsigned long long *dist_evals, unsigned long long *hops, float *ms);
 

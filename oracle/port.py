@@ -93,6 +93,13 @@ def lib():
         L.vso_hnsw_topk.argtypes = [vp, vp, sz, sz, vp, vp]
         L.vso_hnsw_range.restype = sz
         L.vso_hnsw_range.argtypes = [vp, vp, dbl, dbl, sz, vp, vp]
+        L.vso_hnsw_bi_new.restype = vp
+        L.vso_hnsw_bi_new.argtypes = [vp, vp, sz]
+        L.vso_hnsw_bi_free.argtypes = [vp]
+        L.vso_hnsw_bi_reset.argtypes = [vp]
+        L.vso_hnsw_bi_has_next.argtypes = [vp]
+        L.vso_hnsw_bi_next.restype = sz
+        L.vso_hnsw_bi_next.argtypes = [vp, sz, sz, vp, vp]
         _lib = L
     return _lib
 
@@ -315,3 +322,34 @@ class PortHnsw:
 
     def dist_count(self):
         return lib().vso_hnsw_dist_count(self.h)
+
+    def batch_iterator(self, q, ef_runtime=0):
+        return PortHnswBatchIterator(self, q, ef_runtime)
+
+
+class PortHnswBatchIterator:
+    def __init__(self, index, q, ef_runtime=0):
+        q = np.ascontiguousarray(q)
+        self.index = index
+        self.it = lib().vso_hnsw_bi_new(index.h, _ptr(q), ef_runtime)
+
+    def next(self, n, order=BY_SCORE):
+        labels = np.empty(max(n, 1), dtype=np.uint64)
+        scores = np.empty(max(n, 1), dtype=np.float64)
+        m = lib().vso_hnsw_bi_next(self.it, n, self.index.size(), _ptr(labels), _ptr(scores))
+        labels, scores = labels[:m].copy(), scores[:m].copy()
+        if order == BY_ID:
+            o = np.argsort(labels, kind="stable")
+            labels, scores = labels[o], scores[o]
+        return labels, scores, 0
+
+    def has_next(self):
+        return bool(lib().vso_hnsw_bi_has_next(self.it))
+
+    def reset(self):
+        lib().vso_hnsw_bi_reset(self.it)
+
+    def close(self):
+        if self.it:
+            lib().vso_hnsw_bi_free(self.it)
+            self.it = None

@@ -96,6 +96,13 @@ size_t vso_hnsw_topk(vso_hnsw *g, const void *query, size_t k, size_t ef_runtime
 size_t vso_hnsw_range(vso_hnsw *g, const void *query, double radius, double epsilon, size_t cap, size_t *labels,
                       double *scores);
 
+typedef struct vso_hnsw_bi vso_hnsw_bi;
+vso_hnsw_bi *vso_hnsw_bi_new(vso_hnsw *g, const void *query, size_t ef_runtime);
+void vso_hnsw_bi_free(vso_hnsw_bi *it);
+void vso_hnsw_bi_reset(vso_hnsw_bi *it);
+int vso_hnsw_bi_has_next(const vso_hnsw_bi *it);
+size_t vso_hnsw_bi_next(vso_hnsw_bi *it, size_t n_res, size_t label_count, size_t *labels, double *scores);
+
 #ifdef __cplusplus
 }
 #endif

@@ -503,3 +503,148 @@ size_t vso_hnsw_range(vso_hnsw *g, const void *query, double radius_in, double e
     free(q);
     return found;
 }
+
+/* ---- batch iterator (hnsw_batch_iterator.h:59-267, hnsw_single_batch_iterator.h:36-78) ---- */
+struct vso_hnsw_bi {
+    vso_hnsw *g;
+    void *q;
+    size_t ef, returned;
+    long entry; /* -1 = not computed */
+    int depleted;
+    double lower;
+    heap_t cand, extras; /* min-heaps: stored negated through pr_greater */
+    uint8_t *visited;
+};
+
+/* std::greater<pair>: min-heap ordering for the same push/pop machinery */
+static void mh_sift_up(pr_t *a, size_t hole, pr_t v) {
+    while (hole > 0) {
+        size_t parent = (hole - 1) / 2;
+        if (!pr_less(v, a[parent])) break; /* comp(parent, v) = parent > v */
+        a[hole] = a[parent];
+        hole = parent;
+    }
+    a[hole] = v;
+}
+static void mh_push(heap_t *h, double d, size_t key) {
+    h_reserve(h, h->n + 1);
+    pr_t v = {d, key};
+    h->n++;
+    mh_sift_up(h->a, h->n - 1, v);
+}
+static void mh_pop(heap_t *h) {
+    size_t len = h->n - 1;
+    pr_t v = h->a[len];
+    h->n = len;
+    if (len == 0) return;
+    size_t hole = 0, child = 0;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (pr_less(h->a[child - 1], h->a[child])) child--; /* comp(child, child-1) = child > child-1 */
+        h->a[hole] = h->a[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        h->a[hole] = h->a[child - 1];
+        hole = child - 1;
+    }
+    mh_sift_up(h->a, hole, v);
+}
+
+vso_hnsw_bi *vso_hnsw_bi_new(vso_hnsw *g, const void *query, size_t ef_runtime) {
+    vso_hnsw_bi *it = (vso_hnsw_bi *)calloc(1, sizeof(*it));
+    it->g = g;
+    it->q = processed(g, query);
+    it->ef = ef_runtime ? ef_runtime : g->ef;
+    it->entry = -1;
+    it->lower = INFINITY;
+    it->visited = (uint8_t *)calloc(g->n + 1, 1);
+    return it;
+}
+void vso_hnsw_bi_free(vso_hnsw_bi *it) {
+    if (!it) return;
+    free(it->q);
+    free(it->cand.a);
+    free(it->extras.a);
+    free(it->visited);
+    free(it);
+}
+void vso_hnsw_bi_reset(vso_hnsw_bi *it) {
+    it->returned = 0;
+    it->depleted = 0;
+    it->lower = INFINITY;
+    it->cand.n = it->extras.n = 0;
+    it->entry = -1; /* the reference keeps entry_point; it is recomputed identically on the next call */
+    memset(it->visited, 0, it->g->n + 1);
+}
+int vso_hnsw_bi_has_next(const vso_hnsw_bi *it) { return !(it->depleted && it->extras.n == 0); }
+
+/* getNextResults (:206-249): ascending (score, label); returns the number written */
+size_t vso_hnsw_bi_next(vso_hnsw_bi *it, size_t n_res, size_t label_count, size_t *labels, double *scores) {
+    vso_hnsw *g = it->g;
+    size_t orig_ef = it->ef;
+    if (orig_ef < n_res) it->ef = n_res;
+    if (it->returned == 0) {
+        double cd;
+        it->entry = bottom_ep(g, it->q, &cd);
+    }
+    heap_t top = {0};
+    size_t n = 0;
+    if (it->entry < 0) {
+        it->depleted = 1;
+    } else {
+        if (it->returned == 0 && it->extras.n == 0 && it->cand.n == 0) {
+            size_t ep = (size_t)it->entry;
+            it->lower = g->deleted[ep] ? dist_max(g) : dist(g, ep, it->q);
+            it->visited[ep] = 1;
+            mh_push(&it->cand, it->lower, ep);
+        }
+        while (top.n < it->ef && it->extras.n) { /* fillFromExtras */
+            h_push(&top, it->extras.a[0].d, it->extras.a[0].key);
+            mh_pop(&it->extras);
+        }
+        if (top.n != it->ef) {
+            while (it->cand.n) { /* scanGraphInternal */
+                double cd = it->cand.a[0].d;
+                size_t cur = it->cand.a[0].key;
+                if (cd > it->lower && top.n >= it->ef) break;
+                if (!g->deleted[cur]) { /* updateHeaps */
+                    if (top.n < it->ef) {
+                        h_push(&top, cd, g->labels[cur]);
+                        it->lower = top.a[0].d;
+                    } else if (it->lower > cd) {
+                        h_push(&top, cd, g->labels[cur]);
+                        mh_push(&it->extras, top.a[0].d, top.a[0].key);
+                        h_pop(&top);
+                        it->lower = top.a[0].d;
+                    }
+                }
+                mh_pop(&it->cand);
+                const uint32_t *r = rec(g, cur, 0);
+                for (uint32_t j = 0; j < r[0]; j++) {
+                    size_t id = r[1 + j];
+                    if (it->visited[id]) continue;
+                    it->visited[id] = 1;
+                    mh_push(&it->cand, dist(g, id, it->q), id);
+                }
+            }
+            if (top.n < it->ef) it->depleted = 1;
+        }
+        while (top.n > n_res) { /* prepareResults */
+            mh_push(&it->extras, top.a[0].d, top.a[0].key);
+            h_pop(&top);
+        }
+        n = top.n;
+        for (size_t i = n; i-- > 0;) {
+            scores[i] = top.a[0].d;
+            labels[i] = top.a[0].key;
+            h_pop(&top);
+        }
+    }
+    free(top.a);
+    it->returned += n;
+    if (it->returned == label_count) it->depleted = 1;
+    it->ef = orig_ef;
+    return n;
+}

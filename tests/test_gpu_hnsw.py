@@ -235,3 +235,45 @@ def test_empty_and_small(capi):
     assert not it.has_next()
     it.close()
     G.close()
+
+
+@pytest.mark.parametrize("vtype,metric,dim", [(0, 0, 16), (0, 2, 32), (4, 2, 64), (1, 1, 12)], ids=lambda v: str(v))
+def test_batch_iterator_matches_oracle(capi, port, vtype, metric, dim):
+    """VecSimBatchIterator on an HNSW index: the resumable device traversal returns the same batches as the
+    reference's HNSW_BatchIterator (oracle pinned by test_hnsw_port_batch_iterator_matches_reference)."""
+    port.set_tier(port.TIER_AVX512)
+    n = 800
+    X = make_vectors(vtype, n, dim, seed=71 + metric)
+    Q = make_vectors(vtype, 3, dim, seed=72 + metric)
+    if metric == 2:
+        X[(X == 0).all(1), 0] = 1
+        Q[(Q == 0).all(1), 0] = 1
+    P = port.PortHnsw(vtype, dim, metric, M=6, ef_construction=40, ef_runtime=10)
+    P.add_many(X)
+    G = new_index(capi, vtype, dim, metric, M=6, efc=40, ef=10)
+    G.add_vectors(X)
+    for q in Q:
+        for sched in ([5, 5, 5, 20, 1, 100], [1, 2, 3], [50, 50], [1000]):
+            gi, pi = G.create_batch_iterator(q), P.batch_iterator(q)
+            for rounds in range(2):
+                for nres in sched:
+                    assert bool(gi.has_next()) == pi.has_next()
+                    gl, gs = gi.get_next_results(nres)
+                    pl, ps, _ = pi.next(nres)
+                    assert np.array_equal(gl[0], pl.astype(np.int64)) and np.array_equal(gs[0], ps), (sched, nres)
+                assert bool(gi.has_next()) == pi.has_next()
+                gi.reset()
+                pi.reset()
+            gi.close()
+            pi.close()
+    # BY_ID order + efRuntime from the query params
+    qp = capi.VecSimQueryParams()
+    qp.hnswRuntimeParams.efRuntime = 30
+    gi, pi = G.create_batch_iterator(Q[0], qp), P.batch_iterator(Q[0], ef_runtime=30)
+    gl, gs = gi.get_next_results(12, capi.BY_ID)
+    pl, ps, _ = pi.next(12, port.BY_ID)
+    assert np.array_equal(gl[0], pl.astype(np.int64)) and np.array_equal(gs[0], ps)
+    gi.close()
+    pi.close()
+    G.close()
+    P.close()

@@ -249,3 +249,32 @@ def test_hnsw_port_queries_match_reference_all_types(port, ref, vtype, metric, d
     R.close()
     P.close()
     ref.set_disabled_features()
+
+
+@pytest.mark.parametrize("metric", [0, 2], ids=["L2", "Cosine"])
+def test_hnsw_port_batch_iterator_matches_reference(port, ref, metric):
+    """HNSW_BatchIterator: same batches (labels and scores, in order) for several batch-size schedules, incl. reset."""
+    from datagen import make_vectors
+    n, dim = 800, 16
+    X = make_vectors(0, n, dim, seed=71 + metric)
+    Q = make_vectors(0, 4, dim, seed=72 + metric)
+    R = ref.RefIndex(0, dim, metric, algo="hnsw", M=6, ef_construction=40, ef_runtime=10)
+    R.add_many(X)
+    P = port.PortHnsw(0, dim, metric, M=6, ef_construction=40, ef_runtime=10)
+    P.add_many(X)
+    for q in Q:
+        for sched in ([5, 5, 5, 20, 1, 100], [1, 2, 3], [50, 50], [1000]):
+            ri, pi = R.batch_iterator(q), P.batch_iterator(q)
+            for rounds in range(2):
+                for nres in sched:
+                    assert ri.has_next() == pi.has_next()
+                    rl, rs, _ = ri.next(nres)
+                    pl, ps, _ = pi.next(nres)
+                    assert np.array_equal(rl, pl) and np.array_equal(rs, ps), (sched, nres)
+                assert ri.has_next() == pi.has_next()
+                ri.reset()
+                pi.reset()
+            ri.close()
+            pi.close()
+    R.close()
+    P.close()

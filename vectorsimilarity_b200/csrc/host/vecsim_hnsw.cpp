@@ -251,58 +251,75 @@ VecSimQueryReply *HnswIndex::rangeQuery(const void *blob, double radius, VecSimQ
     return rep;
 }
 
-namespace {
-// Batches through repeated top-k with a growing k: results already returned are skipped. This keeps
-// the contract of VecSimBatchIterator_Next (n best not yet returned, hnsw_batch_iterator.h:206-249)
-// on top of the batched traversal; the resumable single-traversal form is SURVEY §8 row a15.
+// HNSW_BatchIterator (hnsw_batch_iterator.h:59-267): the traversal state stays on the device between
+// calls (vsgpu_hnsw_iter_*), each Next is one resumed scan with the reference's heap rules.
 class HnswBatchIterator final : public VecSimBatchIterator {
   public:
-    HnswBatchIterator(HnswIndex *idx, const void *raw_query, size_t bytes, VecSimQueryParams *qp)
-        : idx_(idx), query_((const uint8_t *)raw_query, (const uint8_t *)raw_query + bytes) {
-        if (qp) qp_ = *qp;
-        has_qp_ = qp != nullptr;
-    }
+    HnswBatchIterator(HnswIndex *idx, vsgpu_hnsw_iter *it, void *tctx) : idx_(idx), it_(it), tctx_(tctx) {}
+    ~HnswBatchIterator() override { idx_->iterDestroy(it_); }
     VecSimQueryReply *next(size_t n, VecSimQueryReply_Order order) override {
         auto *rep = new VecSimQueryReply();
-        const size_t total = idx_->indexLabelCount();
-        const size_t want = std::min(returned_.size() + n, total);
-        if (want == returned_.size()) {
+        if (!it_) {
             depleted_ = true;
             return rep;
         }
-        VecSimQueryParams qp = qp_;
-        if (qp.hnswRuntimeParams.efRuntime < want) qp.hnswRuntimeParams.efRuntime = std::max(want, idx_->efRuntime());
-        VecSimQueryReply *all = idx_->topKQuery(query_.data(), want, &qp);
-        rep->code = all->code;
-        for (auto &r : all->results) {
-            if (rep->results.size() == n) break;
-            if (returned_.insert(r.id).second) rep->results.push_back(r);
+        if (timed_out(tctx_)) {
+            rep->code = VecSim_QueryReply_TimedOut;
+            return rep;
         }
-        delete all;
-        if (rep->results.size() < n || returned_.size() == total) depleted_ = true;
+        std::vector<size_t> labels(std::max<size_t>(n, 1));
+        std::vector<double> scores(std::max<size_t>(n, 1));
+        size_t count = 0;
+        int dep = 0;
+        if (idx_->iterNext(it_, n, labels.data(), scores.data(), &count, &dep) != 0) return rep;
+        depleted_ = dep != 0;
+        rep->results.resize(count);
+        for (size_t i = 0; i < count; i++) rep->results[i] = {labels[i], scores[i]};
         if (order == BY_ID)
             std::sort(rep->results.begin(), rep->results.end(),
                       [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id < b.id; });
         return rep;
     }
-    bool hasNext() override { return !depleted_ && returned_.size() < idx_->indexLabelCount(); }
+    bool hasNext() override { return !depleted_; }
     void reset() override {
-        returned_.clear();
+        if (it_) idx_->iterReset(it_);
         depleted_ = false;
     }
 
   private:
     HnswIndex *idx_;
-    std::vector<uint8_t> query_;
-    VecSimQueryParams qp_{};
-    bool has_qp_ = false;
-    std::unordered_set<size_t> returned_;
+    vsgpu_hnsw_iter *it_;
+    void *tctx_;
     bool depleted_ = false;
 };
-} // namespace
 
 VecSimBatchIterator *HnswIndex::newBatchIterator(const void *blob, VecSimQueryParams *qp) {
-    return new HnswBatchIterator(this, blob, data_size_, qp);
+    std::lock_guard<std::mutex> g(mu_);
+    vsgpu_hnsw_iter *it = nullptr;
+    if (flush() == 0) {
+        std::vector<uint8_t> q(stored_size_);
+        preprocess(blob, q.data());
+        size_t ef = ef_;
+        if (qp && qp->hnswRuntimeParams.efRuntime > 0) ef = qp->hnswRuntimeParams.efRuntime;
+        it = vsgpu_hnsw_iter_create(graph_, q.data(), ef);
+    }
+    return new HnswBatchIterator(this, it, qp ? qp->timeoutCtx : nullptr);
+}
+
+int HnswIndex::iterNext(vsgpu_hnsw_iter *it, size_t n, size_t *labels, double *scores, size_t *count, int *depleted) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (flush() != 0) return -1;
+    static_assert(sizeof(size_t) == sizeof(uint64_t), "labelType is 64-bit");
+    return vsgpu_hnsw_iter_next(it, n, label_to_id_.size(), (uint64_t *)labels, scores, nullptr, count, depleted) == VSGPU_OK ? 0
+                                                                                                                              : -1;
+}
+void HnswIndex::iterReset(vsgpu_hnsw_iter *it) {
+    std::lock_guard<std::mutex> g(mu_);
+    vsgpu_hnsw_iter_reset(it);
+}
+void HnswIndex::iterDestroy(vsgpu_hnsw_iter *it) {
+    std::lock_guard<std::mutex> g(mu_);
+    vsgpu_hnsw_iter_destroy(it);
 }
 
 VecSimIndexBasicInfo HnswIndex::basicInfo() {

@@ -171,6 +171,9 @@ class HnswIndex final : public VecSimIndexInterface {
     void lastStats(vsgpu_stats *out) override;
 
     vsgpu_hnsw *deviceGraph();
+    int iterNext(vsgpu_hnsw_iter *it, size_t n, size_t *labels, double *scores, size_t *count, int *depleted);
+    void iterReset(vsgpu_hnsw_iter *it);
+    void iterDestroy(vsgpu_hnsw_iter *it);
     size_t efRuntime() const { return ef_; }
     size_t M() const { return M_; }
     int importGraph(const void *blobs, int processed, size_t n, const size_t *labels, const uint32_t *levels,

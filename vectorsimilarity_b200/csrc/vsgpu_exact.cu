@@ -9,6 +9,7 @@
 // the CPU's _mm512_reduce_add_ps performs. Rows stream from HBM once per query chunk, R rows per
 // thread group are register-tiled against QC queries held in shared memory.
 #include "vsgpu_dist.cuh"
+#include <cstdlib>
 
 namespace vsgpu {
 
@@ -609,6 +610,8 @@ int launch_exact_scan(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_str
     const ChainPlan &p = s->plan;
     if (p.kind == CK_INT) return launch_int(s, q_dev, nq, q_stride, q_norms, scores, ld, nullptr, 0, nullptr, 0);
     if (p.kind == CK_SEQ) return launch_seq(s, q_dev, nq, q_stride, scores, ld, nullptr, 0, s->count);
+    static const bool legacy = getenv("VSGPU_LEGACY_SCAN") != nullptr; // A/B switch for profiling
+    if (!legacy && nq <= 16 && tma_scan_supported(s)) return launch_tma_scan(s, q_dev, nq, q_stride, scores, ld);
     const void *qchain = nullptr;
     VS_TRY(prep_queries(s, q_dev, nq, q_stride, &qchain));
     ScanArgs a{};

@@ -293,6 +293,7 @@ __device__ __forceinline__ bool test_and_set(const Visited &v, uint32_t id) {
 template <typename DT> struct Work {
     void *pivot;
     uint32_t *nb_ids;
+    uint8_t *nb_del; // deleted flag of each gathered neighbour (fetched with the links, off the serial path)
     DT *nb_dist;
     DT *top_d;
     uint32_t *top_id;
@@ -311,24 +312,36 @@ template <typename DT> struct Work {
 };
 enum { SC_TOPN = 0, SC_CANDN, SC_NBN, SC_STOP, SC_CUR, SC_STATUS, SC_ADMN, SC_AUX0, SC_AUX1, SC_AUX2, SC_AUX3, SC_COUNT = 16 };
 
-// warp 0: links of `node` at `level` that were not visited yet, in link order -> w.nb_ids, SC_NBN
+// warp 0: links of `node` at `level` that were not visited yet, in link order -> w.nb_ids / nb_del, SC_NBN.
+// The count and the link words are fetched together (the record is always fully allocated), the
+// visited test, the deleted flag and an L2 prefetch of the row are issued back to back: one hop costs
+// two dependent memory round trips before the distance evaluation instead of four.
 template <typename DT>
-__device__ __forceinline__ void gather_unvisited(const GraphDev &g, const Work<DT> &w, uint32_t node, int level,
+__device__ __forceinline__ void gather_unvisited(const KCtx &k, const GraphDev &g, const Work<DT> &w, uint32_t node, int level,
                                                  const Visited *vis) {
     if (threadIdx.x >= 32) return;
     const uint32_t *rec = links_of(g, node, level);
-    const int cnt = (int)rec[0];
+    const int width = level == 0 ? g.M0 : g.M;
     int base = 0;
-    for (int i0 = 0; i0 < cnt; i0 += 32) {
+    int cnt = 0;
+    for (int i0 = 0; i0 < width; i0 += 32) {
         const int i = i0 + threadIdx.x;
-        uint32_t id = INV;
+        uint32_t id = i < width ? rec[1 + i] : INV;
+        if (i0 == 0) cnt = (int)rec[0];
+        if (i0 >= cnt) break;
         bool take = false;
+        uint8_t del = 0;
         if (i < cnt) {
-            id = rec[1 + i];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(k.rows + (size_t)id * k.row_stride));
+            del = g.flags[id];
             take = vis ? !test_and_set(*vis, id) : true;
         }
         const unsigned m = __ballot_sync(0xffffffffu, take);
-        if (take) w.nb_ids[base + __popc(m & ((1u << threadIdx.x) - 1))] = id;
+        if (take) {
+            const int pos = base + __popc(m & ((1u << threadIdx.x) - 1));
+            w.nb_ids[pos] = id;
+            w.nb_del[pos] = del & 1;
+        }
         base += __popc(m);
     }
     if (threadIdx.x == 0) w.sc[SC_NBN] = base;
@@ -344,7 +357,7 @@ __device__ void greedy_level(const KCtx &k, const GraphDev &g, const Work<typena
     for (;;) {
         __syncthreads();
         const uint32_t cur = (uint32_t)w.sc[SC_CUR];
-        gather_unvisited<DT>(g, w, cur, level, nullptr);
+        gather_unvisited<DT>(k, g, w, cur, level, nullptr);
         __syncthreads();
         const int n = w.sc[SC_NBN];
         eval_dists<P, true>(k, w.pivot, n, w.nb_dist, [&](int j, uint32_t &a, uint32_t &) { a = w.nb_ids[j]; });
@@ -357,7 +370,7 @@ __device__ void greedy_level(const KCtx &k, const GraphDev &g, const Work<typena
                     best = w.nb_dist[j];
                     w.sc[SC_CUR] = (int)w.nb_ids[j];
                     changed = true;
-                    if (track_deleted && !is_deleted(g, w.nb_ids[j])) w.sc[SC_AUX0] = (int)w.nb_ids[j];
+                    if (track_deleted && !w.nb_del[j]) w.sc[SC_AUX0] = (int)w.nb_ids[j];
                 }
             }
             w.sdt[0] = best;
@@ -371,48 +384,105 @@ __device__ void greedy_level(const KCtx &k, const GraphDev &g, const Work<typena
     __syncthreads();
 }
 
-// thread 0: push to the candidate set, pruning entries that can no longer be expanded or spilling to HBM
+// ---- warp-cooperative sorted arrays (warp 0 only) ----
+// Both traversal queues are kept sorted ascending under the reference's pair order, so the element a
+// std::priority_queue would expose as top() is the LAST one: pop = n--. An insertion counts the
+// elements ordered before the new one (strided over the lanes), then shifts the tail by one slot,
+// 32 elements per step — a few hundred cycles where a one-thread binary heap in shared memory
+// costs thousands (every sift level is a dependent LDS). Any container with the same total order
+// pops the same sequence, so results are unchanged.
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+template <typename DT, typename Less>
+__device__ __forceinline__ void sorted_insert(DT *ad, uint32_t *aid, int &n, DT d, uint32_t id, Less less) {
+    const int lane = threadIdx.x & 31;
+    int cnt = 0;
+    for (int i = lane; i < n; i += 32) cnt += less(ad[i], aid[i], d, id) ? 1 : 0;
+    cnt = warp_sum(cnt);
+    for (int hi = n - 1; hi >= cnt; hi -= 32) {
+        const int i = hi - lane;
+        const bool act = i >= cnt;
+        DT td = DT(0);
+        uint32_t ti = 0;
+        if (act) {
+            td = ad[i];
+            ti = aid[i];
+        }
+        __syncwarp();
+        if (act) {
+            ad[i + 1] = td;
+            aid[i + 1] = ti;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        ad[cnt] = d;
+        aid[cnt] = id;
+    }
+    __syncwarp();
+    n++;
+}
+// drop the first t elements
+template <typename DT> __device__ __forceinline__ void sorted_drop_prefix(DT *ad, uint32_t *aid, int &n, int t) {
+    const int lane = threadIdx.x & 31;
+    if (t <= 0) return;
+    for (int lo = t; lo < n; lo += 32) {
+        const int i = lo + lane;
+        const bool act = i < n;
+        DT td = DT(0);
+        uint32_t ti = 0;
+        if (act) {
+            td = ad[i];
+            ti = aid[i];
+        }
+        __syncwarp();
+        if (act) {
+            ad[i - t] = td;
+            aid[i - t] = ti;
+        }
+        __syncwarp();
+    }
+    n -= t;
+}
+
+// warp 0: insert into the candidate set; on overflow prune entries that can no longer be expanded
+// (they are the prefix: largest distances first), then spill to HBM. false = out of room.
 template <typename DT>
-__device__ __forceinline__ bool cand_push(Work<DT> &w, int &cand_n, DT d, uint32_t id, bool top_full, DT lower) {
+__device__ __forceinline__ bool cand_insert(Work<DT> &w, int &cand_n, DT d, uint32_t id, bool can_prune, DT lower) {
     CandLess<DT> cl;
+    const int lane = threadIdx.x & 31;
     if (cand_n >= w.cand_cap) {
-        if (top_full) {
+        if (can_prune) {
             // entries farther than the current bound are never expanded: the bound only shrinks once the
-            // result heap is full, and the stop rule fires before they are reached
-            int m = 0;
-            for (int i = 0; i < cand_n; i++)
-                if (!(w.cand_d[i] > lower)) {
-                    w.cand_d[m] = w.cand_d[i];
-                    w.cand_id[m] = w.cand_id[i];
-                    m++;
-                }
-            const int kept = m;
-            cand_n = 0;
-            for (int i = 0; i < kept; i++) {
-                const DT dd = w.cand_d[i];
-                const uint32_t ii = w.cand_id[i];
-                heap_push(w.cand_d, w.cand_id, cand_n, dd, ii, cl);
-            }
+            // result set is full, and the stop rule fires before they are reached
+            int t = 0;
+            for (int i = lane; i < cand_n; i += 32) t += (w.cand_d[i] > lower) ? 1 : 0;
+            t = warp_sum(t);
+            sorted_drop_prefix(w.cand_d, w.cand_id, cand_n, t);
         }
         if (cand_n >= w.cand_cap) {
             if (!w.spill_d || w.cand_d == w.spill_d) return false;
-            for (int i = 0; i < cand_n; i++) {
+            for (int i = lane; i < cand_n; i += 32) {
                 w.spill_d[i] = w.cand_d[i];
                 w.spill_id[i] = w.cand_id[i];
             }
+            __syncwarp();
             w.cand_d = w.spill_d;
             w.cand_id = w.spill_id;
             w.cand_cap = w.spill_cap;
             if (cand_n >= w.cand_cap) return false;
         }
     }
-    heap_push(w.cand_d, w.cand_id, cand_n, d, id, cl);
+    sorted_insert(w.cand_d, w.cand_id, cand_n, d, id, cl);
     return true;
 }
 
-// searchLayer / searchBottomLayer (hnsw.h:682-721, 1983-2035) from entry w.sc[SC_CUR]. Result heap in
-// w.top_* (SC_TOPN entries, max-heap under TopLess). labels != nullptr: query flavour (heap keyed by
-// label); else builder flavour (keyed by id, admissions logged). Returns through w.sc[SC_STATUS].
+// searchLayer / searchBottomLayer (hnsw.h:682-721, 1983-2035) from entry w.sc[SC_CUR]. Result set in
+// w.top_* (SC_TOPN entries, ascending under TopLess). labels != nullptr: query flavour (keyed by
+// label); else builder flavour (keyed by id, admissions logged). Status through w.sc[SC_STATUS].
 template <class P>
 __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::DT> &w, int level, int ef,
                              const uint64_t *labels, const Visited &vis, unsigned long long &evals,
@@ -420,7 +490,9 @@ __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::
     using DT = typename P::DT;
     TopLess<DT> tl{labels};
     CandLess<DT> cl;
-    int top_n = 0, cand_n = 0, adm_n = 0; // thread 0's copies
+    const bool warp0 = threadIdx.x < 32;
+    const int lane = threadIdx.x & 31;
+    int top_n = 0, cand_n = 0, adm_n = 0; // warp 0's (uniform) copies
     DT lower = DT(0);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -431,65 +503,77 @@ __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::
     __syncthreads();
     eval_dists<P, true>(k, w.pivot, 1, w.nb_dist, [&](int j, uint32_t &a, uint32_t &) { a = w.nb_ids[j]; });
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp0) {
         const uint32_t ep = w.nb_ids[0];
-        evals += 1;
+        if (lane == 0) evals += 1;
         if (!is_deleted(g, ep)) {
             lower = w.nb_dist[0];
-            heap_push(w.top_d, w.top_id, top_n, lower, ep, tl);
-            if (w.adm_cap > 0) {
+            sorted_insert(w.top_d, w.top_id, top_n, lower, ep, tl);
+            if (lane == 0 && w.adm_cap > 0) {
                 w.adm_d[0] = lower;
                 w.adm_id[0] = ep;
             }
             adm_n = 1;
-            heap_push(w.cand_d, w.cand_id, cand_n, lower, ep, cl);
         } else {
             lower = dt_max<DT>();
-            heap_push(w.cand_d, w.cand_id, cand_n, lower, ep, cl);
         }
-        test_and_set(vis, ep);
+        sorted_insert(w.cand_d, w.cand_id, cand_n, lower, ep, cl);
+        if (lane == 0) test_and_set(vis, ep);
     }
     for (;;) {
-        if (threadIdx.x == 0) {
+        if (warp0) {
             int stop = 0;
             if (cand_n == 0) stop = 1;
-            else if (w.cand_d[0] > lower && top_n >= ef) stop = 1;
+            else if (w.cand_d[cand_n - 1] > lower && top_n >= ef) stop = 1;
             else {
-                w.sc[SC_CUR] = (int)w.cand_id[0];
-                heap_pop(w.cand_d, w.cand_id, cand_n, cl);
-                hops++;
+                if (lane == 0) {
+                    w.sc[SC_CUR] = (int)w.cand_id[cand_n - 1];
+                    hops++;
+                }
+                cand_n--;
             }
-            w.sc[SC_STOP] = stop;
+            if (lane == 0) w.sc[SC_STOP] = stop;
         }
         __syncthreads();
         if (w.sc[SC_STOP]) break;
-        gather_unvisited<DT>(g, w, (uint32_t)w.sc[SC_CUR], level, &vis);
+        gather_unvisited<DT>(k, g, w, (uint32_t)w.sc[SC_CUR], level, &vis);
         __syncthreads();
         const int n = w.sc[SC_NBN];
         eval_dists<P, true>(k, w.pivot, n, w.nb_dist, [&](int j, uint32_t &a, uint32_t &) { a = w.nb_ids[j]; });
         __syncthreads();
-        if (threadIdx.x == 0) {
-            evals += n;
-            for (int j = 0; j < n; j++) {
-                const DT d = w.nb_dist[j];
-                const uint32_t id = w.nb_ids[j];
-                if (lower > d || top_n < ef) {
-                    if (!cand_push(w, cand_n, d, id, top_n >= ef, lower)) {
-                        w.sc[SC_STATUS] = 1;
-                        cand_n = 0; // abandon: the caller reruns with a spill area
+        if (warp0) {
+            if (lane == 0) evals += n;
+            bool failed = false;
+            for (int j0 = 0; j0 < n && !failed; j0 += 32) {
+                const int j = j0 + lane;
+                const DT dj = j < n ? w.nb_dist[j] : DT(0);
+                // whoever fails the test now fails it later too (the bound only shrinks once the set is full)
+                unsigned mask = __ballot_sync(0xffffffffu, j < n && (lower > dj || top_n < ef));
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const DT d = __shfl_sync(0xffffffffu, dj, b);
+                    if (!(lower > d || top_n < ef)) continue;
+                    const uint32_t id = w.nb_ids[j0 + b];
+                    if (!cand_insert(w, cand_n, d, id, top_n >= ef, lower)) {
+                        failed = true;
                         break;
                     }
-                    if (!is_deleted(g, id)) {
-                        heap_push(w.top_d, w.top_id, top_n, d, id, tl);
-                        if (adm_n < w.adm_cap) {
+                    if (!w.nb_del[j0 + b]) {
+                        sorted_insert(w.top_d, w.top_id, top_n, d, id, tl);
+                        if (lane == 0 && adm_n < w.adm_cap) {
                             w.adm_d[adm_n] = d;
                             w.adm_id[adm_n] = id;
                         }
                         adm_n++;
                     }
-                    if (top_n > ef) heap_pop(w.top_d, w.top_id, top_n, tl);
-                    if (top_n > 0) lower = w.top_d[0];
+                    if (top_n > ef) top_n--;
+                    if (top_n > 0) lower = w.top_d[top_n - 1];
                 }
+            }
+            if (failed) {
+                if (lane == 0) w.sc[SC_STATUS] = 1;
+                cand_n = 0; // abandon: the caller reruns with a spill area
             }
         }
         // nb_* are rewritten only after the next __syncthreads (top of the loop)
@@ -542,6 +626,7 @@ template <typename DT> __device__ __forceinline__ Work<DT> carve(unsigned char *
     w.sdt = (DT *)take(4 * sizeof(DT));
     w.nb_dist = (DT *)take((size_t)max_links * sizeof(DT));
     w.nb_ids = (uint32_t *)take((size_t)max_links * 4);
+    w.nb_del = (uint8_t *)take((size_t)max_links);
     w.top_d = (DT *)take((size_t)top_cap * sizeof(DT));
     w.top_id = (uint32_t *)take((size_t)top_cap * 4);
     w.cand_d = (DT *)take((size_t)cand_cap * sizeof(DT));
@@ -555,7 +640,7 @@ template <typename DT> __device__ __forceinline__ Work<DT> carve(unsigned char *
 __host__ __device__ static size_t carve_bytes(size_t dt, size_t pivot_bytes, int max_links, int top_cap, int cand_cap, int adm_cap) {
     auto al = [](size_t b) { return (b + 15) / 16 * 16; };
     return al(pivot_bytes) + al(SC_COUNT * sizeof(int)) + al(4 * dt) + al((size_t)max_links * dt) + al((size_t)max_links * 4) +
-           al((size_t)top_cap * dt) + al((size_t)top_cap * 4) + al((size_t)cand_cap * dt) + al((size_t)cand_cap * 4) +
+           al((size_t)max_links) + al((size_t)top_cap * dt) + al((size_t)top_cap * 4) + al((size_t)cand_cap * dt) + al((size_t)cand_cap * 4) +
            al((size_t)adm_cap * dt) + al((size_t)adm_cap * 4);
 }
 
@@ -599,24 +684,15 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_k
     if (descend<P>(a.k, a.g, w, evals)) {
         Visited vis{a.visited + q * a.vis_words, 0};
         search_layer<P>(a.k, a.g, w, 0, a.ef, a.labels, vis, evals, hops);
-        if (threadIdx.x == 0) {
-            TopLess<DT> tl{a.labels};
-            int top_n = w.sc[SC_TOPN];
-            while (top_n > a.k_out) heap_pop(w.top_d, w.top_id, top_n, tl);
-            count = top_n;
-            for (int i = count - 1; i >= 0; i--) {
-                const size_t o = q * a.out_ld + i;
-                const uint32_t id = w.top_id[0];
-                if (a.out_ids) a.out_ids[o] = id;
-                if (a.out_scores) ((DT *)a.out_scores)[o] = w.top_d[0];
-                if (a.out_labels) a.out_labels[o] = a.labels[id];
-                heap_pop(w.top_d, w.top_id, top_n, tl);
-            }
-            w.sc[SC_AUX1] = count;
-            if (a.status) a.status[q] = (uint32_t)w.sc[SC_STATUS];
+        count = min(w.sc[SC_TOPN], a.k_out); // ascending (score, label): the k best are the first k
+        for (int i = threadIdx.x; i < count; i += blockDim.x) {
+            const size_t o = q * a.out_ld + i;
+            const uint32_t id = w.top_id[i];
+            if (a.out_ids) a.out_ids[o] = id;
+            if (a.out_scores) ((DT *)a.out_scores)[o] = w.top_d[i];
+            if (a.out_labels) a.out_labels[o] = a.labels[id];
         }
-        __syncthreads();
-        count = w.sc[SC_AUX1];
+        if (threadIdx.x == 0 && a.status) a.status[q] = (uint32_t)w.sc[SC_STATUS];
     } else if (threadIdx.x == 0 && a.status) {
         a.status[q] = 0;
     }
@@ -659,9 +735,11 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_range_ke
     const DT radius = (DT)a.radius;
     Visited vis{a.visited + q * a.vis_words, 0};
     CandLess<DT> cl;
-    int cand_n = 0;
+    const bool warp0 = threadIdx.x < 32;
+    const int lane = threadIdx.x & 31;
+    int cand_n = 0; // warp 0's (uniform) copies
     DT dyn = DT(0), bound = DT(0);
-    auto emit = [&](uint32_t id, DT d) {
+    auto emit = [&](uint32_t id, DT d) { // lane 0
         if (found < a.range_cap) {
             const size_t o = q * a.range_cap + found;
             if (a.out_ids) a.out_ids[o] = id;
@@ -670,10 +748,10 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_range_ke
         }
         found++;
     };
-    if (threadIdx.x == 0) {
+    if (warp0) {
         const uint32_t ep = (uint32_t)w.sc[SC_CUR];
         DT ep_dist;
-        w.sc[SC_STATUS] = 0;
+        if (lane == 0) w.sc[SC_STATUS] = 0;
         if (is_deleted(a.g, ep)) {
             ep_dist = dt_max<DT>();
             bound = dyn = ep_dist;
@@ -681,56 +759,249 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_range_ke
             ep_dist = w.sdt[0]; // distance of the greedy descent's final node
             dyn = ep_dist;
             if (ep_dist <= radius) {
-                emit(ep, ep_dist);
+                if (lane == 0) emit(ep, ep_dist);
                 dyn = radius;
             }
             bound = (DT)((double)dyn * (1.0 + a.epsilon));
         }
-        heap_push(w.cand_d, w.cand_id, cand_n, ep_dist, ep, cl);
-        test_and_set(vis, ep);
+        sorted_insert(w.cand_d, w.cand_id, cand_n, ep_dist, ep, cl);
+        if (lane == 0) test_and_set(vis, ep);
     }
     for (;;) {
-        if (threadIdx.x == 0) {
+        if (warp0) {
             int stop = 0;
-            if (cand_n == 0 || w.cand_d[0] > bound) stop = 1;
+            if (cand_n == 0 || w.cand_d[cand_n - 1] > bound) stop = 1;
             else {
-                const DT cd = w.cand_d[0];
-                w.sc[SC_CUR] = (int)w.cand_id[0];
-                heap_pop(w.cand_d, w.cand_id, cand_n, cl);
-                hops++;
+                const DT cd = w.cand_d[cand_n - 1];
+                if (lane == 0) {
+                    w.sc[SC_CUR] = (int)w.cand_id[cand_n - 1];
+                    hops++;
+                }
+                cand_n--;
                 if (cd < dyn && cd >= radius) {
                     dyn = cd;
                     bound = (DT)((double)dyn * (1.0 + a.epsilon));
                 }
             }
-            w.sc[SC_STOP] = stop;
+            if (lane == 0) w.sc[SC_STOP] = stop;
         }
         __syncthreads();
         if (w.sc[SC_STOP]) break;
-        gather_unvisited<DT>(a.g, w, (uint32_t)w.sc[SC_CUR], 0, &vis);
+        gather_unvisited<DT>(a.k, a.g, w, (uint32_t)w.sc[SC_CUR], 0, &vis);
         __syncthreads();
         const int n = w.sc[SC_NBN];
         eval_dists<P, true>(a.k, w.pivot, n, w.nb_dist, [&](int j, uint32_t &x, uint32_t &) { x = w.nb_ids[j]; });
         __syncthreads();
-        if (threadIdx.x == 0) {
-            evals += n;
-            for (int j = 0; j < n; j++) {
-                const DT d = w.nb_dist[j];
-                const uint32_t id = w.nb_ids[j];
-                if (d < bound) {
-                    if (!cand_push(w, cand_n, d, id, true, bound)) {
-                        w.sc[SC_STATUS] = 1;
-                        cand_n = 0;
+        if (warp0) {
+            if (lane == 0) evals += n;
+            bool failed = false;
+            for (int j0 = 0; j0 < n && !failed; j0 += 32) {
+                const int j = j0 + lane;
+                const DT dj = j < n ? w.nb_dist[j] : DT(0);
+                unsigned mask = __ballot_sync(0xffffffffu, j < n && dj < bound); // the bound is fixed during a hop
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const DT d = __shfl_sync(0xffffffffu, dj, b);
+                    const uint32_t id = w.nb_ids[j0 + b];
+                    if (!cand_insert(w, cand_n, d, id, true, bound)) {
+                        failed = true;
                         break;
                     }
-                    if (d <= radius && !is_deleted(a.g, id)) emit(id, d);
+                    if (lane == 0 && d <= radius && !w.nb_del[j0 + b]) emit(id, d);
                 }
+            }
+            if (failed) {
+                if (lane == 0) w.sc[SC_STATUS] = 1;
+                cand_n = 0;
             }
         }
     }
     if (threadIdx.x == 0) {
         a.range_counts[q] = found;
         if (a.status) a.status[q] = (uint32_t)w.sc[SC_STATUS];
+        if (a.counters) {
+            atomicAdd(&a.counters[0], evals);
+            atomicAdd(&a.counters[1], hops);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batch iterator (hnsw_batch_iterator.h:93-267, hnsw_single_batch_iterator.h:36-78): one resumable
+// traversal whose state — visited bitmap, the candidates min-heap on (dist, id), the "extras"
+// min-heap on (dist, label), lower bound, entry point — lives in HBM between calls. Every call
+// returns the next n results exactly as HNSW_BatchIterator::getNextResults does.
+struct BiState {
+    int entry;          // bottom-layer entry point, -1 = not computed yet, -2 = empty graph
+    int depleted;
+    unsigned long long returned;
+    unsigned long long cand_n, extra_n;
+    double lower;       // lower_bound (DistType widened)
+};
+struct BiArgs {
+    KCtx k;
+    GraphDev g;
+    const uint8_t *q;
+    float q_norm;
+    const uint64_t *labels;
+    uint32_t *visited;
+    BiState *state;
+    void *cand_d;       // [cap] DistType
+    uint32_t *cand_id;
+    void *extra_d;
+    uint32_t *extra_id;
+    void *top_d;        // [ef + 1]
+    uint32_t *top_id;
+    int ef, n_res, max_links;
+    unsigned long long label_count;
+    uint32_t *out_ids;
+    void *out_scores;
+    uint64_t *out_labels;
+    uint32_t *out_count;
+    size_t pivot_bytes;
+    unsigned long long *counters;
+};
+// std::greater on pair<DistType, key>: min-heap. Expressed as the "less" our max-heap helpers take.
+template <typename DT> struct MinLess {
+    const uint64_t *labels; // nullptr: key = id
+    __device__ __forceinline__ bool operator()(DT ad, uint32_t ai, DT bd, uint32_t bi) const {
+        // a "less" than b in heap order  <=>  pair(a) > pair(b)
+        if (bd < ad) return true;
+        if (ad < bd) return false;
+        if (labels) return labels[bi] < labels[ai];
+        return bi < ai;
+    }
+};
+
+template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_bi_kernel(BiArgs a) {
+    using DT = typename P::DT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Work<DT> w = carve<DT>(smem_raw, a.pivot_bytes, a.max_links, 1, 1, 0);
+    P::load_pivot(a.k, w.pivot, a.q, a.q_norm);
+    __syncthreads();
+    unsigned long long evals = 0, hops = 0;
+    BiState *st = a.state;
+    // first call: greedy descent to the bottom-layer entry point
+    if (st->entry == -1) {
+        const bool ok = descend<P>(a.k, a.g, w, evals);
+        __syncthreads();
+        if (threadIdx.x == 0) st->entry = ok ? w.sc[SC_CUR] : -2;
+        __syncthreads();
+    }
+    DT *cand_d = (DT *)a.cand_d, *extra_d = (DT *)a.extra_d, *top_d = (DT *)a.top_d;
+    TopLess<DT> tl{a.labels};
+    MinLess<DT> cl{nullptr}, el{a.labels};
+    int top_n = 0, cand_n = 0, extra_n = 0;
+    DT lower = DT(0);
+    const int ef = a.ef;
+    bool skip_scan = false;
+    if (threadIdx.x == 0) {
+        cand_n = (int)st->cand_n;
+        extra_n = (int)st->extra_n;
+        lower = (DT)st->lower;
+        int stop = 0;
+        if (st->entry < 0) {
+            st->depleted = 1;
+            stop = 2; // nothing to scan, nothing to return
+        } else {
+            if (st->returned == 0 && extra_n == 0 && cand_n == 0) {
+                w.sc[SC_AUX0] = 1; // need the entry point's distance
+            } else {
+                w.sc[SC_AUX0] = 0;
+            }
+        }
+        w.sc[SC_STOP] = stop;
+        w.nb_ids[0] = (uint32_t)max(st->entry, 0);
+    }
+    __syncthreads();
+    if (w.sc[SC_STOP] == 2) {
+        if (threadIdx.x == 0) *a.out_count = 0;
+        return;
+    }
+    if (w.sc[SC_AUX0]) {
+        eval_dists<P, true>(a.k, w.pivot, 1, w.nb_dist, [&](int j, uint32_t &x, uint32_t &) { x = w.nb_ids[j]; });
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t ep = w.nb_ids[0];
+            lower = is_deleted(a.g, ep) ? dt_max<DT>() : w.nb_dist[0];
+            a.visited[ep >> 5] |= 1u << (ep & 31);
+            heap_push(cand_d, a.cand_id, cand_n, lower, ep, cl);
+            evals += 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        // fillFromExtras
+        while (top_n < ef && extra_n > 0) {
+            heap_push(top_d, a.top_id, top_n, extra_d[0], a.extra_id[0], tl);
+            heap_pop(extra_d, a.extra_id, extra_n, el);
+        }
+        skip_scan = top_n == ef;
+        w.sc[SC_AUX1] = skip_scan ? 1 : 0;
+    }
+    __syncthreads();
+    if (!w.sc[SC_AUX1]) {
+        Visited vis{a.visited, 0};
+        for (;;) {
+            if (threadIdx.x == 0) {
+                int stop = 0;
+                if (cand_n == 0) stop = 1;
+                else if (cand_d[0] > lower && top_n >= ef) stop = 1;
+                else {
+                    const DT d = cand_d[0];
+                    const uint32_t id = a.cand_id[0];
+                    if (!is_deleted(a.g, id)) {
+                        // updateHeaps
+                        if (top_n < ef) {
+                            heap_push(top_d, a.top_id, top_n, d, id, tl);
+                            lower = top_d[0];
+                        } else if (lower > d) {
+                            heap_push(top_d, a.top_id, top_n, d, id, tl);
+                            heap_push(extra_d, a.extra_id, extra_n, top_d[0], a.top_id[0], el);
+                            heap_pop(top_d, a.top_id, top_n, tl);
+                            lower = top_d[0];
+                        }
+                    }
+                    heap_pop(cand_d, a.cand_id, cand_n, cl);
+                    w.sc[SC_CUR] = (int)id;
+                    hops++;
+                }
+                w.sc[SC_STOP] = stop;
+            }
+            __syncthreads();
+            if (w.sc[SC_STOP]) break;
+            gather_unvisited<DT>(a.k, a.g, w, (uint32_t)w.sc[SC_CUR], 0, &vis);
+            __syncthreads();
+            const int n = w.sc[SC_NBN];
+            eval_dists<P, true>(a.k, w.pivot, n, w.nb_dist, [&](int j, uint32_t &x, uint32_t &) { x = w.nb_ids[j]; });
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                evals += n;
+                for (int j = 0; j < n; j++) heap_push(cand_d, a.cand_id, cand_n, w.nb_dist[j], w.nb_ids[j], cl);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (!skip_scan && top_n < ef) st->depleted = 1;
+        // prepareResults: spare results go back to the extras
+        while (top_n > a.n_res) {
+            heap_push(extra_d, a.extra_id, extra_n, top_d[0], a.top_id[0], el);
+            heap_pop(top_d, a.top_id, top_n, tl);
+        }
+        const int count = top_n;
+        for (int i = count - 1; i >= 0; i--) {
+            const uint32_t id = a.top_id[0];
+            a.out_ids[i] = id;
+            ((DT *)a.out_scores)[i] = top_d[0];
+            a.out_labels[i] = a.labels[id];
+            heap_pop(top_d, a.top_id, top_n, tl);
+        }
+        *a.out_count = (uint32_t)count;
+        st->returned += (unsigned long long)count;
+        if (st->returned == a.label_count) st->depleted = 1;
+        st->cand_n = (unsigned long long)cand_n;
+        st->extra_n = (unsigned long long)extra_n;
+        st->lower = (double)lower;
         if (a.counters) {
             atomicAdd(&a.counters[0], evals);
             atomicAdd(&a.counters[1], hops);
@@ -948,12 +1219,13 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_insert_k
                 __syncthreads();
                 ns = n;
             } else {
+                // the result set is already sorted ascending by (dist, id)
                 for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                    h.in_d[i] = w.top_d[i];
-                    h.in_id[i] = w.top_id[i];
+                    h.sd[i] = w.top_d[i];
+                    h.sid[i] = w.top_id[i];
+                    h.spos[i] = (uint32_t)i;
                 }
                 __syncthreads();
-                rank_sort<DT>(h, n);
                 heuristic<P>(a.k, h, w.sc, n, M);
                 ns = w.sc[SC_AUX2];
                 if (threadIdx.x == 0) w.sc[SC_AUX3] = (int)h.sid[h.sel[0]];
@@ -1581,6 +1853,176 @@ int vsgpu_hnsw_range(vsgpu_hnsw *g, const void *query, double radius, double eps
             std::vector<float> tmp(cnt);
             VS_CUDA(cudaMemcpy(tmp.data(), d_sc, cnt * 4, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < cnt; i++) out_scores[i] = tmp[i];
+        }
+    }
+    return VSGPU_OK;
+}
+
+/* ---- resumable batch iterator ---- */
+struct vsgpu_hnsw_iter {
+    vsgpu_hnsw *g = nullptr;
+    size_t cap = 0;     // nodes the state was sized for
+    size_t ef = 0;
+    uint8_t *query = nullptr; // staged (packed) query on the device
+    float q_norm = 0.f;
+    uint32_t *visited = nullptr;
+    BiState *state = nullptr;
+    void *cand_d = nullptr, *extra_d = nullptr, *top_d = nullptr;
+    uint32_t *cand_id = nullptr, *extra_id = nullptr, *top_id = nullptr;
+    size_t top_cap = 0;
+    void *out = nullptr;
+    size_t out_cap = 0;
+};
+
+static int iter_reset_state(vsgpu_hnsw_iter *it) {
+    vsgpu_store *s = it->g->s;
+    BiState st{};
+    st.entry = -1;
+    st.lower = std::numeric_limits<double>::infinity();
+    VS_CUDA(cudaMemcpyAsync(it->state, &st, sizeof(st), cudaMemcpyHostToDevice, s->stream));
+    VS_CUDA(cudaMemsetAsync(it->visited, 0, ((it->cap + 31) / 32) * 4, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    return VSGPU_OK;
+}
+
+vsgpu_hnsw_iter *vsgpu_hnsw_iter_create(vsgpu_hnsw *g, const void *query, size_t ef) {
+    vsgpu_store *s = g->s;
+    if (!query || cudaSetDevice(s->device) != cudaSuccess) return nullptr;
+    auto *it = new vsgpu_hnsw_iter();
+    it->g = g;
+    it->cap = std::max<size_t>(g->count, 1);
+    it->ef = std::max<size_t>(ef, 1);
+    const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    bool ok = cudaMalloc(&it->query, s->row_stride + 256) == cudaSuccess;
+    ok = ok && cudaMalloc(&it->visited, ((it->cap + 31) / 32) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&it->state, sizeof(BiState)) == cudaSuccess;
+    ok = ok && cudaMalloc(&it->cand_d, (it->cap + 1) * dt) == cudaSuccess && cudaMalloc(&it->cand_id, (it->cap + 1) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&it->extra_d, (it->cap + 1) * dt) == cudaSuccess && cudaMalloc(&it->extra_id, (it->cap + 1) * 4) == cudaSuccess;
+    if (ok) {
+        // stage the query: raw blob -> device -> the layout the kernels read
+        ok = ensure_pinned(s, s->blob_bytes + 256) == VSGPU_OK && ensure_scratch(s, s->q_raw, s->blob_bytes + 256) == VSGPU_OK;
+        if (ok) {
+            memcpy(s->pinned, query, s->blob_bytes);
+            ok = cudaMemcpyAsync(s->q_raw.ptr, s->pinned, s->blob_bytes, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+        }
+        const void *q = nullptr;
+        size_t qs = 0;
+        const float *qn = nullptr;
+        ok = ok && stage_queries_device(s, s->q_raw.ptr, 1, s->blob_bytes, &q, &qs, &qn) == VSGPU_OK;
+        if (ok) {
+            const size_t bytes = s->plan.kind == CK_INT ? s->row_stride : s->row_bytes;
+            ok = cudaMemcpyAsync(it->query, q, bytes, cudaMemcpyDeviceToDevice, s->stream) == cudaSuccess;
+            if (ok && qn) ok = cudaMemcpyAsync(&it->q_norm, qn, 4, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess;
+            ok = ok && cudaStreamSynchronize(s->stream) == cudaSuccess;
+        }
+    }
+    if (!ok || iter_reset_state(it) != VSGPU_OK) {
+        set_error("vsgpu_hnsw_iter_create: device allocation / staging failed");
+        vsgpu_hnsw_iter_destroy(it);
+        return nullptr;
+    }
+    return it;
+}
+
+void vsgpu_hnsw_iter_destroy(vsgpu_hnsw_iter *it) {
+    if (!it) return;
+    cudaSetDevice(it->g->s->device);
+    cudaStreamSynchronize(it->g->s->stream);
+    for (void *p : {(void *)it->query, (void *)it->visited, (void *)it->state, it->cand_d, (void *)it->cand_id, it->extra_d,
+                    (void *)it->extra_id, it->top_d, (void *)it->top_id, it->out})
+        if (p) cudaFree(p);
+    delete it;
+}
+
+int vsgpu_hnsw_iter_reset(vsgpu_hnsw_iter *it) {
+    VS_CUDA(cudaSetDevice(it->g->s->device));
+    return iter_reset_state(it);
+}
+
+int vsgpu_hnsw_iter_next(vsgpu_hnsw_iter *it, size_t n_res, size_t label_count, uint64_t *out_labels, double *out_scores,
+                         uint32_t *out_ids, size_t *out_count, int *depleted) {
+    vsgpu_hnsw *g = it->g;
+    vsgpu_store *s = g->s;
+    VS_CUDA(cudaSetDevice(s->device));
+    if (g->count > it->cap) {
+        set_error("vsgpu_hnsw_iter_next: the graph grew since the iterator was created");
+        return VSGPU_ERR_ARG;
+    }
+    const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    const size_t ef = std::max(it->ef, n_res); // hnsw_batch_iterator.h:210-213
+    if (ef + 1 > it->top_cap) {
+        if (it->top_d) cudaFree(it->top_d);
+        if (it->top_id) cudaFree(it->top_id);
+        it->top_d = it->top_id = nullptr;
+        VS_CUDA(cudaMalloc(&it->top_d, (ef + 1) * dt));
+        VS_CUDA(cudaMalloc(&it->top_id, (ef + 1) * 4));
+        it->top_cap = ef + 1;
+    }
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t nr = std::max<size_t>(n_res, 1);
+    const size_t need = al(nr * 8) + al(nr * dt) + al(nr * 4) + 256;
+    if (need > it->out_cap) {
+        if (it->out) cudaFree(it->out);
+        it->out = nullptr;
+        VS_CUDA(cudaMalloc(&it->out, need));
+        it->out_cap = need;
+    }
+    uint64_t *d_lab = (uint64_t *)it->out;
+    uint8_t *d_sc = (uint8_t *)it->out + al(nr * 8);
+    uint32_t *d_id = (uint32_t *)(d_sc + al(nr * dt));
+    uint32_t *d_cnt = (uint32_t *)((uint8_t *)d_id + al(nr * 4));
+    BiArgs a{};
+    a.k = make_kctx(s);
+    a.g = make_graph(g);
+    a.q = it->query;
+    a.q_norm = it->q_norm;
+    a.labels = s->labels;
+    a.visited = it->visited;
+    a.state = it->state;
+    a.cand_d = it->cand_d;
+    a.cand_id = it->cand_id;
+    a.extra_d = it->extra_d;
+    a.extra_id = it->extra_id;
+    a.top_d = it->top_d;
+    a.top_id = it->top_id;
+    a.ef = (int)ef;
+    a.n_res = (int)n_res;
+    a.max_links = g->M0;
+    a.label_count = label_count;
+    a.out_ids = d_id;
+    a.out_scores = d_sc;
+    a.out_labels = d_lab;
+    a.out_count = d_cnt;
+    a.counters = g->counters;
+    VS_CUDA(cudaMemsetAsync(g->counters, 0, 16, s->stream));
+    const int rc = dispatch_policy(s, [&]<class P>() -> int {
+        a.pivot_bytes = P::pivot_bytes(s);
+        const size_t smem = carve_bytes(dt, a.pivot_bytes, a.max_links, 1, 1, 0);
+        auto kern = hnsw_bi_kernel<P>;
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<1, HNSW_THREADS, smem, s->stream>>>(a);
+        VS_CUDA(cudaGetLastError());
+        return (int)VSGPU_OK;
+    });
+    VS_TRY(rc);
+    uint32_t cnt = 0;
+    BiState st{};
+    VS_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(&st, it->state, sizeof(st), cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    if (out_count) *out_count = cnt;
+    if (depleted) *depleted = (st.depleted && st.extra_n == 0) ? 1 : 0; // isDepleted(), hnsw_batch_iterator.h:251-254
+    if (cnt) {
+        if (out_labels) VS_CUDA(cudaMemcpy(out_labels, d_lab, cnt * 8, cudaMemcpyDeviceToHost));
+        if (out_ids) VS_CUDA(cudaMemcpy(out_ids, d_id, cnt * 4, cudaMemcpyDeviceToHost));
+        if (out_scores) {
+            if (dt == 8) {
+                VS_CUDA(cudaMemcpy(out_scores, d_sc, cnt * 8, cudaMemcpyDeviceToHost));
+            } else {
+                std::vector<float> tmp(cnt);
+                VS_CUDA(cudaMemcpy(tmp.data(), d_sc, cnt * 4, cudaMemcpyDeviceToHost));
+                for (size_t i = 0; i < cnt; i++) out_scores[i] = tmp[i];
+            }
         }
     }
     return VSGPU_OK;

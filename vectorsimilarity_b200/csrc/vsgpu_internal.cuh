@@ -145,6 +145,10 @@ int launch_exact_gather(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_s
                         const uint32_t *ids, size_t ids_ld, const uint32_t *counts, size_t max_count,
                         void *out, size_t ld);
 
+// ---- staged streaming scan (vsgpu_scan.cu): fp32 / fp16 stores, dim % 32 == 0, <= 16 raw queries per pass ----
+bool tma_scan_supported(const vsgpu_store *s);
+int launch_tma_scan(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, void *scores, size_t ld);
+
 // ---- selection (vsgpu_select.cu) ----
 // For each of nq score rows (DistType, length n, leading dim ld): the k smallest by (score, id),
 // sorted, into out_ids/out_scores ([nq][k]) and labels gathered from s->labels.

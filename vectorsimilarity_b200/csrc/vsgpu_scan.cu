@@ -1,0 +1,311 @@
+// Streaming exact scan for the AVX512F "lanes" tier without residual (fp32 / fp16 stores, dim % 32
+// == 0 — the benchmark shapes d = 128 / 768 / 1024): same bit-exact arithmetic as exact_scan_kernel
+// (vsgpu_exact.cu; reference spaces/IP/IP_AVX512F_FP32.h:19-56, L2/L2_AVX512F_FP32.h:21-59,
+// IP/IP_AVX512F_FP16.h:27-68), restructured so the HBM stream, the FMA pipe and shared memory all
+// stay busy at once:
+//
+//   * rows never touch registers on their way in: a producer warp issues TMA bulk copies
+//     (cp.async.bulk, one per row segment) of [64 rows x KC elements] tiles into a ring of
+//     shared-memory stages guarded by mbarriers; 8 consumer warps drain them;
+//   * a consumer warp owns 8 rows x up to 16 queries = 128 accumulators: lane c is chain c (the
+//     x86 lane / accumulator pair), one LDS feeds 16 FMAs, and the FMAs are issued as packed
+//     FFMA2 (fma.rn.f32x2: two independently IEEE-rounded FMAs per issue slot — bit-identical to
+//     scalar fma.rn.f32) over pairs of queries;
+//   * the 32-lane reduction of _mm512_reduce_add_ps is a transposing butterfly: each round halves
+//     the number of live values per lane instead of reducing every value on every lane (same
+//     pairing tree xor 16, 8, 4, 2, 1, fp add is commutative, so the bits are unchanged).
+//
+// Roofline: HBM. Algorithmic bytes per launch = n * dim * sizeof(T) + nq * n * 4 (scores out).
+#include "vsgpu_dist.cuh"
+#include <algorithm>
+
+namespace vsgpu {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool bar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    while (!bar_try_wait(bar, parity)) {
+    }
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+constexpr int TILE_ROWS = 64;    // rows per stage: 8 consumer warps x 8 rows
+constexpr int ROWS_PER_WARP = 8;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int SCAN_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int MAX_STAGES = 8;
+
+struct ScanTmaArgs {
+    const uint8_t *rows;
+    size_t row_stride;
+    size_t n;
+    int dim;
+    int kc;      // elements per stage row segment (multiple of 32, divides dim)
+    int nstages;
+    const uint8_t *q; // raw query blobs (same element type as the rows)
+    size_t q_stride;
+    int nq;
+    float *scores; // [nq][ld]
+    size_t ld;
+};
+
+template <typename ET> __device__ __forceinline__ float elem_to_float(ET v);
+template <> __device__ __forceinline__ float elem_to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float elem_to_float<__half>(__half v) { return __half2float(v); }
+
+// QP = query pairs per pass (2, 4 or 8)
+template <typename ET, int QP, bool L2> __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(ScanTmaArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int QC = 2 * QP;
+    constexpr int V = ROWS_PER_WARP * QC;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + MAX_STAGES;
+    float2 *qs = reinterpret_cast<float2 *>(smem + 128);                           // [QP][dim]
+    unsigned char *stage0 = smem + 128 + (((size_t)QP * a.dim * sizeof(float2) + 127) / 128) * 128;
+    const size_t seg_bytes = (size_t)a.kc * sizeof(ET);
+    const size_t stage_bytes = (size_t)TILE_ROWS * seg_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = a.dim / a.kc;
+    const int steps = a.kc / 32;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.nstages; i++) {
+            bar_init(&full[i], 1);
+            bar_init(&empty[i], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // queries, pair-interleaved: qs[p][e] = (q[2p][e], q[2p+1][e]); absent queries are zero
+    for (int i = threadIdx.x; i < QP * a.dim; i += blockDim.x) {
+        const int p = i / a.dim, e = i % a.dim;
+        float2 v = make_float2(0.f, 0.f);
+        if (2 * p < a.nq) v.x = elem_to_float<ET>(reinterpret_cast<const ET *>(a.q + (size_t)(2 * p) * a.q_stride)[e]);
+        if (2 * p + 1 < a.nq) v.y = elem_to_float<ET>(reinterpret_cast<const ET *>(a.q + (size_t)(2 * p + 1) * a.q_stride)[e]);
+        qs[i] = v;
+    }
+    __syncthreads();
+
+    const size_t ntiles = (a.n + TILE_ROWS - 1) / TILE_ROWS;
+    if (warp == CONSUMER_WARPS) {
+        // ---- producer: one TMA bulk copy per (row, column chunk) ----
+        uint32_t it = 0;
+        for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const size_t row0 = tile * TILE_ROWS;
+            for (int ch = 0; ch < nchunks; ch++, it++) {
+                const int st = it % a.nstages;
+                const uint32_t ph = (it / a.nstages) & 1;
+                bar_wait(&empty[st], ph ^ 1);
+                if (lane == 0) bar_expect_tx(&full[st], (uint32_t)stage_bytes);
+                __syncwarp();
+                unsigned char *dst = stage0 + (size_t)st * stage_bytes;
+#pragma unroll
+                for (int rr = 0; rr < TILE_ROWS / 32; rr++) {
+                    const int rl = rr * 32 + lane;
+                    size_t row = row0 + rl;
+                    if (row >= a.n) row = a.n - 1; // tail tile: duplicates, results discarded
+                    bulk_load(dst + (size_t)rl * seg_bytes, a.rows + row * a.row_stride + (size_t)ch * seg_bytes, (uint32_t)seg_bytes,
+                              &full[st]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    uint32_t it = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        u64 acc[ROWS_PER_WARP][QP];
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_WARP; r++)
+#pragma unroll
+            for (int p = 0; p < QP; p++) acc[r][p] = 0ull;
+        for (int ch = 0; ch < nchunks; ch++, it++) {
+            const int st = it % a.nstages;
+            const uint32_t ph = (it / a.nstages) & 1;
+            bar_wait(&full[st], ph);
+            const ET *xb = reinterpret_cast<const ET *>(stage0 + (size_t)st * stage_bytes + (size_t)(warp * ROWS_PER_WARP) * seg_bytes) + lane;
+            const float2 *qb = qs + (size_t)ch * a.kc + lane;
+#pragma unroll 2
+            for (int s = 0; s < steps; s++) {
+                u64 qv[QP];
+#pragma unroll
+                for (int p = 0; p < QP; p++) qv[p] = *reinterpret_cast<const u64 *>(qb + (size_t)p * a.dim + s * 32);
+#pragma unroll
+                for (int r = 0; r < ROWS_PER_WARP; r++) {
+                    const float x = elem_to_float<ET>(xb[(size_t)r * a.kc + s * 32]);
+                    const u64 xx = pack2(x, x);
+#pragma unroll
+                    for (int p = 0; p < QP; p++) {
+                        if constexpr (L2) {
+                            const u64 d = sub2(xx, qv[p]);
+                            acc[r][p] = fma2(d, d, acc[r][p]);
+                        } else {
+                            acc[r][p] = fma2(xx, qv[p], acc[r][p]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) bar_arrive(&empty[st]);
+        }
+        // ---- reduce over the 32 chains: transposing butterfly (xor 16, 8, 4, 2, 1) ----
+        float v[V];
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_WARP; r++)
+#pragma unroll
+            for (int p = 0; p < QP; p++) unpack2(acc[r][p], v[r * QC + 2 * p], v[r * QC + 2 * p + 1]);
+        {
+            int half = V / 2;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const bool up = (lane & m) != 0;
+#pragma unroll
+                for (int i = 0; i < V / 2; i++) {
+                    if (i < half) {
+                        const float lo = v[i], hi = v[i + half];
+                        const float send = up ? lo : hi, keep = up ? hi : lo;
+                        v[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, m));
+                    }
+                }
+                half >>= 1;
+            }
+        }
+        // lane L now holds value indices L * (V/32) + j: row L >> 2, queries (L & 3) * (QC/4) + j
+        constexpr int PER = V / 32;
+        const size_t row = tile * TILE_ROWS + (size_t)warp * ROWS_PER_WARP + (lane >> 2);
+        if (row < a.n) {
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                const int q = (lane & 3) * PER + j;
+                if (q < a.nq) a.scores[(size_t)q * a.ld + row] = L2 ? v[j] : __fsub_rn(1.0f, v[j]);
+            }
+        }
+    }
+}
+
+int sm_count(int device) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+    return v;
+}
+
+template <typename ET, bool L2> int launch_t(vsgpu_store *s, ScanTmaArgs &a, size_t smem_bytes) {
+#define VS_LAUNCH_TMA(QPV)                                                                                             \
+    do {                                                                                                               \
+        auto kern = scan_tma_kernel<ET, QPV, L2>;                                                                      \
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));             \
+        kern<<<(unsigned)std::min<size_t>((size_t)sm_count(s->device), (a.n + TILE_ROWS - 1) / TILE_ROWS), SCAN_THREADS, \
+               smem_bytes, s->stream>>>(a);                                                                            \
+    } while (0)
+    if (a.nq <= 4) VS_LAUNCH_TMA(2);
+    else if (a.nq <= 8) VS_LAUNCH_TMA(4);
+    else VS_LAUNCH_TMA(8);
+#undef VS_LAUNCH_TMA
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
+}
+
+} // namespace
+
+bool tma_scan_supported(const vsgpu_store *s) {
+    const ChainPlan &p = s->plan;
+    if (p.kind != CK_LANES || p.G != 32 || p.prefix != 0) return false;
+    if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_FLOAT16) return false;
+    return s->dim % 32 == 0 && s->dim <= 4096;
+}
+
+// scores[q * ld + id] for up to 16 queries (raw blobs on the device)
+int launch_tma_scan(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, void *scores, size_t ld) {
+    if (nq == 0 || s->count == 0) return VSGPU_OK;
+    if (nq > 16) {
+        set_error("launch_tma_scan: at most 16 queries per pass");
+        return VSGPU_ERR_ARG;
+    }
+    const int dim = (int)s->dim;
+    const size_t esz = s->elem;
+    const int qp = nq <= 4 ? 2 : (nq <= 8 ? 4 : 8);
+    const size_t q_bytes = (((size_t)qp * dim * sizeof(float2) + 127) / 128) * 128;
+    int dev_smem = 0;
+    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device) != cudaSuccess || dev_smem <= 0)
+        dev_smem = 227 * 1024;
+    const size_t budget = (size_t)dev_smem - 128 - q_bytes - 1024;
+    // widest row segment that still leaves >= 3 stages in flight
+    int kc = 0, nst = 0;
+    for (int c = std::min(dim, 256); c >= 32; c -= 32) {
+        if (dim % c) continue;
+        const size_t stage = (size_t)TILE_ROWS * c * esz;
+        const int n = (int)std::min<size_t>(budget / stage, MAX_STAGES);
+        if (n >= 3) {
+            kc = c;
+            nst = n;
+            break;
+        }
+    }
+    if (!kc) {
+        set_error("launch_tma_scan: dimension too large for the staged scan");
+        return VSGPU_ERR_ARG;
+    }
+    nst = std::min(nst, 6);
+    ScanTmaArgs a{};
+    a.rows = s->rows;
+    a.row_stride = s->row_stride;
+    a.n = s->count;
+    a.dim = dim;
+    a.kc = kc;
+    a.nstages = nst;
+    a.q = (const uint8_t *)q_dev;
+    a.q_stride = q_stride;
+    a.nq = (int)nq;
+    a.scores = (float *)scores;
+    a.ld = ld;
+    const size_t smem_bytes = 128 + q_bytes + (size_t)nst * TILE_ROWS * kc * esz;
+    const bool l2 = s->plan.is_l2;
+    if (s->type == VSGPU_FLOAT32) return l2 ? launch_t<float, true>(s, a, smem_bytes) : launch_t<float, false>(s, a, smem_bytes);
+    return l2 ? launch_t<__half, true>(s, a, smem_bytes) : launch_t<__half, false>(s, a, smem_bytes);
+}
+
+} // namespace vsgpu
