@@ -64,7 +64,7 @@ static int timeout_cb(void *) { return g_timeout_flag; }
 /* Install a timeout callback that returns `flag` (tests/unit/test_bruteforce.cpp:1489-1517). */
 void vsref_set_timeout(int flag) {
     g_timeout_flag = flag;
-    VecSimIndexInterface::setTimeoutCallbackFunction(flag ? timeout_cb : nullptr);
+    VecSimIndexInterface::setTimeoutCallbackFunction(timeout_cb); /* never nullptr: the reference calls it unchecked */
 }
 
 /* ---- distance kernels through the reference dispatcher ---------------------------------- */

@@ -66,6 +66,12 @@ def main():
     fl, _ = F.knn_batch(Q, a.k)
     out["recall_at_k"] = float(np.mean([len(set(labels[i]) & set(fl[i])) / a.k for i in range(a.batch)]))
     F.close()
+    # throughput at a larger batch (several waves of CTAs: the tail of the slowest query no longer dominates)
+    if a.batch < 4096:
+        Qb = rng.uniform(-1, 1, (4096, a.dim)).astype(np.float32)
+        G.knn_batch(Qb, a.k)
+        G.knn_batch(Qb, a.k)
+        out["search_qps_device_b4096"] = 4096 / (G.hnsw_stats()["ms"] * 1e-3)
     if a.ref:
         from oracle import ref
         ref.lib()

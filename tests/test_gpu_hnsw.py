@@ -277,3 +277,16 @@ def test_batch_iterator_matches_oracle(capi, port, vtype, metric, dim):
     pi.close()
     G.close()
     P.close()
+
+
+def test_builder_cta_wide_revisit_path(capi, monkeypatch):
+    """The builder's fallback when shared memory has no room for per-warp revisit scratch (large M): same graph."""
+    levels, links, counts, entry, maxl = gold_graph("l2")
+    monkeypatch.setenv("VSGPU_HNSW_RV_WARPS", "0")
+    G = new_index(capi, 0, DIM, 0, M=M, efc=EFC)
+    G.add_vectors(GOLD["l2_X"])
+    g = G.export_graph(N)
+    l0, upper = graph_records(levels, links, counts, M)
+    assert np.array_equal(g["levels"], levels) and (g["entry"], g["max_level"]) == (entry, maxl)
+    assert np.array_equal(masked(g["l0"]), l0) and np.array_equal(masked(g["upper"]), upper)
+    G.close()

@@ -5,6 +5,6 @@ libvecsim_b200.so), capi.py (ctypes mirror of the reference's Python binding), s
 per GPU, NCCL all-gather of per-shard top-K). Nothing here imports oracle/.
 """
 from . import capi  # noqa: F401
-from .capi import (BFIndex, BFParams, BY_ID, BY_SCORE, VecSimMetric_Cosine, VecSimMetric_IP, VecSimMetric_L2,  # noqa: F401
+from .capi import (BFIndex, BFParams, BY_ID, BY_SCORE, HNSWIndex, HNSWParams, VecSimMetric_Cosine, VecSimMetric_IP, VecSimMetric_L2,  # noqa: F401
                    VecSimType_BFLOAT16, VecSimType_FLOAT16, VecSimType_FLOAT32, VecSimType_FLOAT64, VecSimType_INT8,
                    VecSimType_UINT8)

@@ -19,6 +19,7 @@
 // are per-query bitmaps in HBM/L2.
 #include "vsgpu_dist.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
 #include <vector>
 
@@ -61,7 +62,17 @@ __device__ __forceinline__ bool is_deleted(const GraphDev &g, uint32_t node) { r
 // ------------------------------------------------------------------------------------------------
 // Distance policies: P::dists<PIVOT> evaluates RU (row, other) pairs per thread group of G lanes;
 // `other` is the pivot staged in shared memory (the query) or a second stored row.
-template <typename CT_, int G_, bool FTZ, bool L2> struct PolChain {
+// element load with the storage type fixed at compile time: no branch between the loads of a hop, so the
+// compiler issues them back to back (with a run-time type switch every load waited for the previous one:
+// 16 dependent L2 round trips per distance evaluation, measured 6.7 k cycles per hop)
+template <int ST, typename DT> __device__ __forceinline__ DT load_st(const uint8_t *row, int e) {
+    if constexpr (ST == VSGPU_FLOAT64) return (DT)__ldg(reinterpret_cast<const double *>(row) + e);
+    else if constexpr (ST == VSGPU_FLOAT32) return (DT)__ldg(reinterpret_cast<const float *>(row) + e);
+    else if constexpr (ST == VSGPU_BFLOAT16) return (DT)__uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short *>(row) + e) << 16);
+    else return (DT)__half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short *>(row) + e)));
+}
+
+template <typename CT_, int G_, bool FTZ, bool L2, int ST> struct PolChain {
     using DT = CT_;
     static constexpr int G = G_;
     static constexpr int RU = sizeof(CT_) == 8 ? 2 : 4;
@@ -71,7 +82,7 @@ template <typename CT_, int G_, bool FTZ, bool L2> struct PolChain {
         const int total = k.plan.S * G;
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int e = chain_elem(k.plan, i % G, i / G);
-            pv[i] = e < 0 ? DT(0) : Loader<DT>::load(src, k.type, e);
+            pv[i] = e < 0 ? DT(0) : load_st<ST, DT>(src, e);
         }
     }
     template <bool PIVOT>
@@ -89,20 +100,47 @@ template <typename CT_, int G_, bool FTZ, bool L2> struct PolChain {
         for (int r = 0; r < RU; r++) acc[r] = DT(0);
         const bool fast = k.plan.kind == CK_LANES && k.plan.prefix == 0;
         const int S = k.plan.S;
+        if (fast) {
+            // no residual: chain c reads element G*s + c — straight-line loads, 4 steps x RU rows in flight
 #pragma unroll 4
-        for (int s = 0; s < S; s++) {
-            const int e = fast ? G * s + c : chain_elem(k.plan, c, s);
+            for (int s = 0; s < S; s++) {
+                const int e = G * s + c;
 #pragma unroll
-            for (int r = 0; r < RU; r++) {
-                const DT x = e < 0 ? DT(0) : Loader<DT>::load(ra[r], k.type, e);
-                DT y;
-                if constexpr (PIVOT) y = pv[s * G];
-                else y = e < 0 ? DT(0) : Loader<DT>::load(rb[r], k.type, e);
-                if constexpr (L2) {
-                    const DT d = sub_rn(x, y);
-                    acc[r] = fma_step<FTZ>(d, d, acc[r]);
-                } else {
-                    acc[r] = fma_step<FTZ>(x, y, acc[r]);
+                for (int r = 0; r < RU; r++) {
+                    const DT x = load_st<ST, DT>(ra[r], e);
+                    DT y;
+                    if constexpr (PIVOT) y = pv[s * G];
+                    else y = load_st<ST, DT>(rb[r], e);
+                    if constexpr (L2) {
+                        const DT d = sub_rn(x, y);
+                        acc[r] = fma_step<FTZ>(d, d, acc[r]);
+                    } else {
+                        acc[r] = fma_step<FTZ>(x, y, acc[r]);
+                    }
+                }
+            }
+        } else {
+            for (int s = 0; s < S; s++) {
+                const int e = chain_elem(k.plan, c, s);
+                const int ee = e < 0 ? 0 : e; // padded slots: load element 0, multiply by zero below is NOT exact for inf/nan -> select
+                DT x[RU], y[RU];
+#pragma unroll
+                for (int r = 0; r < RU; r++) {
+                    x[r] = load_st<ST, DT>(ra[r], ee);
+                    if constexpr (!PIVOT) y[r] = load_st<ST, DT>(rb[r], ee);
+                }
+#pragma unroll
+                for (int r = 0; r < RU; r++) {
+                    const DT xv = e < 0 ? DT(0) : x[r];
+                    DT yv;
+                    if constexpr (PIVOT) yv = pv[s * G];
+                    else yv = e < 0 ? DT(0) : y[r];
+                    if constexpr (L2) {
+                        const DT d = sub_rn(xv, yv);
+                        acc[r] = fma_step<FTZ>(d, d, acc[r]);
+                    } else {
+                        acc[r] = fma_step<FTZ>(xv, yv, acc[r]);
+                    }
                 }
             }
         }
@@ -112,6 +150,58 @@ template <typename CT_, int G_, bool FTZ, bool L2> struct PolChain {
             if (!L2) v = sub_rn(DT(1), v);
             out[r] = v;
         }
+    }
+    // one thread evaluates a whole (row, row) pair: the G chain sums live in registers and are folded
+    // with the same pairing tree as the warp butterfly (acc[c] + acc[c + w], w = G/2 .. 1). Used where
+    // many independent pairs are wanted at once (neighbour-selection heuristic), so a thread per pair
+    // gives far more loads in flight than a warp per pair.
+    __device__ static DT dist_thread(const KCtx &k, uint32_t a, uint32_t b) {
+        const uint8_t *ra = k.rows + (size_t)a * k.row_stride, *rb = k.rows + (size_t)b * k.row_stride;
+        DT acc[G];
+#pragma unroll
+        for (int c = 0; c < G; c++) acc[c] = DT(0);
+        const bool fast = k.plan.kind == CK_LANES && k.plan.prefix == 0;
+        const int S = k.plan.S;
+        if (ST == VSGPU_FLOAT32 && fast) {
+            for (int s = 0; s < S; s++) {
+#pragma unroll
+                for (int c4 = 0; c4 < G / 4; c4++) {
+                    const float4 x = __ldg(reinterpret_cast<const float4 *>(ra) + s * (G / 4) + c4);
+                    const float4 y = __ldg(reinterpret_cast<const float4 *>(rb) + s * (G / 4) + c4);
+                    const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        if constexpr (L2) {
+                            const DT d = sub_rn((DT)xs[t], (DT)ys[t]);
+                            acc[4 * c4 + t] = fma_step<FTZ>(d, d, acc[4 * c4 + t]);
+                        } else {
+                            acc[4 * c4 + t] = fma_step<FTZ>((DT)xs[t], (DT)ys[t], acc[4 * c4 + t]);
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int s = 0; s < S; s++) {
+#pragma unroll
+                for (int c = 0; c < G; c++) {
+                    const int e = fast ? G * s + c : chain_elem(k.plan, c, s);
+                    const DT x = e < 0 ? DT(0) : load_st<ST, DT>(ra, e);
+                    const DT y = e < 0 ? DT(0) : load_st<ST, DT>(rb, e);
+                    if constexpr (L2) {
+                        const DT d = sub_rn(x, y);
+                        acc[c] = fma_step<FTZ>(d, d, acc[c]);
+                    } else {
+                        acc[c] = fma_step<FTZ>(x, y, acc[c]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int w = G / 2; w >= 1; w >>= 1)
+#pragma unroll
+            for (int c = 0; c < G / 2; c++)
+                if (c < w) acc[c] = add_rn(acc[c], acc[c + w]);
+        return L2 ? acc[0] : sub_rn(DT(1), acc[0]);
     }
 };
 
@@ -172,6 +262,18 @@ template <bool U> struct PolInt {
             out[r] = int_score(k.metric, dot, aa, PIVOT ? tail->qq : bb, rn, qn);
         }
     }
+    __device__ static DT dist_thread(const KCtx &k, uint32_t a, uint32_t b) {
+        const uint4 *ra = reinterpret_cast<const uint4 *>(k.rows + (size_t)a * k.row_stride);
+        const uint4 *rb = reinterpret_cast<const uint4 *>(k.rows + (size_t)b * k.row_stride);
+        long long dot = 0, aa = 0, bb = 0;
+        for (int ch = 0; ch < k.chunks; ch++) {
+            const uint4 x = __ldg(ra + ch), y = __ldg(rb + ch);
+            dot += dot4<U>(x.x, y.x, 0) + dot4<U>(x.y, y.y, 0) + dot4<U>(x.z, y.z, 0) + dot4<U>(x.w, y.w, 0);
+            aa += dot4<U>(x.x, x.x, 0) + dot4<U>(x.y, x.y, 0) + dot4<U>(x.z, x.z, 0) + dot4<U>(x.w, x.w, 0);
+            bb += dot4<U>(y.x, y.x, 0) + dot4<U>(y.y, y.y, 0) + dot4<U>(y.z, y.z, 0) + dot4<U>(y.w, y.w, 0);
+        }
+        return int_score(k.metric, dot, aa, bb, k.norms ? k.norms[a] : 0.f, k.norms ? k.norms[b] : 0.f);
+    }
 };
 
 template <typename CT_> struct PolSeq {
@@ -191,6 +293,10 @@ template <typename CT_> struct PolSeq {
         const uint8_t *rb = k.rows + (size_t)(b[0] == INV ? 0 : b[0]) * k.row_stride;
         if constexpr (PIVOT) out[0] = seq_dist<DT>(ra, k.type, k.plan, [&](int e) { return pv[e]; });
         else out[0] = seq_dist<DT>(ra, k.type, k.plan, [&](int e) { return Loader<DT>::load(rb, k.type, e); });
+    }
+    __device__ static DT dist_thread(const KCtx &k, uint32_t a, uint32_t b) {
+        const uint8_t *ra = k.rows + (size_t)a * k.row_stride, *rb = k.rows + (size_t)b * k.row_stride;
+        return seq_dist<DT>(ra, k.type, k.plan, [&](int e) { return Loader<DT>::load(rb, k.type, e); });
     }
 };
 
@@ -309,6 +415,7 @@ template <typename DT> struct Work {
     DT *adm_d;
     uint32_t *adm_id;
     int adm_cap;
+    long long *prof; // thread 0: cycles per phase (gather, eval, admit, pop), or nullptr
 };
 enum { SC_TOPN = 0, SC_CANDN, SC_NBN, SC_STOP, SC_CUR, SC_STATUS, SC_ADMN, SC_AUX0, SC_AUX1, SC_AUX2, SC_AUX3, SC_COUNT = 16 };
 
@@ -399,9 +506,27 @@ __device__ __forceinline__ int warp_sum(int v) {
 template <typename DT, typename Less>
 __device__ __forceinline__ void sorted_insert(DT *ad, uint32_t *aid, int &n, DT d, uint32_t id, Less less) {
     const int lane = threadIdx.x & 31;
-    int cnt = 0;
-    for (int i = lane; i < n; i += 32) cnt += less(ad[i], aid[i], d, id) ? 1 : 0;
-    cnt = warp_sum(cnt);
+    // position = number of elements ordered before the new one: 32-ary search over the sorted array
+    int lo = 0, hi_s = n;
+    while (hi_s - lo > 32) {
+        const int step = (hi_s - lo + 31) / 32;
+        const int idx = lo + lane * step;
+        const bool pred = idx < hi_s && less(ad[idx], aid[idx], d, id);
+        const int t = __popc(__ballot_sync(0xffffffffu, pred)); // predicates are monotone: t leading trues
+        if (t == 0) {
+            hi_s = lo;
+            break;
+        }
+        const int nlo = lo + (t - 1) * step + 1;
+        hi_s = min(lo + t * step, hi_s);
+        lo = nlo;
+    }
+    int cnt = lo;
+    if (hi_s > lo) {
+        const int idx = lo + lane;
+        const bool pred = idx < hi_s && less(ad[idx], aid[idx], d, id);
+        cnt = lo + __popc(__ballot_sync(0xffffffffu, pred));
+    }
     for (int hi = n - 1; hi >= cnt; hi -= 32) {
         const int i = hi - lane;
         const bool act = i >= cnt;
@@ -448,20 +573,74 @@ template <typename DT> __device__ __forceinline__ void sorted_drop_prefix(DT *ad
     n -= t;
 }
 
-// warp 0: insert into the candidate set; on overflow prune entries that can no longer be expanded
-// (they are the prefix: largest distances first), then spill to HBM. false = out of room.
+// ---- candidate set: an unordered bag (warp 0) ----
+// Adding is one store; the element a priority queue would pop — the maximum under pair(-dist, id) — is
+// found by a strided scan + warp arg-max when it is needed, once per hop. (A sorted array cost ~2.5 k
+// cycles per admission at efConstruction-sized sets; the hop's single pop costs less than one of those.)
+template <typename DT> __device__ __forceinline__ int cand_best(const DT *cd, const uint32_t *cid, int n, DT &bd, uint32_t &bid) {
+    CandLess<DT> cl;
+    const int lane = threadIdx.x & 31;
+    int bi = -1;
+    for (int i = lane; i < n; i += 32) {
+        const DT d = cd[i];
+        const uint32_t id = cid[i];
+        if (bi < 0 || cl(bd, bid, d, id)) {
+            bd = d;
+            bid = id;
+            bi = i;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const DT od = __shfl_xor_sync(0xffffffffu, bd, m);
+        const uint32_t oid = __shfl_xor_sync(0xffffffffu, bid, m);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+        if (oi >= 0 && (bi < 0 || cl(bd, bid, od, oid))) {
+            bd = od;
+            bid = oid;
+            bi = oi;
+        }
+    }
+    return bi;
+}
+template <typename DT> __device__ __forceinline__ void cand_remove(DT *cd, uint32_t *cid, int &n, int idx) {
+    if ((threadIdx.x & 31) == 0) {
+        cd[idx] = cd[n - 1];
+        cid[idx] = cid[n - 1];
+    }
+    __syncwarp();
+    n--;
+}
+// add; on overflow first drop entries that can no longer be expanded, then spill to HBM. false = out of room.
 template <typename DT>
 __device__ __forceinline__ bool cand_insert(Work<DT> &w, int &cand_n, DT d, uint32_t id, bool can_prune, DT lower) {
-    CandLess<DT> cl;
     const int lane = threadIdx.x & 31;
     if (cand_n >= w.cand_cap) {
         if (can_prune) {
             // entries farther than the current bound are never expanded: the bound only shrinks once the
             // result set is full, and the stop rule fires before they are reached
-            int t = 0;
-            for (int i = lane; i < cand_n; i += 32) t += (w.cand_d[i] > lower) ? 1 : 0;
-            t = warp_sum(t);
-            sorted_drop_prefix(w.cand_d, w.cand_id, cand_n, t);
+            int out = 0;
+            for (int base = 0; base < cand_n; base += 32) {
+                const int i = base + lane;
+                DT td = DT(0);
+                uint32_t ti = 0;
+                bool keep = false;
+                if (i < cand_n) {
+                    td = w.cand_d[i];
+                    ti = w.cand_id[i];
+                    keep = !(td > lower);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                __syncwarp();
+                if (keep) {
+                    const int pos = out + __popc(m & ((1u << lane) - 1));
+                    w.cand_d[pos] = td;
+                    w.cand_id[pos] = ti;
+                }
+                __syncwarp();
+                out += __popc(m);
+            }
+            cand_n = out;
         }
         if (cand_n >= w.cand_cap) {
             if (!w.spill_d || w.cand_d == w.spill_d) return false;
@@ -476,7 +655,12 @@ __device__ __forceinline__ bool cand_insert(Work<DT> &w, int &cand_n, DT d, uint
             if (cand_n >= w.cand_cap) return false;
         }
     }
-    sorted_insert(w.cand_d, w.cand_id, cand_n, d, id, cl);
+    if (lane == 0) {
+        w.cand_d[cand_n] = d;
+        w.cand_id[cand_n] = id;
+    }
+    __syncwarp();
+    cand_n++;
     return true;
 }
 
@@ -517,30 +701,42 @@ __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::
         } else {
             lower = dt_max<DT>();
         }
-        sorted_insert(w.cand_d, w.cand_id, cand_n, lower, ep, cl);
+        cand_insert(w, cand_n, lower, ep, false, lower);
         if (lane == 0) test_and_set(vis, ep);
     }
     for (;;) {
         if (warp0) {
             int stop = 0;
-            if (cand_n == 0) stop = 1;
-            else if (w.cand_d[cand_n - 1] > lower && top_n >= ef) stop = 1;
+            DT bd = DT(0);
+            uint32_t bid = 0;
+            const int bi = cand_n ? cand_best(w.cand_d, w.cand_id, cand_n, bd, bid) : -1;
+            if (bi < 0) stop = 1;
+            else if (bd > lower && top_n >= ef) stop = 1;
             else {
                 if (lane == 0) {
-                    w.sc[SC_CUR] = (int)w.cand_id[cand_n - 1];
+                    w.sc[SC_CUR] = (int)bid;
                     hops++;
                 }
-                cand_n--;
+                cand_remove(w.cand_d, w.cand_id, cand_n, bi);
             }
             if (lane == 0) w.sc[SC_STOP] = stop;
         }
         __syncthreads();
         if (w.sc[SC_STOP]) break;
+        long long t0 = 0, t1 = 0, t2 = 0;
+        if (w.prof && threadIdx.x == 0) t0 = clock64();
         gather_unvisited<DT>(k, g, w, (uint32_t)w.sc[SC_CUR], level, &vis);
         __syncthreads();
+        if (w.prof && threadIdx.x == 0) t1 = clock64();
         const int n = w.sc[SC_NBN];
         eval_dists<P, true>(k, w.pivot, n, w.nb_dist, [&](int j, uint32_t &a, uint32_t &) { a = w.nb_ids[j]; });
         __syncthreads();
+        if (w.prof && threadIdx.x == 0) {
+            t2 = clock64();
+            w.prof[0] += t1 - t0;
+            w.prof[1] += t2 - t1;
+            w.prof[3] = t2; // admit starts
+        }
         if (warp0) {
             if (lane == 0) evals += n;
             bool failed = false;
@@ -575,6 +771,7 @@ __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::
                 if (lane == 0) w.sc[SC_STATUS] = 1;
                 cand_n = 0; // abandon: the caller reruns with a spill area
             }
+            if (w.prof && lane == 0) w.prof[2] += clock64() - w.prof[3];
         }
         // nb_* are rewritten only after the next __syncthreads (top of the loop)
     }
@@ -764,20 +961,22 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_range_ke
             }
             bound = (DT)((double)dyn * (1.0 + a.epsilon));
         }
-        sorted_insert(w.cand_d, w.cand_id, cand_n, ep_dist, ep, cl);
+        cand_insert(w, cand_n, ep_dist, ep, false, bound);
         if (lane == 0) test_and_set(vis, ep);
     }
     for (;;) {
         if (warp0) {
             int stop = 0;
-            if (cand_n == 0 || w.cand_d[cand_n - 1] > bound) stop = 1;
+            DT cd = DT(0);
+            uint32_t bid = 0;
+            const int bi = cand_n ? cand_best(w.cand_d, w.cand_id, cand_n, cd, bid) : -1;
+            if (bi < 0 || cd > bound) stop = 1;
             else {
-                const DT cd = w.cand_d[cand_n - 1];
                 if (lane == 0) {
-                    w.sc[SC_CUR] = (int)w.cand_id[cand_n - 1];
+                    w.sc[SC_CUR] = (int)bid;
                     hops++;
                 }
-                cand_n--;
+                cand_remove(w.cand_d, w.cand_id, cand_n, bi);
                 if (cd < dyn && cd >= radius) {
                     dyn = cd;
                     bound = (DT)((double)dyn * (1.0 + a.epsilon));
@@ -1023,6 +1222,7 @@ struct InsertArgs {
     size_t pivot_bytes;
     unsigned long long *counters;
     uint32_t *status;
+    int rv_warps; // warps that run revisits side by side (0: the CTA-wide path)
 };
 
 // Scratch of the neighbour-selection heuristic, carved after the Work arrays
@@ -1037,7 +1237,7 @@ template <typename DT> struct Heur {
     uint32_t *in_id;
     int cap, maxM;
 };
-static size_t heur_bytes(size_t dt, int cap, int maxM) {
+__host__ __device__ static size_t heur_bytes(size_t dt, int cap, int maxM) {
     auto al = [](size_t b) { return (b + 15) / 16 * 16; };
     return al(cap * dt) + 2 * al((size_t)cap * 4) + al(cap) + al((size_t)maxM * 4) +
            al((size_t)HEUR_CHUNK * (maxM + HEUR_CHUNK) * dt) + al(cap * dt) + al((size_t)cap * 4);
@@ -1095,9 +1295,9 @@ template <class P> __device__ void heuristic(const KCtx &k, const Heur<typename 
         if (ns0 >= maxM) break;
         const int C = min(HEUR_CHUNK, n - pos);
         const int cols = ns0 + C;
-        eval_dists<P, false>(k, nullptr, C * cols, h.pd, [&](int j, uint32_t &a, uint32_t &b) {
-            // pd index is a * W + col; map the dense pair index back
+        for (int j = threadIdx.x; j < C * cols; j += blockDim.x) {
             const int ca = j / cols, col = j % cols;
+            uint32_t a = INV, b = INV;
             if (col < ns0) {
                 a = h.sid[pos + ca];
                 b = h.sid[h.sel[col]];
@@ -1105,8 +1305,8 @@ template <class P> __device__ void heuristic(const KCtx &k, const Heur<typename 
                 a = h.sid[pos + ca];
                 b = h.sid[pos + col - ns0];
             }
-        });
-        // eval_dists wrote out[j] densely with row length `cols`
+            if (a != INV) h.pd[j] = P::dist_thread(k, a, b);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             int ns = ns0;
@@ -1128,7 +1328,117 @@ template <class P> __device__ void heuristic(const KCtx &k, const Heur<typename 
     }
 }
 
-template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_insert_kernel(InsertArgs a) {
+// Per-warp scratch of revisitNeighborConnections: the (<= M0 + 1) candidates, their sorted order and
+// the lower triangle of their pairwise distances.
+template <typename DT> struct RvScratch {
+    DT *cd, *sd, *D;
+    uint32_t *cid, *sid, *spos, *kept;
+    uint8_t *keep;
+};
+__host__ __device__ static size_t rv_bytes(size_t dt, int nc) {
+    auto al = [](size_t b) { return (b + 15) / 16 * 16; };
+    return 2 * al((size_t)nc * dt) + al((size_t)nc * nc * dt) + 4 * al((size_t)nc * 4) + al((size_t)nc);
+}
+template <typename DT> __device__ __forceinline__ RvScratch<DT> carve_rv(unsigned char *p, int nc) {
+    RvScratch<DT> r{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        unsigned char *q = p + off;
+        off += (bytes + 15) / 16 * 16;
+        return q;
+    };
+    r.cd = (DT *)take((size_t)nc * sizeof(DT));
+    r.sd = (DT *)take((size_t)nc * sizeof(DT));
+    r.D = (DT *)take((size_t)nc * nc * sizeof(DT));
+    r.cid = (uint32_t *)take((size_t)nc * 4);
+    r.sid = (uint32_t *)take((size_t)nc * 4);
+    r.spos = (uint32_t *)take((size_t)nc * 4);
+    r.kept = (uint32_t *)take((size_t)nc * 4);
+    r.keep = (uint8_t *)take((size_t)nc);
+    return r;
+}
+
+// revisitNeighborConnections (hnsw.h:801-868) for ONE full neighbour, by ONE warp: the neighbour's links
+// plus the new element compete for its max_M slots under getNeighborsByHeuristic2. The revisits of an
+// insertion touch disjoint link lists, so the warps of the CTA run them side by side; inside, every
+// lane evaluates whole (row, row) distances (dist_thread): all candidate-to-neighbour distances, then
+// the lower triangle of candidate-to-candidate distances, then the sequential keep/drop rule is a
+// ballot per candidate.
+template <class P>
+__device__ void warp_revisit(const KCtx &k, const GraphDev &g, const RvScratch<typename P::DT> &r, uint32_t e, uint32_t nb,
+                             typename P::DT d_nb, uint32_t *nb_rec, int maxM) {
+    using DT = typename P::DT;
+    const int lane = threadIdx.x & 31;
+    const int cnt = (int)nb_rec[0];
+    const int nc = cnt + 1;
+    for (int j = lane; j < cnt; j += 32) {
+        const uint32_t id = nb_rec[1 + j];
+        r.cid[1 + j] = id;
+        r.cd[1 + j] = P::dist_thread(k, id, nb);
+    }
+    if (lane == 0) {
+        r.cid[0] = e;
+        r.cd[0] = d_nb;
+    }
+    __syncwarp();
+    for (int i = lane; i < nc; i += 32) {
+        const DT d = r.cd[i];
+        const uint32_t id = r.cid[i];
+        int rank = 0;
+        for (int j = 0; j < nc; j++) {
+            const DT dj = r.cd[j];
+            rank += (dj < d || (dj == d && r.cid[j] < id)) ? 1 : 0;
+        }
+        r.sd[rank] = d;
+        r.sid[rank] = id;
+        r.spos[rank] = (uint32_t)i;
+        r.keep[i] = 0;
+    }
+    __syncwarp();
+    const int npairs = nc * (nc - 1) / 2;
+    for (int p = lane; p < npairs; p += 32) {
+        int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+        while (i * (i - 1) / 2 > p) i--;
+        while ((i + 1) * i / 2 <= p) i++;
+        const int j = p - i * (i - 1) / 2;
+        r.D[i * nc + j] = P::dist_thread(k, r.sid[i], r.sid[j]);
+    }
+    __syncwarp();
+    int nkeep = 0;
+    for (int i = 0; i < nc && nkeep < maxM; i++) {
+        const DT dq = r.sd[i];
+        bool bad = false;
+        for (int k0 = 0; k0 < nkeep; k0 += 32) {
+            const int kk = k0 + lane;
+            const bool b = kk < nkeep && r.D[i * nc + r.kept[kk]] < dq;
+            if (__any_sync(0xffffffffu, b)) {
+                bad = true;
+                break;
+            }
+        }
+        if (!bad) {
+            if (lane == 0) {
+                r.kept[nkeep] = (uint32_t)i;
+                r.keep[r.spos[i]] = 1;
+            }
+            nkeep++;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        // keep flags by original position: 0 = the new element, 1 + j = link j
+        int out = 0;
+        for (int j = 0; j < cnt; j++)
+            if (r.keep[1 + j]) nb_rec[1 + out++] = nb_rec[1 + j];
+        if (r.keep[0] && out < maxM) nb_rec[1 + out++] = e; // the caller appends nb to the new element's list
+        nb_rec[0] = (uint32_t)out;
+    }
+    __syncwarp();
+    (void)g;
+}
+
+template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_insert_kernel(InsertArgs a) {
     using DT = typename P::DT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int M = a.g.M, M0 = a.g.M0;
@@ -1137,6 +1447,8 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_insert_k
     const size_t work_bytes = carve_bytes(sizeof(DT), a.pivot_bytes, a.max_links, top_cap, a.cand_cap, M);
     const int hcap = max(top_cap, M0 + 1);
     Heur<DT> h = carve_heur<DT>(smem_raw + work_bytes, hcap, M0);
+    const size_t rv_off = work_bytes + heur_bytes(sizeof(DT), hcap, M0);
+    const size_t rv_each = rv_bytes(sizeof(DT), M0 + 1);
     DT *const cand_d0 = w.cand_d;
     uint32_t *const cand_id0 = w.cand_id;
     const int cand_cap0 = w.cand_cap;
@@ -1147,6 +1459,10 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_insert_k
     }
     unsigned long long evals = 0, hops = 0;
     __shared__ uint32_t s_tag;
+    __shared__ long long s_prof[8]; // 0 gather 1 eval 2 admit 3 scratch 4 search_layer total 5 select 6 connect 7 greedy+setup
+    if (threadIdx.x < 8) s_prof[threadIdx.x] = 0;
+    w.prof = s_prof;
+    long long tp = 0;
 
     for (uint32_t e = a.first; e < a.first + a.n; e++) {
         __syncthreads();
@@ -1191,7 +1507,12 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_insert_k
             w.cand_cap = cand_cap0;
             __syncthreads();
             Visited vis{a.tags, s_tag};
+            if (threadIdx.x == 0) tp = clock64();
             search_layer<P>(a.k, a.g, w, level, a.efc, nullptr, vis, evals, hops);
+            if (threadIdx.x == 0) {
+                s_prof[4] += clock64() - tp;
+                tp = clock64();
+            }
             if (w.sc[SC_STATUS]) {
                 if (threadIdx.x == 0) *a.status = 1;
                 return;
@@ -1248,61 +1569,96 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_insert_k
             }
             __syncthreads();
             uint32_t *new_rec = links_of(a.g, e, level);
-            for (int si = 0; si < ns; si++) {
-                __syncthreads();
-                const uint32_t nb = sel_id[si];
-                uint32_t *nb_rec = links_of(a.g, nb, level);
-                if (threadIdx.x == 0) {
-                    int action = 0; // 0 nothing/simple, 1 revisit, 2 stop
-                    if ((int)new_rec[0] == maxMcur) action = 2;
-                    else if (is_deleted(a.g, nb)) action = 0;
-                    else if ((int)nb_rec[0] < maxMcur) {
-                        new_rec[1 + new_rec[0]] = nb;
-                        new_rec[0]++;
-                        nb_rec[1 + nb_rec[0]] = e;
-                        nb_rec[0]++;
-                    } else action = 1;
-                    w.sc[SC_AUX1] = action;
-                }
-                __syncthreads();
-                const int action = w.sc[SC_AUX1];
-                if (action == 2) break;
-                if (action == 0) continue;
-                // ---- revisitNeighborConnections (:801-868) ----
-                const int cnt = (int)nb_rec[0];
-                const int nc = cnt + 1;
-                eval_dists<P, false>(a.k, nullptr, cnt, h.in_d + 1, [&](int j, uint32_t &x, uint32_t &y) {
-                    x = nb_rec[1 + j];
-                    y = nb;
-                });
-                for (int j = threadIdx.x; j < cnt; j += blockDim.x) h.in_id[1 + j] = nb_rec[1 + j];
-                if (threadIdx.x == 0) {
-                    h.in_d[0] = sel_d[si];
-                    h.in_id[0] = e;
-                    evals += cnt;
-                }
-                __syncthreads();
-                rank_sort<DT>(h, nc);
-                heuristic<P>(a.k, h, w.sc, nc, maxMcur);
-                if (threadIdx.x == 0) {
-                    // keep flags by original position: 0 = the new element, 1 + j = link j
-                    bool new_chosen = false;
-                    int kept = 0;
-                    // sorted position -> original position; mark in nb_ids scratch
-                    for (int i = 0; i < nc; i++) w.nb_ids[h.spos[i]] = h.keep[i];
-                    new_chosen = w.nb_ids[0] != 0;
-                    for (int j = 0; j < cnt; j++)
-                        if (w.nb_ids[1 + j]) nb_rec[1 + kept++] = nb_rec[1 + j];
-                    if ((int)new_rec[0] < maxMcur && !is_deleted(a.g, nb)) {
-                        new_rec[1 + new_rec[0]] = nb;
-                        new_rec[0]++;
-                        if (new_chosen && kept < maxMcur) nb_rec[1 + kept++] = e;
+            if (threadIdx.x == 0) {
+                s_prof[5] += clock64() - tp;
+                tp = clock64();
+            }
+            if (a.rv_warps > 0) {
+                // The selected neighbours own disjoint link lists and the new element always has room for all of
+                // them (ns <= M <= max_M), so the per-neighbour updates are independent: one warp each.
+                const int warp = threadIdx.x >> 5;
+                if (warp < a.rv_warps) {
+                    const RvScratch<DT> rv = carve_rv<DT>(smem_raw + rv_off + (size_t)warp * rv_each, M0 + 1);
+                    for (int si = warp; si < ns; si += a.rv_warps) {
+                        const uint32_t nb = sel_id[si];
+                        if (is_deleted(a.g, nb)) continue;
+                        uint32_t *nb_rec = links_of(a.g, nb, level);
+                        if ((int)nb_rec[0] < maxMcur) {
+                            if ((threadIdx.x & 31) == 0) {
+                                nb_rec[1 + nb_rec[0]] = e;
+                                nb_rec[0]++;
+                            }
+                            __syncwarp();
+                        } else {
+                            warp_revisit<P>(a.k, a.g, rv, e, nb, sel_d[si], nb_rec, maxMcur);
+                        }
                     }
-                    nb_rec[0] = (uint32_t)kept;
                 }
                 __syncthreads();
+                if (threadIdx.x == 0) {
+                    uint32_t c = 0;
+                    for (int si = 0; si < ns && (int)c < maxMcur; si++)
+                        if (!is_deleted(a.g, sel_id[si])) new_rec[1 + c++] = sel_id[si];
+                    new_rec[0] = c;
+                }
+            } else {
+                for (int si = 0; si < ns; si++) {
+                    __syncthreads();
+                    const uint32_t nb = sel_id[si];
+                    uint32_t *nb_rec = links_of(a.g, nb, level);
+                    if (threadIdx.x == 0) {
+                        int action = 0; // 0 nothing/simple, 1 revisit, 2 stop
+                        if ((int)new_rec[0] == maxMcur) action = 2;
+                        else if (is_deleted(a.g, nb)) action = 0;
+                        else if ((int)nb_rec[0] < maxMcur) {
+                            new_rec[1 + new_rec[0]] = nb;
+                            new_rec[0]++;
+                            nb_rec[1 + nb_rec[0]] = e;
+                            nb_rec[0]++;
+                        } else action = 1;
+                        w.sc[SC_AUX1] = action;
+                    }
+                    __syncthreads();
+                    const int action = w.sc[SC_AUX1];
+                    if (action == 2) break;
+                    if (action == 0) continue;
+                    // ---- revisitNeighborConnections (:801-868) ----
+                    const int cnt = (int)nb_rec[0];
+                    const int nc = cnt + 1;
+                    eval_dists<P, false>(a.k, nullptr, cnt, h.in_d + 1, [&](int j, uint32_t &x, uint32_t &y) {
+                        x = nb_rec[1 + j];
+                        y = nb;
+                    });
+                    for (int j = threadIdx.x; j < cnt; j += blockDim.x) h.in_id[1 + j] = nb_rec[1 + j];
+                    if (threadIdx.x == 0) {
+                        h.in_d[0] = sel_d[si];
+                        h.in_id[0] = e;
+                        evals += cnt;
+                    }
+                    __syncthreads();
+                    rank_sort<DT>(h, nc);
+                    heuristic<P>(a.k, h, w.sc, nc, maxMcur);
+                    if (threadIdx.x == 0) {
+                        // keep flags by original position: 0 = the new element, 1 + j = link j
+                        bool new_chosen = false;
+                        int kept = 0;
+                        // sorted position -> original position; mark in nb_ids scratch
+                        for (int i = 0; i < nc; i++) w.nb_ids[h.spos[i]] = h.keep[i];
+                        new_chosen = w.nb_ids[0] != 0;
+                        for (int j = 0; j < cnt; j++)
+                            if (w.nb_ids[1 + j]) nb_rec[1 + kept++] = nb_rec[1 + j];
+                        if ((int)new_rec[0] < maxMcur && !is_deleted(a.g, nb)) {
+                            new_rec[1 + new_rec[0]] = nb;
+                            new_rec[0]++;
+                            if (new_chosen && kept < maxMcur) nb_rec[1 + kept++] = e;
+                        }
+                        nb_rec[0] = (uint32_t)kept;
+                    }
+                    __syncthreads();
+                }
             }
             __syncthreads();
+            if (threadIdx.x == 0) s_prof[6] += clock64() - tp;
             if (threadIdx.x == 0) w.sc[SC_CUR] = w.sc[SC_AUX3];
             __syncthreads();
         }
@@ -1316,6 +1672,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_insert_k
     if (threadIdx.x == 0 && a.counters) {
         atomicAdd(&a.counters[0], evals);
         atomicAdd(&a.counters[1], hops);
+        for (int i = 0; i < 8; i++) a.counters[2 + i] = (unsigned long long)s_prof[i];
     }
 }
 
@@ -1339,6 +1696,7 @@ struct vsgpu_hnsw {
     unsigned long long *counters = nullptr; // [0] evals [1] hops
     uint32_t *status = nullptr;
     unsigned long long last_evals = 0, last_hops = 0;
+    unsigned long long last_prof[8] = {0};
     float last_ms = 0;
     uint32_t host_tag = 0;
 };
@@ -1375,10 +1733,15 @@ template <typename F> static int dispatch_policy(const vsgpu_store *s, F &&f) {
     if (p.kind == CK_INT) return s->type == VSGPU_UINT8 ? f.template operator()<PolInt<true>>() : f.template operator()<PolInt<false>>();
     if (p.kind == CK_SEQ) return s->type == VSGPU_FLOAT64 ? f.template operator()<PolSeq<double>>() : f.template operator()<PolSeq<float>>();
     if (s->type == VSGPU_FLOAT64)
-        return l2 ? f.template operator()<PolChain<double, 16, false, true>>() : f.template operator()<PolChain<double, 16, false, false>>();
-    if (p.kind == CK_BF16_DP) return f.template operator()<PolChain<float, 16, true, false>>();
-    if (p.kind == CK_BF16_VBMI2) return f.template operator()<PolChain<float, 16, false, true>>();
-    return l2 ? f.template operator()<PolChain<float, 32, false, true>>() : f.template operator()<PolChain<float, 32, false, false>>();
+        return l2 ? f.template operator()<PolChain<double, 16, false, true, VSGPU_FLOAT64>>()
+                  : f.template operator()<PolChain<double, 16, false, false, VSGPU_FLOAT64>>();
+    if (p.kind == CK_BF16_DP) return f.template operator()<PolChain<float, 16, true, false, VSGPU_BFLOAT16>>();
+    if (p.kind == CK_BF16_VBMI2) return f.template operator()<PolChain<float, 16, false, true, VSGPU_BFLOAT16>>();
+    if (s->type == VSGPU_FLOAT16)
+        return l2 ? f.template operator()<PolChain<float, 32, false, true, VSGPU_FLOAT16>>()
+                  : f.template operator()<PolChain<float, 32, false, false, VSGPU_FLOAT16>>();
+    return l2 ? f.template operator()<PolChain<float, 32, false, true, VSGPU_FLOAT32>>()
+              : f.template operator()<PolChain<float, 32, false, false, VSGPU_FLOAT32>>();
 }
 
 template <typename T> static int regrow(T *&p, size_t old_n, size_t new_n, cudaStream_t st, bool zero) {
@@ -1444,7 +1807,7 @@ vsgpu_hnsw *vsgpu_hnsw_create(vsgpu_store *s, size_t M, size_t ef_construction) 
     g->M0 = (int)(2 * M);
     g->efc = (int)std::max(ef_construction, M);
     bool ok = cudaMalloc(&g->state, 2 * sizeof(int)) == cudaSuccess;
-    ok = ok && cudaMalloc(&g->counters, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&g->counters, 16 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&g->status, sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&g->tag_counter, sizeof(uint32_t)) == cudaSuccess;
     if (ok) {
@@ -1512,7 +1875,7 @@ int vsgpu_hnsw_insert(vsgpu_hnsw *g, size_t n, const uint32_t *levels) {
         g->host_tag = 0;
     }
     VS_CUDA(cudaMemsetAsync(g->status, 0, 4, s->stream));
-    VS_CUDA(cudaMemsetAsync(g->counters, 0, 16, s->stream));
+    VS_CUDA(cudaMemsetAsync(g->counters, 0, 128, s->stream));
     VS_CUDA(cudaStreamSynchronize(s->stream)); // offs goes out of scope
     const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
     VS_TRY(ensure_scratch(s, g->spill, (g->capacity + 1) * (dt + 4)));
@@ -1532,8 +1895,13 @@ int vsgpu_hnsw_insert(vsgpu_hnsw *g, size_t n, const uint32_t *levels) {
     a.status = g->status;
     const int rc = dispatch_policy(s, [&]<class P>() -> int {
         a.pivot_bytes = P::pivot_bytes(s);
-        const size_t smem = carve_bytes(dt, a.pivot_bytes, a.max_links, a.efc + 1, a.cand_cap, g->M) +
-                            heur_bytes(dt, std::max(a.efc + 1, g->M0 + 1), g->M0);
+        size_t smem = carve_bytes(dt, a.pivot_bytes, a.max_links, a.efc + 1, a.cand_cap, g->M) +
+                      heur_bytes(dt, std::max(a.efc + 1, g->M0 + 1), g->M0);
+        const size_t rv_each = rv_bytes(dt, g->M0 + 1);
+        a.rv_warps = 0;
+        if (smem < smem_limit(s->device)) a.rv_warps = (int)std::min<size_t>(HNSW_THREADS / 32, (smem_limit(s->device) - smem) / rv_each);
+        if (const char *ev = getenv("VSGPU_HNSW_RV_WARPS")) a.rv_warps = std::min(a.rv_warps, std::max(0, atoi(ev))); // tests: force the CTA-wide path
+        smem += (size_t)a.rv_warps * rv_each;
         if (smem > smem_limit(s->device)) {
             set_error("vsgpu_hnsw_insert: efConstruction / dim too large for the shared-memory builder");
             return (int)VSGPU_ERR_ARG;
@@ -1548,13 +1916,17 @@ int vsgpu_hnsw_insert(vsgpu_hnsw *g, size_t n, const uint32_t *levels) {
     });
     VS_TRY(rc);
     uint32_t st = 0;
-    unsigned long long ctr[2] = {0, 0};
+    unsigned long long ctr[10] = {0};
     VS_CUDA(cudaMemcpyAsync(&st, g->status, 4, cudaMemcpyDeviceToHost, s->stream));
-    VS_CUDA(cudaMemcpyAsync(ctr, g->counters, 16, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(ctr, g->counters, 80, cudaMemcpyDeviceToHost, s->stream));
     VS_CUDA(cudaStreamSynchronize(s->stream));
     cudaEventElapsedTime(&g->last_ms, s->ev0, s->ev1);
     g->last_evals = ctr[0];
     g->last_hops = ctr[1];
+    for (int i = 0; i < 8; i++) g->last_prof[i] = ctr[2 + i];
+    if (getenv("VSGPU_HNSW_PROFILE"))
+        fprintf(stderr, "[vsgpu_hnsw_insert] n=%zu ms=%.2f evals=%llu hops=%llu cycles: gather=%llu eval=%llu admit=%llu search=%llu select=%llu connect=%llu\n", n,
+                g->last_ms, ctr[0], ctr[1], ctr[2], ctr[3], ctr[4], ctr[6], ctr[7], ctr[8]);
     if (st != 0) {
         set_error("vsgpu_hnsw_insert: candidate set overflow");
         return VSGPU_ERR_OVERFLOW;
@@ -1728,7 +2100,7 @@ int vsgpu_hnsw_topk_device(vsgpu_hnsw *g, const void *queries, size_t nq, size_t
     VS_TRY(stage_queries_device(s, queries, nq, qstride, &q, &qs, &qn));
     VS_TRY(ensure_scratch(s, g->misc, nq * 4 + 256));
     uint32_t *status = (uint32_t *)g->misc.ptr;
-    VS_CUDA(cudaMemsetAsync(g->counters, 0, 16, s->stream));
+    VS_CUDA(cudaMemsetAsync(g->counters, 0, 128, s->stream));
     VS_CUDA(cudaEventRecord(s->ev0, s->stream));
     VS_TRY(hnsw_search_core(g, q, nq, qs, qn, k, ef, false, 0, 0, 0, out_ids, out_scores, out_labels, out_counts, nullptr,
                             status, false));
@@ -1830,7 +2202,7 @@ int vsgpu_hnsw_range(vsgpu_hnsw *g, const void *query, double radius, double eps
     uint32_t *d_id = (uint32_t *)(d_sc + al(capd * dt));
     unsigned long long *d_cnt = (unsigned long long *)((uint8_t *)d_id + al(capd * 4));
     uint32_t *d_status = (uint32_t *)(d_cnt + 1);
-    VS_CUDA(cudaMemsetAsync(g->counters, 0, 16, s->stream));
+    VS_CUDA(cudaMemsetAsync(g->counters, 0, 128, s->stream));
     unsigned long long cnt = 0;
     uint32_t st = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -1994,7 +2366,7 @@ int vsgpu_hnsw_iter_next(vsgpu_hnsw_iter *it, size_t n_res, size_t label_count, 
     a.out_labels = d_lab;
     a.out_count = d_cnt;
     a.counters = g->counters;
-    VS_CUDA(cudaMemsetAsync(g->counters, 0, 16, s->stream));
+    VS_CUDA(cudaMemsetAsync(g->counters, 0, 128, s->stream));
     const int rc = dispatch_policy(s, [&]<class P>() -> int {
         a.pivot_bytes = P::pivot_bytes(s);
         const size_t smem = carve_bytes(dt, a.pivot_bytes, a.max_links, 1, 1, 0);

@@ -18,6 +18,7 @@
 // Roofline: HBM. Algorithmic bytes per launch = n * dim * sizeof(T) + nq * n * 4 (scores out).
 #include "vsgpu_dist.cuh"
 #include <algorithm>
+#include <cuda.h>
 
 namespace vsgpu {
 
@@ -44,13 +45,17 @@ __device__ __forceinline__ bool bar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    const long long t0 = clock64();
     while (!bar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap(); // a lost arrival must not hang the device
     }
 }
-// TMA bulk copy global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+// TMA tile copy global -> shared ([box rows x box columns] of the row-major store), completion counted in
+// bytes on `bar`; rows past the end of the store are zero-filled by the engine
+__device__ __forceinline__ void tma_tile(void *dst, const CUtensorMap *map, uint64_t *bar, int col, int row) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(map), "r"(smem_addr(bar)), "r"(col), "r"(row)
                  : "memory");
 }
 
@@ -97,7 +102,8 @@ template <> __device__ __forceinline__ float elem_to_float<float>(float v) { ret
 template <> __device__ __forceinline__ float elem_to_float<__half>(__half v) { return __half2float(v); }
 
 // QP = query pairs per pass (2, 4 or 8)
-template <typename ET, int QP, bool L2> __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(ScanTmaArgs a) {
+template <typename ET, int QP, bool L2>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const __grid_constant__ CUtensorMap map, ScanTmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int QC = 2 * QP;
     constexpr int V = ROWS_PER_WARP * QC;
@@ -130,24 +136,17 @@ template <typename ET, int QP, bool L2> __global__ void __launch_bounds__(SCAN_T
 
     const size_t ntiles = (a.n + TILE_ROWS - 1) / TILE_ROWS;
     if (warp == CONSUMER_WARPS) {
-        // ---- producer: one TMA bulk copy per (row, column chunk) ----
-        uint32_t it = 0;
-        for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const size_t row0 = tile * TILE_ROWS;
-            for (int ch = 0; ch < nchunks; ch++, it++) {
-                const int st = it % a.nstages;
-                const uint32_t ph = (it / a.nstages) & 1;
-                bar_wait(&empty[st], ph ^ 1);
-                if (lane == 0) bar_expect_tx(&full[st], (uint32_t)stage_bytes);
-                __syncwarp();
-                unsigned char *dst = stage0 + (size_t)st * stage_bytes;
-#pragma unroll
-                for (int rr = 0; rr < TILE_ROWS / 32; rr++) {
-                    const int rl = rr * 32 + lane;
-                    size_t row = row0 + rl;
-                    if (row >= a.n) row = a.n - 1; // tail tile: duplicates, results discarded
-                    bulk_load(dst + (size_t)rl * seg_bytes, a.rows + row * a.row_stride + (size_t)ch * seg_bytes, (uint32_t)seg_bytes,
-                              &full[st]);
+        // ---- producer: one TMA tile copy per (row tile, column chunk), issued by one elected lane ----
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
+            uint32_t it = 0;
+            for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int ch = 0; ch < nchunks; ch++, it++) {
+                    const int st = it % a.nstages;
+                    const uint32_t ph = (it / a.nstages) & 1;
+                    bar_wait(&empty[st], ph ^ 1);
+                    bar_expect_tx(&full[st], (uint32_t)stage_bytes);
+                    tma_tile(stage0 + (size_t)st * stage_bytes, &map, &full[st], ch * a.kc, (int)(tile * TILE_ROWS));
                 }
             }
         }
@@ -232,13 +231,46 @@ int sm_count(int device) {
     return v;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
 template <typename ET, bool L2> int launch_t(vsgpu_store *s, ScanTmaArgs &a, size_t smem_bytes) {
+    CUtensorMap map;
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)a.dim, (cuuint64_t)a.n};
+        cuuint64_t gstride[1] = {(cuuint64_t)a.row_stride};
+        cuuint32_t box[2] = {(cuuint32_t)a.kc, (cuuint32_t)TILE_ROWS};
+        cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode_fn()(&map, sizeof(ET) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                       const_cast<uint8_t *>(a.rows), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled (scan) failed with code " + std::to_string((int)r));
+            return VSGPU_ERR_CUDA;
+        }
+    }
 #define VS_LAUNCH_TMA(QPV)                                                                                             \
     do {                                                                                                               \
         auto kern = scan_tma_kernel<ET, QPV, L2>;                                                                      \
         VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));             \
         kern<<<(unsigned)std::min<size_t>((size_t)sm_count(s->device), (a.n + TILE_ROWS - 1) / TILE_ROWS), SCAN_THREADS, \
-               smem_bytes, s->stream>>>(a);                                                                            \
+               smem_bytes, s->stream>>>(map, a);                                                                            \
     } while (0)
     if (a.nq <= 4) VS_LAUNCH_TMA(2);
     else if (a.nq <= 8) VS_LAUNCH_TMA(4);
@@ -255,7 +287,7 @@ bool tma_scan_supported(const vsgpu_store *s) {
     const ChainPlan &p = s->plan;
     if (p.kind != CK_LANES || p.G != 32 || p.prefix != 0) return false;
     if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_FLOAT16) return false;
-    return s->dim % 32 == 0 && s->dim <= 4096;
+    return s->dim % 32 == 0 && s->dim <= 4096 && encode_fn() != nullptr;
 }
 
 // scores[q * ld + id] for up to 16 queries (raw blobs on the device)
