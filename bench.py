@@ -137,6 +137,19 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel, rows, applicable):
+    """DRAM bytes (read + write) of the dominant kernel's launches in one step, from the committed ncu capture
+    (profiles/r1_traffic.json: bytes per row measured by ncu x the rows this step streams). None when the capture
+    was taken on another shape."""
+    if not applicable:
+        return None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]
+        return float(t["bytes_per_row"]) * rows
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -375,7 +388,8 @@ def main():
             flops = 2.0 * batch * n_local * dim
             ach = flops / (stl["scan_ms"] / 1e3) / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": ncu_traffic("coarse_gemm_filter_kernel", n_local, tname == "fp32" and dim == 768),
                     "kernel": "coarse_gemm_filter_kernel", "kernel_ms": stl["scan_ms"], "peak_source": peak_src + " (sustained bf16)",
                     "note": "2*B*N*d flops over the summed CUDA-event time of the step's coarse GEMM launches (one per phase)"}
         elif stl["scan_ms"] > 0:
@@ -384,8 +398,11 @@ def main():
             byts = n_local * dim * es + qc * dim * es + qc * n_local * 4
             ach = byts / (stl["scan_ms"] / 1e3) / 1e9
             peak = float(peaks.get("hbm_gbs", 6650.0))
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "kernel": "exact_scan_kernel", "kernel_ms": stl["scan_ms"], "peak_source": peak_src,
+            staged = tname in ("fp32", "fp16") and dim % 32 == 0 and not os.environ.get("VSGPU_LEGACY_SCAN")
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": ncu_traffic("scan_tma_kernel_qc16" if qc > 8 else "scan_tma_kernel_qc1", n_local,
+                                           staged and tname == "fp32" and dim == 768),
+                    "kernel": "scan_tma_kernel" if staged else "exact_scan_kernel", "kernel_ms": stl["scan_ms"], "peak_source": peak_src,
                     "note": "per launch: N*d*s + qc*d*s + qc*N*4 bytes, qc=%d queries per launch" % qc}
 
     cpu_base = None

@@ -807,6 +807,7 @@ struct SearchArgs {
     double radius, epsilon;
     unsigned long long *range_counts; // per query
     size_t range_cap;
+    int profile; // VSGPU_HNSW_PROFILE: per-phase cycle counters
 };
 
 template <typename DT> __device__ __forceinline__ Work<DT> carve(unsigned char *smem, size_t pivot_bytes, int max_links,
@@ -875,12 +876,21 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_k
         w.spill_cap = a.spill_cap;
     }
     P::load_pivot(a.k, w.pivot, a.q + q * a.q_stride, a.q_norms ? a.q_norms[q] : 0.f);
+    __shared__ long long s_prof[8]; // cycles: 0 gather 1 eval 2 admit 3 scratch 4 bottom layer 5 descent
+    if (threadIdx.x < 8) s_prof[threadIdx.x] = 0;
+    w.prof = a.profile ? s_prof : nullptr;
     __syncthreads();
     unsigned long long evals = 0, hops = 0;
     int count = 0;
+    long long tp = a.profile ? clock64() : 0;
     if (descend<P>(a.k, a.g, w, evals)) {
+        if (a.profile && threadIdx.x == 0) {
+            s_prof[5] = clock64() - tp;
+            tp = clock64();
+        }
         Visited vis{a.visited + q * a.vis_words, 0};
         search_layer<P>(a.k, a.g, w, 0, a.ef, a.labels, vis, evals, hops);
+        if (a.profile && threadIdx.x == 0) s_prof[4] = clock64() - tp;
         count = min(w.sc[SC_TOPN], a.k_out); // ascending (score, label): the k best are the first k
         for (int i = threadIdx.x; i < count; i += blockDim.x) {
             const size_t o = q * a.out_ld + i;
@@ -904,6 +914,10 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_k
         if (a.counters) {
             atomicAdd(&a.counters[0], evals);
             atomicAdd(&a.counters[1], hops);
+            if (a.profile) {
+                for (int i = 0; i < 6; i++) atomicAdd(&a.counters[2 + i], (unsigned long long)s_prof[i]);
+                atomicMax(&a.counters[8], hops);
+            }
         }
     }
 }
@@ -2049,6 +2063,7 @@ static int hnsw_search_core(vsgpu_hnsw *g, const void *q, size_t nq, size_t q_st
     a.epsilon = epsilon;
     a.range_counts = range_counts;
     a.range_cap = range_cap;
+    a.profile = getenv("VSGPU_HNSW_PROFILE") != nullptr;
     if (with_spill) {
         VS_TRY(ensure_scratch(s, g->spill, nq * (g->count + 1) * (dt + 4)));
         a.spill = g->spill.ptr;
@@ -2107,13 +2122,16 @@ int vsgpu_hnsw_topk_device(vsgpu_hnsw *g, const void *queries, size_t nq, size_t
     VS_CUDA(cudaEventRecord(s->ev1, s->stream));
     // overflowed candidate sets (pathological ties / mostly deleted graphs): redo those queries with a spill area
     std::vector<uint32_t> st(nq);
-    unsigned long long ctr[2];
+    unsigned long long ctr[10];
     VS_CUDA(cudaMemcpyAsync(st.data(), status, nq * 4, cudaMemcpyDeviceToHost, s->stream));
-    VS_CUDA(cudaMemcpyAsync(ctr, g->counters, 16, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(ctr, g->counters, 80, cudaMemcpyDeviceToHost, s->stream));
     VS_CUDA(cudaStreamSynchronize(s->stream));
     cudaEventElapsedTime(&g->last_ms, s->ev0, s->ev1);
     g->last_evals = ctr[0];
     g->last_hops = ctr[1];
+    if (getenv("VSGPU_HNSW_PROFILE"))
+        fprintf(stderr, "[vsgpu_hnsw_topk] nq=%zu ms=%.3f evals=%llu hops=%llu max_hops=%llu cycles/query: gather=%llu eval=%llu admit=%llu bottom=%llu descent=%llu\n",
+                nq, g->last_ms, ctr[0], ctr[1], ctr[8], ctr[2] / nq, ctr[3] / nq, ctr[4] / nq, ctr[6] / nq, ctr[7] / nq);
     const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
     for (size_t i = 0; i < nq; i++) {
         if (!st[i]) continue;
