@@ -128,3 +128,70 @@ def test_candidate_overflow_falls_back_to_exact(capi, port):
     assert st["fallback_queries"] > 0
     G.close()
     P.close()
+
+
+# ---- int8 / uint8: exact integer GEMM on tcgen05 kind::i8 (vsgpu_tensor_i8.cu) ----
+@pytest.mark.parametrize("vtype,dim", [(4, 512), (5, 512), (4, 100), (5, 33), (4, 1024)])
+def test_i8_pipeline_matches_integer_matmul(capi, vtype, dim):
+    """The raw TMA / kind::i8 MMA / TMEM pipeline: int32 accumulators equal the integer dot products exactly."""
+    G_ = C.CDLL(os.path.join(ROOT, "vectorsimilarity_b200", "libvsgpu.so"))
+    G_.vsgpu_debug_i8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    G_.vsgpu_last_error.restype = C.c_char_p
+    n, nq = 1000, 300
+    X = make_vectors(vtype, n, dim, seed=dim)
+    Q = make_vectors(vtype, nq, dim, seed=dim + 1)
+    G = _index(capi, vtype, dim, 1, X)
+    out = np.zeros((n - 128, nq), dtype=np.int32)
+    rc = G_.vsgpu_debug_i8(G.device_store(), Q.ctypes.data, nq, Q.strides[0], 128, n - 128, out.ctypes.data)
+    assert rc == 0, G_.vsgpu_last_error()
+    want = X[128:].astype(np.int64) @ Q.astype(np.int64).T
+    assert np.array_equal(out.astype(np.int64), want)
+    G.close()
+
+
+@pytest.mark.parametrize("vtype,metric,dim,n,k,nq", [
+    (4, 2, 512, 40000, 10, 64),      # configs[2] shape: int8 cosine d=512 K=10
+    (4, 1, 128, 40000, 100, 40),
+    (4, 0, 96, 36000, 50, 33),
+    (5, 2, 200, 40000, 10, 70),
+    (5, 0, 64, 40000, 100, 32),
+    (5, 1, 48, 33000, 25, 300),
+])
+def test_i8_tensor_path_equals_oracle(capi, port, vtype, metric, dim, n, k, nq):
+    X = make_vectors(vtype, n, dim, seed=n + dim)
+    Q = make_vectors(vtype, nq, dim, seed=n + dim + 1)
+    if metric == 2:
+        X[(X == 0).all(1), 0] = 1
+        Q[(Q == 0).all(1), 0] = 1
+    G = _index(capi, vtype, dim, metric, X)
+    P = port.PortIndex(vtype, dim, metric)
+    P.add_many(X)
+    st = _check_against(capi, G, P, Q, k, mode=2)
+    assert st["path"] == 1 and st["candidates"] > 0 and st["fallback_queries"] == 0
+    X2 = make_vectors(vtype, 700, dim, seed=5)
+    G.add_vectors(X2, first_label=n)
+    P.add_many(X2, first_label=n)
+    _check_against(capi, G, P, Q[:32], k, mode=2)
+    assert G.delete_vector(5) == P.delete(5) == 1
+    _check_against(capi, G, P, Q[:32], k, mode=2)
+    G.close()
+    P.close()
+
+
+def test_i8_tensor_path_ties_and_exact_path_agree(capi):
+    """Coarse-valued int8 rows: thousands of exact score ties at the k-th place; tensor path == exact scan."""
+    n, dim, k, nq = 60000, 64, 20, 48
+    rng = np.random.default_rng(3)
+    X = rng.integers(-2, 3, (n, dim)).astype(np.int8)
+    Q = rng.integers(-2, 3, (nq, dim)).astype(np.int8)
+    X[(X == 0).all(1), 0] = 1
+    Q[(Q == 0).all(1), 0] = 1
+    for metric in (0, 1, 2):
+        G = _index(capi, 4, dim, metric, X)
+        capi.set_topk_mode(1)
+        el, es = G.knn_batch(Q, k)
+        capi.set_topk_mode(2)
+        tl, ts = G.knn_batch(Q, k)
+        assert G.last_query_stats()["path"] == 1
+        assert np.array_equal(el, tl) and np.array_equal(es, ts), metric
+        G.close()

@@ -168,5 +168,10 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, c
                 uint32_t *out_ids, void *out_scores, uint64_t *out_labels);
 int tensor_sync_mirrors(vsgpu_store *s);
 void tensor_release(vsgpu_store *s);
+// int8 / uint8 stores: exact integer GEMM on tcgen05 kind::i8 (vsgpu_tensor_i8.cu)
+bool tensor_i8_supported(const vsgpu_store *s, size_t nq, size_t k);
+int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, size_t k,
+                   uint32_t *out_ids, void *out_scores, uint64_t *out_labels);
+void tensor_i8_release(vsgpu_store *s);
 
 } // namespace vsgpu

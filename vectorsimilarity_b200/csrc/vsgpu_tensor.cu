@@ -15,8 +15,7 @@
 // The result is exactly the exact path's result: the bound makes the candidate set a superset of
 // the true top-k (proof in DESIGN.md §5.3), and a query whose candidate buffer overflows is redone
 // on the exact path.
-#include "vsgpu_internal.cuh"
-#include <cuda.h>
+#include "vsgpu_tc.cuh"
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <cmath>
@@ -47,71 +46,6 @@ struct GemmSmem {
     uint32_t tmem_base;
 };
 
-// ---- PTX wrappers --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "setp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B operand descriptor: rows at a 128-byte pitch, 8-row groups 1024 bytes apart
-// (SBO = 64 x 16 B), LBO unused (1), descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3fff) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 // kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), both
 // K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -438,24 +372,7 @@ template <typename T> __global__ void fill_t(T *p, T v, size_t n) {
 
 // ------------------------------------------------------------------------------------------------
 // host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-        cudaGetLastError();
-    }
-    return fn;
-}
+static EncodeTiledFn encode_fn() { return tc_encode_fn(); }
 
 static int make_map(CUtensorMap *map, const void *base, size_t rows, size_t dim_elems, size_t stride_bytes, int box_rows) {
     EncodeTiledFn fn = encode_fn();
@@ -492,6 +409,10 @@ static TensorState *state(vsgpu_store *s) {
 }
 
 void tensor_release(vsgpu_store *s) {
+    if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8) {
+        tensor_i8_release(s);
+        return;
+    }
     auto *t = (TensorState *)s->tmap_cache;
     if (t) {
         if (t->max_l2_bits) cudaFree(t->max_l2_bits);
@@ -510,6 +431,7 @@ static bool g_tensor_disabled = false;
 
 bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k) {
     if (g_tensor_disabled) return false;
+    if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8) return tensor_i8_supported(s, nq, k);
     if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16) return false;
     if (s->metric != VSGPU_IP && s->metric != VSGPU_COSINE) return false;
     if (s->plan.kind == CK_SEQ) return false;
@@ -588,7 +510,8 @@ static int launch_gemm(vsgpu_store *s, TensorState *t, const CUtensorMap &ma, co
 
 int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_stride, const float *q_norms, size_t k,
                 uint32_t *out_ids, void *out_scores, uint64_t *out_labels) {
-    (void)q_norms;
+    if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8)
+        return tensor_i8_topk(s, q_dev, nq_all, q_stride, q_norms, k, out_ids, out_scores, out_labels);
     TensorState *t = state(s);
     VS_TRY(tensor_sync_mirrors(s));
     const size_t n = s->count;

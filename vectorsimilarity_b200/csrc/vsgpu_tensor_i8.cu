@@ -1,0 +1,595 @@
+// Tensor-core path for int8 / uint8 stores (BASELINE configs[2]: int8 Cosine, d = 512, batch 4096).
+//
+// For 8-bit integers the batched scan is an EXACT integer GEMM: tcgen05.mma kind::i8 accumulates
+// sum(a_i * b_i) in int32 in TMEM, which is precisely the integer the reference's VNNI kernels compute
+// (spaces/IP/IP_AVX512F_BW_VL_VNNI_INT8.h:27-77, L2/L2_AVX512F_BW_VL_VNNI_INT8.h:28-65, the uint8
+// twins). So there is no coarse pass and no re-rank here: the epilogue turns "score <= T_q" into a
+// test on the accumulator (dot >= c_q * row_mul + row_add, loosened by a few ulps so the admitted
+// set is a superset), the few admitted (row, dot) pairs are scored with the reference's exact final
+// formula — float(1 - dot), float(aa + qq - 2 dot), 1.0f - float(dot) / (norm_a * norm_b) with .rn
+// intrinsics (vsgpu_dist.cuh int_score) — and merged into the running top-k by (score, id).
+//
+// Pipeline = the bf16 kernel's (vsgpu_tensor.cu): TMA 128B-swizzled [128 x 128 B] row boxes and
+// [256 x 128 B] query boxes, 4-stage mbarrier ring, one MMA-issuing thread, 128 x 256 int32
+// accumulator double-buffered in TMEM, 8 epilogue warps. Rows are scanned in geometric phases; after
+// each phase one block per query merges the phase's candidates and tightens T_q.
+#include "vsgpu_dist.cuh"
+#include "vsgpu_tc.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace vsgpu {
+
+namespace {
+
+constexpr int BM = 128;           // rows per tile
+constexpr int BN = 256;           // queries per tile
+constexpr int BKB = 128;          // bytes (= int8 elements) per k-block: one 128-byte swizzle row
+constexpr int UKB = 32;           // bytes per tcgen05.mma kind::i8 (K = 32)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BKB; // 16 KB
+constexpr int B_BYTES = BN * BKB; // 32 KB
+constexpr int MAX_NQ = 4096;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+constexpr uint32_t CAND_CAP = 3072; // candidates per query and phase
+constexpr uint32_t RUN_CAP = 1024;  // k <= RUN_CAP
+
+struct I8Smem {
+    uint8_t a[STAGES][A_BYTES];
+    uint8_t b[STAGES][B_BYTES];
+    float cq[MAX_NQ];
+    uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+struct I8Args {
+    uint32_t row0, row_end, nq, n_qtiles, k_blocks, idesc;
+    const float *cq;      // [nq] admit when float(dot) >= cq * row_mul + row_add (loosened)
+    const float *row_mul; // per row, or NULL = 1 (cosine: the stored norm)
+    const float *row_add; // per row, or NULL = 0 (L2: sum a^2 / 2)
+    uint32_t *cnt;        // [nq]
+    uint2 *cand;          // [nq][CAND_CAP] (row id, dot)
+    int *dump;            // debug: [rows][dump_ld] raw accumulators
+    uint32_t dump_ld;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, I8Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    I8Smem &sm = *reinterpret_cast<I8Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t m_tiles = (g.row_end - g.row0 + BM - 1) / BM;
+    const uint32_t items = m_tiles * g.n_qtiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.tfull[i], 1);
+            mbar_init(&sm.tempty[i], EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x)
+        sm.cq[i] = (i < g.nq && g.cq) ? g.cq[i] : __int_as_float(0x7f800000);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) { // ===== TMA producer =====
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
+                const int row = (int)(g.row0 + mt * BM), qrow = (int)(nt * BN);
+                for (uint32_t kb = 0; kb < g.k_blocks; kb++) {
+                    mbar_wait(&sm.empty[stage], phase ^ 1);
+                    mbar_expect_tx(&sm.full[stage], A_BYTES + B_BYTES);
+                    tma_load_2d(sm.a[stage], &map_a, &sm.full[stage], (int)(kb * BKB), row);
+                    tma_load_2d(sm.b[stage], &map_b, &sm.full[stage], (int)(kb * BKB), qrow);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) { // ===== MMA issuer =====
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+                mbar_wait(&sm.tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + as * BN;
+                for (uint32_t kb = 0; kb < g.k_blocks; kb++) {
+                    mbar_wait(&sm.full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc(smem_u32(sm.a[stage]));
+                    const uint64_t bdesc = make_desc(smem_u32(sm.b[stage]));
+#pragma unroll
+                    for (int k = 0; k < BKB / UKB; k++) // 32 bytes (2 x 16 B) along K inside the swizzled row
+                        tc_mma_i8(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), g.idesc, (kb | (uint32_t)k) != 0);
+                    tc_commit(&sm.empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&sm.tfull[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM int32 -> bound test -> (row, dot) candidates =====
+        const int ew = warp - 4;
+        const uint32_t quad = (uint32_t)(warp & 3);
+        const uint32_t half = (uint32_t)(ew >> 2);
+        uint32_t as = 0, aphase = 0;
+        for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
+            const uint32_t row = g.row0 + mt * BM + quad * 32 + (uint32_t)lane;
+            const bool row_ok = row < g.row_end;
+            const float rm = (row_ok && g.row_mul) ? g.row_mul[row] : 1.0f;
+            const float ra = (row_ok && g.row_add) ? g.row_add[row] : 0.0f;
+            mbar_wait(&sm.tfull[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t col = half * 128 + c * 32;
+                uint32_t r[32];
+                tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
+                tc_wait_ld();
+                const float *cq = &sm.cq[nt * BN + col];
+                if (g.dump) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const uint32_t q = nt * BN + col + j;
+                            if (q < g.nq) g.dump[(size_t)(row - g.row0) * g.dump_ld + q] = (int)r[j];
+                        }
+                    }
+                } else if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float f = __int2float_rn((int)r[j]);
+                        const float bound = fmaf(cq[j], rm, ra);
+                        // superset of {score <= T_q}: a few ulps of every quantity involved, plus 2 dot units
+                        // (padded query columns carry c_q = +inf: never admitted)
+                        if (bound < 3.0e38f && f + (fabsf(f) + fabsf(bound) + fabsf(ra)) * 3.8146973e-6f + 2.0f >= bound) {
+                            const uint32_t q = nt * BN + col + j;
+                            const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
+                            if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = make_uint2(row, r[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&sm.tempty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    }
+}
+
+// ---- per-row / per-query integer side data --------------------------------------------------------
+// row_sq[i] = sum a^2 (exact, u32: 255^2 * dim < 2^32 for dim < 66 051), row_add[i] = row_sq / 2 as float
+__global__ void i8_row_sq_kernel(const uint8_t *__restrict__ rows, size_t row_stride, int chunks, int is_unsigned, size_t first,
+                                 size_t n, uint32_t *__restrict__ row_sq, float *__restrict__ row_add) {
+    const size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const size_t ng = ((size_t)gridDim.x * blockDim.x) >> 3;
+    const int c = threadIdx.x & 7;
+    for (size_t i = gid; i < (n + ng - 1) / ng * ng; i += ng) {
+        const bool ok = i < n;
+        unsigned long long t = 0;
+        if (ok) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(rows + (first + i) * row_stride);
+            for (int ch = c; ch < chunks; ch += 8) {
+                const uint4 v = __ldg(rp + ch);
+                if (is_unsigned) t += (unsigned)dot4<true>(v.x, v.x, 0) + (unsigned)dot4<true>(v.y, v.y, 0) + (unsigned)dot4<true>(v.z, v.z, 0) + (unsigned)dot4<true>(v.w, v.w, 0);
+                else t += dot4<false>(v.x, v.x, 0) + dot4<false>(v.y, v.y, 0) + dot4<false>(v.z, v.z, 0) + dot4<false>(v.w, v.w, 0);
+            }
+        }
+        for (int w = 4; w >= 1; w >>= 1) t += __shfl_xor_sync(0xffffffffu, t, w);
+        if (ok && c == 0) {
+            row_sq[first + i] = (uint32_t)t;
+            row_add[first + i] = 0.5f * (float)t;
+        }
+    }
+}
+__global__ void i8_query_sq_kernel(const uint8_t *__restrict__ q, size_t q_stride, int chunks, int is_unsigned, size_t nq,
+                                   long long *__restrict__ qq) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 *qp = reinterpret_cast<const uint4 *>(q + i * q_stride);
+        long long t = 0;
+        for (int ch = 0; ch < chunks; ch++) {
+            const uint4 v = qp[ch];
+            if (is_unsigned) t += (long long)(unsigned)dot4<true>(v.x, v.x, 0) + (unsigned)dot4<true>(v.y, v.y, 0) + (long long)(unsigned)dot4<true>(v.z, v.z, 0) + (unsigned)dot4<true>(v.w, v.w, 0);
+            else t += (long long)dot4<false>(v.x, v.x, 0) + dot4<false>(v.y, v.y, 0) + (long long)dot4<false>(v.z, v.z, 0) + dot4<false>(v.w, v.w, 0);
+        }
+        qq[i] = t;
+    }
+}
+
+__device__ __forceinline__ uint32_t score_key(float v) {
+    uint32_t u = __float_as_uint(v);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu; // NaN last
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct I8MergeArgs {
+    uint32_t nq, k;
+    int metric;
+    uint2 *run;         // [nq][RUN_CAP] (row id, exact score bits), ascending (score, id)
+    uint32_t *run_cnt;  // [nq]
+    uint32_t *cnt;      // [nq] candidates of this phase (reset here)
+    const uint2 *cand;  // [nq][CAND_CAP] (row id, dot)
+    const uint32_t *row_sq;
+    const float *row_norm;
+    const long long *qq;
+    const float *q_norm;
+    float *cq;          // [nq] next phase's admission constant
+    uint32_t *overflow; // [nq]
+    unsigned long long *total_cand;
+};
+
+// One block per query: exact scores of this phase's candidates, merge with the running top-k by
+// (score, id), tighten the admission constant.
+__global__ void __launch_bounds__(1024) i8_merge_kernel(I8MergeArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t q = blockIdx.x;
+    uint32_t cnt = a.cnt[q];
+    const uint32_t rcnt = a.run_cnt[q];
+    if (threadIdx.x == 0 && cnt) atomicAdd(a.total_cand, (unsigned long long)min(cnt, CAND_CAP));
+    if (cnt > CAND_CAP) {
+        if (threadIdx.x == 0) a.overflow[q] = 1;
+        cnt = CAND_CAP;
+    }
+    const uint32_t total = rcnt + cnt;
+    uint32_t P = 32;
+    while (P < total) P <<= 1;
+    uint32_t *sk = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *si = sk + P;
+    const long long qq = a.qq[q];
+    const float qn = a.q_norm ? a.q_norm[q] : 0.f;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        uint32_t key = 0xffffffffu, id = 0xffffffffu;
+        if (i < rcnt) {
+            const uint2 e = a.run[(size_t)q * RUN_CAP + i];
+            id = e.x;
+            key = score_key(__uint_as_float(e.y));
+        } else if (i < total) {
+            const uint2 e = a.cand[(size_t)q * CAND_CAP + (i - rcnt)];
+            id = e.x;
+            const long long dot = (long long)(int)e.y;
+            const long long aa = a.metric == VSGPU_L2 ? (long long)a.row_sq[id] : 0;
+            const float rn = a.row_norm ? a.row_norm[id] : 0.f;
+            key = score_key(int_score(a.metric, dot, aa, qq, rn, qn));
+        }
+        if (i < total && key == 0xffffffffu) key = 0xfffffffeu; // real entries ahead of the padding
+        sk[i] = key;
+        si[i] = id;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const uint32_t ka = sk[lo], kb = sk[hi], ia = si[lo], ib = si[hi];
+                const bool gt = ka > kb || (ka == kb && ia > ib);
+                if (gt == asc) { sk[lo] = kb; sk[hi] = ka; si[lo] = ib; si[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t keep = min(total, a.k);
+    auto key_score = [](uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); };
+    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x)
+        a.run[(size_t)q * RUN_CAP + i] = make_uint2(si[i], __float_as_uint(sk[i] >= 0xfffffffeu ? __int_as_float(0x7fc00000) : key_score(sk[i])));
+    if (threadIdx.x == 0) {
+        a.run_cnt[q] = keep;
+        a.cnt[q] = 0;
+        float cq = -__int_as_float(0x7f800000); // admit everything until k rows are known
+        if (total >= a.k && sk[a.k - 1] < 0xfffffffeu) {
+            const float T = key_score(sk[a.k - 1]);
+            // score <= T  <=>  dot >= c_q * row_mul + row_add, each loosened by a few ulps of its terms
+            if (a.metric == VSGPU_COSINE) cq = qn * ((1.0f - T) - 3.8146973e-6f);          // dot >= (1 - T) |a| |q|
+            else if (a.metric == VSGPU_IP) cq = (1.0f - T) - fabsf(T) * 9.5367432e-7f - 1.0f; // dot >= 1 - T
+            else cq = 0.5f * ((float)qq - T) - (fabsf((float)qq) + fabsf(T)) * 4.7683716e-7f - 1.0f; // dot >= aa/2 + (qq - T)/2
+        }
+        a.cq[q] = cq;
+    }
+}
+
+__global__ void i8_emit_kernel(const uint2 *__restrict__ run, const uint32_t *__restrict__ run_cnt, const uint64_t *__restrict__ labels,
+                               size_t nq, size_t k, uint32_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                               uint64_t *__restrict__ out_labels) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq * k; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t q = i / k, j = i % k;
+        const bool ok = j < run_cnt[q];
+        const uint2 e = ok ? run[q * RUN_CAP + j] : make_uint2(0xffffffffu, 0x7fc00000u);
+        if (out_ids) out_ids[i] = e.x;
+        if (out_scores) out_scores[i] = __uint_as_float(e.y);
+        if (out_labels) out_labels[i] = ok ? labels[e.x] : ~0ull;
+    }
+}
+
+struct I8State {
+    size_t synced = 0; // rows [0, synced) have row_sq / row_add
+    size_t cap = 0;
+    uint32_t *row_sq = nullptr;
+    float *row_add = nullptr;
+    int sms = 0;
+    bool attr_set = false;
+};
+
+int make_map_u8(CUtensorMap *map, const void *base, size_t rows, size_t dim_bytes, size_t stride_bytes, int box_rows) {
+    EncodeTiledFn fn = tc_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available");
+        return VSGPU_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)dim_bytes, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (u8) failed with code " + std::to_string((int)r));
+        return VSGPU_ERR_CUDA;
+    }
+    return VSGPU_OK;
+}
+
+size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+I8State *i8_state(vsgpu_store *s) {
+    if (!s->tmap_cache) s->tmap_cache = new I8State();
+    return (I8State *)s->tmap_cache;
+}
+
+} // namespace
+
+void tensor_i8_release(vsgpu_store *s) {
+    auto *t = (I8State *)s->tmap_cache;
+    if (!t) return;
+    if (t->row_sq) cudaFree(t->row_sq);
+    if (t->row_add) cudaFree(t->row_add);
+    delete t;
+    s->tmap_cache = nullptr;
+}
+
+bool tensor_i8_supported(const vsgpu_store *s, size_t nq, size_t k) {
+    if (s->type != VSGPU_INT8 && s->type != VSGPU_UINT8) return false;
+    if (nq < 32 || k == 0 || k > RUN_CAP) return false;
+    if (s->dim < 32 || s->dim > 33024) return false; // int32 accumulator: the reference's own cap (spaces.h:57-66)
+    if (s->count < 32768 || s->count < 16 * k) return false;
+    if (!tc_encode_fn()) return false;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, s->device);
+    return v == 10;
+}
+
+static int i8_sync_side(vsgpu_store *s, I8State *t) {
+    if (!t->sms) {
+        cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, s->device);
+        if (t->sms <= 0) t->sms = 148;
+    }
+    if (s->metric != VSGPU_L2) return VSGPU_OK;
+    if (t->cap < s->capacity) {
+        uint32_t *nsq = nullptr;
+        float *nadd = nullptr;
+        VS_CUDA(cudaMalloc(&nsq, s->capacity * 4));
+        VS_CUDA(cudaMalloc(&nadd, s->capacity * 4));
+        if (t->row_sq) cudaFree(t->row_sq);
+        if (t->row_add) cudaFree(t->row_add);
+        t->row_sq = nsq;
+        t->row_add = nadd;
+        t->cap = s->capacity;
+        t->synced = 0;
+    }
+    if (t->synced < s->count) {
+        const size_t n = s->count - t->synced;
+        const unsigned blocks = (unsigned)std::min<size_t>((n * 8 + 255) / 256, (size_t)t->sms * 16);
+        i8_row_sq_kernel<<<blocks, 256, 0, s->stream>>>(s->rows, s->row_stride, (int)(s->row_stride / 16), s->type == VSGPU_UINT8, t->synced,
+                                                       n, t->row_sq, t->row_add);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+        t->synced = s->count;
+    }
+    return VSGPU_OK;
+}
+
+static int i8_launch_gemm(vsgpu_store *s, I8State *t, const CUtensorMap &ma, const CUtensorMap &mb, I8Args &g) {
+    const size_t smem = sizeof(I8Smem) + 1024;
+    if (!t->attr_set) {
+        VS_CUDA(cudaFuncSetAttribute(i8_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        t->attr_set = true;
+    }
+    const uint32_t m_tiles = (g.row_end - g.row0 + BM - 1) / BM;
+    const unsigned grid = (unsigned)std::min<uint32_t>(m_tiles * g.n_qtiles, (uint32_t)t->sms);
+    i8_gemm_filter_kernel<<<grid, GEMM_THREADS, smem, s->stream>>>(ma, mb, g);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
+}
+
+static uint32_t i8_idesc(const vsgpu_store *s) {
+    const uint32_t fmt = s->type == VSGPU_INT8 ? 1u : 0u; // S8: 0 unsigned, 1 signed
+    // D = S32 (bits 4-5 = 2), A/B formats at bits 7-9 / 10-12, K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+    return (2u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// q_dev: queries packed at the store's row stride (zero padded), q_norms for cosine (stage_queries_device)
+int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_stride, const float *q_norms, size_t k,
+                   uint32_t *out_ids, void *out_scores, uint64_t *out_labels) {
+    I8State *t = i8_state(s);
+    VS_TRY(i8_sync_side(s, t));
+    const size_t n = s->count;
+    const bool uns = s->type == VSGPU_UINT8;
+    CUtensorMap map_a;
+    VS_TRY(make_map_u8(&map_a, s->rows, n, s->dim, s->row_stride, BM));
+    std::vector<std::pair<uint32_t, uint32_t>> phases;
+    {
+        size_t s0 = std::max<size_t>(BM, std::min<size_t>(CAND_CAP, 2048) / BM * BM);
+        s0 = std::max(s0, (std::min<size_t>(2 * k, CAND_CAP) + BM - 1) / BM * BM);
+        size_t a = 0, b = std::min(n, s0);
+        const double growth = std::max(3.0, std::min(8.0, (double)CAND_CAP / (2.5 * (double)k)));
+        while (a < n) {
+            phases.emplace_back((uint32_t)a, (uint32_t)b);
+            a = b;
+            size_t nb = (size_t)((double)b * growth) / BM * BM;
+            b = std::min(n, std::max(nb, a + BM));
+        }
+    }
+    VS_CUDA(cudaEventRecord(s->ev2, s->stream));
+    for (size_t q0 = 0; q0 < nq_all; q0 += MAX_NQ) {
+        const size_t nq = std::min<size_t>(MAX_NQ, nq_all - q0);
+        const uint8_t *qp = (const uint8_t *)q_dev + q0 * q_stride;
+        const float *qn = q_norms ? q_norms + q0 : nullptr;
+        const size_t nq_pad = (nq + BN - 1) / BN * BN;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+        const size_t o_cq = take(nq * 4), o_cnt = take(nq * 4), o_ovf = take(nq * 4), o_rcnt = take(nq * 4), o_qq = take(nq * 8),
+                     o_tot = take(8), o_run = take(nq * RUN_CAP * 8), o_cand = take(nq * CAND_CAP * 8);
+        VS_TRY(ensure_scratch(s, s->cand, off));
+        uint8_t *base = (uint8_t *)s->cand.ptr;
+        float *cq = (float *)(base + o_cq);
+        uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = (uint32_t *)(base + o_ovf), *rcnt = (uint32_t *)(base + o_rcnt);
+        long long *qq = (long long *)(base + o_qq);
+        auto *tot = (unsigned long long *)(base + o_tot);
+        uint2 *run = (uint2 *)(base + o_run), *cand = (uint2 *)(base + o_cand);
+        // cnt, ovf, rcnt, qq, tot are adjacent: clear in one go; cq = -inf (admit all) is written by the first merge,
+        // the first phase runs with cq = NULL -> +inf ... so give it -inf explicitly
+        VS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)((uint8_t *)run - (uint8_t *)cnt), s->stream));
+        {
+            std::vector<float> ninf(nq, -INFINITY);
+            VS_CUDA(cudaMemcpyAsync(cq, ninf.data(), nq * 4, cudaMemcpyHostToDevice, s->stream));
+            VS_CUDA(cudaStreamSynchronize(s->stream));
+        }
+        i8_query_sq_kernel<<<(unsigned)std::min<size_t>((nq + 127) / 128, 1024), 128, 0, s->stream>>>(qp, q_stride, (int)(s->row_stride / 16),
+                                                                                                  uns, nq, qq);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+        CUtensorMap map_b;
+        VS_TRY(make_map_u8(&map_b, qp, nq, s->dim, q_stride, BN));
+        for (size_t p = 0; p < phases.size(); p++) {
+            I8Args g{};
+            g.row0 = phases[p].first;
+            g.row_end = phases[p].second;
+            g.nq = (uint32_t)nq;
+            g.n_qtiles = (uint32_t)(nq_pad / BN);
+            g.k_blocks = (uint32_t)((s->dim + BKB - 1) / BKB);
+            g.idesc = i8_idesc(s);
+            g.cq = cq;
+            g.row_mul = s->metric == VSGPU_COSINE ? s->norms : nullptr;
+            g.row_add = s->metric == VSGPU_L2 ? t->row_add : nullptr;
+            g.cnt = cnt;
+            g.cand = cand;
+            VS_TRY(i8_launch_gemm(s, t, map_a, map_b, g));
+            I8MergeArgs m{};
+            m.nq = (uint32_t)nq;
+            m.k = (uint32_t)k;
+            m.metric = s->metric;
+            m.run = run;
+            m.run_cnt = rcnt;
+            m.cnt = cnt;
+            m.cand = cand;
+            m.row_sq = t->row_sq;
+            m.row_norm = s->metric == VSGPU_COSINE ? s->norms : nullptr;
+            m.qq = qq;
+            m.q_norm = s->metric == VSGPU_COSINE ? qn : nullptr;
+            m.cq = cq;
+            m.overflow = ovf;
+            m.total_cand = tot;
+            const size_t msm = 2 * 4096 * 4;
+            static bool mattr = false;
+            if (!mattr) {
+                VS_CUDA(cudaFuncSetAttribute(i8_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+                mattr = true;
+            }
+            i8_merge_kernel<<<(unsigned)nq, 1024, msm, s->stream>>>(m);
+            VS_CUDA(cudaGetLastError());
+            s->stats.kernel_launches++;
+        }
+        i8_emit_kernel<<<(unsigned)std::min<size_t>((nq * k + 255) / 256, 2048), 256, 0, s->stream>>>(
+            run, rcnt, s->labels, nq, k, out_ids ? out_ids + q0 * k : nullptr, out_scores ? (float *)out_scores + q0 * k : nullptr,
+            out_labels ? out_labels + q0 * k : nullptr);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+        VS_CUDA(cudaEventRecord(s->ev3, s->stream));
+        // queries whose candidate buffer overflowed (adversarial ties) are redone on the exact path
+        std::vector<uint32_t> h_ovf(nq);
+        unsigned long long h_tot = 0;
+        VS_CUDA(cudaMemcpyAsync(h_ovf.data(), ovf, nq * 4, cudaMemcpyDeviceToHost, s->stream));
+        VS_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, s->stream));
+        VS_CUDA(cudaStreamSynchronize(s->stream));
+        s->stats.candidates += h_tot;
+        const size_t ld = (n + 63) / 64 * 64;
+        for (size_t q = 0; q < nq; q++) {
+            if (!h_ovf[q]) continue;
+            s->stats.fallback_queries++;
+            VS_TRY(ensure_scratch(s, s->scores, ld * 4));
+            VS_TRY(launch_exact_scan(s, qp + q * q_stride, 1, q_stride, qn ? qn + q : nullptr, s->scores.ptr, ld));
+            VS_TRY(launch_select_topk(s, s->scores.ptr, ld, 1, n, k, k, out_ids ? out_ids + (q0 + q) * k : nullptr,
+                                      out_scores ? (float *)out_scores + (q0 + q) * k : nullptr,
+                                      out_labels ? out_labels + (q0 + q) * k : nullptr));
+        }
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s->ev2, s->ev3) == cudaSuccess) s->stats.scan_ms = ms;
+    return VSGPU_OK;
+}
+
+} // namespace vsgpu
+
+// Debug / test hook: raw int32 accumulators of rows [row0, row0 + nrows) against nq queries (HOST pointers; queries
+// are dim bytes each; out is [nrows][nq] int32). Exercises the production TMA / kind::i8 MMA / TMEM pipeline.
+extern "C" int vsgpu_debug_i8(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t row0, size_t nrows, int *out) {
+    using namespace vsgpu;
+    if (!s || !queries || !out || nq == 0 || nrows == 0 || row0 % BM != 0 || row0 + nrows > s->count || nq > MAX_NQ ||
+        (s->type != VSGPU_INT8 && s->type != VSGPU_UINT8)) {
+        set_error("vsgpu_debug_i8: bad arguments");
+        return VSGPU_ERR_ARG;
+    }
+    VS_CUDA(cudaSetDevice(s->device));
+    I8State *t = i8_state(s);
+    VS_TRY(i8_sync_side(s, t));
+    uint8_t *d_q = nullptr;
+    int *dump = nullptr;
+    VS_CUDA(cudaMalloc(&d_q, nq * s->row_stride));
+    VS_CUDA(cudaMalloc(&dump, nrows * nq * 4));
+    VS_CUDA(cudaMemset(d_q, 0, nq * s->row_stride));
+    VS_CUDA(cudaMemcpy2D(d_q, s->row_stride, queries, qstride, s->row_bytes, nq, cudaMemcpyHostToDevice));
+    VS_CUDA(cudaMemsetAsync(dump, 0, nrows * nq * 4, s->stream));
+    CUtensorMap map_a, map_b;
+    VS_TRY(make_map_u8(&map_a, s->rows, s->count, s->dim, s->row_stride, BM));
+    VS_TRY(make_map_u8(&map_b, d_q, nq, s->dim, s->row_stride, BN));
+    I8Args g{};
+    g.row0 = (uint32_t)row0;
+    g.row_end = (uint32_t)(row0 + nrows);
+    g.nq = (uint32_t)nq;
+    g.n_qtiles = (uint32_t)((nq + BN - 1) / BN);
+    g.k_blocks = (uint32_t)((s->dim + BKB - 1) / BKB);
+    g.idesc = i8_idesc(s);
+    g.dump = dump;
+    g.dump_ld = (uint32_t)nq;
+    VS_TRY(i8_launch_gemm(s, t, map_a, map_b, g));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    VS_CUDA(cudaMemcpy(out, dump, nrows * nq * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_q);
+    cudaFree(dump);
+    return VSGPU_OK;
+}
