@@ -111,6 +111,19 @@ typedef struct {
 typedef int (*timeoutCallbackFunction)(void *ctx);
 typedef void (*logCallbackFunction)(void *ctx, const char *level, const char *message);
 
+/* ---- debug info iterator (info_iterator.h:21-81) and debug commands (vec_sim_debug.h, vec_sim_common.h:119-124) ---- */
+typedef struct VecSimDebugInfoIterator VecSimDebugInfoIterator;
+typedef enum { INFOFIELD_STRING, INFOFIELD_INT64, INFOFIELD_UINT64, INFOFIELD_FLOAT64, INFOFIELD_ITERATOR } VecSim_InfoFieldType;
+typedef union {
+    double floatingPointValue; int64_t integerValue; uint64_t uintegerValue; const char *stringValue;
+    VecSimDebugInfoIterator *iteratorValue;
+} FieldValue;
+typedef struct { const char *fieldName; VecSim_InfoFieldType fieldType; FieldValue fieldValue; } VecSim_InfoField;
+typedef enum {
+    VecSimDebugCommandCode_OK = 0, VecSimDebugCommandCode_BadIndex, VecSimDebugCommandCode_LabelNotExists,
+    VecSimDebugCommandCode_MultiNotSupported
+} VecSimDebugCommandCode;
+
 /* ---- replies (query_results.h:21-138) ---- */
 typedef enum { BY_SCORE, BY_ID, BY_SCORE_THEN_ID } VecSimQueryReply_Order;
 typedef enum { VecSim_QueryReply_OK = VecSim_OK, VecSim_QueryReply_TimedOut } VecSimQueryReply_Code;
@@ -155,6 +168,16 @@ VecSimQueryReply *VecSimIndex_TopKQuery(VecSimIndex *index, const void *queryBlo
 VecSimQueryReply *VecSimIndex_RangeQuery(VecSimIndex *index, const void *queryBlob, double radius,
                                          VecSimQueryParams *queryParams, VecSimQueryReply_Order);
 VecSimIndexDebugInfo VecSimIndex_DebugInfo(VecSimIndex *index);
+/* vec_sim.h:196-202, info_iterator.h:57-81: field names / order as the reference's debugInfoIterator()
+ * (brute_force.h:348-365, hnsw.h:2217-2272). The caller frees the iterator. */
+VecSimDebugInfoIterator *VecSimIndex_DebugInfoIterator(VecSimIndex *index);
+size_t VecSimDebugInfoIterator_NumberOfFields(VecSimDebugInfoIterator *infoIterator);
+bool VecSimDebugInfoIterator_HasNextField(VecSimDebugInfoIterator *infoIterator);
+VecSim_InfoField *VecSimDebugInfoIterator_NextField(VecSimDebugInfoIterator *infoIterator);
+void VecSimDebugInfoIterator_Free(VecSimDebugInfoIterator *infoIterator);
+/* vec_sim_debug.h: per level, [count, neighbour labels...]; the array ends with a NULL row (hnsw.h:2414-2441) */
+int VecSimDebug_GetElementNeighborsInHNSWGraph(VecSimIndex *index, size_t label, int ***neighborsData);
+void VecSimDebug_ReleaseElementNeighborsInHNSWGraph(int **neighborsData);
 VecSimIndexBasicInfo VecSimIndex_BasicInfo(VecSimIndex *index);
 VecSimIndexStatsInfo VecSimIndex_StatsInfo(VecSimIndex *index);
 VecSimBatchIterator *VecSimBatchIterator_New(VecSimIndex *index, const void *queryBlob, VecSimQueryParams *queryParams);

@@ -142,6 +142,9 @@ int vsgpu_hnsw_import(vsgpu_hnsw *g, size_t n, const uint32_t *levels, const uin
                       size_t upper_records, long entry, long max_level);
 int vsgpu_hnsw_export(const vsgpu_hnsw *g, uint32_t *levels, uint32_t *l0, uint32_t *upper, size_t upper_cap_records,
                       size_t *upper_records);
+/* One node's records (HOST): level 0 record (2M+1 words) then one (M+1)-word record per upper level.
+ * records == NULL: only the level. VSGPU_ERR_OVERFLOW when cap_words is too small. */
+int vsgpu_hnsw_node(const vsgpu_hnsw *g, size_t id, uint32_t *level_out, uint32_t *records, size_t cap_words);
 /* markDelete / unmark (VecSimIndexTombstone): deleted nodes are traversed but never returned. */
 int vsgpu_hnsw_set_deleted(vsgpu_hnsw *g, size_t id, int deleted);
 /* Batched top-k, ef = max(ef, k) (hnsw.h:2072). Layout and padding as vsgpu_topk; results ascending

@@ -325,3 +325,20 @@ def test_against_reference_if_present(capi, ref):
             R.close()
     finally:
         ref.set_disabled_features()
+
+
+def test_debug_info_iterator_flat(capi):
+    """VecSimIndex_DebugInfoIterator: names and order of brute_force.h:348-365 + vec_sim_index.h:268-310."""
+    G = capi.BFIndex(capi.BFParams(type=2, dim=40, metric=2, multi=False, initialCapacity=0, blockSize=77))
+    G.add_vectors(make_vectors(2, 10, 40, seed=1))
+    info = G.debug_info()
+    assert [k for k, _ in info] == ["ALGORITHM", "TYPE", "DIMENSION", "METRIC", "IS_MULTI_VALUE", "IS_DISK", "INDEX_SIZE",
+                                    "INDEX_LABEL_COUNT", "MEMORY", "LAST_SEARCH_MODE", "BLOCK_SIZE"]
+    d = dict(info)
+    assert (d["ALGORITHM"], d["TYPE"], d["METRIC"], d["DIMENSION"], d["INDEX_SIZE"], d["BLOCK_SIZE"]) == \
+        ("FLAT", "BFLOAT16", "COSINE", 40, 10, 77)
+    rc = capi.lib().VecSimDebug_GetElementNeighborsInHNSWGraph  # flat index -> BadIndex
+    import ctypes as C
+    out = C.POINTER(C.POINTER(C.c_int))()
+    assert rc(G._h, 0, C.byref(out)) == 1
+    G.close()

@@ -290,3 +290,35 @@ def test_builder_cta_wide_revisit_path(capi, monkeypatch):
     assert np.array_equal(g["levels"], levels) and (g["entry"], g["max_level"]) == (entry, maxl)
     assert np.array_equal(masked(g["l0"]), l0) and np.array_equal(masked(g["upper"]), upper)
     G.close()
+
+
+def test_debug_info_iterator_and_element_neighbors(capi, port):
+    """VecSimIndex_DebugInfoIterator field names/order (hnsw.h:2217-2272) and
+    VecSimDebug_GetElementNeighborsInHNSWGraph (hnsw.h:2414-2441) against the oracle's graph."""
+    n, dim, Mv = 500, 16, 5
+    X = make_vectors(0, n, dim, seed=9)
+    labels = np.arange(n, dtype=np.uint64) * 3 + 7          # labels != internal ids
+    G = new_index(capi, 0, dim, 0, M=Mv, efc=30, ef=12)
+    G.add_vectors(X, labels=labels)
+    P = port.PortHnsw(0, dim, 0, M=Mv, ef_construction=30, ef_runtime=12)
+    P.add_many(X, labels=labels)
+    G.knn_query(X[0], 3)
+    info = G.debug_info()
+    assert [k for k, _ in info] == ["ALGORITHM", "TYPE", "DIMENSION", "METRIC", "IS_MULTI_VALUE", "IS_DISK", "INDEX_SIZE",
+                                    "INDEX_LABEL_COUNT", "MEMORY", "LAST_SEARCH_MODE", "BLOCK_SIZE", "M", "EF_CONSTRUCTION",
+                                    "EF_RUNTIME", "MAX_LEVEL", "ENTRYPOINT", "EPSILON", "NUMBER_OF_MARKED_DELETED"]
+    d = dict(info)
+    gp = P.export()
+    assert d["ALGORITHM"] == "HNSW" and d["TYPE"] == "FLOAT32" and d["METRIC"] == "L2" and d["DIMENSION"] == dim
+    assert d["INDEX_SIZE"] == n and d["M"] == Mv and d["EF_CONSTRUCTION"] == 30 and d["EF_RUNTIME"] == 12
+    assert d["MAX_LEVEL"] == gp["max_level"] and d["ENTRYPOINT"] == int(labels[gp["entry"]])
+    assert d["LAST_SEARCH_MODE"] == "STANDARD_KNN" and d["EPSILON"] == 0.01
+    for node in (0, 17, gp["entry"], n - 1):
+        rc, levels = G.element_neighbors(int(labels[node]))
+        assert rc == 0 and len(levels) == int(gp["levels"][node]) + 1
+        for lvl, got in enumerate(levels):
+            c = int(gp["counts"][lvl][node])
+            assert got == [int(labels[i]) for i in gp["links"][lvl][node][:c]]
+    assert G.element_neighbors(1)[0] == 2                    # VecSimDebugCommandCode_LabelNotExists
+    G.close()
+    P.close()

@@ -67,6 +67,15 @@ class VecSimIndexStatsInfo(C.Structure):
                 ("directHNSWInsertions", C.c_size_t), ("flatBufferSize", C.c_size_t)]
 
 
+class FieldValue(C.Union):
+    _fields_ = [("floatingPointValue", C.c_double), ("integerValue", C.c_int64), ("uintegerValue", C.c_uint64),
+                ("stringValue", C.c_char_p), ("iteratorValue", C.c_void_p)]
+
+
+class VecSim_InfoField(C.Structure):
+    _fields_ = [("fieldName", C.c_char_p), ("fieldType", C.c_int), ("fieldValue", FieldValue)]
+
+
 assert C.sizeof(BFParams) == 40 and C.sizeof(VecSimParams) == 136 and C.sizeof(VecSimQueryParams) == 56
 
 TIMEOUT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
@@ -91,6 +100,9 @@ EXPORTS = [
     "VecSimGPU_SetDevice", "VecSimGPU_GetDevice", "VecSimGPU_DeviceCount", "VecSimGPU_SetTopKMode",
     "VecSimGPU_LastQueryStats", "VecSimGPU_GetStore", "VecSimGPU_LastError", "VecSimGPU_AppendDeviceRows",
     "VecSimGPU_GetGraph", "VecSimGPU_HNSWImportGraph", "VecSimGPU_HNSWExportGraph", "VecSimGPU_HNSWLastStats",
+    "VecSimIndex_DebugInfoIterator", "VecSimDebugInfoIterator_NumberOfFields", "VecSimDebugInfoIterator_HasNextField",
+    "VecSimDebugInfoIterator_NextField", "VecSimDebugInfoIterator_Free", "VecSimDebug_GetElementNeighborsInHNSWGraph",
+    "VecSimDebug_ReleaseElementNeighborsInHNSWGraph",
 ]
 
 
@@ -174,6 +186,17 @@ def lib():
     L.VecSimGPU_GetStore.restype = vp
     L.VecSimGPU_GetStore.argtypes = [vp]
     L.VecSimGPU_LastError.restype = C.c_char_p
+    L.VecSimIndex_DebugInfoIterator.restype = vp
+    L.VecSimIndex_DebugInfoIterator.argtypes = [vp]
+    L.VecSimDebugInfoIterator_NumberOfFields.restype = sz
+    L.VecSimDebugInfoIterator_NumberOfFields.argtypes = [vp]
+    L.VecSimDebugInfoIterator_HasNextField.restype = C.c_bool
+    L.VecSimDebugInfoIterator_HasNextField.argtypes = [vp]
+    L.VecSimDebugInfoIterator_NextField.restype = C.POINTER(VecSim_InfoField)
+    L.VecSimDebugInfoIterator_NextField.argtypes = [vp]
+    L.VecSimDebugInfoIterator_Free.argtypes = [vp]
+    L.VecSimDebug_GetElementNeighborsInHNSWGraph.argtypes = [vp, sz, C.POINTER(C.POINTER(C.POINTER(C.c_int)))]
+    L.VecSimDebug_ReleaseElementNeighborsInHNSWGraph.argtypes = [C.POINTER(C.POINTER(C.c_int))]
     L.VecSimGPU_GetGraph.restype = vp
     L.VecSimGPU_GetGraph.argtypes = [vp]
     L.VecSimGPU_HNSWImportGraph.argtypes = [vp, vp, i32, sz, vp, vp, vp, vp, sz, C.c_long, C.c_long]
@@ -365,6 +388,21 @@ class VecSimIndex:
     def device_store(self):
         return lib().VecSimGPU_GetStore(self._h)
 
+    def debug_info(self):
+        """VecSimIndex_DebugInfoIterator drained into an ordered list of (name, value)."""
+        L = lib()
+        it = L.VecSimIndex_DebugInfoIterator(self._h)
+        out = []
+        n = L.VecSimDebugInfoIterator_NumberOfFields(it)
+        while L.VecSimDebugInfoIterator_HasNextField(it):
+            f = L.VecSimDebugInfoIterator_NextField(it).contents
+            v = {0: f.fieldValue.stringValue, 1: f.fieldValue.integerValue, 2: f.fieldValue.uintegerValue,
+                 3: f.fieldValue.floatingPointValue}[f.fieldType]
+            out.append((f.fieldName.decode(), v.decode() if isinstance(v, bytes) else v))
+        assert len(out) == n
+        L.VecSimDebugInfoIterator_Free(it)
+        return out
+
 
 class BFIndex(VecSimIndex):
     def __init__(self, params):
@@ -444,6 +482,22 @@ class HNSWIndex(VecSimIndex):
                                                  C.byref(entry), C.byref(maxl))
             assert rc == 0, lib().VecSimGPU_LastError()
         return dict(levels=levels, l0=l0, upper=upper, entry=entry.value, max_level=maxl.value)
+
+    def element_neighbors(self, label):
+        """VecSimDebug_GetElementNeighborsInHNSWGraph -> list (one per level) of neighbour labels."""
+        L = lib()
+        out = C.POINTER(C.POINTER(C.c_int))()
+        rc = L.VecSimDebug_GetElementNeighborsInHNSWGraph(self._h, int(label), C.byref(out))
+        if rc != 0:
+            return rc, None
+        levels = []
+        i = 0
+        while out[i]:
+            cnt = out[i][0]
+            levels.append([out[i][1 + j] for j in range(cnt)])
+            i += 1
+        L.VecSimDebug_ReleaseElementNeighborsInHNSWGraph(out)
+        return 0, levels
 
     def hnsw_stats(self):
         ev, hops, ms = C.c_ulonglong(), C.c_ulonglong(), C.c_float()

@@ -204,6 +204,86 @@ VecSimQueryReply *VecSimIndex_RangeQuery(VecSimIndex *index, const void *queryBl
 
 VecSimIndexDebugInfo VecSimIndex_DebugInfo(VecSimIndex *index) { return index->debugInfo(); }
 VecSimIndexBasicInfo VecSimIndex_BasicInfo(VecSimIndex *index) { return index->basicInfo(); }
+
+static const char *algo_str(VecSimAlgo a) {
+    switch (a) {
+    case VecSimAlgo_BF: return "FLAT";
+    case VecSimAlgo_HNSWLIB: return "HNSW";
+    case VecSimAlgo_TIERED: return "TIERED";
+    default: return "SVS";
+    }
+}
+static const char *type_str(VecSimType t) {
+    static const char *n[] = {"FLOAT32", "FLOAT64", "BFLOAT16", "FLOAT16", "INT8", "UINT8", "INT32", "INT64"};
+    return (unsigned)t < 8 ? n[t] : nullptr;
+}
+static const char *metric_str(VecSimMetric m) { return m == VecSimMetric_Cosine ? "COSINE" : (m == VecSimMetric_IP ? "IP" : "L2"); }
+static const char *mode_str(VecSearchMode m) {
+    static const char *n[] = {"EMPTY_MODE", "STANDARD_KNN", "HYBRID_ADHOC_BF", "HYBRID_BATCHES", "HYBRID_BATCHES_TO_ADHOC_BF", "RANGE_QUERY"};
+    return (unsigned)m < 6 ? n[m] : nullptr;
+}
+// field names and order: brute_force.h:348-365, vec_sim_index.h:268-310 (common block), hnsw.h:2217-2272
+VecSimDebugInfoIterator *VecSimIndex_DebugInfoIterator(VecSimIndex *index) {
+    const VecSimIndexDebugInfo info = index->debugInfo();
+    auto *it = new VecSimDebugInfoIterator();
+    auto str = [&](const char *name, const char *v) {
+        VecSim_InfoField f{};
+        f.fieldName = name;
+        f.fieldType = INFOFIELD_STRING;
+        f.fieldValue.stringValue = v;
+        it->fields.push_back(f);
+    };
+    auto u64 = [&](const char *name, uint64_t v) {
+        VecSim_InfoField f{};
+        f.fieldName = name;
+        f.fieldType = INFOFIELD_UINT64;
+        f.fieldValue.uintegerValue = v;
+        it->fields.push_back(f);
+    };
+    const CommonInfo &c = info.commonInfo;
+    str("ALGORITHM", algo_str(c.basicInfo.algo));
+    str("TYPE", type_str(c.basicInfo.type));
+    u64("DIMENSION", c.basicInfo.dim);
+    str("METRIC", metric_str(c.basicInfo.metric));
+    u64("IS_MULTI_VALUE", c.basicInfo.isMulti);
+    u64("IS_DISK", c.basicInfo.isDisk);
+    u64("INDEX_SIZE", c.indexSize);
+    u64("INDEX_LABEL_COUNT", c.indexLabelCount);
+    u64("MEMORY", c.memory);
+    str("LAST_SEARCH_MODE", mode_str(c.lastMode));
+    u64("BLOCK_SIZE", c.basicInfo.blockSize);
+    if (c.basicInfo.algo == VecSimAlgo_HNSWLIB) {
+        u64("M", info.hnswInfo.M);
+        u64("EF_CONSTRUCTION", info.hnswInfo.efConstruction);
+        u64("EF_RUNTIME", info.hnswInfo.efRuntime);
+        u64("MAX_LEVEL", info.hnswInfo.max_level);
+        u64("ENTRYPOINT", info.hnswInfo.entrypoint);
+        VecSim_InfoField f{};
+        f.fieldName = "EPSILON";
+        f.fieldType = INFOFIELD_FLOAT64;
+        f.fieldValue.floatingPointValue = info.hnswInfo.epsilon;
+        it->fields.push_back(f);
+        u64("NUMBER_OF_MARKED_DELETED", info.hnswInfo.numberOfMarkedDeletedNodes);
+    }
+    return it;
+}
+size_t VecSimDebugInfoIterator_NumberOfFields(VecSimDebugInfoIterator *it) { return it->fields.size(); }
+bool VecSimDebugInfoIterator_HasNextField(VecSimDebugInfoIterator *it) { return it->pos < it->fields.size(); }
+VecSim_InfoField *VecSimDebugInfoIterator_NextField(VecSimDebugInfoIterator *it) {
+    return it->pos < it->fields.size() ? &it->fields[it->pos++] : nullptr;
+}
+void VecSimDebugInfoIterator_Free(VecSimDebugInfoIterator *it) { delete it; }
+
+int VecSimDebug_GetElementNeighborsInHNSWGraph(VecSimIndex *index, size_t label, int ***neighborsData) {
+    *neighborsData = nullptr;
+    if (index->basicInfo().algo != VecSimAlgo_HNSWLIB) return VecSimDebugCommandCode_BadIndex;
+    return index->elementNeighbors(label, neighborsData);
+}
+void VecSimDebug_ReleaseElementNeighborsInHNSWGraph(int **neighborsData) {
+    if (!neighborsData) return;
+    for (size_t i = 0; neighborsData[i] != nullptr; i++) delete[] neighborsData[i];
+    delete[] neighborsData;
+}
 VecSimIndexStatsInfo VecSimIndex_StatsInfo(VecSimIndex *index) { return index->statsInfo(); }
 VecSimBatchIterator *VecSimBatchIterator_New(VecSimIndex *index, const void *queryBlob, VecSimQueryParams *queryParams) {
     return index->newBatchIterator(queryBlob, queryParams);

@@ -400,6 +400,29 @@ void HnswIndex::lastStats(vsgpu_stats *out) {
     out->total_ms = ms;
 }
 
+// getHNSWElementNeighbors (hnsw.h:2414-2441): per level [count, neighbour labels...], NULL-terminated
+int HnswIndex::elementNeighbors(size_t label, int ***out) {
+    std::lock_guard<std::mutex> g(mu_);
+    *out = nullptr;
+    auto it = label_to_id_.find(label);
+    if (it == label_to_id_.end()) return VecSimDebugCommandCode_LabelNotExists;
+    if (flush() != 0) return VecSimDebugCommandCode_BadIndex;
+    uint32_t lvl = 0;
+    if (vsgpu_hnsw_node(graph_, it->second, &lvl, nullptr, 0) != VSGPU_OK) return VecSimDebugCommandCode_BadIndex;
+    std::vector<uint32_t> rec((2 * M_ + 1) + (size_t)lvl * (M_ + 1));
+    if (vsgpu_hnsw_node(graph_, it->second, &lvl, rec.data(), rec.size()) != VSGPU_OK) return VecSimDebugCommandCode_BadIndex;
+    int **res = new int *[lvl + 2];
+    for (uint32_t l = 0; l <= lvl; l++) {
+        const uint32_t *r = l == 0 ? rec.data() : rec.data() + (2 * M_ + 1) + (size_t)(l - 1) * (M_ + 1);
+        res[l] = new int[r[0] + 1];
+        res[l][0] = (int)r[0];
+        for (uint32_t i = 0; i < r[0]; i++) res[l][i + 1] = (int)id_to_label_[r[1 + i]];
+    }
+    res[lvl + 1] = nullptr;
+    *out = res;
+    return VecSimDebugCommandCode_OK;
+}
+
 // Adopt a graph built elsewhere over rows in insertion order (bulk load; the serialized-file reader of
 // SURVEY §8 row f3 lands on this).
 int HnswIndex::importGraph(const void *blobs, int processed, size_t n, const size_t *labels, const uint32_t *levels,

@@ -44,6 +44,11 @@ void normalize_blob(void *blob, size_t dim, VecSimType type); // VecSim_Normaliz
 
 } // namespace vsb
 
+struct VecSimDebugInfoIterator {
+    std::vector<VecSim_InfoField> fields;
+    size_t pos = 0;
+};
+
 struct VecSimBatchIterator {
     virtual ~VecSimBatchIterator() = default;
     virtual VecSimQueryReply *next(size_t n, VecSimQueryReply_Order order) = 0;
@@ -74,6 +79,11 @@ struct VecSimIndexInterface {
     virtual std::vector<uint8_t> preprocessQuery(const void *blob) = 0;
     virtual vsgpu_store *deviceStore() = 0;
     virtual void lastStats(vsgpu_stats *out) = 0;
+    // VecSimDebug_GetElementNeighborsInHNSWGraph (HNSW only)
+    virtual int elementNeighbors(size_t, int ***out) {
+        *out = nullptr;
+        return VecSimDebugCommandCode_BadIndex;
+    }
 };
 
 namespace vsb {
@@ -176,6 +186,7 @@ class HnswIndex final : public VecSimIndexInterface {
     void iterDestroy(vsgpu_hnsw_iter *it);
     size_t efRuntime() const { return ef_; }
     size_t M() const { return M_; }
+    int elementNeighbors(size_t label, int ***out) override;
     int importGraph(const void *blobs, int processed, size_t n, const size_t *labels, const uint32_t *levels,
                     const uint32_t *l0, const uint32_t *upper, size_t upper_records, long entry, long max_level);
 

@@ -2019,6 +2019,34 @@ int vsgpu_hnsw_set_deleted(vsgpu_hnsw *g, size_t id, int deleted) {
     return VSGPU_OK;
 }
 
+/* One node's link records read back to the host: level 0 record (2M + 1 words: count, links) followed by one
+ * (M + 1)-word record per upper level. Debug / introspection path (VecSimDebug_GetElementNeighborsInHNSWGraph). */
+int vsgpu_hnsw_node(const vsgpu_hnsw *g, size_t id, uint32_t *level_out, uint32_t *records, size_t cap_words) {
+    vsgpu_store *s = g->s;
+    if (id >= g->count || !level_out) {
+        set_error("vsgpu_hnsw_node: bad id");
+        return VSGPU_ERR_ARG;
+    }
+    VS_CUDA(cudaSetDevice(s->device));
+    uint32_t lvl = 0, off = 0;
+    VS_CUDA(cudaMemcpyAsync(&lvl, g->levels + id, 4, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaMemcpyAsync(&off, g->up_off + id, 4, cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    *level_out = lvl;
+    const size_t need = (size_t)(g->M0 + 1) + (size_t)lvl * (g->M + 1);
+    if (!records) return VSGPU_OK;
+    if (cap_words < need) {
+        set_error("vsgpu_hnsw_node: buffer too small");
+        return VSGPU_ERR_OVERFLOW;
+    }
+    VS_CUDA(cudaMemcpyAsync(records, g->l0 + id * (size_t)(g->M0 + 1), (size_t)(g->M0 + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (lvl)
+        VS_CUDA(cudaMemcpyAsync(records + (g->M0 + 1), g->up + (size_t)off * (g->M + 1), (size_t)lvl * (g->M + 1) * 4,
+                                cudaMemcpyDeviceToHost, s->stream));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    return VSGPU_OK;
+}
+
 int vsgpu_hnsw_last_stats(const vsgpu_hnsw *g, unsigned long long *dist_evals, unsigned long long *hops, float *ms) {
     if (dist_evals) *dist_evals = g->last_evals;
     if (hops) *hops = g->last_hops;

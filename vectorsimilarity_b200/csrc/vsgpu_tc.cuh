@@ -64,6 +64,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                  : "r"(taddr)
                  : "memory");
 }
+// 32 floats from shared memory as 8 x LDS.128 (the operand structs are reached through an integer-aligned
+// pointer, so plain indexing compiles to generic LD.E — one dependent generic load per element)
+__device__ __forceinline__ void lds_f32x32(uint32_t saddr, float (&t)[32]) {
+#pragma unroll
+    for (int v = 0; v < 8; v++)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(t[4 * v]), "=f"(t[4 * v + 1]), "=f"(t[4 * v + 2]), "=f"(t[4 * v + 3])
+                     : "r"(saddr + 16u * v));
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B operand descriptor: rows at a 128-byte pitch, 8-row groups 1024 bytes apart

@@ -154,7 +154,8 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
                 tc_wait_ld();
-                const float *thr = &sm.athr[nt * BN + col];
+                float thr[32];
+                lds_f32x32(smem_u32(&sm.athr[nt * BN + col]), thr);
                 if (g.dump) {
                     if (row_ok) {
 #pragma unroll
@@ -164,12 +165,18 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                         }
                     }
                 } else if (row_ok) {
+                    // all 32 compares first (independent, no branch in between), then the rare hits
+                    uint32_t hit = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        if (__uint_as_float(r[j]) >= thr[j]) {
-                            const uint32_t q = nt * BN + col + j;
-                            const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
-                            if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = make_uint2(row, r[j]);
+                    for (int j = 0; j < 32; j++) hit |= (__uint_as_float(r[j]) >= thr[j] ? 1u : 0u) << j;
+                    if (hit) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if ((hit >> j) & 1u) {
+                                const uint32_t q = nt * BN + col + j;
+                                const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
+                                if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = make_uint2(row, r[j]);
+                            }
                         }
                     }
                 }

@@ -134,8 +134,11 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
             const uint32_t row = g.row0 + mt * BM + quad * 32 + (uint32_t)lane;
             const bool row_ok = row < g.row_end;
+            // admit when float(dot) >= c_q * rm + ra2: c_q arrives already lowered by the merge kernel, ra2 is the
+            // row's additive term lowered by a few ulps and two dot units (the admitted set must be a superset)
             const float rm = (row_ok && g.row_mul) ? g.row_mul[row] : 1.0f;
             const float ra = (row_ok && g.row_add) ? g.row_add[row] : 0.0f;
+            const float ra2 = ra - fabsf(ra) * 3.8146973e-6f - 2.0f;
             mbar_wait(&sm.tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1
@@ -144,7 +147,8 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
                 tc_wait_ld();
-                const float *cq = &sm.cq[nt * BN + col];
+                float cq[32];
+                lds_f32x32(smem_u32(&sm.cq[nt * BN + col]), cq);
                 if (g.dump) {
                     if (row_ok) {
 #pragma unroll
@@ -154,16 +158,19 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         }
                     }
                 } else if (row_ok) {
+                    // 3 instructions per accumulator (I2F, FFMA, FSETP), all 32 first, then the rare hits; padded
+                    // query columns carry c_q = +inf
+                    uint32_t hit = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float f = __int2float_rn((int)r[j]);
-                        const float bound = fmaf(cq[j], rm, ra);
-                        // superset of {score <= T_q}: a few ulps of every quantity involved, plus 2 dot units
-                        // (padded query columns carry c_q = +inf: never admitted)
-                        if (bound < 3.0e38f && f + (fabsf(f) + fabsf(bound) + fabsf(ra)) * 3.8146973e-6f + 2.0f >= bound) {
-                            const uint32_t q = nt * BN + col + j;
-                            const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
-                            if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = make_uint2(row, r[j]);
+                    for (int j = 0; j < 32; j++) hit |= (__int2float_rn((int)r[j]) >= fmaf(cq[j], rm, ra2) ? 1u : 0u) << j;
+                    if (hit) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if ((hit >> j) & 1u) {
+                                const uint32_t q = nt * BN + col + j;
+                                const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
+                                if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = make_uint2(row, r[j]);
+                            }
                         }
                     }
                 }
@@ -307,7 +314,9 @@ __global__ void __launch_bounds__(1024) i8_merge_kernel(I8MergeArgs a) {
             else if (a.metric == VSGPU_IP) cq = (1.0f - T) - fabsf(T) * 9.5367432e-7f - 1.0f; // dot >= 1 - T
             else cq = 0.5f * ((float)qq - T) - (fabsf((float)qq) + fabsf(T)) * 4.7683716e-7f - 1.0f; // dot >= aa/2 + (qq - T)/2
         }
-        a.cq[q] = cq;
+        // lowered once more by 2^-18 of its magnitude: covers the rounding of c_q * row_mul + row_add and of
+        // float(dot) in the epilogue (row_mul > 0)
+        a.cq[q] = cq - fabsf(cq) * 3.8146973e-6f;
     }
 }
 
