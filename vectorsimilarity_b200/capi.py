@@ -396,8 +396,15 @@ class VecSimIndex:
         n = L.VecSimDebugInfoIterator_NumberOfFields(it)
         while L.VecSimDebugInfoIterator_HasNextField(it):
             f = L.VecSimDebugInfoIterator_NextField(it).contents
-            v = {0: f.fieldValue.stringValue, 1: f.fieldValue.integerValue, 2: f.fieldValue.uintegerValue,
-                 3: f.fieldValue.floatingPointValue}[f.fieldType]
+            # read only the union member the type names (a char* view of an integer field would be dereferenced)
+            if f.fieldType == 0:
+                v = f.fieldValue.stringValue
+            elif f.fieldType == 1:
+                v = f.fieldValue.integerValue
+            elif f.fieldType == 2:
+                v = f.fieldValue.uintegerValue
+            else:
+                v = f.fieldValue.floatingPointValue
             out.append((f.fieldName.decode(), v.decode() if isinstance(v, bytes) else v))
         assert len(out) == n
         L.VecSimDebugInfoIterator_Free(it)

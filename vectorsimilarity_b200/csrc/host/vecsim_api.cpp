@@ -69,8 +69,13 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
             const BFParams &p = params->algoParams.bfParams;
             if (p.dim == 0 || p.type > VecSimType_UINT8 || p.metric > VecSimMetric_Cosine) return nullptr;
             if (p.multi) {
-                g_api_err = "multi-value flat indexes are not built yet (SURVEY §8 row f2)";
-                return nullptr;
+                auto *midx = new FlatMultiIndex(p, params->logCtx);
+                if (!midx->ok()) {
+                    g_api_err = std::string("device store: ") + vsgpu_last_error();
+                    delete midx;
+                    return nullptr;
+                }
+                return midx;
             }
             auto *idx = new FlatIndex(p, params->logCtx);
             if (!idx->ok()) {

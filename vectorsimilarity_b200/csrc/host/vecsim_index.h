@@ -151,6 +151,54 @@ class FlatIndex final : public VecSimIndexInterface {
 };
 
 
+// Flat, several vectors per label: vecsim_flat_multi.cpp
+class FlatMultiIndex final : public VecSimIndexInterface {
+  public:
+    FlatMultiIndex(const BFParams &p, void *logCtx);
+    ~FlatMultiIndex() override;
+    bool ok() const { return store_ != nullptr; }
+    int addVector(const void *blob, size_t label) override;
+    long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) override;
+    int deleteVector(size_t label) override;
+    double getDistanceFrom(size_t label, const void *blob) override;
+    size_t indexSize() override { return id_to_label_.size(); }
+    size_t indexLabelCount() override { return label_to_ids_.size(); }
+    VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) override;
+    int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels, double *scores,
+                  uint32_t *counts) override;
+    VecSimQueryReply *rangeQuery(const void *blob, double radius, VecSimQueryParams *qp,
+                                 VecSimQueryReply_Order order) override;
+    VecSimBatchIterator *newBatchIterator(const void *blob, VecSimQueryParams *qp) override;
+    VecSimIndexBasicInfo basicInfo() override;
+    VecSimIndexDebugInfo debugInfo() override;
+    VecSimIndexStatsInfo statsInfo() override;
+    bool preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) override;
+    void setLastSearchMode(VecSearchMode m) override { last_mode_ = m; }
+    void exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) override;
+    std::vector<uint8_t> preprocessQuery(const void *blob) override;
+    vsgpu_store *deviceStore() override;
+    void lastStats(vsgpu_stats *out) override;
+    int allScores(const void *processed_query, std::vector<std::pair<double, size_t>> &out);
+    static bool reduce(const uint64_t *labels, const double *scores, size_t cnt, size_t want, bool exhausted,
+                       std::vector<VecSimQueryResult> &out);
+
+  private:
+    void preprocess(const void *blob, uint8_t *out) const;
+    int flush();
+    int removeRow(idType id);
+    VecSimType type_;
+    VecSimMetric metric_;
+    size_t dim_, block_size_, data_size_, stored_size_;
+    void *log_ctx_;
+    vsgpu_store *store_ = nullptr;
+    std::vector<size_t> id_to_label_;
+    std::unordered_map<size_t, std::vector<idType>> label_to_ids_;
+    std::vector<uint8_t> pending_rows_;
+    std::vector<uint64_t> pending_labels_;
+    VecSearchMode last_mode_ = EMPTY_MODE;
+    std::mutex mu_;
+};
+
 // HNSW (single value per label): vecsim_hnsw.cpp
 class HnswIndex final : public VecSimIndexInterface {
   public:
