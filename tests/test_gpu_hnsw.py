@@ -322,3 +322,25 @@ def test_debug_info_iterator_and_element_neighbors(capi, port):
     assert G.element_neighbors(1)[0] == 2                    # VecSimDebugCommandCode_LabelNotExists
     G.close()
     P.close()
+
+
+def test_batched_builder_equals_sequential_builder(capi, monkeypatch):
+    """The builder searches for up to one element per SM concurrently and commits them in order while their read sets
+    are untouched (csrc/vsgpu_hnsw.cu, mode 1 / mode 2). The graph must be the sequential one, link for link."""
+    n, dim, Mv = 9000, 24, 8
+    X = make_vectors(0, n, dim, seed=123)
+    monkeypatch.setenv("VSGPU_HNSW_SEQ_BUILD", "1")
+    A = new_index(capi, 0, dim, 0, M=Mv, efc=60)
+    A.add_vectors(X)
+    ga = A.export_graph(n)
+    monkeypatch.delenv("VSGPU_HNSW_SEQ_BUILD")
+    monkeypatch.setenv("VSGPU_HNSW_BATCH_BUILD", "1")
+    B = new_index(capi, 0, dim, 0, M=Mv, efc=60)
+    B.add_vectors(X[:5000])
+    B.add_vectors(X[5000:], first_label=5000)
+    gb = B.export_graph(n)
+    assert np.array_equal(ga["levels"], gb["levels"]) and (ga["entry"], ga["max_level"]) == (gb["entry"], gb["max_level"])
+    assert np.array_equal(masked(ga["l0"]), masked(gb["l0"]))
+    assert np.array_equal(masked(ga["upper"]), masked(gb["upper"]))
+    A.close()
+    B.close()

@@ -36,7 +36,7 @@ def _index(capi, vtype, dim, metric, X):
     return G
 
 
-@pytest.mark.parametrize("vtype,dim", [(0, 768), (0, 128), (0, 100), (2, 1024), (2, 72), (0, 64)])
+@pytest.mark.parametrize("vtype,dim", [(0, 768), (0, 128), (0, 100), (2, 1024), (2, 72), (0, 64), (3, 256), (3, 80)])
 def test_coarse_pipeline_matches_matmul(capi, gpulib, vtype, dim):
     n, nq = 1000, 300                       # ragged: last row tile and last query tile partly empty
     X = make_vectors(vtype, n, dim, seed=dim, dist="normal")
@@ -47,6 +47,8 @@ def test_coarse_pipeline_matches_matmul(capi, gpulib, vtype, dim):
     assert rc == 0, gpulib.vsgpu_last_error()
     if vtype == 0:
         xb, qb = from_bf16(to_bf16(X)).astype(np.float64), from_bf16(to_bf16(Q)).astype(np.float64)
+    elif vtype == 3:
+        xb, qb = X.astype(np.float64), Q.astype(np.float64)
     else:
         xb, qb = from_bf16(X).astype(np.float64), from_bf16(Q).astype(np.float64)
     want = xb[128:] @ qb.T
@@ -72,6 +74,8 @@ def _check_against(capi, G, P, Q, k, mode):
     (0, 2, 96, 40000, 50, 64),       # cosine: rows and queries normalised by the index
     (2, 1, 128, 40000, 100, 70),     # bf16 store, no mirror
     (2, 2, 200, 36000, 10, 32),
+    (3, 1, 128, 40000, 50, 64),      # fp16 store: fp16 x fp16 MMA (kind::f16, format F16), exact products
+    (3, 2, 96, 36000, 10, 33),
 ])
 def test_tensor_path_equals_oracle(capi, port, vtype, metric, dim, n, k, nq):
     dist = "normal" if metric == 1 else "uniform"

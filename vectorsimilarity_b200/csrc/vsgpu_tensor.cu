@@ -17,6 +17,7 @@
 // on the exact path.
 #include "vsgpu_tc.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -49,6 +50,8 @@ struct GemmSmem {
 // kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), both
 // K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// same with A/B format 0 = fp16 (fp16 stores go through the MMA as they are: fp16 x fp16 products are exact in fp32)
+constexpr uint32_t IDESC_FP16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 struct GemmArgs {
     uint32_t row0;       // first row of this phase (multiple of BM)
@@ -61,6 +64,7 @@ struct GemmArgs {
     uint2 *cand;         // [nq][CAND_CAP] (row id, coarse accumulator bits)
     float *dump;         // debug: [rows][dump_ld] raw accumulators (else NULL)
     uint32_t dump_ld;
+    uint32_t idesc;      // IDESC_BF16 / IDESC_FP16
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -127,7 +131,7 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 #pragma unroll
                     for (int k = 0; k < BK / UK; k++) {
                         // advance 32 bytes (2 x 16 B) along K inside the swizzled row
-                        tc_mma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_BF16, (kb | (uint32_t)k) != 0);
+                        tc_mma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), g.idesc, (kb | (uint32_t)k) != 0);
                     }
                     tc_commit(&sm.empty[stage]);   // frees the smem slot once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -222,7 +226,7 @@ __global__ void shadow_rows_kernel(const float *__restrict__ rows, size_t row_st
 }
 
 __global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t row_stride_e, size_t dim, size_t first, size_t n,
-                                  float *__restrict__ row_l2, unsigned *__restrict__ max_l2_bits) {
+                                  float *__restrict__ row_l2, unsigned *__restrict__ max_l2_bits, int is_fp16) {
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -230,7 +234,7 @@ __global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t
         const __nv_bfloat16 *src = rows + (first + i) * row_stride_e;
         float ss = 0.f;
         for (size_t e = lane; e < dim; e += 32) {
-            const float v = __bfloat162float(src[e]);
+            const float v = is_fp16 ? __half2float(reinterpret_cast<const __half *>(src)[e]) : __bfloat162float(src[e]);
             ss = fmaf(v, v, ss);
         }
         for (int w = 16; w >= 1; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
@@ -257,9 +261,12 @@ __global__ void prep_coarse_queries_kernel(const uint8_t *__restrict__ q, size_t
             float v = 0.f;
             __nv_bfloat16 b = __float2bfloat16_rn(0.f);
             if (e < dim) {
-                if (is_f32) {
+                if (is_f32 == 1) {
                     v = reinterpret_cast<const float *>(src)[e];
                     b = __float2bfloat16_rn(v);
+                } else if (is_f32 == 2) { // fp16 store: the 16-bit pattern is the operand
+                    b = reinterpret_cast<const __nv_bfloat16 *>(src)[e];
+                    v = __half2float(reinterpret_cast<const __half *>(src)[e]);
                 } else {
                     b = reinterpret_cast<const __nv_bfloat16 *>(src)[e];
                     v = __bfloat162float(b);
@@ -439,7 +446,8 @@ static bool g_tensor_disabled = false;
 bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k) {
     if (g_tensor_disabled) return false;
     if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8) return tensor_i8_supported(s, nq, k);
-    if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16) return false;
+    if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16 && s->type != VSGPU_FLOAT16) return false;
+    if (s->type == VSGPU_FLOAT16 && s->plan.kind != CK_LANES) return false; // dim >= 16: the fp32-accumulating tier
     if (s->metric != VSGPU_IP && s->metric != VSGPU_COSINE) return false;
     if (s->plan.kind == CK_SEQ) return false;
     if (nq < 32 || k > 384 || k == 0) return false;
@@ -489,7 +497,7 @@ int tensor_sync_mirrors(vsgpu_store *s) {
             const size_t n = s->count - t->mirrored;
             const unsigned blocks = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)t->sms * 16);
             bf16_norms_kernel<<<blocks, 256, 0, s->stream>>>((const __nv_bfloat16 *)s->rows, s->row_stride / 2, s->dim, t->mirrored,
-                                                            n, nullptr, t->max_l2_bits);
+                                                            n, nullptr, t->max_l2_bits, s->type == VSGPU_FLOAT16 ? 1 : 0);
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
             t->mirrored = s->count;
@@ -528,7 +536,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
     const size_t qb_stride = (s->dim + 7) / 8 * 8;
     // error bound of the coarse score relative to ||q|| * ||row||
     const float c_rel = f32 ? (float)(1.0 / 256 + 1.0 / 65536 + 4.0 * (double)s->dim / 8388608.0)
-                            : (float)(6.0 * (double)s->dim / 8388608.0);
+                            : (float)((s->type == VSGPU_FLOAT16 ? 8.0 : 6.0) * (double)s->dim / 8388608.0);
     CUtensorMap map_a;
     VS_TRY(make_map(&map_a, a_base, n, s->dim, a_stride, BM));
 
@@ -574,7 +582,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         VS_CUDA(cudaMemsetAsync(tot, 0, 8, s->stream));
         fill_t<float><<<64, 256, 0, s->stream>>>(athr, -INFINITY, nq);
         prep_coarse_queries_kernel<<<(unsigned)std::min<size_t>((nq + 7) / 8, 1024), 256, 0, s->stream>>>(
-            qp, q_stride, f32 ? 1 : 0, s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps);
+            qp, q_stride, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches += 2;
         CUtensorMap map_b;
@@ -591,6 +599,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             g.cnt = cnt;
             g.cand = cand;
             g.dump = nullptr;
+            g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
             while (t->evs.size() < 2 * (p + 1)) {
                 cudaEvent_t e;
                 VS_CUDA(cudaEventCreate(&e));
@@ -659,8 +668,8 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
         set_error("vsgpu_debug_coarse: bad arguments");
         return VSGPU_ERR_ARG;
     }
-    if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16) {
-        set_error("vsgpu_debug_coarse: fp32 / bf16 stores only");
+    if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16 && s->type != VSGPU_FLOAT16) {
+        set_error("vsgpu_debug_coarse: fp32 / bf16 / fp16 stores only");
         return VSGPU_ERR_ARG;
     }
     VS_CUDA(cudaSetDevice(s->device));
@@ -680,7 +689,7 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
     VS_CUDA(cudaMemcpy2D(d_q, s->row_bytes, queries, qstride, s->row_bytes, nq, cudaMemcpyHostToDevice));
     VS_CUDA(cudaMemsetAsync(qb, 0, nq_pad * qb_stride * 2, s->stream));
     VS_CUDA(cudaMemsetAsync(dump, 0, nrows * nq * 4, s->stream));
-    prep_coarse_queries_kernel<<<64, 256, 0, s->stream>>>(d_q, s->row_bytes, f32 ? 1 : 0, s->dim, nq, qb, qb_stride, 0.f,
+    prep_coarse_queries_kernel<<<64, 256, 0, s->stream>>>(d_q, s->row_bytes, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, 0.f,
                                                          t->max_l2_bits, eps);
     CUtensorMap map_a, map_b;
     VS_TRY(make_map(&map_a, f32 ? (const void *)s->shadow : (const void *)s->rows, s->count, s->dim,
@@ -697,6 +706,7 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
     g.cand = nullptr;
     g.dump = dump;
     g.dump_ld = (uint32_t)nq;
+    g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
     VS_TRY(launch_gemm(s, t, map_a, map_b, g));
     VS_CUDA(cudaStreamSynchronize(s->stream));
     VS_CUDA(cudaMemcpy(out, dump, nrows * nq * 4, cudaMemcpyDeviceToHost));
