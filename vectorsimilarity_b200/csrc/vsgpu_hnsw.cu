@@ -1264,6 +1264,12 @@ struct InsertArgs {
     void *res_d;          // [slots][BATCH_MAX_LEVELS][M] DistType
     uint32_t *mod_stamp;  // [capacity] id of the last inserted element that rewrote the node's links
     uint32_t *committed;  // mode 2: number of elements committed
+    // mode 3 (parallel build, opt-in): CTA b connects element first + b without validation; neighbours' records are
+    // guarded by per-node spin locks (a warp holds at most one lock at a time), the entry point by locks[capacity].
+    // Like the reference's multi-threaded ingestion, elements of one round do not see each other and the graph
+    // depends on timing; it is a valid HNSW graph, not the sequential one.
+    uint32_t *locks;
+    uint32_t state_lock_idx;
 };
 constexpr int BATCH_MAX_LEVELS = 16;
 
@@ -1408,7 +1414,7 @@ template <typename DT> __device__ __forceinline__ RvScratch<DT> carve_rv(unsigne
 // ballot per candidate.
 template <class P>
 __device__ bool warp_revisit(const KCtx &k, const GraphDev &g, const RvScratch<typename P::DT> &r, uint32_t e, uint32_t nb,
-                             typename P::DT d_nb, uint32_t *nb_rec, int maxM) {
+                             typename P::DT d_nb, volatile uint32_t *nb_rec, int maxM) {
     using DT = typename P::DT;
     const int lane = threadIdx.x & 31;
     const int cnt = (int)nb_rec[0];
@@ -1486,6 +1492,15 @@ __device__ bool warp_revisit(const KCtx &k, const GraphDev &g, const RvScratch<t
     return __shfl_sync(0xffffffffu, changed, 0) != 0;
 }
 
+__device__ __forceinline__ void node_lock(uint32_t *locks, uint32_t i) {
+    while (atomicCAS(&locks[i], 0u, 1u) != 0u) __nanosleep(64);
+    __threadfence();
+}
+__device__ __forceinline__ void node_unlock(uint32_t *locks, uint32_t i) {
+    __threadfence();
+    atomicExch(&locks[i], 0u);
+}
+
 template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_insert_kernel(InsertArgs a) {
     using DT = typename P::DT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1513,14 +1528,17 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
     long long tp = 0;
 
     __shared__ int s_rlog_n, s_valid;
-    const uint32_t e_begin = a.mode == 1 ? a.first + blockIdx.x : a.first;
-    const uint32_t e_end = a.mode == 1 ? e_begin + 1 : a.first + a.n;
+    const bool per_cta = a.mode == 1 || a.mode == 3;
+    const uint32_t e_begin = per_cta ? a.first + blockIdx.x : a.first;
+    const uint32_t e_end = per_cta ? e_begin + 1 : a.first + a.n;
     for (uint32_t e = e_begin; e < e_end; e++) {
         __syncthreads();
-        const int ep = a.g.state[0], maxl = a.g.state[1];
-        const int lvl = (int)a.g.levels[e];
         const uint32_t slot = e - a.first;
         int *meta = a.res_meta ? a.res_meta + (size_t)slot * (4 + BATCH_MAX_LEVELS) : nullptr;
+        const bool commit_mode = a.mode == 2 || a.mode == 3;
+        // mode 3 works from the state its search saw (other CTAs may be raising the entry point right now)
+        const int ep = a.mode == 3 ? meta[1] : a.g.state[0], maxl = a.mode == 3 ? meta[2] : a.g.state[1];
+        const int lvl = (int)a.g.levels[e];
         if (a.mode == 1) {
             if (threadIdx.x == 0) {
                 s_rlog_n = 0;
@@ -1534,6 +1552,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
             __syncthreads();
             if (!meta[0]) return;
         }
+        if (a.mode == 3 && !meta[0]) return; // could not be recorded: the host inserts it sequentially afterwards
         if (a.mode == 2) {
             // valid while the graph state and every link list this element's search read are as it saw them
             if (threadIdx.x == 0) s_valid = (meta[0] == 1 && meta[1] == ep && meta[2] == maxl && meta[3] <= a.rlog_cap) ? 1 : 0;
@@ -1559,7 +1578,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
             }
             continue;
         }
-        if (a.mode != 2) P::load_pivot(a.k, w.pivot, a.k.rows + (size_t)e * a.k.row_stride, a.k.norms ? a.k.norms[e] : 0.f);
+        if (!commit_mode) P::load_pivot(a.k, w.pivot, a.k.rows + (size_t)e * a.k.row_stride, a.k.norms ? a.k.norms[e] : 0.f);
         if (threadIdx.x == 0) {
             w.sc[SC_CUR] = ep;
             w.nb_ids[0] = (uint32_t)ep;
@@ -1567,7 +1586,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
         __syncthreads();
         int max_common = maxl;
         if (lvl < maxl) max_common = lvl;
-        if (lvl < maxl && a.mode != 2) {
+        if (lvl < maxl && !commit_mode) {
             eval_dists<P, true>(a.k, w.pivot, 1, w.nb_dist, [&](int j, uint32_t &x, uint32_t &) { x = w.nb_ids[j]; });
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -1582,7 +1601,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
             DT *sel_d = w.top_d; // selected neighbours (distance, id) live in the result arrays once the search is over
             uint32_t *sel_id = w.top_id;
             int ns = 0;
-            if (a.mode == 2) {
+            if (commit_mode) {
                 // load what the search CTA selected for this level
                 ns = meta[4 + level];
                 if (threadIdx.x == 0) tp = clock64();
@@ -1686,7 +1705,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
                 __syncthreads();
                 continue;
             }
-            } // mode != 2
+            } // !commit_mode
             uint32_t *new_rec = links_of(a.g, e, level);
             if (threadIdx.x == 0) {
                 s_prof[5] += clock64() - tp;
@@ -1701,12 +1720,16 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
                     for (int si = warp; si < ns; si += a.rv_warps) {
                         const uint32_t nb = sel_id[si];
                         if (is_deleted(a.g, nb)) continue;
-                        uint32_t *nb_rec = links_of(a.g, nb, level);
+                        volatile uint32_t *nb_rec = links_of(a.g, nb, level); // volatile: other CTAs rewrite it (mode 3)
+                        if (a.mode == 3) {
+                            if ((threadIdx.x & 31) == 0) node_lock(a.locks, nb);
+                            __syncwarp();
+                        }
                         bool changed = true;
                         if ((int)nb_rec[0] < maxMcur) {
                             if ((threadIdx.x & 31) == 0) {
                                 nb_rec[1 + nb_rec[0]] = e;
-                                nb_rec[0]++;
+                                nb_rec[0] = nb_rec[0] + 1;
                             }
                             __syncwarp();
                         } else {
@@ -1715,6 +1738,10 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
                         // a full neighbour that rejects the new element and keeps all its links is untouched: later
                         // elements of the round that read its list are still valid
                         if (a.mod_stamp && changed && (threadIdx.x & 31) == 0) a.mod_stamp[nb] = e;
+                        if (a.mode == 3) {
+                            __syncwarp();
+                            if ((threadIdx.x & 31) == 0) node_unlock(a.locks, nb);
+                        }
                     }
                 }
                 __syncthreads();
@@ -1791,7 +1818,17 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
             if (threadIdx.x == 0) meta[3] = s_rlog_n;
             break;
         }
-        if (threadIdx.x == 0 && lvl > maxl) {
+        if (threadIdx.x == 0 && a.mode == 3) {
+            if (lvl > maxl) { // re-check under the lock: several elements of the round may be taller than the graph
+                node_lock(a.locks, a.state_lock_idx);
+                volatile int *st = a.g.state;
+                if (lvl > st[1]) {
+                    st[0] = (int)e;
+                    st[1] = lvl;
+                }
+                node_unlock(a.locks, a.state_lock_idx);
+            }
+        } else if (threadIdx.x == 0 && lvl > maxl) {
             a.g.state[0] = (int)e;
             a.g.state[1] = lvl;
         }
