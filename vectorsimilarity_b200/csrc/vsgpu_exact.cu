@@ -215,52 +215,84 @@ __global__ void seq_scan_kernel(const uint8_t *__restrict__ rows, size_t row_str
     }
 }
 
-// Chosen rows (re-rank / ad-hoc distances): one thread group per (query, candidate) pair.
+// Chosen rows (re-rank / ad-hoc distances): one thread group per (query, candidate) pair. Grid = (chunks of
+// GATHER_CHUNK candidates, queries): a block reads its query's count once and the chunks past it exit at once (the
+// re-rank passes RUN_CAP-wide lists of which a quarter is in use). The chain is sequential in s but the loads are not:
+// a group keeps GP pairs x GU steps of row loads in flight and shares the query operand between its pairs (one load
+// per FMA on one pair at a time had left the re-rank of a 1024-query batch latency-bound at ~1 TB/s).
+constexpr int GATHER_CHUNK = 256;
 template <typename CT, int G, bool FTZ, bool L2>
 __global__ void __launch_bounds__(256) exact_gather_kernel(ScanArgs a, const uint32_t *__restrict__ ids, size_t ids_ld,
                                                            const uint32_t *__restrict__ counts, size_t max_count) {
     constexpr int GROUPS = 32 / G;
+    constexpr int GP = 2, GU = 8;
     const ChainPlan plan = a.plan;
     const int S = plan.S;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const int c = lane % G, grp = lane / G;
     const size_t per_q = (size_t)S * G;
-    const size_t group_id = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + grp;
-    const size_t n_groups = (size_t)gridDim.x * (blockDim.x >> 5) * GROUPS;
-    const size_t total = a.nq * max_count;
-    // all groups of a warp iterate the same number of times (shuffles need the full warp)
-    const size_t iters = (total + n_groups - 1) / n_groups;
-    for (size_t it = 0; it < iters; it++) {
-        const size_t pair = it * n_groups + group_id;
-        bool valid = pair < total;
-        size_t qi = 0, j = 0;
-        uint32_t id = 0xffffffffu;
-        if (valid) {
-            qi = pair / max_count;
-            j = pair % max_count;
-            const uint32_t cnt = counts ? counts[qi] : (uint32_t)max_count;
-            if (j < cnt) id = ids[qi * ids_ld + j];
-            valid = id != 0xffffffffu;
-        }
-        const uint8_t *rp = a.rows + (valid ? (size_t)id : 0) * a.row_stride;
+    for (size_t qi = blockIdx.y; qi < a.nq; qi += gridDim.y) {
+        size_t cnt = max_count;
+        if (counts) cnt = min((size_t)counts[qi], max_count);
+        const size_t chunk_end = min(cnt, ((size_t)blockIdx.x + 1) * GATHER_CHUNK);
         const CT *qp = reinterpret_cast<const CT *>(a.qchain) + qi * per_q + c;
-        CT acc = CT(0);
-        if (valid) {
-            for (int s = 0; s < S; s++) {
-                const int e = chain_elem(plan, c, s);
-                const CT x = e < 0 ? CT(0) : Loader<CT>::load(rp, a.type, e);
-                const CT y = qp[(size_t)s * G];
-                if constexpr (L2) {
-                    const CT d = sub_rn(x, y);
-                    acc = fma_step<FTZ>(d, d, acc);
-                } else {
-                    acc = fma_step<FTZ>(x, y, acc);
+        const uint32_t *idq = ids + qi * ids_ld;
+        // all groups of a warp iterate the same number of times (the butterfly needs the full warp)
+        for (size_t base = (size_t)blockIdx.x * GATHER_CHUNK + (size_t)warp * (GROUPS * GP); base < chunk_end;
+             base += (size_t)warps * (GROUPS * GP)) {
+            size_t j[GP];
+            bool valid[GP];
+            const uint8_t *rp[GP];
+            CT acc[GP];
+#pragma unroll
+            for (int p = 0; p < GP; p++) {
+                j[p] = base + (size_t)p * GROUPS + grp;
+                uint32_t id = 0xffffffffu;
+                if (j[p] < chunk_end) id = idq[j[p]];
+                valid[p] = id != 0xffffffffu;
+                rp[p] = a.rows + (valid[p] ? (size_t)id : 0) * a.row_stride;
+                acc[p] = CT(0);
+            }
+            for (int s0 = 0; s0 < S; s0 += GU) {
+                CT x[GP][GU], y[GU];
+#pragma unroll
+                for (int u = 0; u < GU; u++) {
+                    const int s = s0 + u;
+                    y[u] = CT(0);
+#pragma unroll
+                    for (int p = 0; p < GP; p++) x[p][u] = CT(0);
+                    if (s < S) {
+                        const int e = chain_elem(plan, c, s);
+                        y[u] = qp[(size_t)s * G];
+                        if (e >= 0) {
+#pragma unroll
+                            for (int p = 0; p < GP; p++)
+                                if (valid[p]) x[p][u] = Loader<CT>::load(rp[p], a.type, e);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < GU; u++) {
+                    if (s0 + u < S) {
+#pragma unroll
+                        for (int p = 0; p < GP; p++) {
+                            if constexpr (L2) {
+                                const CT d = sub_rn(x[p][u], y[u]);
+                                acc[p] = fma_step<FTZ>(d, d, acc[p]);
+                            } else {
+                                acc[p] = fma_step<FTZ>(x[p][u], y[u], acc[p]);
+                            }
+                        }
+                    }
                 }
             }
+#pragma unroll
+            for (int p = 0; p < GP; p++) {
+                CT v = butterfly<CT, G>(acc[p]);
+                if (!L2) v = sub_rn(CT(1), v);
+                if (valid[p] && c == 0) reinterpret_cast<CT *>(a.scores)[qi * a.ld + j[p]] = v;
+            }
         }
-        CT v = butterfly<CT, G>(acc);
-        if (!L2) v = sub_rn(CT(1), v);
-        if (valid && c == 0) reinterpret_cast<CT *>(a.scores)[qi * a.ld + j] = v;
     }
 }
 
@@ -485,13 +517,8 @@ static int launch_scan_t(vsgpu_store *s, ScanArgs &a) {
 template <typename CT, int G, bool FTZ, bool L2>
 static int launch_gather_t(vsgpu_store *s, ScanArgs &a, const uint32_t *ids, size_t ids_ld, const uint32_t *counts,
                            size_t max_count) {
-    const size_t pairs = a.nq * max_count;
-    const size_t groups_per_block = 8 * (32 / G);
-    size_t blocks = (pairs + groups_per_block - 1) / groups_per_block;
-    const size_t max_blocks = (size_t)grid_for(s->device, 8);
-    if (blocks > max_blocks) blocks = max_blocks;
-    if (blocks == 0) blocks = 1;
-    exact_gather_kernel<CT, G, FTZ, L2><<<(unsigned)blocks, 256, 0, s->stream>>>(a, ids, ids_ld, counts, max_count);
+    const dim3 blocks((unsigned)((max_count + GATHER_CHUNK - 1) / GATHER_CHUNK), (unsigned)std::min<size_t>(a.nq, 65535));
+    exact_gather_kernel<CT, G, FTZ, L2><<<blocks, 256, 0, s->stream>>>(a, ids, ids_ld, counts, max_count);
     VS_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return VSGPU_OK;

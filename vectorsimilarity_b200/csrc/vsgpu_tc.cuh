@@ -3,6 +3,11 @@
 #pragma once
 #include "vsgpu_internal.cuh"
 #include <cuda.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <utility>
+#include <vector>
 
 namespace vsgpu {
 
@@ -73,6 +78,38 @@ __device__ __forceinline__ void lds_f32x32(uint32_t saddr, float (&t)[32]) {
                      : "=f"(t[4 * v]), "=f"(t[4 * v + 1]), "=f"(t[4 * v + 2]), "=f"(t[4 * v + 3])
                      : "r"(saddr + 16u * v));
 }
+// Appends the hits of one 32-row x 32-column accumulator chunk to the per-query candidate lists; the whole warp calls it.
+// `hit` is this lane's (row's) mask over the chunk's 32 columns (queries q0 .. q0+31). The masks are transposed with
+// ballots so that lane j owns column j and reserves that column's slots with ONE atomic — 32 different counters in a
+// single instruction, one round trip per chunk. (One atomic per hit serialised ~30 dependent round trips per chunk at
+// the 1-8 % pass rates of the early phases and left the epilogue, not the MMAs, as the critical path.)
+template <uint32_t CAP>
+__device__ __forceinline__ void warp_append_hits(uint32_t hit, uint32_t q0, uint32_t row, const uint32_t (&r)[32],
+                                                 uint32_t *__restrict__ cnt, uint2 *__restrict__ cand, int lane) {
+    const uint32_t any = __reduce_or_sync(0xffffffffu, hit);
+    if (!any) return;
+    uint32_t mine = 0; // rows of this warp that hit column `lane`
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if ((any >> j) & 1u) { // warp-uniform
+            const uint32_t b = __ballot_sync(0xffffffffu, (hit >> j) & 1u);
+            if (lane == j) mine = b;
+        }
+    }
+    uint32_t base = 0;
+    if (mine) base = atomicAdd(&cnt[q0 + (uint32_t)lane], (uint32_t)__popc(mine));
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if ((any >> j) & 1u) {
+            const uint32_t b = __shfl_sync(0xffffffffu, mine, j), bs = __shfl_sync(0xffffffffu, base, j);
+            if ((hit >> j) & 1u) {
+                const uint32_t slot = bs + (uint32_t)__popc(b & lt);
+                if (slot < CAP) cand[(size_t)(q0 + (uint32_t)j) * CAP + slot] = make_uint2(row, r[j]);
+            }
+        }
+    }
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B operand descriptor: rows at a 128-byte pitch, 8-row groups 1024 bytes apart
@@ -104,6 +141,34 @@ inline EncodeTiledFn tc_encode_fn() {
         cudaGetLastError();
     }
     return fn;
+}
+
+// Row ranges of the filtered GEMM's phases: [0, s0) unfiltered, then edges in a common ratio <= growth so that a phase
+// admits ~ (growth - 1) * k rows per query (growth is what the per-phase candidate buffer affords). The fewest phases
+// with that property, the last one ending exactly at n: every launch carries a fixed ~50-80 us (pipeline fill, tail,
+// the merge that follows), so a short trailing phase is the most expensive way to finish.
+inline std::vector<std::pair<uint32_t, uint32_t>> make_phases(size_t n, size_t k, size_t cand_cap, size_t bm) {
+    std::vector<std::pair<uint32_t, uint32_t>> phases;
+    size_t s0 = std::max<size_t>(bm, std::min<size_t>(cand_cap, 2048) / bm * bm);
+    s0 = std::max(s0, (std::min<size_t>(2 * k, cand_cap) + bm - 1) / bm * bm);
+    if (const char *e = getenv("VSGPU_PHASE_S0")) { // experiments only
+        const size_t v = (size_t)atol(e) / bm * bm;
+        if (v >= s0 && v <= cand_cap) s0 = v;
+    }
+    const double growth = std::max(3.0, std::min(8.0, (double)cand_cap / (2.5 * (double)k)));
+    size_t np = 1;
+    if (n > s0) np += (size_t)std::ceil(std::log((double)n / (double)s0) / std::log(growth) - 1e-9);
+    const double ratio = np > 1 ? std::pow((double)n / (double)s0, 1.0 / (double)(np - 1)) : 1.0;
+    size_t a = 0;
+    double edge = (double)std::min(n, s0);
+    for (size_t p = 0; p < np && a < n; p++) {
+        const size_t b = p + 1 == np ? n : std::min(n, std::max((size_t)edge / bm * bm, a + bm));
+        phases.emplace_back((uint32_t)a, (uint32_t)b);
+        a = b;
+        edge *= ratio;
+    }
+    if (a < n) phases.emplace_back((uint32_t)a, (uint32_t)n);
+    return phases;
 }
 
 } // namespace vsgpu

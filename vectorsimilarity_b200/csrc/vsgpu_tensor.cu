@@ -168,21 +168,12 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             if (q < g.nq) g.dump[(size_t)(row - g.row0) * g.dump_ld + q] = __uint_as_float(r[j]);
                         }
                     }
-                } else if (row_ok) {
-                    // all 32 compares first (independent, no branch in between), then the rare hits
+                } else {
+                    // all 32 compares first (independent, no branch in between), then the hits of the whole warp
                     uint32_t hit = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) hit |= (__uint_as_float(r[j]) >= thr[j] ? 1u : 0u) << j;
-                    if (hit) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if ((hit >> j) & 1u) {
-                                const uint32_t q = nt * BN + col + j;
-                                const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
-                                if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = make_uint2(row, r[j]);
-                            }
-                        }
-                    }
+                    warp_append_hits<CAND_CAP>(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane);
                 }
             }
             tc_fence_before();
@@ -306,14 +297,21 @@ struct MergeArgs {
     unsigned long long *total_cand;
 };
 
-// One block per query. Sort (survivors U this phase's candidates) by coarse accumulator, descending.
-// With A_K the k-th largest accumulator seen so far, every row of the exact top-k — including every
-// row tied with the k-th exact score — has acc >= A_K - 2*eps, so that is both the
-// survivor cut and the next phase's admission bound.
-__global__ void __launch_bounds__(1024) merge_phase_kernel(MergeArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint32_t s_keep;
+// One block per query over (survivors U this phase's candidates). With A_K the k-th largest coarse accumulator seen so
+// far, every row of the exact top-k — including every row tied with the k-th exact score — has acc >= A_K - 2*eps
+// (DESIGN.md §5.3), so that is both the survivor cut and the next phase's admission bound. Only A_K is needed, not an
+// order: an 8-bit radix select over (key - min key) finds it in at most four histogram passes over shared memory (the
+// first version sorted all <= 4096 pairs bitonically, 78 block-wide stages: 130 us per phase at 1024 queries); the
+// survivors are then compacted in any order (the re-rank orders the final list by exact score and id).
+constexpr int MERGE_THREADS = 256;
+__global__ void __launch_bounds__(MERGE_THREADS) merge_phase_kernel(MergeArgs a) {
+    __shared__ uint32_t s_key[RUN_CAP + CAND_CAP]; // ~key(acc): ascending key = descending acc
+    __shared__ uint32_t s_rid[RUN_CAP];            // run[] is rewritten in place: stage the survivors' ids
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_red[2 * (MERGE_THREADS / 32)];
+    __shared__ uint32_t s_digit, s_below, s_keep;
     const uint32_t q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t cnt = a.cnt[q];
     const uint32_t rcnt = a.run_cnt[q];
     if (threadIdx.x == 0 && cnt) atomicAdd(a.total_cand, (unsigned long long)min(cnt, CAND_CAP));
@@ -322,54 +320,99 @@ __global__ void __launch_bounds__(1024) merge_phase_kernel(MergeArgs a) {
         cnt = CAND_CAP;
     }
     const uint32_t total = rcnt + cnt;
-    uint32_t P = 32;
-    while (P < total) P <<= 1;
-    uint32_t *sk = reinterpret_cast<uint32_t *>(smem_raw); // ~key(acc): ascending key = descending acc
-    uint32_t *si = sk + P;
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
-        uint32_t key = 0xffffffffu, id = 0xffffffffu;
-        if (i < total) {
-            const uint2 e = i < rcnt ? a.run[(size_t)q * RUN_CAP + i] : a.cand[(size_t)q * CAND_CAP + (i - rcnt)];
-            id = e.x;
-            key = ~f2key(__uint_as_float(e.y));
-            if (key == 0xffffffffu) key = 0xfffffffeu; // keep real entries ahead of padding
+    const uint2 *run_q = a.run + (size_t)q * RUN_CAP;
+    const uint2 *cand_q = a.cand + (size_t)q * CAND_CAP;
+    uint32_t kmin = 0xffffffffu, kmax = 0;
+    for (uint32_t i = threadIdx.x; i < total; i += MERGE_THREADS) {
+        uint2 e;
+        if (i < rcnt) {
+            e = run_q[i];
+            s_rid[i] = e.x;
+        } else {
+            e = cand_q[i - rcnt];
         }
-        sk[i] = key;
-        si[i] = id;
+        const uint32_t key = ~f2key(__uint_as_float(e.y));
+        s_key[i] = key;
+        kmin = min(kmin, key);
+        kmax = max(kmax, key);
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) {
+        s_red[2 * warp] = kmin;
+        s_red[2 * warp + 1] = kmax;
     }
     if (threadIdx.x == 0) s_keep = 0;
     __syncthreads();
-    for (uint32_t size = 2; size <= P; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = threadIdx.x; t < P / 2; t += blockDim.x) {
-                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                const bool asc = (lo & size) == 0;
-                const uint32_t ka = sk[lo], kb = sk[hi], ia = si[lo], ib = si[hi];
-                const bool gt = ka > kb || (ka == kb && ia > ib);
-                if (gt == asc) { sk[lo] = kb; sk[hi] = ka; si[lo] = ib; si[hi] = ia; }
-            }
-            __syncthreads();
-        }
-    }
     float bound = -__int_as_float(0x7f800000);
     if (total >= a.k) {
-        const float ak = key2f(~sk[a.k - 1]);
+#pragma unroll
+        for (int w = 0; w < MERGE_THREADS / 32; w++) {
+            kmin = min(kmin, s_red[2 * w]);
+            kmax = max(kmax, s_red[2 * w + 1]);
+        }
+        const uint32_t range = kmax - kmin;
+        const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
+        uint32_t prefix = 0;      // digits of (k-th smallest key - kmin) decided so far
+        uint32_t want = a.k - 1;  // 0-based rank among the keys that share those digits
+        for (int shift = 8 * (passes - 1); shift >= 0; shift -= 8) {
+            s_hist[threadIdx.x] = 0; // MERGE_THREADS == 256 bins
+            __syncthreads();
+            const bool first = shift == 8 * (passes - 1); // no digits decided yet (and shift + 8 may be 32)
+            for (uint32_t i = threadIdx.x; i < total; i += MERGE_THREADS) {
+                const uint32_t d = s_key[i] - kmin;
+                if (first || (d >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&s_hist[(d >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t h[8], sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    h[b] = s_hist[8 * lane + b];
+                    sum += h[b];
+                }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                uint32_t below = incl - sum;
+                if (want >= below && want < incl) {
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        if (want >= below && want < below + h[b]) {
+                            s_digit = (uint32_t)(8 * lane + b);
+                            s_below = below;
+                        }
+                        below += h[b];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= s_digit << shift;
+            want -= s_below;
+        }
+        const float ak = key2f(~(kmin + prefix));
         bound = __fsub_rd(ak, __fmul_ru(2.0f, a.eps[q]));
         bound = __fsub_rd(bound, fabsf(bound) * 1e-6f);
     }
-    // survivors: a prefix of the sorted list
-    uint32_t local = 0;
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) local += key2f(~sk[i]) >= bound ? 1u : 0u;
-    if (local) atomicAdd(&s_keep, local);
-    __syncthreads();
-    uint32_t keep = s_keep;
-    if (keep > RUN_CAP) {
-        if (threadIdx.x == 0) a.overflow[q] = 1;
-        keep = RUN_CAP;
+    // survivors, in any order
+    uint2 *run_out = a.run + (size_t)q * RUN_CAP;
+    for (uint32_t i = threadIdx.x; i < total; i += MERGE_THREADS) {
+        const float acc = key2f(~s_key[i]);
+        if (acc >= bound) {
+            const uint32_t slot = atomicAdd(&s_keep, 1u);
+            if (slot < RUN_CAP) run_out[slot] = make_uint2(i < rcnt ? s_rid[i] : cand_q[i - rcnt].x, __float_as_uint(acc));
+        }
     }
-    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x)
-        a.run[(size_t)q * RUN_CAP + i] = make_uint2(si[i], __float_as_uint(key2f(~sk[i])));
+    __syncthreads();
     if (threadIdx.x == 0) {
+        uint32_t keep = s_keep;
+        if (keep > RUN_CAP) {
+            a.overflow[q] = 1;
+            keep = RUN_CAP;
+        }
         a.run_cnt[q] = keep;
         a.cnt[q] = 0;
         a.athr[q] = bound;
@@ -540,21 +583,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
     CUtensorMap map_a;
     VS_TRY(make_map(&map_a, a_base, n, s->dim, a_stride, BM));
 
-    // phases: [0,S0) unfiltered, then geometric growth so a phase admits ~ (growth-1) * k rows per query
-    std::vector<std::pair<uint32_t, uint32_t>> phases;
-    {
-        size_t s0 = std::max<size_t>(BM, std::min<size_t>(CAND_CAP, 2048) / BM * BM);
-        s0 = std::max(s0, (std::min<size_t>(2 * k, CAND_CAP) + BM - 1) / BM * BM);
-        size_t a = 0, b = std::min(n, s0);
-        const double growth = std::max(3.0, std::min(8.0, (double)CAND_CAP / (2.5 * (double)k)));
-        while (a < n) {
-            phases.emplace_back((uint32_t)a, (uint32_t)b);
-            a = b;
-            size_t nb = (size_t)((double)b * growth);
-            nb = nb / BM * BM;
-            b = std::min(n, std::max(nb, a + BM));
-        }
-    }
+    const std::vector<std::pair<uint32_t, uint32_t>> phases = make_phases(n, k, CAND_CAP, BM);
 
     for (size_t q0 = 0; q0 < nq_all; q0 += MAX_NQ) {
         const size_t nq = std::min<size_t>(MAX_NQ, nq_all - q0);
@@ -619,8 +648,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             m.athr = athr;
             m.overflow = ovf;
             m.total_cand = tot;
-            const size_t msmem = (size_t)4096 * 8;
-            merge_phase_kernel<<<(unsigned)nq, 1024, msmem, s->stream>>>(m);
+            merge_phase_kernel<<<(unsigned)nq, MERGE_THREADS, 0, s->stream>>>(m);
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
         }

@@ -157,22 +157,13 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             if (q < g.nq) g.dump[(size_t)(row - g.row0) * g.dump_ld + q] = (int)r[j];
                         }
                     }
-                } else if (row_ok) {
-                    // 3 instructions per accumulator (I2F, FFMA, FSETP), all 32 first, then the rare hits; padded
-                    // query columns carry c_q = +inf
+                } else {
+                    // 3 instructions per accumulator (I2F, FFMA, FSETP), all 32 first, then the hits of the whole warp;
+                    // padded query columns carry c_q = +inf
                     uint32_t hit = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) hit |= (__int2float_rn((int)r[j]) >= fmaf(cq[j], rm, ra2) ? 1u : 0u) << j;
-                    if (hit) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if ((hit >> j) & 1u) {
-                                const uint32_t q = nt * BN + col + j;
-                                const uint32_t slot = atomicAdd(&g.cnt[q], 1u);
-                                if (slot < CAND_CAP) g.cand[(size_t)q * CAND_CAP + slot] = make_uint2(row, r[j]);
-                            }
-                        }
-                    }
+                    warp_append_hits<CAND_CAP>(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane);
                 }
             }
             tc_fence_before();
@@ -450,19 +441,7 @@ int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_st
     const bool uns = s->type == VSGPU_UINT8;
     CUtensorMap map_a;
     VS_TRY(make_map_u8(&map_a, s->rows, n, s->dim, s->row_stride, BM));
-    std::vector<std::pair<uint32_t, uint32_t>> phases;
-    {
-        size_t s0 = std::max<size_t>(BM, std::min<size_t>(CAND_CAP, 2048) / BM * BM);
-        s0 = std::max(s0, (std::min<size_t>(2 * k, CAND_CAP) + BM - 1) / BM * BM);
-        size_t a = 0, b = std::min(n, s0);
-        const double growth = std::max(3.0, std::min(8.0, (double)CAND_CAP / (2.5 * (double)k)));
-        while (a < n) {
-            phases.emplace_back((uint32_t)a, (uint32_t)b);
-            a = b;
-            size_t nb = (size_t)((double)b * growth) / BM * BM;
-            b = std::min(n, std::max(nb, a + BM));
-        }
-    }
+    const std::vector<std::pair<uint32_t, uint32_t>> phases = make_phases(n, k, CAND_CAP, BM);
     VS_CUDA(cudaEventRecord(s->ev2, s->stream));
     for (size_t q0 = 0; q0 < nq_all; q0 += MAX_NQ) {
         const size_t nq = std::min<size_t>(MAX_NQ, nq_all - q0);
