@@ -8,7 +8,7 @@
  * links against this library unchanged. Struct layouts are an ABI contract: every struct below is
  * byte-compatible with its namesake there (sizes and offsets are static_assert-ed in
  * vectorsimilarity_b200/csrc/host/vecsim_api.cpp against values measured from the reference).
- * Members this library never reads (SVS / tiered parameter blocks) are carried as opaque storage.
+ * Members this library never reads (SVS parameter blocks) are carried as opaque storage.
  *
  * New, non-breaking additions: VecSimIndex_TopKQueryBatch, VecSimGPU_*.
  */
@@ -57,10 +57,23 @@ typedef struct {
     size_t M; size_t efConstruction; size_t efRuntime; double epsilon;
 } HNSWParams;
 typedef struct VecSimParams VecSimParams;
+/* tiered index (vec_sim_common.h:126-141, 206-241): jobs are opaque to the caller, which only hands each job back to
+ * its callback from one of its worker threads */
+typedef struct AsyncJob AsyncJob;
+typedef void (*JobCallback)(AsyncJob *);
+typedef int (*SubmitCB)(void *job_queue, void *index_ctx, AsyncJob **jobs, JobCallback *CBs, size_t jobs_len);
+typedef struct { size_t swapJobThreshold; } TieredHNSWParams;
+typedef struct {
+    void *jobQueue; void *jobQueueCtx; SubmitCB submitCb;
+    size_t flatBufferLimit;            /* flat buffer full -> in-place insertion into the backend */
+    VecSimParams *primaryIndexParams;  /* the backend index (HNSW) */
+    union { TieredHNSWParams tieredHnswParams; uint64_t _opaque[3]; /* SVS / disk variants */ } specificParams;
+} TieredIndexParams;
 typedef union {
     HNSWParams hnswParams;
     BFParams bfParams;
-    uint64_t _opaque[15]; /* TieredIndexParams / SVSParams storage (120 bytes): never read here */
+    TieredIndexParams tieredParams;
+    uint64_t _opaque[15]; /* SVSParams storage (120 bytes): never read here */
 } AlgoParams;
 struct VecSimParams {
     VecSimAlgo algo;
@@ -96,9 +109,16 @@ typedef struct {
     size_t M, efConstruction, efRuntime; double epsilon; size_t max_level, entrypoint, visitedNodesPoolSize, numberOfMarkedDeletedNodes;
 } hnswInfoStruct;
 typedef struct { char dummy; } bfInfoStruct;
+typedef struct { size_t pendingSwapJobsThreshold; } HnswTieredInfo;
+typedef struct {
+    union { hnswInfoStruct hnswInfo; uint64_t _opaque[13]; /* svsInfoStruct */ } backendInfo;
+    union { HnswTieredInfo hnswTieredInfo; uint64_t _opaque[4]; /* SvsTieredInfo */ } specificTieredBackendInfo;
+    CommonInfo backendCommonInfo; CommonInfo frontendCommonInfo; bfInfoStruct bfInfo;
+    uint64_t management_layer_memory; VecSimBool backgroundIndexing; size_t bufferLimit;
+} tieredInfoStruct;
 typedef struct {
     CommonInfo commonInfo;
-    union { bfInfoStruct bfInfo; hnswInfoStruct hnswInfo; uint64_t _opaque[37]; /* svs / tiered info */ };
+    union { bfInfoStruct bfInfo; hnswInfoStruct hnswInfo; tieredInfoStruct tieredInfo; uint64_t _opaque[37]; /* svs */ };
 } VecSimIndexDebugInfo;
 
 /* ---- callbacks (vec_sim_common.h:452-490) ---- */

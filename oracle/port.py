@@ -353,3 +353,48 @@ class PortHnswBatchIterator:
         if self.it:
             lib().vso_hnsw_bi_free(self.it)
             self.it = None
+
+
+# ---- tiered index: merge of the two tiers' replies -------------------------------------------------------------------
+VECSIM_EPSILON = 1e-6  # /root/reference/src/VecSim/utils/query_result_utils.h:14
+
+
+def _cmp_score_then_id(a, b):
+    """cmpVecSimQueryResultByScoreThenId (query_result_utils.h:18-23); a, b = (id, score)."""
+    if not abs(a[1] - b[1]) < VECSIM_EPSILON:
+        return 1 if a[1] > b[1] else -1
+    d = (int(a[0]) - int(b[0])) & 0xFFFFFFFFFFFFFFFF  # size_t difference ...
+    d &= 0xFFFFFFFF                                     # ... truncated to int
+    return d - (1 << 32) if d & 0x80000000 else d
+
+
+def merge_results(first, second, limit):
+    """merge_results<withSet=false> (query_result_utils.h:44-92): both lists ascending by (score, id), entries are
+    (id, score); a result present in both (same score) is emitted once. -> (merged, taken_first, taken_second)."""
+    out, i, j = [], 0, 0
+    limit = (1 << 64) - 1 if limit is None or limit < 0 else limit
+    while limit and i < len(first) and j < len(second):
+        c = _cmp_score_then_id(first[i], second[j])
+        if c > 0:
+            out.append(second[j])
+            j += 1
+        elif c < 0:
+            out.append(first[i])
+            i += 1
+        else:
+            out.append(first[i])
+            i += 1
+            j += 1
+        limit -= 1
+    if limit:
+        if i == len(first):
+            while limit and j < len(second):
+                out.append(second[j])
+                j += 1
+                limit -= 1
+        else:
+            while limit and i < len(first):
+                out.append(first[i])
+                i += 1
+                limit -= 1
+    return out, i, j

@@ -115,3 +115,38 @@ def test_tie_resolution_matches_oracle(capi, port):
         assert m == len(want_l), trial
         assert np.array_equal(out_l[:m], want_l), trial
         assert np.array_equal(out_s[:m], want_s), trial
+
+
+def test_tiered_merge_matches_reference_merge_results(capi, port):
+    """The tiered index's reply merge (csrc/host/vecsim_tiered.cpp) against the restated merge_results
+    (query_result_utils.h:44-92): score-then-id order with the 1e-6 score epsilon, duplicates emitted once, limit."""
+    L = capi.lib()
+    L.vsb_test_tiered_merge.restype = C.c_size_t
+    L.vsb_test_tiered_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        n_all = int(rng.integers(0, 60))
+        ids = rng.permutation(200)[:n_all].astype(np.uint64)
+        # few distinct scores (ties), some within the epsilon of each other
+        scores = rng.integers(0, 8, n_all).astype(np.float64) + rng.choice([0.0, 2e-7, 4e-7], n_all)
+        in_a = rng.random(n_all) < 0.6
+        in_b = (rng.random(n_all) < 0.6) | ~in_a
+        def side(mask):
+            sel = np.nonzero(mask)[0]
+            order = np.lexsort((ids[sel], scores[sel]))
+            return np.ascontiguousarray(ids[sel][order]), np.ascontiguousarray(scores[sel][order])
+        ai, asc = side(in_a)
+        bi, bsc = side(in_b)
+        limit = int(rng.integers(0, 70)) if trial % 5 else (1 << 64) - 1
+        want, ta, tb = port.merge_results(list(zip(ai.tolist(), asc.tolist())), list(zip(bi.tolist(), bsc.tolist())),
+                                          None if limit == (1 << 64) - 1 else limit)
+        out_i = np.empty(len(ai) + len(bi) + 1, dtype=np.uint64)
+        out_s = np.empty(len(ai) + len(bi) + 1, dtype=np.float64)
+        taken = np.zeros(2, dtype=np.uint64)
+        m = L.vsb_test_tiered_merge(ai.ctypes.data, asc.ctypes.data, len(ai), bi.ctypes.data, bsc.ctypes.data, len(bi), limit,
+                                    out_i.ctypes.data, out_s.ctypes.data, taken.ctypes.data)
+        assert m == len(want), trial
+        assert out_i[:m].tolist() == [w[0] for w in want], trial
+        assert out_s[:m].tolist() == [w[1] for w in want], trial
+        assert (int(taken[0]), int(taken[1])) == (ta, tb), trial

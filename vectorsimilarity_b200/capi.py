@@ -35,8 +35,26 @@ class HNSWParams(C.Structure):
                 ("efConstruction", C.c_size_t), ("efRuntime", C.c_size_t), ("epsilon", C.c_double)]
 
 
+JOB_CB = C.CFUNCTYPE(None, C.c_void_p)
+SUBMIT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(JOB_CB), C.c_size_t)
+
+
+class TieredHNSWParams(C.Structure):
+    _fields_ = [("swapJobThreshold", C.c_size_t)]
+
+
+class _TieredSpecific(C.Union):
+    _fields_ = [("tieredHnswParams", TieredHNSWParams), ("_opaque", C.c_uint64 * 3)]
+
+
+class TieredIndexParams(C.Structure):
+    _fields_ = [("jobQueue", C.c_void_p), ("jobQueueCtx", C.c_void_p), ("submitCb", SUBMIT_CB),
+                ("flatBufferLimit", C.c_size_t), ("primaryIndexParams", C.c_void_p), ("specificParams", _TieredSpecific)]
+
+
 class AlgoParams(C.Union):
-    _fields_ = [("hnswParams", HNSWParams), ("bfParams", BFParams), ("_opaque", C.c_uint64 * 15)]
+    _fields_ = [("hnswParams", HNSWParams), ("bfParams", BFParams), ("tieredParams", TieredIndexParams),
+                ("_opaque", C.c_uint64 * 15)]
 
 
 class VecSimParams(C.Structure):
@@ -77,6 +95,7 @@ class VecSim_InfoField(C.Structure):
 
 
 assert C.sizeof(BFParams) == 40 and C.sizeof(VecSimParams) == 136 and C.sizeof(VecSimQueryParams) == 56
+assert C.sizeof(TieredIndexParams) == 64
 
 TIMEOUT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
@@ -202,6 +221,10 @@ def lib():
     L.VecSimGPU_HNSWImportGraph.argtypes = [vp, vp, i32, sz, vp, vp, vp, vp, sz, C.c_long, C.c_long]
     L.VecSimGPU_HNSWExportGraph.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz), C.POINTER(C.c_long), C.POINTER(C.c_long)]
     L.VecSimGPU_HNSWLastStats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
+    L.VecSim_SetWriteMode.argtypes = [i32]
+    L.VecSimTieredIndex_GC.argtypes = [vp]
+    L.VecSimTieredIndex_AcquireSharedLocks.argtypes = [vp]
+    L.VecSimTieredIndex_ReleaseSharedLocks.argtypes = [vp]
     _lib = L
     return L
 
@@ -390,8 +413,10 @@ class VecSimIndex:
 
     def debug_info(self):
         """VecSimIndex_DebugInfoIterator drained into an ordered list of (name, value)."""
+        return self._drain_info(lib().VecSimIndex_DebugInfoIterator(self._h), free=True)
+
+    def _drain_info(self, it, free):
         L = lib()
-        it = L.VecSimIndex_DebugInfoIterator(self._h)
         out = []
         n = L.VecSimDebugInfoIterator_NumberOfFields(it)
         while L.VecSimDebugInfoIterator_HasNextField(it):
@@ -403,11 +428,14 @@ class VecSimIndex:
                 v = f.fieldValue.integerValue
             elif f.fieldType == 2:
                 v = f.fieldValue.uintegerValue
+            elif f.fieldType == 4:  # nested iterator (tiered: FRONTEND_INDEX / BACKEND_INDEX), owned by its parent
+                v = self._drain_info(f.fieldValue.iteratorValue, free=False)
             else:
                 v = f.fieldValue.floatingPointValue
             out.append((f.fieldName.decode(), v.decode() if isinstance(v, bytes) else v))
         assert len(out) == n
-        L.VecSimDebugInfoIterator_Free(it)
+        if free:
+            L.VecSimDebugInfoIterator_Free(it)
         return out
 
 
@@ -510,6 +538,98 @@ class HNSWIndex(VecSimIndex):
         ev, hops, ms = C.c_ulonglong(), C.c_ulonglong(), C.c_float()
         lib().VecSimGPU_HNSWLastStats(self._h, C.byref(ev), C.byref(hops), C.byref(ms))
         return dict(dist_evals=ev.value, hops=hops.value, ms=ms.value)
+
+
+class Tiered_HNSWIndex(HNSWIndex):
+    """Mirror of the reference binding's Tiered_HNSWIndex (src/python_bindings/bindings.cpp:486-560): the index is
+    created over a mock job queue owned by this object; add_vector files an insert job, wait_for_index runs the
+    queued jobs (on `threads` Python threads, as RediSearch's workers would) until the flat buffer is drained."""
+
+    def __init__(self, hnsw_params, tiered_hnsw_params=None, flat_buffer_size=1024, threads=0):
+        import collections
+        import threading
+        self._jobs = collections.deque()
+        self._jobs_lock = threading.Lock()
+        self._threads = threads
+
+        def submit(_queue, _ctx, jobs, cbs, n):
+            with self._jobs_lock:
+                for i in range(n):
+                    self._jobs.append((jobs[i], C.cast(cbs[i], C.c_void_p).value))
+            return 0
+
+        self._submit = SUBMIT_CB(submit)  # kept alive with the index
+        self._primary = VecSimParams()
+        self._primary.algo = VecSimAlgo_HNSWLIB
+        self._primary.algoParams.hnswParams = hnsw_params
+        p = VecSimParams()
+        p.algo = VecSimAlgo_TIERED
+        tp = p.algoParams.tieredParams
+        tp.jobQueue = None
+        tp.jobQueueCtx = None
+        tp.submitCb = self._submit
+        tp.flatBufferLimit = flat_buffer_size
+        tp.primaryIndexParams = C.cast(C.pointer(self._primary), C.c_void_p)
+        tp.specificParams.tieredHnswParams.swapJobThreshold = tiered_hnsw_params.swapJobThreshold if tiered_hnsw_params else 0
+        VecSimIndex.__init__(self, p)
+        self.M = hnsw_params.M or 16
+        self._ef = 0
+        self._buffer_limit = flat_buffer_size
+
+    def pending_jobs(self):
+        with self._jobs_lock:
+            return len(self._jobs)
+
+    def run_jobs(self, max_jobs=None):
+        """Execute queued jobs on the calling thread; -> number run."""
+        done = 0
+        while max_jobs is None or done < max_jobs:
+            with self._jobs_lock:
+                if not self._jobs:
+                    break
+                job, cb = self._jobs.popleft()
+            JOB_CB(cb)(job)
+            done += 1
+        return done
+
+    def wait_for_index(self, waiting_duration=10):
+        if self._threads <= 1:
+            self.run_jobs()
+            return
+        import threading
+        ts = [threading.Thread(target=self.run_jobs) for _ in range(self._threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(waiting_duration)
+
+    def get_curr_bf_size(self):
+        return lib().VecSimIndex_StatsInfo(self._h).flatBufferSize
+
+    def get_buffer_limit(self):
+        return self._buffer_limit
+
+    def get_threads_num(self):
+        return max(self._threads, 1)
+
+    def hnsw_label_count(self):
+        return self.index_size() - self.get_curr_bf_size()
+
+    def stats(self):
+        st = lib().VecSimIndex_StatsInfo(self._h)
+        return dict(memory=st.memory, numberOfMarkedDeleted=st.numberOfMarkedDeleted,
+                    directHNSWInsertions=st.directHNSWInsertions, flatBufferSize=st.flatBufferSize)
+
+    def close(self):
+        # queued jobs that never ran still reference the index: run them (they are cheap no-ops once it is drained)
+        if getattr(self, "_h", None):
+            self.run_jobs()
+        super().close()
+
+
+def set_write_mode(in_place):
+    """VecSim_SetWriteMode: False = VecSim_WriteAsync (default), True = VecSim_WriteInPlace."""
+    lib().VecSim_SetWriteMode(1 if in_place else 0)
 
 
 class BatchIterator:

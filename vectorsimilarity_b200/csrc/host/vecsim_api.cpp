@@ -16,6 +16,14 @@
 static_assert(sizeof(BFParams) == 40 && offsetof(BFParams, blockSize) == 32, "BFParams ABI");
 static_assert(sizeof(HNSWParams) == 72 && offsetof(HNSWParams, epsilon) == 64, "HNSWParams ABI");
 static_assert(sizeof(AlgoParams) == 120, "AlgoParams ABI");
+static_assert(sizeof(TieredIndexParams) == 64 && offsetof(TieredIndexParams, submitCb) == 16 &&
+                  offsetof(TieredIndexParams, primaryIndexParams) == 32 && offsetof(TieredIndexParams, specificParams) == 40,
+              "TieredIndexParams ABI");
+static_assert(sizeof(tieredInfoStruct) == 296 && offsetof(tieredInfoStruct, specificTieredBackendInfo) == 104 &&
+                  offsetof(tieredInfoStruct, backendCommonInfo) == 136 && offsetof(tieredInfoStruct, frontendCommonInfo) == 200 &&
+                  offsetof(tieredInfoStruct, bfInfo) == 264 && offsetof(tieredInfoStruct, management_layer_memory) == 272 &&
+                  offsetof(tieredInfoStruct, backgroundIndexing) == 280 && offsetof(tieredInfoStruct, bufferLimit) == 288,
+              "tieredInfoStruct ABI");
 static_assert(sizeof(VecSimParams) == 136 && offsetof(VecSimParams, logCtx) == 128, "VecSimParams ABI");
 static_assert(sizeof(VecSimQueryParams) == 56 && offsetof(VecSimQueryParams, batchSize) == 32 &&
                   offsetof(VecSimQueryParams, timeoutCtx) == 48, "VecSimQueryParams ABI");
@@ -100,7 +108,17 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
             }
             return idx;
         }
-        g_api_err = "VecSimAlgo_BF and VecSimAlgo_HNSWLIB are served by this library (tiered / SVS: SURVEY §8 row f1)";
+        if (params->algo == VecSimAlgo_TIERED) {
+            // index_factories/tiered_factory.cpp: only an HNSW backend (single value per label here)
+            auto *idx = new TieredIndex(params->algoParams.tieredParams, params->logCtx);
+            if (!idx->ok()) {
+                g_api_err = "tiered index: the backend must be a single-value VecSimAlgo_HNSWLIB index";
+                delete idx;
+                return nullptr;
+            }
+            return idx;
+        }
+        g_api_err = "VecSimAlgo_BF, VecSimAlgo_HNSWLIB and VecSimAlgo_TIERED are served by this library (not SVS)";
         return nullptr;
     } catch (...) {
         return nullptr;
@@ -231,6 +249,7 @@ static const char *mode_str(VecSearchMode m) {
 VecSimDebugInfoIterator *VecSimIndex_DebugInfoIterator(VecSimIndex *index) {
     const VecSimIndexDebugInfo info = index->debugInfo();
     auto *it = new VecSimDebugInfoIterator();
+    auto *tiered = dynamic_cast<TieredIndex *>(index);
     auto str = [&](const char *name, const char *v) {
         VecSim_InfoField f{};
         f.fieldName = name;
@@ -246,6 +265,39 @@ VecSimDebugInfoIterator *VecSimIndex_DebugInfoIterator(VecSimIndex *index) {
         it->fields.push_back(f);
     };
     const CommonInfo &c = info.commonInfo;
+    if (tiered) {
+        // vec_sim_tiered_index.h:393-441 + hnsw_tiered.h:1228-1241: the root names itself TIERED, then the common block,
+        // the management fields, one nested iterator per tier and the HNSW-specific threshold
+        str("ALGORITHM", "TIERED");
+        str("TYPE", type_str(c.basicInfo.type));
+        u64("DIMENSION", c.basicInfo.dim);
+        str("METRIC", metric_str(c.basicInfo.metric));
+        u64("IS_MULTI_VALUE", c.basicInfo.isMulti);
+        u64("IS_DISK", c.basicInfo.isDisk);
+        u64("INDEX_SIZE", c.indexSize);
+        u64("INDEX_LABEL_COUNT", c.indexLabelCount);
+        u64("MEMORY", c.memory);
+        str("LAST_SEARCH_MODE", mode_str(c.lastMode));
+        u64("MANAGEMENT_LAYER_MEMORY", info.tieredInfo.management_layer_memory);
+        VecSim_InfoField bg{};
+        bg.fieldName = "BACKGROUND_INDEXING";
+        bg.fieldType = INFOFIELD_INT64;
+        bg.fieldValue.integerValue = info.tieredInfo.backgroundIndexing;
+        it->fields.push_back(bg);
+        u64("TIERED_BUFFER_LIMIT", info.tieredInfo.bufferLimit);
+        VecSim_InfoField fe{};
+        fe.fieldName = "FRONTEND_INDEX";
+        fe.fieldType = INFOFIELD_ITERATOR;
+        fe.fieldValue.iteratorValue = VecSimIndex_DebugInfoIterator(tiered->frontend());
+        it->fields.push_back(fe);
+        VecSim_InfoField be{};
+        be.fieldName = "BACKEND_INDEX";
+        be.fieldType = INFOFIELD_ITERATOR;
+        be.fieldValue.iteratorValue = VecSimIndex_DebugInfoIterator(tiered->backend());
+        it->fields.push_back(be);
+        u64("TIERED_HNSW_SWAP_JOBS_THRESHOLD", info.tieredInfo.specificTieredBackendInfo.hnswTieredInfo.pendingSwapJobsThreshold);
+        return it;
+    }
     str("ALGORITHM", algo_str(c.basicInfo.algo));
     str("TYPE", type_str(c.basicInfo.type));
     u64("DIMENSION", c.basicInfo.dim);
@@ -277,7 +329,12 @@ bool VecSimDebugInfoIterator_HasNextField(VecSimDebugInfoIterator *it) { return 
 VecSim_InfoField *VecSimDebugInfoIterator_NextField(VecSimDebugInfoIterator *it) {
     return it->pos < it->fields.size() ? &it->fields[it->pos++] : nullptr;
 }
-void VecSimDebugInfoIterator_Free(VecSimDebugInfoIterator *it) { delete it; }
+void VecSimDebugInfoIterator_Free(VecSimDebugInfoIterator *it) {
+    if (!it) return;
+    for (auto &f : it->fields) // nested iterators belong to their parent (info_iterator.h:37-45)
+        if (f.fieldType == INFOFIELD_ITERATOR) VecSimDebugInfoIterator_Free(f.fieldValue.iteratorValue);
+    delete it;
+}
 
 int VecSimDebug_GetElementNeighborsInHNSWGraph(VecSimIndex *index, size_t label, int ***neighborsData) {
     *neighborsData = nullptr;
@@ -314,9 +371,14 @@ void VecSimIndex_AdhocBfCtx_GetExactDistances(VecSimAdhocBfCtx *ctx, const size_
     ctx->index->exactDistances(ctx->query.data(), labels, distances_out, count);
 }
 
+// deleted backend nodes are tombstones here: there are no swap jobs to run
 void VecSimTieredIndex_GC(VecSimIndex *) {}
-void VecSimTieredIndex_AcquireSharedLocks(VecSimIndex *) {}
-void VecSimTieredIndex_ReleaseSharedLocks(VecSimIndex *) {}
+void VecSimTieredIndex_AcquireSharedLocks(VecSimIndex *index) {
+    if (auto *t = dynamic_cast<TieredIndex *>(index)) t->acquireSharedLocks();
+}
+void VecSimTieredIndex_ReleaseSharedLocks(VecSimIndex *index) {
+    if (auto *t = dynamic_cast<TieredIndex *>(index)) t->releaseSharedLocks();
+}
 void VecSim_SetMemoryFunctions(VecSimMemoryFunctions f) {
     globals().mem = f;
     globals().mem_set = true;
@@ -429,6 +491,11 @@ size_t vsb_test_resolve(const size_t *labels, const double *scores, const uint32
         out_scores[i] = res[i].score;
     }
     return res.size();
+}
+
+size_t vsb_test_tiered_merge(const size_t *a_ids, const double *a_scores, size_t na, const size_t *b_ids, const double *b_scores,
+                             size_t nb, size_t limit, size_t *out_ids, double *out_scores, size_t *taken) {
+    return tiered_merge_for_test(a_ids, a_scores, na, b_ids, b_scores, nb, limit, out_ids, out_scores, taken);
 }
 
 } // extern "C"

@@ -7,7 +7,9 @@
 #include "../../../include/vsgpu.h"
 #include <cstdint>
 #include <memory>
+#include <atomic>
 #include <mutex>
+#include <shared_mutex>
 #include <random>
 #include <unordered_map>
 #include <utility>
@@ -100,6 +102,11 @@ class FlatIndex final : public VecSimIndexInterface {
     double getDistanceFrom(size_t label, const void *blob) override;
     size_t indexSize() override { return count_; }
     size_t indexLabelCount() override { return count_; }
+    bool hasLabel(size_t label) {
+        std::lock_guard<std::mutex> g(mu_);
+        idType id;
+        return findId(label, &id);
+    }
     long appendDeviceRows(const void *dev_rows, size_t stride, size_t n, size_t first_label);
     VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) override;
     int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels, double *scores,
@@ -229,6 +236,15 @@ class HnswIndex final : public VecSimIndexInterface {
     void lastStats(vsgpu_stats *out) override;
 
     vsgpu_hnsw *deviceGraph();
+    bool hasLabel(size_t label) {
+        std::lock_guard<std::mutex> g(mu_);
+        return label_to_id_.count(label) != 0;
+    }
+    // pushes staged vectors to the device store and graph now (the tiered index ingests from its worker threads)
+    int sync() {
+        std::lock_guard<std::mutex> g(mu_);
+        return flush();
+    }
     int iterNext(vsgpu_hnsw_iter *it, size_t n, size_t *labels, double *scores, size_t *count, int *depleted);
     void iterReset(vsgpu_hnsw_iter *it);
     void iterDestroy(vsgpu_hnsw_iter *it);
@@ -262,5 +278,67 @@ class HnswIndex final : public VecSimIndexInterface {
     VecSearchMode last_mode_ = EMPTY_MODE;
     std::mutex mu_;
 };
+
+// Tiered index (flat buffer in front of an HNSW backend): vecsim_tiered.cpp
+class TieredBatchIterator;
+class TieredIndex final : public VecSimIndexInterface {
+  public:
+    TieredIndex(const TieredIndexParams &p, void *logCtx);
+    ~TieredIndex() override;
+    bool ok() const { return front_ && back_; }
+    int addVector(const void *blob, size_t label) override;
+    long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) override;
+    int deleteVector(size_t label) override;
+    double getDistanceFrom(size_t label, const void *blob) override;
+    size_t indexSize() override;
+    size_t indexLabelCount() override;
+    VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) override;
+    int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels, double *scores,
+                  uint32_t *counts) override;
+    VecSimQueryReply *rangeQuery(const void *blob, double radius, VecSimQueryParams *qp,
+                                 VecSimQueryReply_Order order) override;
+    VecSimBatchIterator *newBatchIterator(const void *blob, VecSimQueryParams *qp) override;
+    VecSimIndexBasicInfo basicInfo() override;
+    VecSimIndexDebugInfo debugInfo() override;
+    VecSimIndexStatsInfo statsInfo() override;
+    bool preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) override;
+    void setLastSearchMode(VecSearchMode m) override;
+    void exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) override;
+    std::vector<uint8_t> preprocessQuery(const void *blob) override;
+    vsgpu_store *deviceStore() override;
+    void lastStats(vsgpu_stats *out) override;
+    int elementNeighbors(size_t label, int ***out) override;
+
+    FlatIndex *frontend() { return front_.get(); }
+    HnswIndex *backend() { return back_.get(); }
+    void acquireSharedLocks();
+    void releaseSharedLocks();
+    size_t pendingJobs() {
+        std::shared_lock<std::shared_mutex> flat(flat_guard_);
+        return pending_.size();
+    }
+
+  private:
+    friend class TieredBatchIterator;
+    static void executeJobWrapper(AsyncJob *job);
+    void executeInsertJob(AsyncJob *job);
+    void invalidateJobLocked(size_t label);
+
+    std::unique_ptr<FlatIndex> front_;
+    std::unique_ptr<HnswIndex> back_;
+    void *job_queue_, *job_queue_ctx_;
+    SubmitCB submit_;
+    size_t flat_limit_, swap_threshold_;
+    size_t data_size_ = 0;
+    std::shared_mutex flat_guard_, main_guard_; // always taken in this order
+    std::mutex drain_mu_;
+    std::unordered_map<size_t, AsyncJob *> label_to_job_; // one pending job per vector in the flat buffer
+    std::vector<AsyncJob *> pending_;                      // the same jobs in submission order
+    std::atomic<size_t> direct_insertions_{0};
+    std::shared_ptr<std::atomic<bool>> alive_;
+};
+
+size_t tiered_merge_for_test(const size_t *a_ids, const double *a_scores, size_t na, const size_t *b_ids, const double *b_scores,
+                             size_t nb, size_t limit, size_t *out_ids, double *out_scores, size_t *taken);
 
 } // namespace vsb

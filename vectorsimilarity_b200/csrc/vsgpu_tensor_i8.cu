@@ -242,7 +242,10 @@ struct I8MergeArgs {
 
 // One block per query: exact scores of this phase's candidates, merge with the running top-k by
 // (score, id), tighten the admission constant.
-__global__ void __launch_bounds__(1024) i8_merge_kernel(I8MergeArgs a) {
+// 256 threads: seven blocks per SM (32 KB of sort space each) — with 1024 threads two fit, and a batch of 4096 queries
+// took 14 waves whose block-wide barriers dominated (0.1 ms per phase, 0.5 ms for the unfiltered first phase).
+constexpr int I8_MERGE_THREADS = 256;
+__global__ void __launch_bounds__(I8_MERGE_THREADS) i8_merge_kernel(I8MergeArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t q = blockIdx.x;
     uint32_t cnt = a.cnt[q];
@@ -508,7 +511,7 @@ int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_st
                 VS_CUDA(cudaFuncSetAttribute(i8_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
                 mattr = true;
             }
-            i8_merge_kernel<<<(unsigned)nq, 1024, msm, s->stream>>>(m);
+            i8_merge_kernel<<<(unsigned)nq, I8_MERGE_THREADS, msm, s->stream>>>(m);
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
         }
