@@ -258,6 +258,12 @@ int VecSimGPU_HNSWImportGraph(VecSimIndex *index, const void *blobs, int process
                               long entry, long max_level);
 int VecSimGPU_HNSWExportGraph(VecSimIndex *index, uint32_t *levels, uint32_t *l0, uint32_t *upper, size_t upper_cap_records,
                               size_t *upper_records, long *entry, long *max_level);
+/* HNSW index files in the reference's serialized format: load = HNSWFactory::NewIndex(location)
+ * (index_factories/hnsw_factory.cpp:171-251; encoding V3 and V4, single value per label; NULL + VecSimGPU_LastError on a
+ * bad file), save = HNSWIndex::saveIndex (algorithms/hnsw/hnsw_serializer_impl.h:247-330; writes encoding V4, which the
+ * reference loads back). Rows land in the device store, links in the device graph. */
+VecSimIndex *VecSimGPU_HNSWLoadIndex(const char *path);
+int VecSimGPU_HNSWSaveIndex(VecSimIndex *index, const char *path);
 int VecSimGPU_HNSWLastStats(VecSimIndex *index, unsigned long long *dist_evals, unsigned long long *hops, float *ms);
 const char *VecSimGPU_LastError(void);
 

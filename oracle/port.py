@@ -398,3 +398,87 @@ def merge_results(first, second, limit):
                 i += 1
                 limit -= 1
     return out, i, j
+
+
+# ---- HNSW index files (encoding V3 / V4) -----------------------------------------------------------------------------
+def read_hnsw_file(path):
+    """Parse a serialized HNSW index the way the reference restores it
+    (/root/reference/src/VecSim/index_factories/hnsw_factory.cpp:171-205 header,
+    algorithms/hnsw/hnsw_serializer_impl.h:145-245 fields / metadata / graph,
+    containers/data_blocks_container.cpp:76-110 vector blocks; V3 stores block counts and lengths, V4 does not).
+    -> dict(version, params..., labels[n], flags[n], vectors[n, stored bytes], levels[n], links[l][n, width],
+    counts[l][n], incoming (number of unidirectional incoming edges, unused by searches))."""
+    import struct
+    buf = open(path, "rb").read()
+    pos = 0
+
+    def rd(fmt):
+        nonlocal pos
+        v = struct.unpack_from("<" + fmt, buf, pos)
+        pos += struct.calcsize("<" + fmt)
+        return v[0] if len(v) == 1 else v
+    version = rd("i")
+    if version not in (3, 4):
+        raise ValueError("encoding version %d is not V3 / V4" % version)
+    algo = rd("i")
+    if algo != 1:
+        raise ValueError("not an HNSW file (algo %d)" % algo)
+    dim, vtype, metric, block_size = rd("Q"), rd("i"), rd("i"), rd("Q")
+    multi, cap = rd("?"), rd("Q")
+    M, M0, efc, ef = rd("Q"), rd("Q"), rd("Q"), rd("Q")
+    epsilon, mult = rd("d"), rd("d")
+    n, n_deleted, max_level, entry = rd("Q"), rd("Q"), rd("Q"), rd("I")
+    labels = np.empty(n, dtype=np.uint64)
+    flags = np.empty(n, dtype=np.uint8)
+    for i in range(n):
+        labels[i], flags[i] = rd("Q"), rd("B")
+    stored = stored_size(vtype, metric, dim)
+    vectors = np.empty((n, stored), dtype=np.uint8)
+    if version == 3:
+        num_blocks = rd("I")
+        got = 0
+        for _ in range(num_blocks):
+            blen = rd("I")
+            vectors[got:got + blen] = np.frombuffer(buf, np.uint8, blen * stored, pos).reshape(blen, stored)
+            pos += blen * stored
+            got += blen
+        assert got == n
+    else:
+        num_blocks = -(-n // block_size) if block_size else 0
+        vectors[:] = np.frombuffer(buf, np.uint8, n * stored, pos).reshape(n, stored)
+        pos += n * stored
+    levels = np.zeros(n, dtype=np.uint32)
+    per_level = {}
+    incoming = 0
+    i = 0
+    for _ in range(num_blocks):
+        blen = rd("I")
+        for _ in range(blen):
+            top = rd("Q")
+            levels[i] = top
+            for lvl in range(top + 1):
+                cnt = rd("H")
+                ids = struct.unpack_from("<%dI" % cnt, buf, pos)
+                pos += 4 * cnt
+                inc = rd("I")
+                pos += 4 * inc
+                incoming += inc
+                per_level.setdefault(lvl, {})[i] = ids
+            i += 1
+    assert i == n and pos == len(buf), (i, n, pos, len(buf))
+    nl = (max(per_level) + 1) if per_level else 0
+    links, counts = [], []
+    for lvl in range(nl):
+        width = M0 if lvl == 0 else M
+        lk = np.full((n, width), 0xFFFFFFFF, dtype=np.uint32)
+        ct = np.zeros(n, dtype=np.uint32)
+        for j, ids in per_level[lvl].items():
+            ct[j] = len(ids)
+            lk[j, :len(ids)] = ids
+        links.append(lk)
+        counts.append(ct)
+    return dict(version=version, dim=dim, type=vtype, metric=metric, block_size=block_size, multi=multi, capacity=cap, M=M, M0=M0,
+                ef_construction=efc, ef_runtime=ef, epsilon=epsilon, mult=mult, n=n, num_deleted=n_deleted,
+                max_level=None if max_level == 0xFFFFFFFFFFFFFFFF else max_level,
+                entry=None if entry == 0xFFFFFFFF else entry, labels=labels, flags=flags, vectors=vectors, levels=levels,
+                links=links, counts=counts, incoming=incoming)

@@ -113,3 +113,31 @@ def test_hnsw_port_reproduces_golden_graph_and_results(port, name, metric):
         assert np.array_equal(s, G[name + "_range_scores"][off:off + n])
         off += n
     P.close()
+
+
+def test_hnsw_file_fixture_parses_and_oracle_rebuilds_its_graph():
+    """The reference's own serialized-index fixture (tests/unit/test_hnsw.cpp:1991-2059 loads it): the restated reader
+    recovers the metadata that test asserts, and the oracle's builder, fed the file's vectors in id order, reproduces
+    the graph stored in the file link for link — a graph written by the reference on its maintainers' machine."""
+    from oracle import port
+    port.build()
+    f = port.read_hnsw_file(os.path.join(HERE, "golden", "ref_hnsw_1k_d4_single.v3"))
+    assert (f["version"], f["n"], f["dim"], f["type"], f["metric"]) == (3, 1001, 4, 0, 0)
+    assert (f["M"], f["M0"], f["ef_construction"], f["ef_runtime"], f["epsilon"], f["block_size"]) == (8, 16, 10, 10, 0.004, 2)
+    assert not f["multi"] and f["num_deleted"] == 0 and np.array_equal(f["labels"], np.arange(1001))
+    X = np.ascontiguousarray(f["vectors"]).view(np.float32)
+    H = port.PortHnsw(0, 4, 0, M=8, ef_construction=10, ef_runtime=10)
+    H.add_many(X, labels=f["labels"])
+    g = H.export()
+    assert g["entry"] == f["entry"] and g["max_level"] == f["max_level"] and np.array_equal(g["levels"], f["levels"])
+    for lvl in range(len(f["links"])):
+        assert np.array_equal(g["counts"][lvl], f["counts"][lvl])
+        mask = np.arange(f["links"][lvl].shape[1])[None, :] < f["counts"][lvl][:, None]
+        assert np.array_equal(np.where(mask, g["links"][lvl], 0), np.where(mask, f["links"][lvl], 0))
+    # and its answers are the unmodified reference's (tests/golden/make_hnsw_file_golden.py)
+    gold = np.load(os.path.join(HERE, "golden", "hnsw_file_case.npz"))
+    for ef in (10, 50):
+        for i, q in enumerate(gold["Q"]):
+            l, s, _ = H.topk(q, 10, ef_runtime=ef)
+            assert np.array_equal(l.astype(np.int64), gold[f"labels_ef{ef}"][i]) and np.array_equal(s, gold[f"scores_ef{ef}"][i])
+    H.close()

@@ -118,6 +118,7 @@ EXPORTS = [
     "VecSimIndex_TopKQueryBatch", "VecSimIndex_TopKQueryBatchRaw", "VecSimIndex_AddVectorBatch",
     "VecSimGPU_SetDevice", "VecSimGPU_GetDevice", "VecSimGPU_DeviceCount", "VecSimGPU_SetTopKMode",
     "VecSimGPU_LastQueryStats", "VecSimGPU_GetStore", "VecSimGPU_LastError", "VecSimGPU_AppendDeviceRows",
+    "VecSimGPU_HNSWLoadIndex", "VecSimGPU_HNSWSaveIndex",
     "VecSimGPU_GetGraph", "VecSimGPU_HNSWImportGraph", "VecSimGPU_HNSWExportGraph", "VecSimGPU_HNSWLastStats",
     "VecSimIndex_DebugInfoIterator", "VecSimDebugInfoIterator_NumberOfFields", "VecSimDebugInfoIterator_HasNextField",
     "VecSimDebugInfoIterator_NextField", "VecSimDebugInfoIterator_Free", "VecSimDebug_GetElementNeighborsInHNSWGraph",
@@ -221,6 +222,9 @@ def lib():
     L.VecSimGPU_HNSWImportGraph.argtypes = [vp, vp, i32, sz, vp, vp, vp, vp, sz, C.c_long, C.c_long]
     L.VecSimGPU_HNSWExportGraph.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz), C.POINTER(C.c_long), C.POINTER(C.c_long)]
     L.VecSimGPU_HNSWLastStats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
+    L.VecSimGPU_HNSWLoadIndex.restype = vp
+    L.VecSimGPU_HNSWLoadIndex.argtypes = [C.c_char_p]
+    L.VecSimGPU_HNSWSaveIndex.argtypes = [vp, C.c_char_p]
     L.VecSim_SetWriteMode.argtypes = [i32]
     L.VecSimTieredIndex_GC.argtypes = [vp]
     L.VecSimTieredIndex_AcquireSharedLocks.argtypes = [vp]
@@ -458,6 +462,25 @@ class HNSWIndex(VecSimIndex):
         super().__init__(p)
         self.M = params.M or 16
         self._ef = 0
+
+    @classmethod
+    def load(cls, path):
+        """HNSWIndex(file_name) of the reference binding (bindings.cpp:300-304): an index restored from a serialized file."""
+        h = lib().VecSimGPU_HNSWLoadIndex(os.fsencode(path))
+        if not h:
+            raise RuntimeError("VecSimGPU_HNSWLoadIndex: " + (lib().VecSimGPU_LastError() or b"").decode())
+        self = cls.__new__(cls)
+        self._h = h
+        info = lib().VecSimIndex_BasicInfo(h)
+        self.type, self.dim, self.metric = info.type, info.dim, info.metric
+        self._blob = TYPE_SIZE[self.type] * self.dim
+        self.M = dict(self.debug_info())["M"]
+        self._ef = 0
+        return self
+
+    def save_index(self, path):
+        if lib().VecSimGPU_HNSWSaveIndex(self._h, os.fsencode(path)) != 0:
+            raise RuntimeError("VecSimGPU_HNSWSaveIndex failed: " + (lib().VecSimGPU_LastError() or b"").decode())
 
     def set_ef(self, ef):
         self._ef = int(ef)

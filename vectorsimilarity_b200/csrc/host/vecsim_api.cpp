@@ -476,6 +476,22 @@ int VecSimGPU_HNSWLastStats(VecSimIndex *index, unsigned long long *dist_evals, 
     if (!h) return -1;
     return vsgpu_hnsw_last_stats(h->deviceGraph(), dist_evals, hops, ms);
 }
+VecSimIndex *VecSimGPU_HNSWLoadIndex(const char *path) {
+    try {
+        std::string err;
+        VecSimIndexInterface *idx = path ? load_hnsw_file(path, err) : nullptr;
+        if (!idx) g_api_err = err.empty() ? "VecSimGPU_HNSWLoadIndex: no path" : err;
+        return idx;
+    } catch (...) {
+        g_api_err = "VecSimGPU_HNSWLoadIndex: out of memory or corrupted file";
+        return nullptr;
+    }
+}
+int VecSimGPU_HNSWSaveIndex(VecSimIndex *index, const char *path) {
+    auto *h = dynamic_cast<HnswIndex *>(index);
+    if (!h || !path) return -1;
+    return h->saveFile(path);
+}
 const char *VecSimGPU_LastError(void) {
     if (!g_api_err.empty()) return g_api_err.c_str();
     return vsgpu_last_error();

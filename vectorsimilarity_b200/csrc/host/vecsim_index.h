@@ -11,6 +11,7 @@
 #include <mutex>
 #include <shared_mutex>
 #include <random>
+#include <string>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -253,6 +254,9 @@ class HnswIndex final : public VecSimIndexInterface {
     int elementNeighbors(size_t label, int ***out) override;
     int importGraph(const void *blobs, int processed, size_t n, const size_t *labels, const uint32_t *levels,
                     const uint32_t *l0, const uint32_t *upper, size_t upper_records, long entry, long max_level);
+    // vecsim_hnsw_file.cpp: the reference's serialized index format
+    int markDeletedById(idType id);
+    int saveFile(const char *path);
 
   private:
     void preprocess(const void *blob, uint8_t *out) const;
@@ -338,6 +342,7 @@ class TieredIndex final : public VecSimIndexInterface {
     std::shared_ptr<std::atomic<bool>> alive_;
 };
 
+VecSimIndexInterface *load_hnsw_file(const char *path, std::string &err);
 size_t tiered_merge_for_test(const size_t *a_ids, const double *a_scores, size_t na, const size_t *b_ids, const double *b_scores,
                              size_t nb, size_t limit, size_t *out_ids, double *out_scores, size_t *taken);
 
