@@ -52,6 +52,27 @@ def main():
             assert np.array_equal(labels[i].view(np.uint64), pl), (rank, vtype, metric, i, labels[i], pl)
             assert np.array_equal(scores[i], ps), (rank, vtype, metric, i)
             checked += 1
+        # range query and batch iterator across the shards (variable-length all-gather)
+        pl, ps, _ = P.topk(Q[0], min(60, n))
+        radius = float(ps[-1]) if ps[-1] >= 0 else 0.25   # IP scores of unnormalised rows go negative; radius may not
+        for order in (capi.BY_SCORE, capi.BY_ID):
+            wl, ws, _ = P.range(Q[0], radius, order=order)
+            gl, gs = S.range_query(Q[0], radius, order=order)
+            assert np.array_equal(gl.view(np.uint64), wl) and np.array_equal(gs, ws), (rank, vtype, metric, "range", order)
+            checked += 1
+        it, pit = S.create_batch_iterator(Q[0]), P.batch_iterator(Q[0])
+        for bs in (1, 10, 37, 100):
+            gl, gs = it.get_next_results(bs)
+            wl, ws, _ = pit.next(bs)
+            assert np.array_equal(gl[0].view(np.uint64), wl) and np.array_equal(gs[0], ws), (rank, vtype, metric, "iterator", bs)
+            checked += 1
+        it.reset()
+        pit.reset()
+        gl, gs = it.get_next_results(5)
+        wl, ws, _ = pit.next(5)
+        assert np.array_equal(gl[0].view(np.uint64), wl) and np.array_equal(gs[0], ws) and it.has_next()
+        it.close()
+        pit.close()
         S.close()
         P.close()
     t = torch.tensor([checked], device="cuda")

@@ -145,6 +145,19 @@ class ShardedFlatIndex:
         torch.cuda.current_stream(self.device).synchronize()
         return out_l.cpu().numpy(), out_s.double().cpu().numpy()
 
+    # ---- range query and batch iterator across shards: variable-length per-shard replies ----
+    def range_query(self, query, radius, order=capi.BY_SCORE):
+        """Raw query blob -> (labels int64 [n], scores float64 [n]) over all shards, ordered like the reference's
+        rangeQuery + sort wrapper (vec_sim_index.h:246-252): by (score, label) or by label."""
+        l, s = self.local.range_query(query, radius, order=capi.BY_SCORE)
+        return merge_varlen(gather_varlen(s[0], l[0], self.group, self._coll_device()), order)
+
+    def create_batch_iterator(self, query):
+        return ShardedBatchIterator(self.local.create_batch_iterator(query), self.group, self._coll_device())
+
+    def _coll_device(self):
+        return self.device if dist.is_initialized() and dist.get_backend(self.group) == "nccl" else None
+
     def last_stats(self):
         st = Stats()
         _vsgpu().vsgpu_last_stats(self.store(), C.byref(st))
@@ -164,3 +177,101 @@ def gather_merge_host(local_scores, local_labels, k, group=None):
     S = np.stack([t.numpy() for t in all_s])
     L = np.stack([t.numpy().view(np.uint64) for t in all_l])
     return merge_topk_host(S, L, k)
+
+
+# ---- variable-length collectives (range replies, batch-iterator tails) -------------------------------------------------
+def gather_varlen(scores, labels, group=None, device=None):
+    """All-gather one (scores float64 [m_r], labels [m_r]) list per rank: counts first, then one padded all-gather.
+    -> [(scores, labels uint64)] indexed by rank, identical on every rank. `device`: CUDA device for NCCL groups (the
+    collective needs device tensors), None for host backends (gloo)."""
+    scores = np.ascontiguousarray(scores, dtype=np.float64)
+    labels = np.ascontiguousarray(labels).astype(np.uint64)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [(scores, labels)]
+    world = dist.get_world_size(group)
+    dev = device if device is not None else torch.device("cpu")
+    cnt = torch.tensor([scores.size], dtype=torch.int64, device=dev)
+    counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts = counts.cpu().numpy()
+    width = int(counts.max())
+    if width == 0:
+        return [(np.zeros(0), np.zeros(0, dtype=np.uint64)) for _ in range(world)]
+    pack = np.zeros((2, width), dtype=np.int64)  # scores travel as their bit patterns: one collective for both
+    pack[0, :scores.size] = scores.view(np.int64)
+    pack[1, :labels.size] = labels.view(np.int64)
+    mine = torch.from_numpy(pack.reshape(-1)).to(dev)
+    everything = torch.empty(world * 2 * width, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(everything, mine, group=group)
+    everything = everything.cpu().numpy().reshape(world, 2, width)
+    return [(everything[r, 0, :counts[r]].view(np.float64).copy(), everything[r, 1, :counts[r]].view(np.uint64).copy())
+            for r in range(world)]
+
+
+def merge_varlen(parts, order=capi.BY_SCORE):
+    """Concatenate per-shard lists and order them as one reply: ascending (score, label), or ascending label (BY_ID).
+    Shards hold disjoint labels, so there is nothing to de-duplicate."""
+    s = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0)
+    l = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, dtype=np.uint64)
+    idx = np.argsort(l, kind="stable") if order == capi.BY_ID else np.lexsort((l, s))
+    return l[idx].astype(np.int64), s[idx]
+
+
+class ShardedBatchIterator:
+    """VecSimBatchIterator over all shards: every Next(n) returns the n globally best results not returned yet, in the
+    order a single index over all rows would (bf_batch_iterator.h:59-214: ascending (score, label), n at a time).
+    Each rank keeps the replicated list of what every shard has fetched but not yet returned; a call tops every shard's
+    list up to n entries (one local Next + one variable-length all-gather), merges, and returns the first n."""
+
+    def __init__(self, local_iterator, group=None, device=None):
+        self.it, self.group, self.device = local_iterator, group, device
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._clear()
+
+    def _clear(self):
+        self.pending = [(np.zeros(0), np.zeros(0, dtype=np.uint64)) for _ in range(self.world)]
+        self.depleted = [False] * self.world
+        self.started = False
+
+    def get_next_results(self, n, order=capi.BY_SCORE):
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        self.started = True
+        want = max(n - self.pending[rank][0].size, 0)
+        if want and self.it.has_next():
+            l, s = self.it.get_next_results(want, order=capi.BY_SCORE)
+            tail = (s[0], l[0].astype(np.uint64))
+        else:
+            tail = (np.zeros(0), np.zeros(0, dtype=np.uint64))
+        # the depleted flag rides along as one extra entry (score NaN, label 1 = depleted)
+        flag = (np.array([np.nan]), np.array([0 if self.it.has_next() else 1], dtype=np.uint64))
+        got = gather_varlen(np.concatenate([tail[0], flag[0]]), np.concatenate([tail[1], flag[1]]), self.group, self.device)
+        for r, (s, l) in enumerate(got):
+            self.depleted[r] = bool(l[-1])
+            self.pending[r] = (np.concatenate([self.pending[r][0], s[:-1]]), np.concatenate([self.pending[r][1], l[:-1]]))
+        s = np.concatenate([p[0] for p in self.pending])
+        l = np.concatenate([p[1] for p in self.pending])
+        src = np.concatenate([np.full(p[0].size, r) for r, p in enumerate(self.pending)]).astype(np.int64)
+        idx = np.lexsort((l, s))[:n]
+        # a shard's entries leave in its own order (each list is ascending), so dropping counts from the front is exact
+        for r in range(self.world):
+            used = int((src[idx] == r).sum())
+            self.pending[r] = (self.pending[r][0][used:], self.pending[r][1][used:])
+        out_l, out_s = l[idx].astype(np.int64), s[idx]
+        if order == capi.BY_ID:
+            o = np.argsort(out_l, kind="stable")
+            out_l, out_s = out_l[o], out_s[o]
+        return out_l.reshape(1, -1), out_s.reshape(1, -1)
+
+    def has_next(self):
+        """False once every shard is depleted and nothing fetched is left (known after a Next, like the reference's
+        tiered iterator: hnsw_tiered.h:1095-1106); before the first Next it is the local iterator's answer."""
+        if not self.started:
+            return self.it.has_next()
+        return not (all(self.depleted) and all(p[0].size == 0 for p in self.pending))
+
+    def reset(self):
+        self.it.reset()
+        self._clear()
+
+    def close(self):
+        self.it.close()
