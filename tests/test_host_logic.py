@@ -150,3 +150,28 @@ def test_tiered_merge_matches_reference_merge_results(capi, port):
         assert out_i[:m].tolist() == [w[0] for w in want], trial
         assert out_s[:m].tolist() == [w[1] for w in want], trial
         assert (int(taken[0]), int(taken[1])) == (ta, tb), trial
+
+
+def test_hybrid_policy_cost_model(capi):
+    """preferAdHocSearch is a cost comparison with device rates (csrc/host/vecsim_hybrid.h): ad hoc
+    for an empty index; once batches win at some subset size they win for every larger one; a flat index prefers ad hoc
+    until the per-label host work outweighs one streamed pass plus its score transfer and selections; on HNSW the
+    crossover grows like sqrt(k * N)."""
+    L = capi.lib()
+    L.vsb_test_prefer_adhoc.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]
+    for algo in (0, 1):
+        assert L.vsb_test_prefer_adhoc(algo, 0, 512, 0, 10) == 1
+        for n, rb, k in ((10_000, 512, 10), (1_000_000, 3072, 100), (50_000_000, 516, 10)):
+            prev = 1
+            for frac in (0.0001, 0.001, 0.01, 0.05, 0.2, 0.5, 0.9, 1.0, 5.0):
+                cur = L.vsb_test_prefer_adhoc(algo, n, rb, max(1, int(frac * n)), k)
+                assert not (cur == 1 and prev == 0), (algo, n, frac)      # monotone: never back to ad hoc
+                prev = cur
+    # flat, 10 M rows of 3 KB: a batch pass costs ~48 ms (scan 4.7 + scores to the host 3.2 + two host selections 40), an
+    # ad-hoc label ~31 ns (gather 1 ns, label lookup 30 ns): crossover near 1.5 M labels
+    assert L.vsb_test_prefer_adhoc(0, 10_000_000, 3072, 500_000, 100) == 1
+    assert L.vsb_test_prefer_adhoc(0, 10_000_000, 3072, 5_000_000, 100) == 0
+    # HNSW, 1 M rows of 512 B, k = 10: crossover near sqrt(hop * k * N / per-label cost) ~ 50 K labels
+    assert L.vsb_test_prefer_adhoc(1, 1_000_000, 512, 10_000, 10) == 1
+    assert L.vsb_test_prefer_adhoc(1, 1_000_000, 512, 200_000, 10) == 0
+    assert L.vsb_test_prefer_adhoc(1, 1_000_000, 512, 200_000, 1000) == 1        # many results wanted: batches get long

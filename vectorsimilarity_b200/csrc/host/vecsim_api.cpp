@@ -2,6 +2,7 @@
 // VecSimBatchIterator_* entry points (see include/vecsim_b200.h for the file:line each replaces)
 // plus the batched / GPU additions. Thin: argument checks, ordering, object lifetime.
 #include "vecsim_index.h"
+#include "vecsim_hybrid.h"
 #include "vecsim_numeric.h"
 #include <algorithm>
 #include <cmath>
@@ -507,6 +508,11 @@ size_t vsb_test_resolve(const size_t *labels, const double *scores, const uint32
         out_scores[i] = res[i].score;
     }
     return res.size();
+}
+
+/* host-logic hook: the hybrid policy alone (algo 0 flat, 1 HNSW) */
+int vsb_test_prefer_adhoc(int algo, size_t index_size, size_t row_bytes, size_t subset, size_t k) {
+    return algo == 0 ? prefer_adhoc_flat(index_size, row_bytes, subset, k) : prefer_adhoc_hnsw(index_size, row_bytes, subset, k);
 }
 
 size_t vsb_test_tiered_merge(const size_t *a_ids, const double *a_scores, size_t na, const size_t *b_ids, const double *b_scores,

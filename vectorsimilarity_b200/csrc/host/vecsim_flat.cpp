@@ -4,6 +4,7 @@
 // libvsgpu.so; there is no CPU fallback — construction fails when no device is available.
 #include "vecsim_index.h"
 #include "vecsim_numeric.h"
+#include "vecsim_hybrid.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -516,14 +517,10 @@ VecSimIndexDebugInfo FlatIndex::debugInfo() {
     return d;
 }
 
-// The reference's tree (brute_force.h:380-451) is fitted to CPU costs. On the device an ad-hoc pass
-// gathers subset*dim bytes while a batch pass streams the whole store, so ad-hoc wins until the
-// subset is a large fraction of the index (re-tuning is SURVEY §8 row f4).
-bool FlatIndex::preferAdHocSearch(size_t subsetSize, size_t, bool initial_check) {
-    const size_t n = indexSize();
-    subsetSize = std::min(subsetSize, n);
-    const float r = n == 0 ? 0.0f : (float)subsetSize / (float)n;
-    const bool res = n <= 5500 || r <= 0.5f;
+// The reference's tree (brute_force.h:380-451) is fitted to CPU costs; here the decision is a cost comparison with device
+// rates (vecsim_hybrid.h).
+bool FlatIndex::preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) {
+    const bool res = prefer_adhoc_flat(indexSize(), stored_size_, subsetSize, k);
     last_mode_ = res ? (initial_check ? HYBRID_ADHOC_BF : HYBRID_BATCHES_TO_ADHOC_BF) : HYBRID_BATCHES;
     return res;
 }

@@ -4,6 +4,7 @@
 // replies hold each label once. Rows live in HBM (vsgpu_store); all distances and the row-level selection run in
 // libvsgpu.so, the per-label reduction of the (few) selected rows is host code. No CPU fallback.
 #include "vecsim_index.h"
+#include "vecsim_hybrid.h"
 #include "vecsim_numeric.h"
 #include <algorithm>
 #include <cmath>
@@ -407,11 +408,11 @@ VecSimIndexDebugInfo FlatMultiIndex::debugInfo() {
     return d;
 }
 
-bool FlatMultiIndex::preferAdHocSearch(size_t subsetSize, size_t, bool initial_check) {
-    const size_t n = indexSize();
-    subsetSize = std::min(subsetSize, n);
-    const float r = n == 0 ? 0.0f : (float)subsetSize / (float)n;
-    const bool res = n <= 5500 || r <= 0.5f;
+bool FlatMultiIndex::preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) {
+    // subsetSize counts labels; every vector of a label is scored ad hoc, so scale by vectors per label
+    const size_t labels = std::max<size_t>(indexLabelCount(), 1);
+    const size_t rows = std::min(indexSize(), (size_t)((double)std::min(subsetSize, labels) * (double)indexSize() / (double)labels));
+    const bool res = prefer_adhoc_flat(indexSize(), stored_size_, rows, k);
     last_mode_ = res ? (initial_check ? HYBRID_ADHOC_BF : HYBRID_BATCHES_TO_ADHOC_BF) : HYBRID_BATCHES;
     return res;
 }

@@ -5,6 +5,7 @@
 // construction run in libvsgpu.so (vsgpu_hnsw_*); there is no CPU fallback.
 #include "vecsim_index.h"
 #include "vecsim_numeric.h"
+#include "vecsim_hybrid.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -365,13 +366,10 @@ VecSimIndexDebugInfo HnswIndex::debugInfo() {
     return d;
 }
 
-// hnsw.h:2340-2400 uses a CPU-fitted tree; on the device graph traversal is latency-bound per query
-// while ad-hoc scoring is a gather, so ad-hoc wins for small subsets (re-tuning: SURVEY §8 row f4).
+// hnsw.h:2340-2400 uses a CPU-fitted tree; here a cost comparison with device rates (vecsim_hybrid.h):
+// a batch pass must surface ~k / r results at one latency-bound hop each, an ad-hoc pass gathers the subset's rows.
 bool HnswIndex::preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) {
-    const size_t n = indexSize();
-    subsetSize = std::min(subsetSize, n);
-    const float r = n == 0 ? 0.0f : (float)subsetSize / (float)n;
-    const bool res = n <= 1000 || r <= 0.05f || (float)k / std::max<float>(1.f, (float)subsetSize) > 0.1f;
+    const bool res = prefer_adhoc_hnsw(indexSize(), stored_size_, subsetSize, k);
     last_mode_ = res ? (initial_check ? HYBRID_ADHOC_BF : HYBRID_BATCHES_TO_ADHOC_BF) : HYBRID_BATCHES;
     return res;
 }
