@@ -37,6 +37,8 @@ WORKLOADS = {
     "flat_fp32_l2_100k_d128_k10_b1": ("fp32", "L2", 100_000, 128, 10, 1),
     "flat_int8_cos_50M_d512_k10_b4096": ("int8", "Cosine", 50_000_000, 512, 10, 4096),
     "flat_bf16_ip_20M_d1024_k100_b1024": ("bf16", "IP", 20_000_000, 1024, 100, 1024),
+    # not a BASELINE config: configs[1] under L2 (the tensor path ranks by a.q - |a|^2 / 2)
+    "flat_fp32_l2_10M_d768_k100_b1024": ("fp32", "L2", 10_000_000, 768, 100, 1024),
 }
 TYPE_ID = {"fp32": 0, "fp64": 1, "bf16": 2, "fp16": 3, "int8": 4, "uint8": 5}
 METRIC_ID = {"L2": 0, "IP": 1, "Cosine": 2}

@@ -76,6 +76,10 @@ def _check_against(capi, G, P, Q, k, mode):
     (2, 2, 200, 36000, 10, 32),
     (3, 1, 128, 40000, 50, 64),      # fp16 store: fp16 x fp16 MMA (kind::f16, format F16), exact products
     (3, 2, 96, 36000, 10, 33),
+    (0, 0, 128, 40000, 10, 40),      # L2: the epilogue ranks by a.q - |a|^2 / 2
+    (0, 0, 200, 36000, 100, 64),
+    (2, 0, 128, 40000, 50, 64),
+    (3, 0, 96, 36000, 10, 33),
 ])
 def test_tensor_path_equals_oracle(capi, port, vtype, metric, dim, n, k, nq):
     dist = "normal" if metric == 1 else "uniform"
@@ -98,12 +102,13 @@ def test_tensor_path_equals_oracle(capi, port, vtype, metric, dim, n, k, nq):
     P.close()
 
 
-def test_tensor_path_equals_exact_path_large(capi):
-    """Config-2 shape at reduced N: fp32 IP d=768 K=100, 256 queries; tensor path vs exact scan."""
+@pytest.mark.parametrize("metric", [1, 0])
+def test_tensor_path_equals_exact_path_large(capi, metric):
+    """Config-2 shape at reduced N: fp32 IP (and L2) d=768 K=100, 256 queries; tensor path vs exact scan."""
     n, dim, k, nq = 200_000, 768, 100, 256
     X = make_vectors(0, n, dim, seed=1, dist="normal")
     Q = make_vectors(0, nq, dim, seed=2, dist="normal")
-    G = _index(capi, 0, dim, 1, X)
+    G = _index(capi, 0, dim, metric, X)
     capi.set_topk_mode(1)
     el, es = G.knn_batch(Q, k)
     capi.set_topk_mode(2)

@@ -65,8 +65,13 @@ struct GemmArgs {
     float *dump;         // debug: [rows][dump_ld] raw accumulators (else NULL)
     uint32_t dump_ld;
     uint32_t idesc;      // IDESC_BF16 / IDESC_FP16
+    const float *row_sub; // L2: ||row||^2 / 2, subtracted from the accumulator (SUB kernels)
 };
 
+// SUB = false: IP / Cosine, the accumulator itself is filtered. SUB = true: L2 — score = ||a||^2 + ||q||^2 - 2 a.q, so with
+// ||q||^2 constant per query the rows are ranked by a' = a.q - ||a||^2 / 2 (larger is better); the epilogue subtracts the
+// row's half square (one FADD per accumulator) and everything downstream (bounds, merge) works on a'.
+template <bool SUB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -150,6 +155,8 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
             const uint32_t row = g.row0 + mt * BM + quad * 32 + (uint32_t)lane;
             const bool row_ok = row < g.row_end;
+            float ra = 0.f;
+            if constexpr (SUB) ra = row_ok ? g.row_sub[row] : 0.f;
             mbar_wait(&sm.tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1
@@ -171,6 +178,10 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 } else {
                     // all 32 compares first (independent, no branch in between), then the hits of the whole warp
                     uint32_t hit = 0;
+                    if constexpr (SUB) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__fsub_rn(__uint_as_float(r[j]), ra));
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j++) hit |= (__uint_as_float(r[j]) >= thr[j] ? 1u : 0u) << j;
                     warp_append_hits<CAND_CAP>(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane);
@@ -193,7 +204,7 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 // mirrors and query preparation
 __global__ void shadow_rows_kernel(const float *__restrict__ rows, size_t row_stride_f, size_t dim, size_t first, size_t n,
                                    __nv_bfloat16 *__restrict__ shadow, size_t shadow_stride, float *__restrict__ row_l2,
-                                   unsigned *__restrict__ max_l2_bits) {
+                                   unsigned *__restrict__ max_l2_bits, float *__restrict__ row_hsq) {
     // one warp per row: bf16 (RNE) copy + ||row||_2 rounded up
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -211,13 +222,15 @@ __global__ void shadow_rows_kernel(const float *__restrict__ rows, size_t row_st
         if (lane == 0) {
             const float nrm = sqrtf(ss) * 1.000001f;
             row_l2[first + i] = nrm;
+            if (row_hsq) row_hsq[first + i] = 0.5f * ss;
             atomicMax(max_l2_bits, __float_as_uint(nrm));
         }
     }
 }
 
 __global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t row_stride_e, size_t dim, size_t first, size_t n,
-                                  float *__restrict__ row_l2, unsigned *__restrict__ max_l2_bits, int is_fp16) {
+                                  float *__restrict__ row_l2, unsigned *__restrict__ max_l2_bits, int is_fp16,
+                                  float *__restrict__ row_hsq) {
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -232,6 +245,7 @@ __global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t
         if (lane == 0) {
             const float nrm = sqrtf(ss) * 1.000001f;
             if (row_l2) row_l2[first + i] = nrm;
+            if (row_hsq) row_hsq[first + i] = 0.5f * ss;
             atomicMax(max_l2_bits, __float_as_uint(nrm));
         }
     }
@@ -241,7 +255,7 @@ __global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t
 // eps[q] = c * ||q|| * max||row||, c from DESIGN.md §5.3
 __global__ void prep_coarse_queries_kernel(const uint8_t *__restrict__ q, size_t q_stride, int is_f32, size_t dim, size_t nq,
                                            __nv_bfloat16 *__restrict__ qb, size_t qb_stride, float c_rel,
-                                           const unsigned *__restrict__ max_l2_bits, float *__restrict__ eps) {
+                                           const unsigned *__restrict__ max_l2_bits, float *__restrict__ eps, float c_l2) {
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -267,7 +281,12 @@ __global__ void prep_coarse_queries_kernel(const uint8_t *__restrict__ q, size_t
             qb[i * qb_stride + e] = b;
         }
         for (int w = 16; w >= 1; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
-        if (lane == 0) eps[i] = c_rel * (sqrtf(ss) * 1.000001f) * __uint_as_float(*max_l2_bits);
+        if (lane == 0) {
+            // IP / Cosine: |acc - exact sum| <= c_rel |q| R. L2 adds the rounding of ||a||^2 / 2, of the subtraction and of the
+            // reference's own fp32 sum of squared differences, all within c_l2 (|q| + R)^2
+            const float qn = sqrtf(ss) * 1.000001f, R = __uint_as_float(*max_l2_bits);
+            eps[i] = c_rel * qn * R + c_l2 * (qn + R) * (qn + R);
+        }
     }
 }
 
@@ -455,6 +474,7 @@ struct TensorState {
     size_t mirrored = 0;         // rows [0, mirrored) have a valid mirror / norm
     size_t cap = 0;              // capacity the mirrors were sized for
     unsigned *max_l2_bits = nullptr;
+    float *row_hsq = nullptr;     // L2 stores: ||row||^2 / 2 per row
     int sms = 0;
     bool attr_set = false;
     std::vector<cudaEvent_t> evs; // per-phase (start, stop) pairs around the coarse GEMM launches
@@ -473,6 +493,7 @@ void tensor_release(vsgpu_store *s) {
     auto *t = (TensorState *)s->tmap_cache;
     if (t) {
         if (t->max_l2_bits) cudaFree(t->max_l2_bits);
+        if (t->row_hsq) cudaFree(t->row_hsq);
         for (cudaEvent_t e : t->evs) cudaEventDestroy(e);
         delete t;
         s->tmap_cache = nullptr;
@@ -491,7 +512,6 @@ bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k) {
     if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8) return tensor_i8_supported(s, nq, k);
     if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16 && s->type != VSGPU_FLOAT16) return false;
     if (s->type == VSGPU_FLOAT16 && s->plan.kind != CK_LANES) return false; // dim >= 16: the fp32-accumulating tier
-    if (s->metric != VSGPU_IP && s->metric != VSGPU_COSINE) return false;
     if (s->plan.kind == CK_SEQ) return false;
     if (nq < 32 || k > 384 || k == 0) return false;
     if (s->dim < 64 || s->dim > 8192) return false;
@@ -517,6 +537,13 @@ int tensor_sync_mirrors(vsgpu_store *s) {
         VS_CUDA(cudaMalloc(&t->max_l2_bits, sizeof(unsigned)));
         VS_CUDA(cudaMemsetAsync(t->max_l2_bits, 0, sizeof(unsigned), s->stream));
     }
+    if (s->metric == VSGPU_L2 && (!t->row_hsq || t->cap != s->capacity)) {
+        if (t->row_hsq) cudaFree(t->row_hsq);
+        t->row_hsq = nullptr;
+        VS_CUDA(cudaMalloc(&t->row_hsq, s->capacity * sizeof(float)));
+        t->cap = s->capacity;
+        t->mirrored = 0;
+    }
     if (s->type == VSGPU_FLOAT32) {
         if (!s->shadow) {
             s->shadow_stride = (s->dim + 7) / 8 * 8;
@@ -530,7 +557,7 @@ int tensor_sync_mirrors(vsgpu_store *s) {
             const unsigned blocks = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)t->sms * 16);
             shadow_rows_kernel<<<blocks, 256, 0, s->stream>>>((const float *)s->rows, s->row_stride / 4, s->dim, t->mirrored, n,
                                                              (__nv_bfloat16 *)s->shadow, s->shadow_stride, s->row_l2,
-                                                             t->max_l2_bits);
+                                                             t->max_l2_bits, t->row_hsq);
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
             t->mirrored = s->count;
@@ -540,7 +567,7 @@ int tensor_sync_mirrors(vsgpu_store *s) {
             const size_t n = s->count - t->mirrored;
             const unsigned blocks = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)t->sms * 16);
             bf16_norms_kernel<<<blocks, 256, 0, s->stream>>>((const __nv_bfloat16 *)s->rows, s->row_stride / 2, s->dim, t->mirrored,
-                                                            n, nullptr, t->max_l2_bits, s->type == VSGPU_FLOAT16 ? 1 : 0);
+                                                            n, nullptr, t->max_l2_bits, s->type == VSGPU_FLOAT16 ? 1 : 0, t->row_hsq);
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
             t->mirrored = s->count;
@@ -554,13 +581,15 @@ static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 static int launch_gemm(vsgpu_store *s, TensorState *t, const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs &g) {
     const size_t smem = sizeof(GemmSmem) + 1024;
     if (!t->attr_set) {
-        VS_CUDA(cudaFuncSetAttribute(coarse_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VS_CUDA(cudaFuncSetAttribute(coarse_gemm_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VS_CUDA(cudaFuncSetAttribute(coarse_gemm_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         t->attr_set = true;
     }
     const uint32_t m_tiles = (g.row_end - g.row0 + BM - 1) / BM;
     const uint32_t items = m_tiles * g.n_qtiles;
     const unsigned grid = (unsigned)std::min<uint32_t>(items, (uint32_t)t->sms);
-    coarse_gemm_filter_kernel<<<grid, GEMM_THREADS, smem, s->stream>>>(ma, mb, g);
+    if (g.row_sub) coarse_gemm_filter_kernel<true><<<grid, GEMM_THREADS, smem, s->stream>>>(ma, mb, g);
+    else coarse_gemm_filter_kernel<false><<<grid, GEMM_THREADS, smem, s->stream>>>(ma, mb, g);
     VS_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
     return VSGPU_OK;
@@ -580,6 +609,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
     // error bound of the coarse score relative to ||q|| * ||row||
     const float c_rel = f32 ? (float)(1.0 / 256 + 1.0 / 65536 + 4.0 * (double)s->dim / 8388608.0)
                             : (float)((s->type == VSGPU_FLOAT16 ? 8.0 : 6.0) * (double)s->dim / 8388608.0);
+    const float c_l2 = s->metric == VSGPU_L2 ? (float)((double)s->dim / 4194304.0) : 0.f; // d * 2^-22
     CUtensorMap map_a;
     VS_TRY(make_map(&map_a, a_base, n, s->dim, a_stride, BM));
 
@@ -611,7 +641,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         VS_CUDA(cudaMemsetAsync(tot, 0, 8, s->stream));
         fill_t<float><<<64, 256, 0, s->stream>>>(athr, -INFINITY, nq);
         prep_coarse_queries_kernel<<<(unsigned)std::min<size_t>((nq + 7) / 8, 1024), 256, 0, s->stream>>>(
-            qp, q_stride, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps);
+            qp, q_stride, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps, c_l2);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches += 2;
         CUtensorMap map_b;
@@ -629,6 +659,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             g.cand = cand;
             g.dump = nullptr;
             g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
+            g.row_sub = s->metric == VSGPU_L2 ? t->row_hsq : nullptr;
             while (t->evs.size() < 2 * (p + 1)) {
                 cudaEvent_t e;
                 VS_CUDA(cudaEventCreate(&e));
@@ -718,7 +749,7 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
     VS_CUDA(cudaMemsetAsync(qb, 0, nq_pad * qb_stride * 2, s->stream));
     VS_CUDA(cudaMemsetAsync(dump, 0, nrows * nq * 4, s->stream));
     prep_coarse_queries_kernel<<<64, 256, 0, s->stream>>>(d_q, s->row_bytes, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, 0.f,
-                                                         t->max_l2_bits, eps);
+                                                         t->max_l2_bits, eps, 0.f);
     CUtensorMap map_a, map_b;
     VS_TRY(make_map(&map_a, f32 ? (const void *)s->shadow : (const void *)s->rows, s->count, s->dim,
                     f32 ? s->shadow_stride * 2 : s->row_stride, BM));
@@ -735,6 +766,7 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
     g.dump = dump;
     g.dump_ld = (uint32_t)nq;
     g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
+    g.row_sub = nullptr;
     VS_TRY(launch_gemm(s, t, map_a, map_b, g));
     VS_CUDA(cudaStreamSynchronize(s->stream));
     VS_CUDA(cudaMemcpy(out, dump, nrows * nq * 4, cudaMemcpyDeviceToHost));
