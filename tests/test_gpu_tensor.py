@@ -204,3 +204,17 @@ def test_i8_tensor_path_ties_and_exact_path_agree(capi):
         assert G.last_query_stats()["path"] == 1
         assert np.array_equal(el, tl) and np.array_equal(es, ts), metric
         G.close()
+
+
+def test_cta_pair_kernel_in_subprocess():
+    """The cta_group::2 variant of the filtered GEMM (VSGPU_GEMM_PAIR=1, read once per process): raw accumulators equal
+    the matmul and the whole path equals the oracle, run in a child process with the flag set."""
+    import subprocess
+    import sys
+    env = dict(os.environ, VSGPU_GEMM_PAIR="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_tensor.py"), "-x", "-q", "-k",
+                        "coarse_pipeline or (tensor_path_equals_oracle and 40000)"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout

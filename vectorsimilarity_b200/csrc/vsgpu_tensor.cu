@@ -201,6 +201,158 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (VSGPU_GEMM_PAIR=1): a cluster of two CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows and HALF of the query tile (128 queries), so a pair moves (256 + 256) operand rows per
+// 256 x 256 tile where two single CTAs move 2 x (128 + 256): a third less L2 -> SM traffic, which is what bounds the
+// single-CTA kernel. The leader (cluster rank 0) issues the MMAs; operands of both CTAs complete on the
+// leader's `full` barriers, commits are multicast to both CTAs' `empty` / `tfull` barriers, and both CTAs' epilogue warps
+// release the accumulator on the leader's `tempty`.
+constexpr int PSTAGES = 6;
+constexpr int BH_BYTES = (BN / 2) * BK * 2; // 16 KB: this CTA's half of the query tile
+struct PairSmem {
+    uint8_t a[PSTAGES][A_BYTES];
+    uint8_t b[PSTAGES][BH_BYTES];
+    float athr[MAX_NQ];
+    uint64_t full[PSTAGES], empty[PSTAGES], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+__host__ __device__ constexpr uint32_t idesc_pair(uint32_t idesc1) { return (idesc1 & ~(0x1fu << 24)) | ((uint32_t)(256 >> 4) << 24); }
+
+template <bool SUB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+coarse_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh, GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    PairSmem &sm = *reinterpret_cast<PairSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const uint32_t p_tiles = (g.row_end - g.row0 + 2 * BM - 1) / (2 * BM);
+    const uint32_t items = p_tiles * g.n_qtiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < PSTAGES; i++) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.tfull[i], 1);
+            mbar_init(&sm.tempty[i], 2 * EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bh) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x)
+        sm.athr[i] = i < g.nq ? g.athr[i] : __int_as_float(0x7f800000);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all(); // both CTAs' barriers exist before anything is signalled across the pair
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own rows, own half of the queries; bytes complete on the leader's barrier =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = cluster_id; item < items; item += n_clusters) {
+                const uint32_t pt = item / g.n_qtiles, nt = item % g.n_qtiles;
+                const int row = (int)(g.row0 + pt * 2 * BM + rank * BM), qrow = (int)(nt * BN + rank * (BN / 2));
+                for (uint32_t kb = 0; kb < g.k_blocks; kb++) {
+                    mbar_wait(&sm.empty[stage], phase ^ 1);
+                    if (leader) mbar_expect_tx(&sm.full[stage], 2 * (A_BYTES + BH_BYTES));
+                    const uint32_t full0 = mapa_u32(smem_u32(&sm.full[stage]), 0);
+                    tma_load_2d_pair(sm.a[stage], &map_a, full0, (int)(kb * BK), row);
+                    tma_load_2d_pair(sm.b[stage], &map_bh, full0, (int)(kb * BK), qrow);
+                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA =====
+        if (leader && lane == 0) {
+            const uint32_t idesc2 = idesc_pair(g.idesc);
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            for (uint32_t item = cluster_id; item < items; item += n_clusters) {
+                mbar_wait(&sm.tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + as * BN;
+                for (uint32_t kb = 0; kb < g.k_blocks; kb++) {
+                    mbar_wait(&sm.full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc(smem_u32(sm.a[stage]));
+                    const uint64_t bdesc = make_desc(smem_u32(sm.b[stage]));
+#pragma unroll
+                    for (int k = 0; k < BK / UK; k++)
+                        tc_mma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc2, (kb | (uint32_t)k) != 0);
+                    tc_commit_pair(&sm.empty[stage]); // frees the slot in both CTAs
+                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_pair(&sm.tfull[as]); // accumulators complete in both CTAs
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): this CTA's 128 rows x 256 queries =====
+        const int ew = warp - 4;
+        const uint32_t quad = (uint32_t)(warp & 3);
+        const uint32_t half = (uint32_t)(ew >> 2);
+        uint32_t as = 0, aphase = 0;
+        for (uint32_t item = cluster_id; item < items; item += n_clusters) {
+            const uint32_t pt = item / g.n_qtiles, nt = item % g.n_qtiles;
+            const uint32_t row = g.row0 + pt * 2 * BM + rank * BM + quad * 32 + (uint32_t)lane;
+            const bool row_ok = row < g.row_end;
+            float ra = 0.f;
+            if constexpr (SUB) ra = row_ok ? g.row_sub[row] : 0.f;
+            mbar_wait(&sm.tfull[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t col = half * 128 + c * 32;
+                uint32_t r[32];
+                tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
+                tc_wait_ld();
+                float thr[32];
+                lds_f32x32(smem_u32(&sm.athr[nt * BN + col]), thr);
+                if (g.dump) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const uint32_t q = nt * BN + col + j;
+                            if (q < g.nq) g.dump[(size_t)(row - g.row0) * g.dump_ld + q] = __uint_as_float(r[j]);
+                        }
+                    }
+                } else {
+                    uint32_t hit = 0;
+                    if constexpr (SUB) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__fsub_rn(__uint_as_float(r[j]), ra));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) hit |= (__uint_as_float(r[j]) >= thr[j] ? 1u : 0u) << j;
+                    warp_append_hits<CAND_CAP>(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sm.tempty[as]), 0));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all(); // nobody signals the leader's barriers or reads TMEM any more
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // mirrors and query preparation
 __global__ void shadow_rows_kernel(const float *__restrict__ rows, size_t row_stride_f, size_t dim, size_t first, size_t n,
                                    __nv_bfloat16 *__restrict__ shadow, size_t shadow_stride, float *__restrict__ row_l2,
@@ -476,7 +628,7 @@ struct TensorState {
     unsigned *max_l2_bits = nullptr;
     float *row_hsq = nullptr;     // L2 stores: ||row||^2 / 2 per row
     int sms = 0;
-    bool attr_set = false;
+    bool attr_set = false, pair_attr_set = false;
     std::vector<cudaEvent_t> evs; // per-phase (start, stop) pairs around the coarse GEMM launches
 };
 
@@ -578,7 +730,34 @@ int tensor_sync_mirrors(vsgpu_store *s) {
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-static int launch_gemm(vsgpu_store *s, TensorState *t, const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs &g) {
+static bool gemm_pair_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("VSGPU_GEMM_PAIR");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
+// mbh: the query matrix as [128 x 64] boxes (the CTA-pair kernel stages half a query tile per CTA); may be null when
+// VSGPU_GEMM_PAIR is off
+static int launch_gemm(vsgpu_store *s, TensorState *t, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap *mbh,
+                       GemmArgs &g) {
+    if (gemm_pair_enabled() && mbh) {
+        const size_t psmem = sizeof(PairSmem) + 1024;
+        if (!t->pair_attr_set) {
+            VS_CUDA(cudaFuncSetAttribute(coarse_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            VS_CUDA(cudaFuncSetAttribute(coarse_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            t->pair_attr_set = true;
+        }
+        const uint32_t p_tiles = (g.row_end - g.row0 + 2 * BM - 1) / (2 * BM);
+        const uint32_t items = p_tiles * g.n_qtiles;
+        const unsigned clusters = (unsigned)std::min<uint32_t>(items, (uint32_t)(t->sms / 2));
+        if (g.row_sub) coarse_gemm_pair_kernel<true><<<2 * clusters, GEMM_THREADS, psmem, s->stream>>>(ma, *mbh, g);
+        else coarse_gemm_pair_kernel<false><<<2 * clusters, GEMM_THREADS, psmem, s->stream>>>(ma, *mbh, g);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+        return VSGPU_OK;
+    }
     const size_t smem = sizeof(GemmSmem) + 1024;
     if (!t->attr_set) {
         VS_CUDA(cudaFuncSetAttribute(coarse_gemm_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -644,8 +823,9 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             qp, q_stride, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps, c_l2);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches += 2;
-        CUtensorMap map_b;
+        CUtensorMap map_b, map_bh;
         VS_TRY(make_map(&map_b, qb, nq_pad, s->dim, qb_stride * 2, BN));
+        if (gemm_pair_enabled()) VS_TRY(make_map(&map_bh, qb, nq_pad, s->dim, qb_stride * 2, BN / 2));
 
         for (size_t p = 0; p < phases.size(); p++) {
             GemmArgs g{};
@@ -666,7 +846,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
                 t->evs.push_back(e);
             }
             VS_CUDA(cudaEventRecord(t->evs[2 * p], s->stream));
-            VS_TRY(launch_gemm(s, t, map_a, map_b, g));
+            VS_TRY(launch_gemm(s, t, map_a, map_b, gemm_pair_enabled() ? &map_bh : nullptr, g));
             VS_CUDA(cudaEventRecord(t->evs[2 * p + 1], s->stream));
             MergeArgs m{};
             m.nq = (uint32_t)nq;
@@ -754,6 +934,8 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
     VS_TRY(make_map(&map_a, f32 ? (const void *)s->shadow : (const void *)s->rows, s->count, s->dim,
                     f32 ? s->shadow_stride * 2 : s->row_stride, BM));
     VS_TRY(make_map(&map_b, qb, nq_pad, s->dim, qb_stride * 2, BN));
+    CUtensorMap map_bh;
+    if (gemm_pair_enabled()) VS_TRY(make_map(&map_bh, qb, nq_pad, s->dim, qb_stride * 2, BN / 2));
     GemmArgs g{};
     g.row0 = (uint32_t)row0;
     g.row_end = (uint32_t)(row0 + nrows);
@@ -767,7 +949,7 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
     g.dump_ld = (uint32_t)nq;
     g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
     g.row_sub = nullptr;
-    VS_TRY(launch_gemm(s, t, map_a, map_b, g));
+    VS_TRY(launch_gemm(s, t, map_a, map_b, gemm_pair_enabled() ? &map_bh : nullptr, g));
     VS_CUDA(cudaStreamSynchronize(s->stream));
     VS_CUDA(cudaMemcpy(out, dump, nrows * nq * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_q);
