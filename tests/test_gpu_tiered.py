@@ -255,3 +255,69 @@ def test_worker_threads_drain_while_queries_run(capi, port):
     assert not errors, errors[:3]
     assert T.get_curr_bf_size() == 0 and T.index_size() == n and T.pending_jobs() == 0
     T.close()
+
+
+def test_empty_k0_timeout_and_locks(capi, port):
+    """Edge cases of tests/unit/test_hnsw_tiered.cpp: an empty tiered index answers with empty replies, k = 0 too; a
+    firing timeout callback gives an empty TimedOut reply from whichever tier is asked first; the shared-lock API
+    brackets reads."""
+    rng = np.random.default_rng(8)
+    X = rng.uniform(-1, 1, (300, DIM)).astype(np.float32)
+    q = X[3]
+    T = new_tiered(capi, limit=100)
+    l, s = T.knn_query(q, 5)
+    assert l.shape == (1, 0) and T.last_code == capi.VecSim_QueryReply_OK
+    l, s = T.range_query(q, 1.0)
+    assert l.shape == (1, 0)
+    assert T.index_size() == 0 and dict(T.debug_info())["INDEX_LABEL_COUNT"] == 0
+    for i in range(300):
+        T.add_vector(X[i], i)          # 100 buffered, 200 direct
+    l, s = T.knn_query(q, 0)
+    assert l.shape == (1, 0)
+    L = capi.lib()
+    L.VecSimTieredIndex_AcquireSharedLocks(T._h)
+    d = T.get_distance_from(3, q)
+    L.VecSimTieredIndex_ReleaseSharedLocks(T._h)
+    assert d == 0.0
+    L.VecSimTieredIndex_GC(T._h)
+    capi.set_timeout_callback(lambda ctx: 1)
+    try:
+        l, s = T.knn_query(q, 5)
+        assert l.shape == (1, 0) and T.last_code == capi.VecSim_QueryReply_TimedOut
+        T.wait_for_index()
+        l, s = T.knn_query(q, 5)       # buffer empty now: the backend alone times out
+        assert l.shape == (1, 0) and T.last_code == capi.VecSim_QueryReply_TimedOut
+    finally:
+        capi.set_timeout_callback(None)
+    l, s = T.knn_query(q, 5)
+    assert l[0][0] == 3 and s[0][0] == 0.0 and T.last_code == capi.VecSim_QueryReply_OK
+    # prefer-ad-hoc follows the bigger tier; a small subset is scored ad hoc
+    assert T.prefer_adhoc(3, 5) is True
+    T.close()
+
+
+def test_cosine_tiered_matches_halves(capi, port):
+    """Cosine: both tiers normalise the caller's blob themselves, so a vector scores the same wherever it sits."""
+    rng = np.random.default_rng(9)
+    n, limit = 300, 90
+    X = rng.uniform(-1, 1, (n, DIM)).astype(np.float32)
+    Q = rng.uniform(-1, 1, (4, DIM)).astype(np.float32)
+    T = new_tiered(capi, limit=limit, metric=2)
+    for i in range(n):
+        T.add_vector(X[i], i)
+    F = port.PortIndex(0, DIM, 2)
+    F.add_many(X[:limit], first_label=0)
+    H = port.PortHnsw(0, DIM, 2, M=M, ef_construction=EFC, ef_runtime=EF)
+    H.add_many(X[limit:], first_label=limit)
+    for q in Q:
+        wl, ws = expected_topk(port, F, H, q, K)
+        l, s = T.knn_query(q, K)
+        assert np.array_equal(l[0], wl) and np.array_equal(s[0], ws)
+    # after ingestion the buffered vectors were appended to the backend in submission order
+    T.wait_for_index()
+    H.add_many(X[:limit], first_label=0)
+    for q in Q:
+        wl, ws = expected_topk(port, None, H, q, K)
+        l, s = T.knn_query(q, K)
+        assert np.array_equal(l[0], wl) and np.array_equal(s[0], ws)
+    F.close(); H.close(); T.close()
