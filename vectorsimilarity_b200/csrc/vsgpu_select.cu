@@ -236,6 +236,48 @@ __global__ void __launch_bounds__(1024) sort_pairs_kernel(const KT *__restrict__
     }
 }
 
+// Small problems (one or a few queries over <= a few hundred thousand rows) are bound by launch latency, not bandwidth:
+// the radix select above is 13 launches. Here each block sorts one 2048-score chunk by (key, id) in shared memory and
+// hands its k best to the final block sort: 2 launches, same (score, id) order and tie rule.
+constexpr int CHUNK = 2048;
+template <typename ST, typename KT>
+__global__ void __launch_bounds__(256) chunk_topk_kernel(const ST *__restrict__ scores, size_t ld, size_t n, uint32_t k,
+                                                         KT *__restrict__ out_keys, uint32_t *__restrict__ out_ids, size_t out_ld) {
+    __shared__ KT sk[CHUNK];
+    __shared__ uint32_t si[CHUNK];
+    const int q = blockIdx.y;
+    const size_t first = (size_t)blockIdx.x * CHUNK;
+    const ST *row = scores + (size_t)q * ld;
+    for (int i = threadIdx.x; i < CHUNK; i += blockDim.x) {
+        const size_t r = first + i;
+        sk[i] = r < n ? to_key(row[r]) : ~KT(0);
+        si[i] = r < n ? (uint32_t)r : 0xffffffffu;
+    }
+    __syncthreads();
+    for (int size = 2; size <= CHUNK; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < CHUNK / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const KT ka = sk[lo], kb = sk[hi];
+                const uint32_t ia = si[lo], ib = si[hi];
+                const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
+                if (a_gt_b == asc) {
+                    sk[lo] = kb; sk[hi] = ka;
+                    si[lo] = ib; si[hi] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+        const size_t o = (size_t)q * out_ld + (size_t)blockIdx.x * k + i;
+        out_keys[o] = sk[i];
+        out_ids[o] = si[i];
+    }
+}
+
 // unsorted finalisation for k beyond the in-block sort limit (the host sorts)
 template <typename ST, typename KT>
 __global__ void finalize_unsorted_kernel(const KT *__restrict__ keys, const uint32_t *__restrict__ ids, size_t total,
@@ -337,6 +379,28 @@ template <typename ST, typename KT>
 static int select_topk_t(vsgpu_store *s, const void *scores_v, size_t ld, size_t nq, size_t n, size_t k, size_t out_ld,
                          uint32_t *out_ids, void *out_scores, uint64_t *out_labels) {
     const ST *scores = (const ST *)scores_v;
+    {
+        // launch-latency-bound shapes: chunk sort + final sort (2 launches instead of 13)
+        const size_t chunks = (n + CHUNK - 1) / CHUNK;
+        if (nq <= 8 && k <= CHUNK && chunks * k <= 4096 && chunks <= 1024) {
+            const size_t cand = chunks * k;
+            auto al2 = [](size_t v) { return (v + 255) / 256 * 256; };
+            VS_TRY(ensure_scratch(s, s->sel_state, al2(sizeof(KT) * nq * cand) + al2(sizeof(uint32_t) * nq * cand)));
+            auto *ck = (KT *)s->sel_state.ptr;
+            auto *ci = (uint32_t *)((unsigned char *)s->sel_state.ptr + al2(sizeof(KT) * nq * cand));
+            chunk_topk_kernel<ST, KT><<<dim3((unsigned)chunks, (unsigned)nq), 256, 0, s->stream>>>(scores, ld, n, (uint32_t)k, ck, ci, cand);
+            const int P = next_pow2(cand);
+            const size_t smem = (size_t)P * (sizeof(KT) + sizeof(uint32_t));
+            auto kern = sort_pairs_kernel<ST, KT>;
+            if (smem > 48 * 1024) VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int threads = std::max(32, std::min(1024, P / 2));
+            kern<<<(unsigned)nq, threads, smem, s->stream>>>(ck, nullptr, ci, cand, nullptr, (uint32_t)cand, P, (uint32_t)k, (uint32_t)out_ld,
+                                                            s->labels, out_ids, (ST *)out_scores, out_labels);
+            VS_CUDA(cudaGetLastError());
+            s->stats.kernel_launches += 2;
+            return VSGPU_OK;
+        }
+    }
     const size_t nseg = (n + SEG - 1) / SEG;
     // scratch: states | tie counts | keys | ids
     const size_t st_bytes = sizeof(SelState<KT>) * nq;
