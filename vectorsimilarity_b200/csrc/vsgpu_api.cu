@@ -475,9 +475,10 @@ int vsgpu_topk(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, s
     const float *qn = nullptr;
     VS_TRY(stage_queries_device(s, raw_dev, nq, s->blob_bytes, &q, &qs, &qn));
     VS_TRY(topk_core(s, q, nq, qs, qn, k_eff, k_eff, flags, d_id, d_sc, d_lab));
-    VS_CUDA(cudaMemcpyAsync(pin + o_lab, d_lab, nq * k_eff * 8, cudaMemcpyDeviceToHost, s->stream));
-    VS_CUDA(cudaMemcpyAsync(pin + o_sc, d_sc, nq * k_eff * ssz, cudaMemcpyDeviceToHost, s->stream));
-    VS_CUDA(cudaMemcpyAsync(pin + o_id, d_id, nq * k_eff * 4, cudaMemcpyDeviceToHost, s->stream));
+    // labels | scores | ids sit at the same 256-byte-aligned offsets on both sides: one copy (a single query is bound by
+    // the number of stream operations, not by bytes)
+    VS_CUDA(cudaMemcpyAsync(pin + o_lab, d_lab, al(nq * k_eff * 8) + al(nq * k_eff * ssz) + nq * k_eff * 4, cudaMemcpyDeviceToHost,
+                            s->stream));
     VS_CUDA(cudaEventRecord(s->ev1, s->stream));
     VS_CUDA(cudaStreamSynchronize(s->stream));
     float ms = 0;
