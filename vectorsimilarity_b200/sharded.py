@@ -138,12 +138,24 @@ class ShardedFlatIndex:
         return out_s, out_l
 
     def knn_batch(self, queries, k, flags=0):
-        """Host queries (processed blobs, numpy [nq, blob]) -> host (labels int64 [nq,k], scores float64 [nq,k])."""
-        q = torch.from_numpy(np.ascontiguousarray(queries).view(np.uint8).reshape(queries.shape[0], -1))
-        q_dev = q.to(self.device, non_blocking=True)
+        """Host queries (processed blobs, numpy [nq, blob] or a pinned uint8 tensor) -> host (labels int64 [nq,k], scores
+        float64 [nq,k]). One H2D copy, the sharded search, one D2H copy per output into pinned buffers, one sync."""
+        if isinstance(queries, torch.Tensor):
+            q = queries
+        else:
+            q = torch.from_numpy(np.ascontiguousarray(queries).view(np.uint8).reshape(queries.shape[0], -1))
+        nq = q.shape[0]
+        q_dev = self._buf("qd", tuple(q.shape), torch.uint8)
+        q_dev.copy_(q, non_blocking=True)
         out_s, out_l = self.topk_device(q_dev, k, flags)
+        key = ("pin", nq, k, out_s.dtype)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty((nq, k), dtype=out_s.dtype).pin_memory(), torch.empty((nq, k), dtype=torch.int64).pin_memory())
+        pin_s, pin_l = self._bufs[key]
+        pin_s.copy_(out_s, non_blocking=True)
+        pin_l.copy_(out_l, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return out_l.cpu().numpy(), out_s.double().cpu().numpy()
+        return pin_l.numpy().copy(), pin_s.numpy().astype(np.float64)  # the pinned buffers are reused by the next call
 
     # ---- range query and batch iterator across shards (SURVEY.md §8e): variable-length per-shard replies ----
     def range_query(self, query, radius, order=capi.BY_SCORE):
