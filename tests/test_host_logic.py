@@ -175,3 +175,21 @@ def test_hybrid_policy_cost_model(capi):
     assert L.vsb_test_prefer_adhoc(1, 1_000_000, 512, 10_000, 10) == 1
     assert L.vsb_test_prefer_adhoc(1, 1_000_000, 512, 200_000, 10) == 0
     assert L.vsb_test_prefer_adhoc(1, 1_000_000, 512, 200_000, 1000) == 1        # many results wanted: batches get long
+
+
+def test_header_is_c_and_a_c_consumer_links(capi, tmp_path):
+    """include/vecsim_b200.h is what a C consumer (RediSearch) includes: a C11 program that fills the parameter structs
+    with designated initialisers — including the tiered block with a submit callback — compiles without warnings, links
+    against libvecsim_b200.so and sees the reference's struct sizes; without a device VecSimIndex_New fails loudly."""
+    import subprocess
+    exe = str(tmp_path / "consumer")
+    libdir = os.path.join(ROOT, "vectorsimilarity_b200")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "consumer.c"), "-o", exe, "-L" + libdir, "-lvecsim_b200",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert lines[0] == "136 64 360"
+    assert lines[1].startswith("index ") and ("(ok)" in lines[1] or "tiered index:" in lines[1])

@@ -113,7 +113,11 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
             // index_factories/tiered_factory.cpp: only an HNSW backend (single value per label here)
             auto *idx = new TieredIndex(params->algoParams.tieredParams, params->logCtx);
             if (!idx->ok()) {
-                g_api_err = "tiered index: the backend must be a single-value VecSimAlgo_HNSWLIB index";
+                const TieredIndexParams &tp = params->algoParams.tieredParams;
+                const bool shape_ok = tp.primaryIndexParams && tp.primaryIndexParams->algo == VecSimAlgo_HNSWLIB &&
+                                      !tp.primaryIndexParams->algoParams.hnswParams.multi;
+                g_api_err = shape_ok ? std::string("tiered index: ") + vsgpu_last_error()
+                                     : std::string("tiered index: the backend must be a single-value VecSimAlgo_HNSWLIB index");
                 delete idx;
                 return nullptr;
             }
