@@ -193,3 +193,27 @@ def test_header_is_c_and_a_c_consumer_links(capi, tmp_path):
     lines = out.stdout.splitlines()
     assert lines[0] == "136 64 360"
     assert lines[1].startswith("index ") and ("(ok)" in lines[1] or "tiered index:" in lines[1])
+
+
+def test_phase_schedule_of_the_filtered_gemm(capi):
+    """make_phases (csrc/vsgpu_tc.cuh): phases tile [0, n) without gaps, every edge but the last is a multiple of the
+    128-row tile, consecutive edges grow by at most the factor the candidate buffer affords (8 for k <= 150, less for
+    larger k), and no schedule with one phase fewer would satisfy that."""
+    capi.lib()
+    G = C.CDLL(os.path.join(ROOT, "vectorsimilarity_b200", "libvsgpu.so"))
+    G.vsgpu_debug_phases.restype = C.c_size_t
+    G.vsgpu_debug_phases.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
+    buf = np.zeros(64, dtype=np.uint32)
+    for n, k in ((32768, 10), (100_000, 1), (1_250_000, 100), (10_000_000, 100), (20_000_000, 100), (6_250_000, 10),
+                 (40_000, 384), (50_000_000, 10), (3_000_001, 37)):
+        m = G.vsgpu_debug_phases(n, k, buf.ctypes.data, 64)
+        edges = buf[:m].astype(np.int64)
+        assert m >= 1 and edges[-1] == n and np.all(np.diff(edges) > 0)
+        assert np.all(edges[:-1] % 128 == 0)
+        growth = max(3.0, min(8.0, 3072 / (2.5 * k)))
+        s0 = edges[0]
+        assert s0 >= min(n, 2048) and s0 >= min(n, 2 * k)
+        ratios = edges[1:] / edges[:-1]
+        assert np.all(ratios <= growth * 1.02), (n, k, ratios)
+        if m > 2:  # fewest phases: one fewer would need a larger ratio than allowed
+            assert (n / s0) ** (1.0 / (m - 2)) > growth * 0.999, (n, k, m)

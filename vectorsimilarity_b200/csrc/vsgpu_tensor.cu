@@ -898,6 +898,14 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
 
 } // namespace vsgpu
 
+// Host-logic test hook (no device needed): the phase schedule of the filtered GEMM for n rows and top-k. Writes up to `cap`
+// phase end rows to `edges`, returns the number of phases.
+extern "C" size_t vsgpu_debug_phases(size_t n, size_t k, uint32_t *edges, size_t cap) {
+    const auto ph = vsgpu::make_phases(n, k, vsgpu::CAND_CAP, vsgpu::BM);
+    for (size_t i = 0; i < ph.size() && i < cap; i++) edges[i] = ph[i].second;
+    return ph.size();
+}
+
 // Debug / test hook: raw coarse accumulators of rows [row0, row0 + nrows) against nq queries
 // (HOST pointers; out is [nrows][nq] fp32). Exercises exactly the production TMA/MMA/TMEM pipeline.
 extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t row0, size_t nrows,
