@@ -420,6 +420,7 @@ template <typename DT> struct Work {
     uint32_t *rlog;
     int rlog_cap;
     int *rlog_n; // shared counter; > cap = overflow
+    bool no_regtop; // A/B switch (VSGPU_HNSW_NO_REGTOP): keep the result set in shared memory even for ef <= 64
 };
 enum { SC_TOPN = 0, SC_CANDN, SC_NBN, SC_STOP, SC_CUR, SC_STATUS, SC_ADMN, SC_AUX0, SC_AUX1, SC_AUX2, SC_AUX3, SC_COUNT = 16 };
 
@@ -690,7 +691,7 @@ __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::
     // is two ballots and six shuffles instead of a 32-ary search plus a shift through shared memory (~250 cycles each, a
     // third of a hop); the arrays in shared memory are written once, when the search ends. A 65th entry falls off the end,
     // which is exactly "insert, then drop the largest" of a full set.
-    const bool regtop = ef <= 64;
+    const bool regtop = ef <= 64 && !w.no_regtop;
     DT t0d = DT(0), t1d = DT(0);
     uint32_t t0i = 0, t1i = 0;
     auto reg_insert = [&](DT d, uint32_t id) {
@@ -874,6 +875,7 @@ struct SearchArgs {
     unsigned long long *range_counts; // per query
     size_t range_cap;
     int profile; // VSGPU_HNSW_PROFILE: per-phase cycle counters
+    int no_regtop; // VSGPU_HNSW_NO_REGTOP
 };
 
 template <typename DT> __device__ __forceinline__ Work<DT> carve(unsigned char *smem, size_t pivot_bytes, int max_links,
@@ -945,6 +947,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_k
     __shared__ long long s_prof[8]; // cycles: 0 gather 1 eval 2 admit 3 scratch 4 bottom layer 5 descent
     if (threadIdx.x < 8) s_prof[threadIdx.x] = 0;
     w.prof = a.profile ? s_prof : nullptr;
+    w.no_regtop = a.no_regtop != 0;
     __syncthreads();
     unsigned long long evals = 0, hops = 0;
     int count = 0;
@@ -2380,6 +2383,7 @@ static int hnsw_search_core(vsgpu_hnsw *g, const void *q, size_t nq, size_t q_st
     a.range_counts = range_counts;
     a.range_cap = range_cap;
     a.profile = getenv("VSGPU_HNSW_PROFILE") != nullptr;
+    a.no_regtop = getenv("VSGPU_HNSW_NO_REGTOP") != nullptr;
     if (with_spill) {
         VS_TRY(ensure_scratch(s, g->spill, nq * (g->count + 1) * (dt + 4)));
         a.spill = g->spill.ptr;
