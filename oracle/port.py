@@ -81,6 +81,7 @@ def lib():
         L.vso_hnsw_add.argtypes = [vp, vp, sz]
         L.vso_hnsw_size.restype = sz
         L.vso_hnsw_size.argtypes = [vp]
+        L.vso_hnsw_set_multi.argtypes = [vp, C.c_int]
         L.vso_hnsw_mark_deleted.argtypes = [vp, sz, i32]
         L.vso_hnsw_info.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
         L.vso_hnsw_level.restype = C.c_uint32
@@ -254,9 +255,12 @@ class PortBatchIterator:
 class PortHnsw:
     """vs_oracle_hnsw.c: the reference's single-threaded HNSW build / top-k / range, restated."""
 
-    def __init__(self, vtype, dim, metric, M=16, ef_construction=200, ef_runtime=10, epsilon=0.01):
+    def __init__(self, vtype, dim, metric, M=16, ef_construction=200, ef_runtime=10, epsilon=0.01, multi=False):
         self.vtype, self.dim, self.metric, self.M = vtype, dim, metric, M
         self.h = lib().vso_hnsw_new(vtype, dim, metric, M, ef_construction, ef_runtime, epsilon)
+        self.multi = bool(multi)
+        if multi:  # HNSWIndex_Multi: labels may repeat, queries return each label once
+            lib().vso_hnsw_set_multi(self.h, 1)
 
     def close(self):
         if self.h:

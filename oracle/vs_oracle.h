@@ -85,6 +85,9 @@ vso_hnsw *vso_hnsw_new(int type, size_t dim, int metric, size_t M, size_t ef_con
 void vso_hnsw_free(vso_hnsw *g);
 void vso_hnsw_add(vso_hnsw *g, const void *blob, size_t label); /* raw caller blob; label must be new */
 size_t vso_hnsw_size(const vso_hnsw *g);
+/* HNSWIndex_Multi (algorithms/hnsw/hnsw_multi.h): labels may repeat; top-k / range return each label once with its best
+ * score. Call before the first query; the graph itself is built exactly as for a single-value index. */
+void vso_hnsw_set_multi(vso_hnsw *g, int multi);
 void vso_hnsw_mark_deleted(vso_hnsw *g, size_t id, int deleted);
 void vso_hnsw_info(const vso_hnsw *g, long *entry, long *max_level); /* -1/-1 when empty */
 uint32_t vso_hnsw_level(const vso_hnsw *g, size_t id);

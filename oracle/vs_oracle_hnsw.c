@@ -99,6 +99,7 @@ struct vso_hnsw {
     uint32_t *tags;
     uint32_t tag;
     size_t n_dist;
+    int multi; /* HNSWIndex_Multi: several vectors per label; queries return each label once with its best score */
 };
 
 static uint32_t *rec(const vso_hnsw *g, size_t id, size_t level) {
@@ -221,11 +222,87 @@ static void search_layer(vso_hnsw *g, size_t ep, const void *q, size_t level, si
     free(cand.a);
 }
 
+/* The result set of a multi-value search: vecsim_stl::updatable_max_heap<DistType, labelType>
+ * (utils/updatable_heap.h:24-130; HNSWIndex_Multi::getNewMaxPriorityQueue / emplaceToHeap, hnsw_multi.h:62-71, :103-106).
+ * One entry per label; emplace inserts a new label or lowers the score of a known one, never raises it; top / pop act on
+ * the maximum under (score, label) — top_ptr() picks the largest label among the largest scores. Kept as a flat array:
+ * this is a checker, not a data structure. */
+static long ms_find(const heap_t *h, size_t label) {
+    for (size_t i = 0; i < h->n; i++)
+        if (h->a[i].key == label) return (long)i;
+    return -1;
+}
+static void ms_emplace(heap_t *h, double d, size_t label) {
+    long i = ms_find(h, label);
+    if (i < 0) {
+        h_reserve(h, h->n + 1);
+        h->a[h->n].d = d;
+        h->a[h->n].key = label;
+        h->n++;
+    } else if (h->a[i].d > d) {
+        h->a[i].d = d;
+    }
+}
+static size_t ms_top(const heap_t *h) {
+    size_t m = 0;
+    for (size_t i = 1; i < h->n; i++)
+        if (pr_less(h->a[m], h->a[i])) m = i;
+    return m;
+}
+static void ms_pop(heap_t *h) {
+    size_t m = ms_top(h);
+    h->a[m] = h->a[h->n - 1];
+    h->n--;
+}
+
+/* searchBottomLayer_WithTimeout on a multi-value index (hnsw.h:530-613, :1983-2035 with the heap above): the candidate
+ * set is keyed by internal id exactly as in the single-value search, the result set by label. */
+static void search_layer_multi(vso_hnsw *g, size_t ep, const void *q, size_t ef, heap_t *top) {
+    heap_t cand = {0};
+    uint32_t tag = fresh_tag(g);
+    double lower;
+    top->n = 0;
+    if (!g->deleted[ep]) {
+        double d = dist(g, ep, q);
+        lower = d;
+        ms_emplace(top, d, g->labels[ep]);
+        h_push(&cand, -d, ep);
+    } else {
+        lower = dist_max(g);
+        h_push(&cand, -lower, ep);
+    }
+    g->tags[ep] = tag;
+    while (cand.n) {
+        pr_t c = cand.a[0];
+        if (-c.d > lower && top->n >= ef) break;
+        h_pop(&cand);
+        const uint32_t *r = rec(g, c.key, 0);
+        for (uint32_t j = 0; j < r[0]; j++) {
+            size_t id = r[1 + j];
+            if (g->tags[id] == tag) continue;
+            g->tags[id] = tag;
+            double d = dist(g, id, q);
+            if (lower > d || top->n < ef) {
+                h_push(&cand, -d, id);
+                if (!g->deleted[id]) ms_emplace(top, d, g->labels[id]);
+                if (top->n > ef) ms_pop(top);
+                if (top->n) lower = top->a[ms_top(top)].d;
+            }
+        }
+    }
+    free(cand.a);
+}
+
 static int cmp_dist_id(const void *a, const void *b) {
     const pr_t *x = (const pr_t *)a, *y = (const pr_t *)b;
     if (x->d < y->d) return -1;
     if (y->d < x->d) return 1;
     return x->key < y->key ? -1 : (x->key > y->key ? 1 : 0);
+}
+static int cmp_key_dist(const void *a, const void *b) {
+    const pr_t *x = (const pr_t *)a, *y = (const pr_t *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->d < y->d ? -1 : (y->d < x->d ? 1 : 0);
 }
 
 /* getNeighborsByHeuristic2_internal (hnsw.h:745-799): list[n] -> kept in place, returns kept
@@ -381,6 +458,7 @@ void vso_hnsw_add(vso_hnsw *g, const void *blob, size_t label) {
 }
 
 size_t vso_hnsw_size(const vso_hnsw *g) { return g->n; }
+void vso_hnsw_set_multi(vso_hnsw *g, int multi) { g->multi = multi != 0; }
 void vso_hnsw_mark_deleted(vso_hnsw *g, size_t id, int deleted) { g->deleted[id] = deleted ? 1 : 0; }
 void vso_hnsw_info(const vso_hnsw *g, long *entry, long *max_level) {
     *entry = g->entry;
@@ -415,13 +493,25 @@ size_t vso_hnsw_topk(vso_hnsw *g, const void *query, size_t k, size_t ef_runtime
     size_t n = 0;
     if (ep >= 0) {
         heap_t top = {0};
-        search_layer(g, (size_t)ep, q, 0, ef, 1, &top);
-        while (top.n > k) h_pop(&top);
-        n = top.n;
-        for (size_t i = n; i-- > 0;) {
-            scores[i] = top.a[0].d;
-            labels[i] = top.a[0].key;
-            h_pop(&top);
+        if (g->multi) {
+            search_layer_multi(g, (size_t)ep, q, ef, &top);
+            while (top.n > k) ms_pop(&top);
+            n = top.n;
+            for (size_t i = n; i-- > 0;) {
+                size_t m = ms_top(&top);
+                scores[i] = top.a[m].d;
+                labels[i] = top.a[m].key;
+                ms_pop(&top);
+            }
+        } else {
+            search_layer(g, (size_t)ep, q, 0, ef, 1, &top);
+            while (top.n > k) h_pop(&top);
+            n = top.n;
+            for (size_t i = n; i-- > 0;) {
+                scores[i] = top.a[0].d;
+                labels[i] = top.a[0].key;
+                h_pop(&top);
+            }
         }
         free(top.a);
     }
@@ -493,6 +583,14 @@ size_t vso_hnsw_range(vso_hnsw *g, const void *query, double radius_in, double e
             }
         }
         free(cand.a);
+    }
+    if (g->multi && found > 1) {
+        /* unique_results_container (containers/vecsim_results_container.h:32-60): one result per label, its lowest score */
+        qsort(res, found, sizeof(pr_t), cmp_key_dist);
+        size_t o = 0;
+        for (size_t i = 0; i < found; i++)
+            if (i == 0 || res[i].key != res[o - 1].key) res[o++] = res[i];
+        found = o;
     }
     qsort(res, found, sizeof(pr_t), cmp_dist_id);
     for (size_t i = 0; i < found && i < cap; i++) {

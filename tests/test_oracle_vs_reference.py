@@ -278,3 +278,42 @@ def test_hnsw_port_batch_iterator_matches_reference(port, ref, metric):
             pi.close()
     R.close()
     P.close()
+
+
+@pytest.mark.parametrize("vtype,metric", [(0, 0), (0, 1), (0, 2), (2, 0), (3, 1), (4, 2), (5, 0), (1, 0)], ids=lambda v: str(v))
+def test_hnsw_multi_port_matches_reference(port, ref, vtype, metric):
+    """HNSWIndex_Multi (hnsw_multi.h): eight vectors per label; the restated label-keyed result set
+    (updatable_max_heap semantics) and the unique range container give the unmodified reference's top-k (several k / ef,
+    k up to the label count) and range replies — labels, order and scores. First half of SURVEY §8 row f2 for HNSW: the
+    checker exists and is pinned before the device kernel is written."""
+    from datagen import make_vectors
+    feats = ref.host_features()
+    if vtype == 2 and metric != 0 and "avx512_bf16" not in feats:
+        pytest.skip("host lacks avx512_bf16")
+    ref.set_disabled_features("avx512_fp16")
+    n, dim = 1200, 16
+    labels = (np.arange(n) % 150).astype(np.uint64)
+    X = make_vectors(vtype, n, dim, seed=3)
+    Q = make_vectors(vtype, 10, dim, seed=4)
+    if metric == 2:
+        X[(X == 0).all(1), 0] = 1
+        Q[(Q == 0).all(1), 0] = 1
+    R = ref.RefIndex(vtype, dim, metric, multi=True, algo="hnsw", M=8, ef_construction=40, ef_runtime=20)
+    R.add_many(X, labels=labels)
+    P = port.PortHnsw(vtype, dim, metric, M=8, ef_construction=40, ef_runtime=20, multi=True)
+    P.add_many(X, labels=labels)
+    for q in Q:
+        for k, ef in ((10, 0), (5, 50), (40, 0), (150, 0)):
+            rl, rs, _ = R.topk(q, k, ef_runtime=ef)
+            pl, ps, _ = P.topk(q, k, ef_runtime=ef)
+            assert len(set(rl.tolist())) == len(rl)                       # each label once
+            assert np.array_equal(rl, pl) and np.array_equal(rs, ps), (vtype, metric, k, ef)
+        rs20 = R.topk(q, 20)[1]
+        radius = float(rs20[-1]) if rs20[-1] > 0 else 0.3
+        rl, rs, _ = R.range(q, radius)
+        pl, ps, _ = P.range(q, radius)
+        o = np.lexsort((rl, rs))
+        assert np.array_equal(rl[o], pl) and np.array_equal(rs[o], ps), (vtype, metric, "range")
+    R.close()
+    P.close()
+    ref.set_disabled_features()
