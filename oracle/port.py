@@ -259,6 +259,7 @@ class PortHnsw:
         self.vtype, self.dim, self.metric, self.M = vtype, dim, metric, M
         self.h = lib().vso_hnsw_new(vtype, dim, metric, M, ef_construction, ef_runtime, epsilon)
         self.multi = bool(multi)
+        self._label_set = set()
         if multi:  # HNSWIndex_Multi: labels may repeat, queries return each label once
             lib().vso_hnsw_set_multi(self.h, 1)
 
@@ -277,11 +278,18 @@ class PortHnsw:
         blobs = np.ascontiguousarray(blobs)
         L = lib()
         for i in range(blobs.shape[0]):
-            L.vso_hnsw_add(self.h, blobs[i].ctypes.data, int(labels[i]) if labels is not None else first_label + i)
+            label = int(labels[i]) if labels is not None else first_label + i
+            L.vso_hnsw_add(self.h, blobs[i].ctypes.data, label)
+            if self.multi:
+                self._label_set.add(label)
         return blobs.shape[0]
 
     def size(self):
         return lib().vso_hnsw_size(self.h)
+
+    def label_count(self):
+        """indexLabelCount: vectors for a single-value index, distinct labels for a multi-value one."""
+        return len(self._label_set) if self.multi else self.size()
 
     def mark_deleted(self, internal_id, deleted=True):
         lib().vso_hnsw_mark_deleted(self.h, internal_id, int(deleted))
@@ -340,7 +348,7 @@ class PortHnswBatchIterator:
     def next(self, n, order=BY_SCORE):
         labels = np.empty(max(n, 1), dtype=np.uint64)
         scores = np.empty(max(n, 1), dtype=np.float64)
-        m = lib().vso_hnsw_bi_next(self.it, n, self.index.size(), _ptr(labels), _ptr(scores))
+        m = lib().vso_hnsw_bi_next(self.it, n, self.index.label_count(), _ptr(labels), _ptr(scores))
         labels, scores = labels[:m].copy(), scores[:m].copy()
         if order == BY_ID:
             o = np.argsort(labels, kind="stable")

@@ -612,7 +612,21 @@ struct vso_hnsw_bi {
     double lower;
     heap_t cand, extras; /* min-heaps: stored negated through pr_greater */
     uint8_t *visited;
+    size_t *ret_labels; /* multi-value: labels handed out so far (HNSWMulti_BatchIterator::returned) */
+    size_t n_ret, cap_ret;
 };
+static int bi_returned(const vso_hnsw_bi *it, size_t label) {
+    for (size_t i = 0; i < it->n_ret; i++)
+        if (it->ret_labels[i] == label) return 1;
+    return 0;
+}
+static void bi_mark_returned(vso_hnsw_bi *it, size_t label) {
+    if (it->n_ret == it->cap_ret) {
+        it->cap_ret = it->cap_ret * 2 + 64;
+        it->ret_labels = (size_t *)realloc(it->ret_labels, it->cap_ret * sizeof(size_t));
+    }
+    it->ret_labels[it->n_ret++] = label;
+}
 
 /* std::greater<pair>: min-heap ordering for the same push/pop machinery */
 static void mh_sift_up(pr_t *a, size_t hole, pr_t v) {
@@ -666,6 +680,7 @@ void vso_hnsw_bi_free(vso_hnsw_bi *it) {
     free(it->cand.a);
     free(it->extras.a);
     free(it->visited);
+    free(it->ret_labels);
     free(it);
 }
 void vso_hnsw_bi_reset(vso_hnsw_bi *it) {
@@ -673,6 +688,7 @@ void vso_hnsw_bi_reset(vso_hnsw_bi *it) {
     it->depleted = 0;
     it->lower = INFINITY;
     it->cand.n = it->extras.n = 0;
+    it->n_ret = 0;
     it->entry = -1; /* the reference keeps entry_point; it is recomputed identically on the next call */
     memset(it->visited, 0, it->g->n + 1);
 }
@@ -698,8 +714,14 @@ size_t vso_hnsw_bi_next(vso_hnsw_bi *it, size_t n_res, size_t label_count, size_
             it->visited[ep] = 1;
             mh_push(&it->cand, it->lower, ep);
         }
+        const int multi = g->multi; /* HNSWMulti_BatchIterator (hnsw_multi_batch_iterator.h:39-99): label-keyed result set,
+                                       labels already handed out are skipped */
         while (top.n < it->ef && it->extras.n) { /* fillFromExtras */
-            h_push(&top, it->extras.a[0].d, it->extras.a[0].key);
+            if (multi) {
+                if (!bi_returned(it, it->extras.a[0].key)) ms_emplace(&top, it->extras.a[0].d, it->extras.a[0].key);
+            } else {
+                h_push(&top, it->extras.a[0].d, it->extras.a[0].key);
+            }
             mh_pop(&it->extras);
         }
         if (top.n != it->ef) {
@@ -708,7 +730,20 @@ size_t vso_hnsw_bi_next(vso_hnsw_bi *it, size_t n_res, size_t label_count, size_
                 size_t cur = it->cand.a[0].key;
                 if (cd > it->lower && top.n >= it->ef) break;
                 if (!g->deleted[cur]) { /* updateHeaps */
-                    if (top.n < it->ef) {
+                    if (multi) {
+                        if (it->lower > cd || top.n < it->ef) {
+                            const size_t label = g->labels[cur];
+                            if (!bi_returned(it, label)) {
+                                ms_emplace(&top, cd, label);
+                                if (top.n > it->ef) {
+                                    const size_t m = ms_top(&top);
+                                    mh_push(&it->extras, top.a[m].d, top.a[m].key);
+                                    ms_pop(&top);
+                                }
+                                it->lower = top.a[ms_top(&top)].d;
+                            }
+                        }
+                    } else if (top.n < it->ef) {
                         h_push(&top, cd, g->labels[cur]);
                         it->lower = top.a[0].d;
                     } else if (it->lower > cd) {
@@ -729,15 +764,31 @@ size_t vso_hnsw_bi_next(vso_hnsw_bi *it, size_t n_res, size_t label_count, size_
             }
             if (top.n < it->ef) it->depleted = 1;
         }
-        while (top.n > n_res) { /* prepareResults */
-            mh_push(&it->extras, top.a[0].d, top.a[0].key);
-            h_pop(&top);
-        }
-        n = top.n;
-        for (size_t i = n; i-- > 0;) {
-            scores[i] = top.a[0].d;
-            labels[i] = top.a[0].key;
-            h_pop(&top);
+        if (multi) {
+            while (top.n > n_res) { /* prepareResults */
+                const size_t m = ms_top(&top);
+                mh_push(&it->extras, top.a[m].d, top.a[m].key);
+                ms_pop(&top);
+            }
+            n = top.n;
+            for (size_t i = n; i-- > 0;) {
+                const size_t m = ms_top(&top);
+                scores[i] = top.a[m].d;
+                labels[i] = top.a[m].key;
+                bi_mark_returned(it, top.a[m].key);
+                ms_pop(&top);
+            }
+        } else {
+            while (top.n > n_res) { /* prepareResults */
+                mh_push(&it->extras, top.a[0].d, top.a[0].key);
+                h_pop(&top);
+            }
+            n = top.n;
+            for (size_t i = n; i-- > 0;) {
+                scores[i] = top.a[0].d;
+                labels[i] = top.a[0].key;
+                h_pop(&top);
+            }
         }
     }
     free(top.a);

@@ -317,3 +317,38 @@ def test_hnsw_multi_port_matches_reference(port, ref, vtype, metric):
     R.close()
     P.close()
     ref.set_disabled_features()
+
+
+@pytest.mark.parametrize("metric", [0, 2], ids=["L2", "Cosine"])
+def test_hnsw_multi_port_batch_iterator_matches_reference(port, ref, metric):
+    """HNSWMulti_BatchIterator (hnsw_multi_batch_iterator.h:39-99): label-keyed result set, labels already handed out are
+    skipped when refilling from the extras or admitting from the graph; same batches as the unmodified reference for
+    several batch-size schedules, incl. reset, until every label was returned exactly once."""
+    from datagen import make_vectors
+    n, dim = 900, 16
+    labels = (np.arange(n) % 100).astype(np.uint64)          # nine vectors per label
+    X = make_vectors(0, n, dim, seed=81 + metric)
+    Q = make_vectors(0, 4, dim, seed=82 + metric)
+    R = ref.RefIndex(0, dim, metric, multi=True, algo="hnsw", M=6, ef_construction=40, ef_runtime=10)
+    R.add_many(X, labels=labels)
+    P = port.PortHnsw(0, dim, metric, M=6, ef_construction=40, ef_runtime=10, multi=True)
+    P.add_many(X, labels=labels)
+    for q in Q:
+        for sched in ([5, 5, 5, 20, 1, 100], [1, 2, 3], [50, 50], [1000]):
+            ri, pi = R.batch_iterator(q), P.batch_iterator(q)
+            for rounds in range(2):
+                seen = []
+                for nres in sched:
+                    assert ri.has_next() == pi.has_next()
+                    rl, rs, _ = ri.next(nres)
+                    pl, ps, _ = pi.next(nres)
+                    assert np.array_equal(rl, pl) and np.array_equal(rs, ps), (sched, nres)
+                    seen += pl.tolist()
+                assert len(seen) == len(set(seen))
+                assert ri.has_next() == pi.has_next()
+                ri.reset()
+                pi.reset()
+            ri.close()
+            pi.close()
+    R.close()
+    P.close()
