@@ -255,3 +255,77 @@ class RefBatchIterator:
         if self.it:
             lib().vsref_bi_free(self.it)
             self.it = None
+
+
+# ---- BUILD_TESTS variant (make -C oracle ref_bt): the reference's own index-file loader / writer --------------------------
+BT_LIB_PATH = os.path.join(_HERE, "_ref", "libvecsim_ref_bt.so")
+_bt = None
+
+
+def bt_available():
+    return os.path.exists(BT_LIB_PATH)
+
+
+def bt_lib():
+    global _bt
+    if _bt is None:
+        L = C.CDLL(BT_LIB_PATH)
+        vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+        L.vsref_hnsw_load.restype = vp
+        L.vsref_hnsw_load.argtypes = [C.c_char_p]
+        L.vsref_hnsw_save.argtypes = [vp, C.c_char_p]
+        L.vsref_hnsw_integrity.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+        L.vsref_index_free.argtypes = [vp]
+        L.vsref_size.restype = sz
+        L.vsref_size.argtypes = [vp]
+        L.vsref_topk.restype = sz
+        L.vsref_topk.argtypes = [vp, vp, sz, i32, sz, vp, vp, C.POINTER(i32)]
+        L.vsref_delete.argtypes = [vp, sz]
+        L.vsref_silence_logs()
+        _bt = L
+    return _bt
+
+
+class RefFileIndex:
+    """An HNSW index restored by the reference's own loader, HNSWFactory::NewIndex(location)
+    (index_factories/hnsw_factory.cpp:171-251) — compiled only under BUILD_TESTS, hence the separate library."""
+
+    def __init__(self, path):
+        self.h = bt_lib().vsref_hnsw_load(os.fsencode(path))
+        if not self.h:
+            raise RuntimeError("the reference could not load " + str(path))
+
+    def close(self):
+        if self.h:
+            bt_lib().vsref_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return bt_lib().vsref_size(self.h)
+
+    def integrity(self):
+        """checkIntegrity (hnsw_serializer_impl.h:54-143, fp32 indexes): (valid, bidirectional, unidirectional)."""
+        d, u = C.c_size_t(), C.c_size_t()
+        ok = bt_lib().vsref_hnsw_integrity(self.h, C.byref(d), C.byref(u))
+        return ok, d.value, u.value
+
+    def save(self, path):
+        if bt_lib().vsref_hnsw_save(self.h, os.fsencode(path)) != 0:
+            raise RuntimeError("the reference could not save the index")
+
+    def delete(self, label):
+        return bt_lib().vsref_delete(self.h, label)
+
+    def topk(self, q, k, ef_runtime=0):
+        q = np.ascontiguousarray(q)
+        labels = np.empty(max(k, 1), dtype=np.uint64)
+        scores = np.empty(max(k, 1), dtype=np.float64)
+        code = C.c_int()
+        n = bt_lib().vsref_topk(self.h, _ptr(q), k, BY_SCORE, ef_runtime, _ptr(labels), _ptr(scores), C.byref(code))
+        return labels[:n].copy(), scores[:n].copy(), code.value

@@ -159,6 +159,36 @@ void *vsref_hnsw_new(int type, size_t dim, int metric, int multi, size_t block_s
     }
 }
 
+#ifdef BUILD_TESTS
+/* Only in the BUILD_TESTS variant (make ref_bt): the reference's own index-file loader and writer
+ * (index_factories/hnsw_factory.cpp:171-251, algorithms/hnsw/hnsw_serializer.cpp:39-52) and its integrity check. */
+void *vsref_hnsw_load(const char *path) {
+    try {
+        return HNSWFactory::NewIndex(std::string(path));
+    } catch (...) {
+        return nullptr;
+    }
+}
+int vsref_hnsw_save(void *h, const char *path) {
+    try {
+        auto *ser = dynamic_cast<HNSWSerializer *>((VecSimIndexInterface *)h);
+        if (!ser) return -1;
+        ser->saveIndex(std::string(path));
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
+int vsref_hnsw_integrity(void *h, size_t *double_conn, size_t *unidir_conn) {
+    auto *f32 = dynamic_cast<HNSWIndex<float, float> *>((VecSimIndexInterface *)h);
+    if (!f32) return -1;
+    HNSWIndexMetaData m = f32->checkIntegrity();
+    if (double_conn) *double_conn = m.double_connections;
+    if (unidir_conn) *unidir_conn = m.unidirectional_connections;
+    return m.valid_state ? 1 : 0;
+}
+#endif
+
 void vsref_index_free(void *h) {
     auto *idx = (VecSimIndexInterface *)h;
     if (!idx) return;

@@ -139,3 +139,36 @@ def test_bad_files_are_refused(capi, tmp_path):
         open(p, "wb").write(data)
         assert not L.VecSimGPU_HNSWLoadIndex(os.fsencode(p)), name
         assert msg in L.VecSimGPU_LastError(), (name, L.VecSimGPU_LastError())
+
+
+@pytest.mark.parametrize("metric", [0, 2])
+def test_reference_loads_what_we_write(capi, tmp_path, metric):
+    """The file VecSimGPU_HNSWSaveIndex writes is loaded by the REFERENCE's own loader (BUILD_TESTS variant of
+    oracle/_ref, HNSWFactory::NewIndex(location)): its integrity check passes, it holds the same number of vectors, and
+    it answers top-k exactly as the device index that wrote the file — deleted marks included."""
+    from oracle import ref
+    if not ref.bt_available():
+        pytest.skip("oracle/_ref/libvecsim_ref_bt.so not built")
+    from datagen import make_vectors
+    n, dim, M = 900, 16, 6
+    X = make_vectors(0, n, dim, seed=41)
+    Q = make_vectors(0, 12, dim, seed=42)
+    G = capi.HNSWIndex(capi.HNSWParams(type=0, dim=dim, metric=metric, multi=False, initialCapacity=0, blockSize=64, M=M,
+                                       efConstruction=30, efRuntime=15, epsilon=0.02))
+    G.add_vectors(X, labels=(np.arange(n) + 100).astype(np.uint64))
+    for lab in (100, 350, 999):
+        assert G.delete_vector(lab) == 1
+    path = str(tmp_path / "ours.hnsw_v4")
+    G.save_index(path)
+    R = ref.RefFileIndex(path)
+    ok, double_conn, unidir = R.integrity()
+    assert ok == 1, "the reference's checkIntegrity rejects the file"
+    assert R.size() == n            # the reference counts mark-deleted nodes in indexSize (hnsw.h:367-369)
+    for ef in (15, 60):
+        G.set_ef(ef)
+        labels, scores = G.knn_batch(Q, 10)
+        for i, q in enumerate(Q):
+            rl, rs, _ = R.topk(q, 10, ef_runtime=ef)
+            assert np.array_equal(labels[i], rl.astype(np.int64)) and np.array_equal(scores[i], rs), (metric, ef, i)
+    R.close()
+    G.close()

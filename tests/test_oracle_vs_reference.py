@@ -1,8 +1,12 @@
 """Pins the C restatement (oracle/vs_oracle.c) against the UNMODIFIED reference (oracle/_ref),
 bit for bit. Mirrors the reference's own strategy of walking the dispatcher down tier by tier
 (tests/unit/test_spaces.cpp:703-709) by masking CPU feature bits."""
+import os
+
 import numpy as np
 import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 from datagen import (BFLOAT16, COSINE, FLOAT16, FLOAT32, FLOAT64, INT8, IP, L2, METRIC_NAMES,
                      TYPE_NAMES, UINT8, make_vectors)
@@ -352,3 +356,34 @@ def test_hnsw_multi_port_batch_iterator_matches_reference(port, ref, metric):
             pi.close()
     R.close()
     P.close()
+
+
+def test_reference_loader_and_writer_agree_with_the_restated_file_reader(port, ref, tmp_path):
+    """The reference's own HNSW file loader / writer (BUILD_TESTS variant of oracle/_ref): it loads its V3 fixture with a
+    valid integrity check, the restated reader counts the same unidirectional edges, and the V4 file the reference then
+    writes parses back to the same index — so oracle/port.py::read_hnsw_file is pinned on both encodings."""
+    if not ref.bt_available():
+        pytest.skip("oracle/_ref/libvecsim_ref_bt.so not built (make -C oracle ref_bt)")
+    fixture = os.path.join(HERE, "golden", "ref_hnsw_1k_d4_single.v3")
+    R = ref.RefFileIndex(fixture)
+    ok, double_conn, unidir = R.integrity()
+    f3 = port.read_hnsw_file(fixture)
+    assert ok == 1 and R.size() == 1001 and unidir == f3["incoming"]
+    assert double_conn == sum(int(c.sum()) for c in f3["counts"]) - unidir   # counted once per direction
+    out = str(tmp_path / "ref_written.hnsw_v4")
+    R.save(out)
+    f4 = port.read_hnsw_file(out)
+    assert f4["version"] == 4 and f4["n"] == 1001 and f4["incoming"] == f3["incoming"]
+    for key in ("dim", "type", "metric", "M", "M0", "ef_construction", "ef_runtime", "epsilon", "block_size", "entry",
+                "max_level", "num_deleted"):
+        assert f4[key] == f3[key], key
+    assert np.array_equal(f4["labels"], f3["labels"]) and np.array_equal(f4["vectors"], f3["vectors"])
+    assert np.array_equal(f4["levels"], f3["levels"])
+    for lvl in range(len(f3["links"])):
+        assert np.array_equal(f4["counts"][lvl], f3["counts"][lvl]) and np.array_equal(f4["links"][lvl], f3["links"][lvl])
+    # the loaded index answers like the golden case
+    gold = np.load(os.path.join(HERE, "golden", "hnsw_file_case.npz"))
+    for i, q in enumerate(gold["Q"]):
+        l, s, _ = R.topk(q, 10, ef_runtime=50)
+        assert np.array_equal(l.astype(np.int64), gold["labels_ef50"][i]) and np.array_equal(s, gold["scores_ef50"][i])
+    R.close()
