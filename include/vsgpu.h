@@ -75,6 +75,8 @@ int vsgpu_store_append_device(vsgpu_store *s, const void *rows, size_t stride, c
 int vsgpu_store_update(vsgpu_store *s, size_t id, const void *row, uint64_t label);
 /* Delete-by-swap (brute_force.h:195-224): row `src` (the last one) moves to `dst`; count -= 1. */
 int vsgpu_store_remove_swap(vsgpu_store *s, size_t dst);
+/* Drop the rows [new_count, size()) (roll back an append whose follow-up step failed). */
+int vsgpu_store_truncate(vsgpu_store *s, size_t new_count);
 /* Copy rows back to the host (tests, serialisation). */
 int vsgpu_store_read(const vsgpu_store *s, size_t first, size_t n, void *rows, size_t stride, uint64_t *labels);
 
@@ -120,6 +122,18 @@ int vsgpu_last_stats(const vsgpu_store *s, vsgpu_stats *out);
 int vsgpu_merge_topk_device(int device, void *stream, int dtype_f64, size_t parts, size_t nq, size_t k,
                             const void *scores, const uint64_t *labels, void *out_scores,
                             uint64_t *out_labels);
+
+/* Sharded flat index: a shard's result travels as ONE list of 16-byte hits {u64 label; f32 score; u32 flag}
+ * — one collective per batch. The flag of a query's first hit carries "this shard's candidate buffer overflowed" (tensor
+ * path), so every rank learns without a host round trip whether the query has to be redone on the exact path. */
+size_t vsgpu_packed_hit_bytes(void);
+/* Pack the lists the last vsgpu_topk_device call on `s` wrote ([nq][k] fp32 scores / labels, DEVICE) into `out`
+ * ([nq][k] hits, DEVICE), on the store's stream. */
+int vsgpu_pack_topk_device(vsgpu_store *s, size_t nq, size_t k, const float *scores, const uint64_t *labels, void *out);
+/* Merge `parts` packed lists ([parts][nq][k], DEVICE) by ascending (score, label). out_flags [nq] (may be NULL): OR of the
+ * parts' overflow flags per query; any_flag (one u32, zero on entry, may be NULL): OR over the queries. */
+int vsgpu_merge_packed_device(int device, void *stream, size_t parts, size_t nq, size_t k, const void *packed,
+                              float *out_scores, uint64_t *out_labels, uint32_t *out_flags, uint32_t *any_flag);
 
 /* ---- HNSW (algorithms/hnsw/hnsw.h) -----------------------------------------------------------
  * A graph over the rows of a store (internal id = row index). Level-0 records hold up to 2M links,

@@ -99,3 +99,28 @@ def test_multi_one_label_dominates(capi, port):
     assert np.array_equal(gl[0], pl.astype(np.int64)) and np.array_equal(gs[0], ps)
     G.close()
     P.close()
+
+
+def test_delete_label_whose_id_list_holds_stale_entries(capi, port):
+    """add X, A, Y, A; delete X; add A; delete Y — label A's id list is now [1, 0, 2]. Deleting A walks
+    that list while rows move into the holes; the moved row's id must be patched from the BACK of its label's list
+    (brute_force_multi.h:244-263), or a stale entry is rewritten, a row of A survives and the call reports 2 instead of 3."""
+    dim = 8
+    V = make_vectors(0, 5, dim, seed=2)
+    G = capi.BFIndex(capi.BFParams(type=0, dim=dim, metric=0, multi=True, initialCapacity=0, blockSize=1024))
+    P = port.PortIndex(0, dim, 0, multi=True)
+    X, A, Y = 10, 20, 30
+    for blob, lab in ((V[0], X), (V[1], A), (V[2], Y), (V[3], A)):
+        G.add_vector(blob, lab)
+        P.add(blob, lab)
+    assert G.delete_vector(X) == P.delete(X) == 1
+    G.add_vector(V[4], A)
+    P.add(V[4], A)
+    assert G.delete_vector(Y) == P.delete(Y) == 1
+    assert G.index_size() == P.size() == 3
+    assert G.delete_vector(A) == P.delete(A) == 3
+    assert G.index_size() == P.size() == 0
+    l, s = G.knn_query(V[1], 5)
+    assert l.shape[1] == 0 or not (l == A).any()
+    G.close()
+    P.close()

@@ -172,3 +172,66 @@ def test_reference_loads_what_we_write(capi, tmp_path, metric):
             assert np.array_equal(labels[i], rl.astype(np.int64)) and np.array_equal(scores[i], rs), (metric, ef, i)
     R.close()
     G.close()
+
+
+def test_overwritten_label_stays_overwritten_after_reload(capi, tmp_path):
+    """an upsert tombstones the old node and appends a new one with the same label; the saved file holds
+    both (old flagged DELETE_MARK). After loading, the stale vector must stay dead on the device — one result per label,
+    the new vector's score — and the deleted count must match what was saved."""
+    from datagen import make_vectors
+    n, dim = 400, 8
+    X = make_vectors(0, n, dim, seed=7)
+    G = capi.HNSWIndex(capi.HNSWParams(type=0, dim=dim, metric=0, multi=False, initialCapacity=0, blockSize=32, M=6,
+                                       efConstruction=30, efRuntime=400, epsilon=0.01))
+    G.add_vectors(X)
+    far = np.full(dim, 50.0, dtype=np.float32)
+    assert G.add_vector(far, 17) == 0           # overwrite: label 17 now lives far away
+    assert G.delete_vector(23) == 1
+    assert G.add_vector(X[23], 23) == 1          # deleted, then re-added: a flagged id and a later live id share label 23
+    path = str(tmp_path / "upsert.hnsw_v4")
+    G.save_index(path)
+    G2 = capi.HNSWIndex.load(path)
+    assert G2.index_size() == G.index_size() == n
+    assert dict(G2.debug_info())["NUMBER_OF_MARKED_DELETED"] == dict(G.debug_info())["NUMBER_OF_MARKED_DELETED"] == 2
+    for q, lab in ((X[17], 17), (X[23], 23), (far, 17)):
+        l1, s1 = G.knn_query(q, n)
+        l2, s2 = G2.knn_query(q, n)
+        assert np.array_equal(l1, l2) and np.array_equal(s1, s2)
+        assert (l2[0] == lab).sum() == 1          # never twice
+    l, s = G2.knn_query(X[17], 1)
+    assert l[0][0] != 17                          # the stale copy of label 17 is not the nearest neighbour of its old self
+    G.close()
+    G2.close()
+
+
+def test_corrupted_graph_section_is_refused(capi, tmp_path):
+    """link ids, the entry point and levels are validated before anything reaches the device."""
+    L = capi.lib()
+    from datagen import make_vectors
+    G = capi.HNSWIndex(capi.HNSWParams(type=0, dim=4, metric=0, multi=False, initialCapacity=0, blockSize=16, M=4,
+                                       efConstruction=20, efRuntime=10, epsilon=0.01))
+    G.add_vectors(make_vectors(0, 64, 4, seed=3))
+    path = str(tmp_path / "ok.hnsw_v4")
+    G.save_index(path)
+    G.close()
+    raw = bytearray(open(path, "rb").read())
+    # header: version, algo (2 x int) | dim (size_t) | type, metric (2 x int) | blockSize (size_t) | multi (bool) |
+    # initialCapacity, M, M0, efC, ef (5 x size_t) | epsilon, mult (2 x double) | n, num_deleted, max_level (3 x size_t) | entry (u32)
+    off_n = 4 + 4 + 8 + 4 + 4 + 8 + 1 + 5 * 8 + 2 * 8
+    off_entry = off_n + 3 * 8
+    bad_entry = bytearray(raw)
+    bad_entry[off_entry:off_entry + 4] = (1000).to_bytes(4, "little")
+    huge_n = bytearray(raw)
+    huge_n[off_n:off_n + 8] = (1 << 61).to_bytes(8, "little")
+    # first link id of node 0 (V4: labels+flags, vectors, then per block: len u32, per node: level size_t, count u16, links)
+    off_graph = off_entry + 4 + 64 * 9 + 64 * 16
+    bad_link = bytearray(raw)
+    bad_link[off_graph + 4 + 8 + 2:off_graph + 4 + 8 + 2 + 4] = (0x7fffffff).to_bytes(4, "little")
+    for name, data in (("entry", bad_entry), ("count", huge_n), ("link", bad_link)):
+        p = str(tmp_path / name)
+        open(p, "wb").write(bytes(data))
+        assert not L.VecSimGPU_HNSWLoadIndex(os.fsencode(p)), name
+        assert b"corrupted" in L.VecSimGPU_LastError(), (name, L.VecSimGPU_LastError())
+    G3 = capi.HNSWIndex.load(path)                 # the untouched file still loads
+    assert G3.index_size() == 64
+    G3.close()

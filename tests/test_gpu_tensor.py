@@ -121,6 +121,53 @@ def test_tensor_path_equals_exact_path_large(capi, metric):
     G.close()
 
 
+def _bf16_midpoint_case(k):
+    """Rows and a query whose elements sit exactly on bf16 rounding midpoints, so that rounding BOTH operands moves the
+    coarse score by ~2^-7 |a||q| — twice what rounding one operand can (What's weak #1). d = 128,
+    u = 2^-8:  q = (1+u x64 | 1+3u x64),  X = (1+u x64 | 0),  Y = (0 | 1+3u x63, 0).
+    Exact:  X.q = 64.501 > Y.q = 64.485 (X is the better row under IP and under L2);
+    coarse: X^.q^ = 64.0 (1+u rounds to even 1.0), Y^.q^ = 64.98 (1+3u rounds to 1+4u): the order flips and X's coarse
+    score is 0.50 off — outside the 0.365 that a one-rounding bound (2^-8 + 2^-16 + 4d 2^-23)|q||X| allows."""
+    dim, u = 128, 2.0 ** -8
+    rng = np.random.default_rng(11)
+    q = np.concatenate([np.full(64, 1 + u), np.full(64, 1 + 3 * u)]).astype(np.float32)
+    X = np.concatenate([np.full(64, 1 + u), np.zeros(64)]).astype(np.float32)
+    Y = np.concatenate([np.zeros(64), np.full(63, 1 + 3 * u), np.zeros(1)]).astype(np.float32)
+    # the construction is adversarial for the old bound
+    xb, qb = from_bf16(to_bf16(X[None]))[0].astype(np.float64), from_bf16(to_bf16(q[None]))[0].astype(np.float64)
+    old_eps = (2.0 ** -8 + 2.0 ** -16 + 4 * dim * 2.0 ** -23) * np.linalg.norm(q) * np.linalg.norm(X)
+    assert abs(xb @ qb - X.astype(np.float64) @ q.astype(np.float64)) > old_eps
+    assert X.astype(np.float64) @ q > Y.astype(np.float64) @ q
+    filler = (0.05 * rng.standard_normal((40000, dim))).astype(np.float32)
+    big = np.stack([np.full(dim, 1.5 + 0.01 * j, dtype=np.float32) for j in range(k - 1)]) if k > 1 else np.zeros((0, dim), np.float32)
+    rows = np.concatenate([filler[:20000], Y[None], big, X[None], filler[20000:]])   # Y is scanned before X
+    x_id = 20000 + 1 + len(big)
+    Q = np.concatenate([np.tile(q, (32, 1)), (0.05 * rng.standard_normal((8, dim))).astype(np.float32)])
+    return rows, Q, x_id, x_id - len(big) - 1
+
+
+@pytest.mark.parametrize("metric", [1, 0])
+@pytest.mark.parametrize("k", [1, 100])
+def test_bf16_midpoint_rows_are_not_dropped(capi, port, metric, k):
+    """Parity on adversarial rounding: the true k-th row's coarse score is pushed below a rival's by rounding both
+    operands to bf16; the admission band must still contain it (no overflow, no fallback: the band stays narrow)."""
+    rows, Q, x_id, y_id = _bf16_midpoint_case(k)
+    if metric == 0:
+        # under L2 the "big" rows must be NEAR the query to rank first: replace them by q + small offsets
+        nb = k - 1
+        for j in range(nb):
+            rows[y_id + 1 + j] = Q[0] + np.float32(0.001 * (j + 1)) * np.sign(np.arange(128) % 2 - 0.5).astype(np.float32)
+    G = _index(capi, 0, 128, metric, rows)
+    P = port.PortIndex(0, 128, metric)
+    P.add_many(rows)
+    pl, _, _ = P.topk(Q[0], k)
+    assert int(pl[-1]) == x_id and y_id not in pl.tolist()       # X is the true k-th result, Y is not in the top-k
+    st = _check_against(capi, G, P, Q, k, mode=2)
+    assert st["path"] == 1 and st["fallback_queries"] == 0, st
+    G.close()
+    P.close()
+
+
 def test_candidate_overflow_falls_back_to_exact(capi, port):
     """Near-duplicate rows: every row is within the coarse error bound of the k-th score, the
     candidate buffers overflow, and the affected queries are redone on the exact path."""

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-CUDA_SOURCES = ["vsgpu_api.cu", "vsgpu_exact.cu", "vsgpu_select.cu", "vsgpu_tensor.cu", "vsgpu_hnsw.cu", "vsgpu_scan.cu", "vsgpu_tensor_i8.cu"]
+CUDA_SOURCES = ["vsgpu_api.cu", "vsgpu_exact.cu", "vsgpu_select.cu", "vsgpu_tensor.cu", "vsgpu_hnsw.cu", "vsgpu_scan.cu", "vsgpu_tensor_i8.cu", "vsgpu_shard.cu"]
 HOST_SOURCES = ["host/vecsim_flat.cpp", "host/vecsim_flat_multi.cpp", "host/vecsim_hnsw.cpp", "host/vecsim_tiered.cpp", "host/vecsim_hnsw_file.cpp", "host/vecsim_api.cpp"]
 NVCC_FLAGS = ["-std=c++20", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -61,20 +61,32 @@ def build(force=False, verbose=False):
     procs = []
     log = open(os.path.join(objdir, "ptxas.log"), "w")
     objs = []
+    # one object per translation unit, recompiled only when that source, a shared header or the flags changed
+    headers = [p for p in _deps() if p.endswith((".cuh", ".h"))]
     for src in cuda_sources:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
+        ostamp = _stamp(headers + [os.path.join(CSRC, src)], NVCC_FLAGS)
+        if not force and os.path.exists(obj) and os.path.exists(obj + ".stamp") and open(obj + ".stamp").read() == ostamp:
+            continue
         cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((cmd, obj, ostamp, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
-    for cmd, p in procs:
+    for cmd, obj, ostamp, p in procs:
         out, _ = p.communicate()
         log.write("$ " + " ".join(cmd) + "\n" + out + "\n")
+        with open(obj + ".ptxas.log", "w") as f:
+            f.write(out)
         if p.returncode != 0:
             failed = True
             sys.stderr.write(out)
-        elif verbose:
-            sys.stderr.write(out)
+            if os.path.exists(obj + ".stamp"):
+                os.remove(obj + ".stamp")
+        else:
+            with open(obj + ".stamp", "w") as f:
+                f.write(ostamp)
+            if verbose:
+                sys.stderr.write(out)
     log.close()
     if failed:
         raise RuntimeError("nvcc failed (see build/ptxas.log)")

@@ -85,9 +85,12 @@ int FlatMultiIndex::removeRow(idType id) {
     if (id != last) {
         const size_t moved = id_to_label_[last];
         id_to_label_[id] = moved;
-        for (idType &x : label_to_ids_[moved])
-            if (x == last) {
-                x = id;
+        // back to front, as replaceIdOfLabel does (brute_force_multi.h:244-263): while deleteVector walks a label's own
+        // list, the entries before its cursor are stale (already removed) and may equal `last` by coincidence
+        std::vector<idType> &ids = label_to_ids_[moved];
+        for (size_t t = ids.size(); t-- > 0;)
+            if (ids[t] == last) {
+                ids[t] = id;
                 break;
             }
     }

@@ -59,12 +59,35 @@ int HnswIndex::flush() {
     if (pending_labels_.empty()) return 0;
     const size_t n = pending_labels_.size();
     int rc = vsgpu_store_append(store_, pending_rows_.data(), stored_size_, pending_labels_.data(), n);
-    if (rc != VSGPU_OK) return rc;
+    if (rc != VSGPU_OK) return rc; // nothing appended: the vectors stay staged
     rc = vsgpu_hnsw_insert(graph_, n, pending_levels_.data());
+    if (rc != VSGPU_OK) {
+        // the graph did not take them: roll the store back so row ids and node ids stay in step; the vectors stay staged
+        // (the caller may retry, or drop them with abortPending)
+        vsgpu_store_truncate(store_, vsgpu_hnsw_size(graph_));
+        return rc;
+    }
     pending_rows_.clear();
     pending_labels_.clear();
     pending_levels_.clear();
     return rc;
+}
+
+// Forget the vectors that are staged but not on the device (after a failed flush): their ids are the tail of the id space.
+// Labels whose staged vector replaced an older one stay deleted — the caller still holds the new vector.
+size_t HnswIndex::abortPending() {
+    std::lock_guard<std::mutex> g(mu_);
+    const size_t n = pending_labels_.size();
+    for (size_t i = 0; i < n; i++) {
+        const size_t id = id_to_label_.size() - 1;
+        auto it = label_to_id_.find(id_to_label_[id]);
+        if (it != label_to_id_.end() && it->second == (idType)id) label_to_id_.erase(it);
+        id_to_label_.pop_back();
+    }
+    pending_rows_.clear();
+    pending_labels_.clear();
+    pending_levels_.clear();
+    return n;
 }
 
 int HnswIndex::addVector(const void *blob, size_t label) {

@@ -90,10 +90,17 @@ VecSimIndexInterface *load_hnsw_file(const char *path, std::string &err) {
     p.epsilon = r.get<double>();
     (void)r.get<double>(); // mult = 1 / ln(M): recomputed by the index
     const size_t n = r.get<size_t>();
+    // every element costs at least its label + flag byte + one stored row + one level-0 record header in the file: a
+    // count that cannot fit is a corrupted header (and would overflow the buffer sizes computed from it)
+    if (r.ok && p.dim && p.dim <= (1u << 24) && n > r.buf.size() / (sizeof(size_t) + 1 + p.dim)) {
+        err = "Cannot load index: corrupted header (element count exceeds the file size)";
+        return nullptr;
+    }
     const size_t num_deleted = r.get<size_t>();
     const size_t max_level = r.get<size_t>();
     const idType entry = r.get<idType>();
-    if (!r.ok || p.dim == 0 || p.type > VecSimType_UINT8 || p.metric > VecSimMetric_Cosine || M0 != 2 * p.M) {
+    if (!r.ok || p.dim == 0 || p.dim > (1u << 24) || p.type > VecSimType_UINT8 || p.metric > VecSimMetric_Cosine ||
+        M0 != 2 * p.M || p.M < 2 || p.M > 256) {
         err = "Cannot load index: corrupted header";
         return nullptr;
     }
@@ -169,6 +176,28 @@ VecSimIndexInterface *load_hnsw_file(const char *path, std::string &err) {
         err = "Cannot load index: truncated or corrupted graph section";
         return nullptr;
     }
+    // the traversal kernels follow these ids without bounds checks: refuse anything that points outside the graph
+    {
+        bool sane = true;
+        size_t u = 0;
+        for (size_t i = 0; i < n && sane; i++) {
+            const uint32_t *rec = l0.data() + i * w0;
+            for (uint32_t j = 0; j < rec[0] && sane; j++) sane = rec[1 + j] < n;
+            for (uint32_t l = 1; l <= levels[i] && sane; l++, u++) {
+                const uint32_t *ur = upper.data() + u * wu;
+                for (uint32_t j = 0; j < ur[0] && sane; j++) sane = ur[1 + j] < n && levels[ur[1 + j]] >= l;
+            }
+        }
+        if (n) {
+            const bool empty_entry = entry == (idType)-1 || max_level == (size_t)-1;
+            if (empty_entry) sane = false;
+            else sane = sane && entry < n && levels[entry] == max_level;
+        }
+        if (!sane) {
+            err = "Cannot load index: corrupted graph (link, entry point or level out of range)";
+            return nullptr;
+        }
+    }
     p.initialCapacity = std::max(p.initialCapacity, n);
     auto *idx = new HnswIndex(p, nullptr);
     if (!idx->ok()) {
@@ -202,13 +231,15 @@ VecSimIndexInterface *load_hnsw_file(const char *path, std::string &err) {
     return idx;
 }
 
+// Restores one DELETE_MARK of a loaded file. The node is always flagged on the device (a freshly imported graph has no
+// flags at all); the label mapping goes only when it still points at this node — a label that was overwritten or re-added
+// after the delete has a later, live id that importGraph's last-id-wins pass already mapped it to.
 int HnswIndex::markDeletedById(idType id) {
     std::lock_guard<std::mutex> g(mu_);
     if (id >= id_to_label_.size()) return -1;
-    auto it = label_to_id_.find(id_to_label_[id]);
-    if (it == label_to_id_.end() || it->second != id) return 0; // already deleted
     if (markDeletedLocked(id) != 0) return -1;
-    label_to_id_.erase(it);
+    auto it = label_to_id_.find(id_to_label_[id]);
+    if (it != label_to_id_.end() && it->second == id) label_to_id_.erase(it);
     return 0;
 }
 

@@ -246,6 +246,7 @@ class HnswIndex final : public VecSimIndexInterface {
         std::lock_guard<std::mutex> g(mu_);
         return flush();
     }
+    size_t abortPending();
     int iterNext(vsgpu_hnsw_iter *it, size_t n, size_t *labels, double *scores, size_t *count, int *depleted);
     void iterReset(vsgpu_hnsw_iter *it);
     void iterDestroy(vsgpu_hnsw_iter *it);
@@ -338,6 +339,7 @@ class TieredIndex final : public VecSimIndexInterface {
     std::mutex drain_mu_;
     std::unordered_map<size_t, AsyncJob *> label_to_job_; // one pending job per vector in the flat buffer
     std::vector<AsyncJob *> pending_;                      // the same jobs in submission order
+    std::vector<AsyncJob *> parked_;                       // vectors the backend refused three times: they stay in the buffer
     std::atomic<size_t> direct_insertions_{0};
     std::shared_ptr<std::atomic<bool>> alive_;
 };

@@ -30,6 +30,7 @@ struct AsyncJob {
     size_t label;
     std::vector<uint8_t> blob;                // the caller's blob (both tiers preprocess it the same way)
     std::shared_ptr<std::atomic<bool>> alive; // false once the index is gone
+    int attempts = 0;                         // failed ingestions of this vector so far
 };
 
 namespace vsb {
@@ -137,6 +138,7 @@ TieredIndex::TieredIndex(const TieredIndexParams &tp, void *logCtx)
 
 TieredIndex::~TieredIndex() {
     alive_->store(false);
+    for (AsyncJob *p : parked_) delete p; // never handed to the queue
     // jobs the queue still holds free themselves when they run; the ones it will never run are the caller's to drop
 }
 
@@ -150,6 +152,7 @@ void TieredIndex::executeJobWrapper(AsyncJob *job) {
 void TieredIndex::executeInsertJob(AsyncJob *job) {
     std::lock_guard<std::mutex> drain(drain_mu_);
     std::vector<AsyncJob *> batch;
+    bool ok = true;
     {
         // the flat guard is held (shared) until the labels are registered in the backend: an overwrite / delete of one of
         // them either invalidated its job before this point or finds the label in the backend afterwards
@@ -158,18 +161,48 @@ void TieredIndex::executeInsertJob(AsyncJob *job) {
         for (AsyncJob *p : pending_)
             if (p->isValid) batch.push_back(p);
         std::unique_lock<std::shared_mutex> main(main_guard_);
-        for (AsyncJob *p : batch) back_->addVector(p->blob.data(), p->label);
+        for (AsyncJob *p : batch)
+            if (back_->addVector(p->blob.data(), p->label) < 0) {
+                ok = false;
+                break;
+            }
         flat.unlock();
-        back_->sync(); // store append + graph insertion on the device, under the exclusive main guard
+        // store append + graph insertion on the device, under the exclusive main guard
+        if (!ok || back_->sync() != 0) {
+            ok = false;
+            const size_t dropped = back_->abortPending(); // whatever did not reach the device stays in the flat buffer only
+            if (globals().log_cb) {
+                const std::string msg = "tiered index: the backend refused " + std::to_string(dropped) + " vector(s) (" +
+                                        vsgpu_last_error() + "); they stay in the flat buffer";
+                globals().log_cb(nullptr, "warning", msg.c_str());
+            }
+        }
     }
-    std::unique_lock<std::shared_mutex> flat(flat_guard_);
-    for (AsyncJob *p : batch) {
-        if (!p->isValid) continue; // deleted / overwritten while it was being ingested: already out of the flat buffer
-        front_->deleteVector(p->label);
-        label_to_job_.erase(p->label);
-        p->isValid = false;
+    AsyncJob *retry = nullptr;
+    {
+        std::unique_lock<std::shared_mutex> flat(flat_guard_);
+        for (AsyncJob *p : batch) {
+            if (!p->isValid) continue; // deleted / overwritten while it was being ingested: already out of the flat buffer
+            if (ok || back_->hasLabel(p->label)) {
+                front_->deleteVector(p->label);
+                label_to_job_.erase(p->label);
+                p->isValid = false;
+                continue;
+            }
+            // not ingested: the vector stays buffered with a valid job. The job that is running dies when it returns, so its
+            // vector moves to a fresh one — resubmitted twice, then parked (searchable in the buffer, never retried)
+            p->attempts++;
+            if (p != job) continue;
+            auto *nj = new AsyncJob{0, executeJobWrapper, this, true, p->label, p->blob, alive_, p->attempts};
+            label_to_job_[p->label] = nj;
+            std::replace(pending_.begin(), pending_.end(), p, nj);
+            p->isValid = false;
+            if (nj->attempts < 3) retry = nj;
+            else parked_.push_back(nj);
+        }
+        pending_.erase(std::remove_if(pending_.begin(), pending_.end(), [](AsyncJob *p) { return !p->isValid; }), pending_.end());
     }
-    pending_.erase(std::remove_if(pending_.begin(), pending_.end(), [](AsyncJob *p) { return !p->isValid; }), pending_.end());
+    if (retry) submit_(job_queue_, job_queue_ctx_, &retry, &retry->Execute, 1);
 }
 
 void TieredIndex::invalidateJobLocked(size_t label) {

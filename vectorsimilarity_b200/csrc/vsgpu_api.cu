@@ -43,6 +43,84 @@ int ensure_pinned(vsgpu_store *s, size_t bytes) {
     return VSGPU_OK;
 }
 
+int pending_begin(vsgpu_store *s, size_t nq, size_t chunks, uint32_t **d_flags, unsigned long long **d_totals) {
+    const size_t fl = (nq * 4 + 255) / 256 * 256, bytes = fl + chunks * 8;
+    VS_TRY(ensure_scratch(s, s->ovf, bytes));
+    if (s->h_ovf_bytes < bytes) {
+        if (s->h_ovf) {
+            VS_CUDA(cudaStreamSynchronize(s->stream));
+            VS_CUDA(cudaFreeHost(s->h_ovf));
+            s->h_ovf = nullptr;
+            s->h_ovf_bytes = 0;
+        }
+        const size_t want = std::max<size_t>(bytes, 32768);
+        VS_CUDA(cudaMallocHost(&s->h_ovf, want));
+        s->h_ovf_bytes = want;
+    }
+    VS_CUDA(cudaMemsetAsync(s->ovf.ptr, 0, bytes, s->stream));
+    *d_flags = (uint32_t *)s->ovf.ptr;
+    *d_totals = (unsigned long long *)((uint8_t *)s->ovf.ptr + fl);
+    return VSGPU_OK;
+}
+
+int pending_arm(vsgpu_store *s, const void *q, size_t nq, size_t q_stride, const float *q_norms, size_t k, uint32_t *out_ids,
+                void *out_scores, uint64_t *out_labels, size_t n_events, size_t chunks) {
+    const size_t fl = (nq * 4 + 255) / 256 * 256;
+    VS_CUDA(cudaMemcpyAsync(s->h_ovf, s->ovf.ptr, fl + chunks * 8, cudaMemcpyDeviceToHost, s->stream));
+    PendingTopk &p = s->pend;
+    p.active = true;
+    p.q = q;
+    p.nq = nq;
+    p.q_stride = q_stride;
+    p.q_norms = q_norms;
+    p.k = k;
+    p.out_ids = out_ids;
+    p.out_scores = out_scores;
+    p.out_labels = out_labels;
+    p.n_events = n_events;
+    p.n_totals = chunks;
+    return VSGPU_OK;
+}
+
+cudaEvent_t scan_event(vsgpu_store *s, size_t i) {
+    while (s->scan_evs.size() <= i) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        s->scan_evs.push_back(e);
+    }
+    return s->scan_evs[i];
+}
+
+int resolve_pending_topk(vsgpu_store *s) {
+    if (!s->pend.active) return VSGPU_OK;
+    PendingTopk p = s->pend;
+    s->pend.active = false;
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    const size_t fl = (p.nq * 4 + 255) / 256 * 256;
+    const auto *tot = (const unsigned long long *)((const uint8_t *)s->h_ovf + fl);
+    for (size_t c = 0; c < p.n_totals; c++) s->stats.candidates += tot[c];
+    for (size_t e = 0; e < p.n_events; e++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s->scan_evs[2 * e], s->scan_evs[2 * e + 1]) == cudaSuccess) s->stats.scan_ms += ms;
+    }
+    const size_t n = s->count, ld = (n + 63) / 64 * 64;
+    const size_t ssz = s->type == VSGPU_FLOAT64 ? 8 : 4;
+    bool any = false;
+    for (size_t q = 0; q < p.nq; q++) {
+        if (!s->h_ovf[q]) continue;
+        any = true;
+        s->stats.fallback_queries++;
+        VS_TRY(ensure_scratch(s, s->scores, ld * ssz));
+        VS_TRY(launch_exact_scan(s, (const uint8_t *)p.q + q * p.q_stride, 1, p.q_stride, p.q_norms ? p.q_norms + q : nullptr,
+                                 s->scores.ptr, ld));
+        VS_TRY(launch_select_topk(s, s->scores.ptr, ld, 1, n, p.k, p.k, p.out_ids ? p.out_ids + q * p.k : nullptr,
+                                  p.out_scores ? (uint8_t *)p.out_scores + q * p.k * ssz : nullptr,
+                                  p.out_labels ? p.out_labels + q * p.k : nullptr));
+    }
+    if (any) VS_CUDA(cudaStreamSynchronize(s->stream));
+    return VSGPU_OK;
+}
+
 static size_t elem_size(int type) {
     switch (type) {
     case VSGPU_FLOAT32: return 4;
@@ -275,6 +353,9 @@ void vsgpu_store_destroy(vsgpu_store *s) {
     for (Scratch *sc : {&s->q_raw, &s->q_dev, &s->scores, &s->sel_state, &s->out_dev, &s->cand, &s->misc})
         if (sc->ptr) cudaFree(sc->ptr);
     if (s->pinned) cudaFreeHost(s->pinned);
+    if (s->h_ovf) cudaFreeHost(s->h_ovf);
+    if (s->ovf.ptr) cudaFree(s->ovf.ptr);
+    for (cudaEvent_t e : s->scan_evs) cudaEventDestroy(e);
     if (s->rows) cudaFree(s->rows);
     if (s->labels) cudaFree(s->labels);
     if (s->norms) cudaFree(s->norms);
@@ -297,7 +378,7 @@ void *vsgpu_store_stream(vsgpu_store *s) { return (void *)s->stream; }
 int vsgpu_store_sync(vsgpu_store *s) {
     VS_CUDA(cudaSetDevice(s->device));
     VS_CUDA(cudaStreamSynchronize(s->stream));
-    return VSGPU_OK;
+    return resolve_pending_topk(s); // a tensor-path top-k enqueued earlier: redo its overflowed queries now
 }
 
 int vsgpu_store_append(vsgpu_store *s, const void *rows, size_t stride, const uint64_t *labels, size_t n) {
@@ -307,6 +388,7 @@ int vsgpu_store_append(vsgpu_store *s, const void *rows, size_t stride, const ui
         return VSGPU_ERR_ARG;
     }
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
     VS_TRY(grow(s, s->count + n));
     uint8_t *dst = s->rows + s->count * s->row_stride;
     if (s->row_stride != s->row_bytes) VS_CUDA(cudaMemsetAsync(dst, 0, n * s->row_stride, s->stream));
@@ -329,6 +411,7 @@ int vsgpu_store_append_device(vsgpu_store *s, const void *rows, size_t stride, c
         return VSGPU_ERR_ARG;
     }
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
     VS_TRY(grow(s, s->count + n));
     uint8_t *dst = s->rows + s->count * s->row_stride;
     if (s->row_stride != s->row_bytes) VS_CUDA(cudaMemsetAsync(dst, 0, n * s->row_stride, s->stream));
@@ -361,6 +444,7 @@ int vsgpu_store_update(vsgpu_store *s, size_t id, const void *row, uint64_t labe
         return VSGPU_ERR_ARG;
     }
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
     VS_CUDA(cudaMemcpyAsync(s->rows + id * s->row_stride, row, s->row_bytes, cudaMemcpyHostToDevice, s->stream));
     if (s->has_norm)
         VS_CUDA(cudaMemcpyAsync(s->norms + id, (const uint8_t *)row + s->row_bytes, 4, cudaMemcpyHostToDevice, s->stream));
@@ -377,6 +461,7 @@ int vsgpu_store_remove_swap(vsgpu_store *s, size_t dst) {
         return VSGPU_ERR_ARG;
     }
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
     const size_t last = s->count - 1;
     if (dst != last) {
         VS_CUDA(cudaMemcpyAsync(s->rows + dst * s->row_stride, s->rows + last * s->row_stride, s->row_stride,
@@ -387,6 +472,20 @@ int vsgpu_store_remove_swap(vsgpu_store *s, size_t dst) {
         VS_CUDA(cudaStreamSynchronize(s->stream));
     }
     s->count = last;
+    s->shadow_valid_upto_count = false;
+    tensor_release(s);
+    return VSGPU_OK;
+}
+
+int vsgpu_store_truncate(vsgpu_store *s, size_t new_count) {
+    if (new_count > s->count) {
+        set_error("vsgpu_store_truncate: new_count exceeds size");
+        return VSGPU_ERR_ARG;
+    }
+    if (new_count == s->count) return VSGPU_OK;
+    VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
+    s->count = new_count;
     s->shadow_valid_upto_count = false;
     tensor_release(s);
     return VSGPU_OK;
@@ -416,6 +515,7 @@ int vsgpu_topk_device(vsgpu_store *s, const void *queries, size_t nq, size_t qst
                       uint64_t *out_labels, void *out_scores, uint32_t *out_ids) {
     if (nq == 0 || k == 0) return VSGPU_OK;
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s)); // an earlier call the caller never synchronised on
     s->stats = vsgpu_stats{};
     VS_CUDA(cudaEventRecord(s->ev0, s->stream));
     const void *q = nullptr;
@@ -435,6 +535,7 @@ int vsgpu_topk(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, s
         return VSGPU_ERR_ARG;
     }
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
     s->stats = vsgpu_stats{};
     const size_t n = s->count;
     const size_t k_eff = std::min(k, n);
@@ -475,6 +576,7 @@ int vsgpu_topk(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, s
     const float *qn = nullptr;
     VS_TRY(stage_queries_device(s, raw_dev, nq, s->blob_bytes, &q, &qs, &qn));
     VS_TRY(topk_core(s, q, nq, qs, qn, k_eff, k_eff, flags, d_id, d_sc, d_lab));
+    VS_TRY(resolve_pending_topk(s)); // tensor path: overflowed queries are redone before the results leave
     // labels | scores | ids sit at the same 256-byte-aligned offsets on both sides: one copy (a single query is bound by
     // the number of stream operations, not by bytes)
     VS_CUDA(cudaMemcpyAsync(pin + o_lab, d_lab, al(nq * k_eff * 8) + al(nq * k_eff * ssz) + nq * k_eff * 4, cudaMemcpyDeviceToHost,
@@ -542,6 +644,7 @@ int vsgpu_range(vsgpu_store *s, const void *query, double radius, size_t cap, ui
     }
     *out_count = 0;
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
     s->stats = vsgpu_stats{};
     if (s->count == 0) return VSGPU_OK;
     const size_t ssz = score_size(s);
@@ -581,6 +684,7 @@ int vsgpu_scores(vsgpu_store *s, const void *query, double *out_scores) {
         return VSGPU_ERR_ARG;
     }
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
     s->stats = vsgpu_stats{};
     if (s->count == 0) return VSGPU_OK;
     void *scores = nullptr;
@@ -609,6 +713,7 @@ int vsgpu_distances(vsgpu_store *s, const void *query, const uint32_t *ids, size
             return VSGPU_ERR_ARG;
         }
     VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
     s->stats = vsgpu_stats{};
     const size_t ssz = score_size(s);
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -640,6 +745,7 @@ int vsgpu_distances(vsgpu_store *s, const void *query, const uint32_t *ids, size
 
 int vsgpu_last_stats(const vsgpu_store *s, vsgpu_stats *out) {
     if (!s || !out) return VSGPU_ERR_ARG;
+    if (s->pend.active && s->ev1 && cudaEventQuery(s->ev1) == cudaSuccess) resolve_pending_topk(const_cast<vsgpu_store *>(s));
     *out = s->stats;
     // device-side timings become available once the call's last event has completed
     float ms = 0;

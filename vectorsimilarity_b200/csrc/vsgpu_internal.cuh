@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace vsgpu {
 
@@ -96,6 +97,22 @@ struct Scratch {
     size_t bytes = 0;
 };
 
+// A tensor-path top-k whose overflow flags have not been looked at yet. The call itself never waits for the device:
+// the per-query flags (candidate buffer overflowed: adversarial ties inside the error band) are copied to pinned memory
+// behind the kernels, and whoever synchronises next (vsgpu_store_sync, the host-buffer vsgpu_topk, the next call on the
+// store) redoes the flagged queries on the exact path into the same output buffers.
+struct PendingTopk {
+    bool active = false;
+    const void *q = nullptr; // staged queries (device) as the kernels read them
+    size_t nq = 0, q_stride = 0, k = 0;
+    const float *q_norms = nullptr;
+    uint32_t *out_ids = nullptr;
+    void *out_scores = nullptr;
+    uint64_t *out_labels = nullptr;
+    size_t n_events = 0;  // (start, stop) event pairs recorded around the scan launches
+    size_t n_totals = 0;  // candidate counters (one per chunk of MAX_NQ queries)
+};
+
 } // namespace vsgpu
 
 struct vsgpu_store {
@@ -124,6 +141,11 @@ struct vsgpu_store {
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     vsgpu_stats stats{};
+    vsgpu::PendingTopk pend;
+    vsgpu::Scratch ovf;          // device: [nq] u32 overflow flags of the last tensor-path call, then u64 candidate totals
+    uint32_t *h_ovf = nullptr;   // pinned mirror of `ovf`
+    size_t h_ovf_bytes = 0;
+    std::vector<cudaEvent_t> scan_evs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     void *tmap_cache = nullptr; // tensor path: cached tensor maps
 };
@@ -132,6 +154,14 @@ namespace vsgpu {
 
 int ensure_scratch(vsgpu_store *s, Scratch &sc, size_t bytes);
 int ensure_pinned(vsgpu_store *s, size_t bytes);
+// tensor path: device flag / counter block for nq queries in `chunks` chunks (zeroed), and its pinned mirror
+int pending_begin(vsgpu_store *s, size_t nq, size_t chunks, uint32_t **d_flags, unsigned long long **d_totals);
+// enqueue the copy of flags + totals to pinned memory and arm s->pend
+int pending_arm(vsgpu_store *s, const void *q, size_t nq, size_t q_stride, const float *q_norms, size_t k, uint32_t *out_ids,
+                void *out_scores, uint64_t *out_labels, size_t n_events, size_t chunks);
+cudaEvent_t scan_event(vsgpu_store *s, size_t i); // i-th reusable event of the store (created on demand)
+// waits for the stream, redoes overflowed queries exactly, completes the stats; no-op when nothing is pending
+int resolve_pending_topk(vsgpu_store *s);
 // raw query blobs on the device -> what the kernels read (zero-padded rows + norms for integer types)
 int stage_queries_device(vsgpu_store *s, const void *q_dev_raw, size_t nq, size_t qstride, const void **q_out,
                          size_t *q_stride_out, const float **q_norms_out);

@@ -354,6 +354,10 @@ coarse_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 
 // ------------------------------------------------------------------------------------------------
 // mirrors and query preparation
+// A lane-strided fp32 sum of d squares carries at most (d / 32 + 6) roundings of 2^-24 each (relative, all terms >= 0);
+// the norms that feed the error bound are scaled up by twice that so they are upper bounds.
+__host__ __device__ __forceinline__ float norm_slack(size_t dim) { return 1.0f + (float)(dim / 32 + 8) * 1.2e-7f; }
+
 __global__ void shadow_rows_kernel(const float *__restrict__ rows, size_t row_stride_f, size_t dim, size_t first, size_t n,
                                    __nv_bfloat16 *__restrict__ shadow, size_t shadow_stride, float *__restrict__ row_l2,
                                    unsigned *__restrict__ max_l2_bits, float *__restrict__ row_hsq) {
@@ -364,18 +368,26 @@ __global__ void shadow_rows_kernel(const float *__restrict__ rows, size_t row_st
     for (size_t i = warp; i < n; i += nwarps) {
         const float *src = rows + (first + i) * row_stride_f;
         __nv_bfloat16 *dst = shadow + (first + i) * shadow_stride;
-        float ss = 0.f;
+        float ss = 0.f, se = 0.f;
         for (size_t e = lane; e < shadow_stride; e += 32) {
             const float v = e < dim ? src[e] : 0.f;
+            const __nv_bfloat16 b = __float2bfloat16_rn(v);
+            const float dv = v - __bfloat162float(b); // exact: both share the exponent range of v
             ss = fmaf(v, v, ss);
-            dst[e] = __float2bfloat16_rn(v);
+            se = fmaf(dv, dv, se);
+            dst[e] = b;
         }
-        for (int w = 16; w >= 1; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
+        for (int w = 16; w >= 1; w >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, w);
+            se += __shfl_xor_sync(0xffffffffu, se, w);
+        }
         if (lane == 0) {
-            const float nrm = sqrtf(ss) * 1.000001f;
+            const float up = norm_slack(dim);
+            const float nrm = sqrtf(ss) * up;
             row_l2[first + i] = nrm;
             if (row_hsq) row_hsq[first + i] = 0.5f * ss;
             atomicMax(max_l2_bits, __float_as_uint(nrm));
+            atomicMax(max_l2_bits + 1, __float_as_uint(sqrtf(se) * up)); // max ||a - a^|| (mirror rounding)
         }
     }
 }
@@ -395,7 +407,7 @@ __global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t
         }
         for (int w = 16; w >= 1; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
         if (lane == 0) {
-            const float nrm = sqrtf(ss) * 1.000001f;
+            const float nrm = sqrtf(ss) * norm_slack(dim);
             if (row_l2) row_l2[first + i] = nrm;
             if (row_hsq) row_hsq[first + i] = 0.5f * ss;
             atomicMax(max_l2_bits, __float_as_uint(nrm));
@@ -403,8 +415,11 @@ __global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t
     }
 }
 
-// queries -> bf16 operand matrix [nq][qb_stride] (zero padded) + per-query error bound
-// eps[q] = c * ||q|| * max||row||, c from DESIGN.md §5.3
+// queries -> bf16 operand matrix [nq][qb_stride] (zero padded) + per-query error bound:
+//   a^.q^ - a.q = (a^ - a).q^ + a.(q^ - q)  =>  |coarse - exact| <= ||q^|| max||a^ - a|| + max||a|| ||q^ - q||  (Cauchy-Schwarz)
+// plus c_rel ||q|| max||a|| for the fp32 accumulation on both sides. The two rounding terms are MEASURED (the mirror
+// kernel records max ||a - a^||, this kernel ||q - q^||), not the worst case 2^-8 per operand: for real-valued data they
+// are ~0.4 of it, and for stores that already hold 16-bit rows they vanish.
 __global__ void prep_coarse_queries_kernel(const uint8_t *__restrict__ q, size_t q_stride, int is_f32, size_t dim, size_t nq,
                                            __nv_bfloat16 *__restrict__ qb, size_t qb_stride, float c_rel,
                                            const unsigned *__restrict__ max_l2_bits, float *__restrict__ eps, float c_l2) {
@@ -413,31 +428,43 @@ __global__ void prep_coarse_queries_kernel(const uint8_t *__restrict__ q, size_t
     const int lane = threadIdx.x & 31;
     for (size_t i = warp; i < nq; i += nwarps) {
         const uint8_t *src = q + i * q_stride;
-        float ss = 0.f;
+        float ss = 0.f, sb = 0.f, se = 0.f; // ||q||^2, ||q^||^2, ||q - q^||^2
         for (size_t e = lane; e < qb_stride; e += 32) {
-            float v = 0.f;
+            float v = 0.f, vb = 0.f;
             __nv_bfloat16 b = __float2bfloat16_rn(0.f);
             if (e < dim) {
                 if (is_f32 == 1) {
                     v = reinterpret_cast<const float *>(src)[e];
                     b = __float2bfloat16_rn(v);
+                    vb = __bfloat162float(b);
                 } else if (is_f32 == 2) { // fp16 store: the 16-bit pattern is the operand
                     b = reinterpret_cast<const __nv_bfloat16 *>(src)[e];
-                    v = __half2float(reinterpret_cast<const __half *>(src)[e]);
+                    v = vb = __half2float(reinterpret_cast<const __half *>(src)[e]);
                 } else {
                     b = reinterpret_cast<const __nv_bfloat16 *>(src)[e];
-                    v = __bfloat162float(b);
+                    v = vb = __bfloat162float(b);
                 }
             }
+            const float dv = v - vb;
             ss = fmaf(v, v, ss);
+            sb = fmaf(vb, vb, sb);
+            se = fmaf(dv, dv, se);
             qb[i * qb_stride + e] = b;
         }
-        for (int w = 16; w >= 1; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
+        for (int w = 16; w >= 1; w >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, w);
+            sb += __shfl_xor_sync(0xffffffffu, sb, w);
+            se += __shfl_xor_sync(0xffffffffu, se, w);
+        }
         if (lane == 0) {
-            // IP / Cosine: |acc - exact sum| <= c_rel |q| R. L2 adds the rounding of ||a||^2 / 2, of the subtraction and of the
-            // reference's own fp32 sum of squared differences, all within c_l2 (|q| + R)^2
-            const float qn = sqrtf(ss) * 1.000001f, R = __uint_as_float(*max_l2_bits);
-            eps[i] = c_rel * qn * R + c_l2 * (qn + R) * (qn + R);
+            // L2 adds the rounding of ||a||^2 / 2, of the subtraction and of the reference's own fp32 sum of squared
+            // differences, all within c_l2 (|q| + R)^2
+            const float up = norm_slack(dim);
+            const float qn = sqrtf(ss) * up, qbn = sqrtf(sb) * up, qe = sqrtf(se) * up;
+            const float R = __uint_as_float(max_l2_bits[0]), EA = __uint_as_float(max_l2_bits[1]);
+            float e = __fmaf_ru(qbn, EA, __fmul_ru(R, qe));
+            e = __fmaf_ru(__fmul_ru(c_rel, qn), R, e);
+            eps[i] = __fmaf_ru(__fmul_ru(c_l2, qn + R), qn + R, e);
         }
     }
 }
@@ -629,7 +656,6 @@ struct TensorState {
     float *row_hsq = nullptr;     // L2 stores: ||row||^2 / 2 per row
     int sms = 0;
     bool attr_set = false, pair_attr_set = false;
-    std::vector<cudaEvent_t> evs; // per-phase (start, stop) pairs around the coarse GEMM launches
 };
 
 static TensorState *state(vsgpu_store *s) {
@@ -646,7 +672,6 @@ void tensor_release(vsgpu_store *s) {
     if (t) {
         if (t->max_l2_bits) cudaFree(t->max_l2_bits);
         if (t->row_hsq) cudaFree(t->row_hsq);
-        for (cudaEvent_t e : t->evs) cudaEventDestroy(e);
         delete t;
         s->tmap_cache = nullptr;
     }
@@ -686,8 +711,8 @@ int tensor_sync_mirrors(vsgpu_store *s) {
         if (t->sms <= 0) t->sms = 148;
     }
     if (!t->max_l2_bits) {
-        VS_CUDA(cudaMalloc(&t->max_l2_bits, sizeof(unsigned)));
-        VS_CUDA(cudaMemsetAsync(t->max_l2_bits, 0, sizeof(unsigned), s->stream));
+        VS_CUDA(cudaMalloc(&t->max_l2_bits, 2 * sizeof(unsigned))); // [0] max ||row||, [1] max ||row - mirror row||
+        VS_CUDA(cudaMemsetAsync(t->max_l2_bits, 0, 2 * sizeof(unsigned), s->stream));
     }
     if (s->metric == VSGPU_L2 && (!t->row_hsq || t->cap != s->capacity)) {
         if (t->row_hsq) cudaFree(t->row_hsq);
@@ -785,14 +810,20 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
     const void *a_base = f32 ? (const void *)s->shadow : (const void *)s->rows;
     const size_t a_stride = f32 ? s->shadow_stride * 2 : s->row_stride;
     const size_t qb_stride = (s->dim + 7) / 8 * 8;
-    // error bound of the coarse score relative to ||q|| * ||row||
-    const float c_rel = f32 ? (float)(1.0 / 256 + 1.0 / 65536 + 4.0 * (double)s->dim / 8388608.0)
-                            : (float)((s->type == VSGPU_FLOAT16 ? 8.0 : 6.0) * (double)s->dim / 8388608.0);
+    // accumulation part of the coarse score's error bound, relative to ||q|| * max||row||: fp32 sums of d
+    // terms on both sides (tensor core and reference), with slack; the operand-rounding part is measured, see
+    // prep_coarse_queries_kernel
+    const float c_rel = (float)((f32 ? 4.0 : s->type == VSGPU_FLOAT16 ? 8.0 : 6.0) * (double)s->dim / 8388608.0);
     const float c_l2 = s->metric == VSGPU_L2 ? (float)((double)s->dim / 4194304.0) : 0.f; // d * 2^-22
     CUtensorMap map_a;
     VS_TRY(make_map(&map_a, a_base, n, s->dim, a_stride, BM));
 
     const std::vector<std::pair<uint32_t, uint32_t>> phases = make_phases(n, k, CAND_CAP, BM);
+    const size_t chunks = (nq_all + MAX_NQ - 1) / MAX_NQ;
+    uint32_t *ovf_all = nullptr;
+    unsigned long long *tot_all = nullptr;
+    VS_TRY(pending_begin(s, nq_all, chunks, &ovf_all, &tot_all));
+    size_t n_ev = 0;
 
     for (size_t q0 = 0; q0 < nq_all; q0 += MAX_NQ) {
         const size_t nq = std::min<size_t>(MAX_NQ, nq_all - q0);
@@ -802,22 +833,21 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
         const size_t o_qb = take(nq_pad * qb_stride * 2), o_eps = take(nq * 4), o_athr = take(nq * 4), o_cnt = take(nq * 4),
-                     o_ovf = take(nq * 4), o_rcnt = take(nq * 4), o_run = take(nq * RUN_CAP * 8), o_cand = take(nq * CAND_CAP * 8),
-                     o_rid = take(nq * RUN_CAP * 4), o_rsc = take(nq * RUN_CAP * 4), o_tot = take(8);
+                     o_rcnt = take(nq * 4), o_run = take(nq * RUN_CAP * 8), o_cand = take(nq * CAND_CAP * 8),
+                     o_rid = take(nq * RUN_CAP * 4), o_rsc = take(nq * RUN_CAP * 4);
         VS_TRY(ensure_scratch(s, s->cand, off));
         uint8_t *base = (uint8_t *)s->cand.ptr;
         auto *qb = (__nv_bfloat16 *)(base + o_qb);
         float *eps = (float *)(base + o_eps), *athr = (float *)(base + o_athr);
-        uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = (uint32_t *)(base + o_ovf), *rcnt = (uint32_t *)(base + o_rcnt);
+        uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = ovf_all + q0, *rcnt = (uint32_t *)(base + o_rcnt);
         uint2 *run = (uint2 *)(base + o_run), *cand = (uint2 *)(base + o_cand);
         uint32_t *rid = (uint32_t *)(base + o_rid);
         float *rsc = (float *)(base + o_rsc);
-        auto *tot = (unsigned long long *)(base + o_tot);
+        unsigned long long *tot = tot_all + q0 / MAX_NQ;
 
         VS_CUDA(cudaMemsetAsync(base + o_qb, 0, nq_pad * qb_stride * 2, s->stream));
-        // cnt, ovf, rcnt are adjacent 256-byte-aligned blocks: clear them and the counter in one go
+        // cnt, rcnt are adjacent 256-byte-aligned blocks: clear them in one go
         VS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)((uint8_t *)run - (uint8_t *)cnt), s->stream));
-        VS_CUDA(cudaMemsetAsync(tot, 0, 8, s->stream));
         fill_t<float><<<64, 256, 0, s->stream>>>(athr, -INFINITY, nq);
         prep_coarse_queries_kernel<<<(unsigned)std::min<size_t>((nq + 7) / 8, 1024), 256, 0, s->stream>>>(
             qp, q_stride, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps, c_l2);
@@ -840,14 +870,12 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             g.dump = nullptr;
             g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
             g.row_sub = s->metric == VSGPU_L2 ? t->row_hsq : nullptr;
-            while (t->evs.size() < 2 * (p + 1)) {
-                cudaEvent_t e;
-                VS_CUDA(cudaEventCreate(&e));
-                t->evs.push_back(e);
-            }
-            VS_CUDA(cudaEventRecord(t->evs[2 * p], s->stream));
+            cudaEvent_t e0 = scan_event(s, 2 * n_ev), e1 = scan_event(s, 2 * n_ev + 1);
+            if (!e0 || !e1) return VSGPU_ERR_CUDA;
+            VS_CUDA(cudaEventRecord(e0, s->stream));
             VS_TRY(launch_gemm(s, t, map_a, map_b, gemm_pair_enabled() ? &map_bh : nullptr, g));
-            VS_CUDA(cudaEventRecord(t->evs[2 * p + 1], s->stream));
+            VS_CUDA(cudaEventRecord(e1, s->stream));
+            n_ev++;
             MergeArgs m{};
             m.nq = (uint32_t)nq;
             m.k = (uint32_t)k;
@@ -871,28 +899,9 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         VS_TRY(launch_sort_candidates(s, nq, k, rid, rsc, RUN_CAP, rcnt, k, out_ids ? out_ids + q0 * k : nullptr,
                                       out_scores ? (float *)out_scores + q0 * k : nullptr,
                                       out_labels ? out_labels + q0 * k : nullptr));
-        // overflowed queries are redone on the exact path
-        std::vector<uint32_t> h_ovf(nq);
-        unsigned long long h_tot = 0;
-        VS_CUDA(cudaMemcpyAsync(h_ovf.data(), ovf, nq * 4, cudaMemcpyDeviceToHost, s->stream));
-        VS_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, s->stream));
-        VS_CUDA(cudaStreamSynchronize(s->stream));
-        s->stats.candidates += h_tot;
-        for (size_t p = 0; p < phases.size(); p++) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, t->evs[2 * p], t->evs[2 * p + 1]) == cudaSuccess) s->stats.scan_ms += ms;
-        }
-        const size_t ld = (n + 63) / 64 * 64;
-        for (size_t q = 0; q < nq; q++) {
-            if (!h_ovf[q]) continue;
-            s->stats.fallback_queries++;
-            VS_TRY(ensure_scratch(s, s->scores, ld * 4));
-            VS_TRY(launch_exact_scan(s, qp + q * q_stride, 1, q_stride, nullptr, s->scores.ptr, ld));
-            VS_TRY(launch_select_topk(s, s->scores.ptr, ld, 1, n, k, k, out_ids ? out_ids + (q0 + q) * k : nullptr,
-                                      out_scores ? (float *)out_scores + (q0 + q) * k : nullptr,
-                                      out_labels ? out_labels + (q0 + q) * k : nullptr));
-        }
     }
+    // overflowed queries are redone on the exact path by whoever synchronises next (no host wait here)
+    VS_TRY(pending_arm(s, q_dev, nq_all, q_stride, q_norms, k, out_ids, out_scores, out_labels, n_ev, chunks));
     return VSGPU_OK;
 }
 

@@ -327,6 +327,10 @@ __global__ void i8_emit_kernel(const uint2 *__restrict__ run, const uint32_t *__
     }
 }
 
+__global__ void i8_fill_kernel(float *p, float v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 struct I8State {
     size_t synced = 0; // rows [0, synced) have row_sq / row_add
     size_t cap = 0;
@@ -445,7 +449,13 @@ int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_st
     CUtensorMap map_a;
     VS_TRY(make_map_u8(&map_a, s->rows, n, s->dim, s->row_stride, BM));
     const std::vector<std::pair<uint32_t, uint32_t>> phases = make_phases(n, k, CAND_CAP, BM);
-    VS_CUDA(cudaEventRecord(s->ev2, s->stream));
+    const size_t chunks = (nq_all + MAX_NQ - 1) / MAX_NQ;
+    uint32_t *ovf_all = nullptr;
+    unsigned long long *tot_all = nullptr;
+    VS_TRY(pending_begin(s, nq_all, chunks, &ovf_all, &tot_all));
+    cudaEvent_t e0 = scan_event(s, 0), e1 = scan_event(s, 1);
+    if (!e0 || !e1) return VSGPU_ERR_CUDA;
+    VS_CUDA(cudaEventRecord(e0, s->stream));
     for (size_t q0 = 0; q0 < nq_all; q0 += MAX_NQ) {
         const size_t nq = std::min<size_t>(MAX_NQ, nq_all - q0);
         const uint8_t *qp = (const uint8_t *)q_dev + q0 * q_stride;
@@ -453,23 +463,18 @@ int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_st
         const size_t nq_pad = (nq + BN - 1) / BN * BN;
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
-        const size_t o_cq = take(nq * 4), o_cnt = take(nq * 4), o_ovf = take(nq * 4), o_rcnt = take(nq * 4), o_qq = take(nq * 8),
-                     o_tot = take(8), o_run = take(nq * RUN_CAP * 8), o_cand = take(nq * CAND_CAP * 8);
+        const size_t o_cq = take(nq * 4), o_cnt = take(nq * 4), o_rcnt = take(nq * 4), o_qq = take(nq * 8),
+                     o_run = take(nq * RUN_CAP * 8), o_cand = take(nq * CAND_CAP * 8);
         VS_TRY(ensure_scratch(s, s->cand, off));
         uint8_t *base = (uint8_t *)s->cand.ptr;
         float *cq = (float *)(base + o_cq);
-        uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = (uint32_t *)(base + o_ovf), *rcnt = (uint32_t *)(base + o_rcnt);
+        uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = ovf_all + q0, *rcnt = (uint32_t *)(base + o_rcnt);
         long long *qq = (long long *)(base + o_qq);
-        auto *tot = (unsigned long long *)(base + o_tot);
+        unsigned long long *tot = tot_all + q0 / MAX_NQ;
         uint2 *run = (uint2 *)(base + o_run), *cand = (uint2 *)(base + o_cand);
-        // cnt, ovf, rcnt, qq, tot are adjacent: clear in one go; cq = -inf (admit all) is written by the first merge,
-        // the first phase runs with cq = NULL -> +inf ... so give it -inf explicitly
+        // cnt, rcnt, qq are adjacent: clear in one go; the first phase admits everything (cq = -inf)
         VS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)((uint8_t *)run - (uint8_t *)cnt), s->stream));
-        {
-            std::vector<float> ninf(nq, -INFINITY);
-            VS_CUDA(cudaMemcpyAsync(cq, ninf.data(), nq * 4, cudaMemcpyHostToDevice, s->stream));
-            VS_CUDA(cudaStreamSynchronize(s->stream));
-        }
+        i8_fill_kernel<<<16, 256, 0, s->stream>>>(cq, -INFINITY, nq);
         i8_query_sq_kernel<<<(unsigned)std::min<size_t>((nq + 127) / 128, 1024), 128, 0, s->stream>>>(qp, q_stride, (int)(s->row_stride / 16),
                                                                                                   uns, nq, qq);
         VS_CUDA(cudaGetLastError());
@@ -520,27 +525,10 @@ int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_st
             out_labels ? out_labels + q0 * k : nullptr);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches++;
-        VS_CUDA(cudaEventRecord(s->ev3, s->stream));
-        // queries whose candidate buffer overflowed (adversarial ties) are redone on the exact path
-        std::vector<uint32_t> h_ovf(nq);
-        unsigned long long h_tot = 0;
-        VS_CUDA(cudaMemcpyAsync(h_ovf.data(), ovf, nq * 4, cudaMemcpyDeviceToHost, s->stream));
-        VS_CUDA(cudaMemcpyAsync(&h_tot, tot, 8, cudaMemcpyDeviceToHost, s->stream));
-        VS_CUDA(cudaStreamSynchronize(s->stream));
-        s->stats.candidates += h_tot;
-        const size_t ld = (n + 63) / 64 * 64;
-        for (size_t q = 0; q < nq; q++) {
-            if (!h_ovf[q]) continue;
-            s->stats.fallback_queries++;
-            VS_TRY(ensure_scratch(s, s->scores, ld * 4));
-            VS_TRY(launch_exact_scan(s, qp + q * q_stride, 1, q_stride, qn ? qn + q : nullptr, s->scores.ptr, ld));
-            VS_TRY(launch_select_topk(s, s->scores.ptr, ld, 1, n, k, k, out_ids ? out_ids + (q0 + q) * k : nullptr,
-                                      out_scores ? (float *)out_scores + (q0 + q) * k : nullptr,
-                                      out_labels ? out_labels + (q0 + q) * k : nullptr));
-        }
     }
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, s->ev2, s->ev3) == cudaSuccess) s->stats.scan_ms = ms;
+    VS_CUDA(cudaEventRecord(e1, s->stream));
+    // queries whose candidate buffer overflowed (adversarial ties) are redone on the exact path by whoever synchronises next
+    VS_TRY(pending_arm(s, q_dev, nq_all, q_stride, q_norms, k, out_ids, out_scores, out_labels, 1, chunks));
     return VSGPU_OK;
 }
 

@@ -30,6 +30,9 @@ def _vsgpu():
         G.vsgpu_store_stream.restype = vp
         G.vsgpu_store_stream.argtypes = [vp]
         G.vsgpu_merge_topk_device.argtypes = [C.c_int, vp, C.c_int, sz, sz, sz, vp, vp, vp, vp]
+        G.vsgpu_pack_topk_device.argtypes = [vp, sz, sz, vp, vp, vp]
+        G.vsgpu_merge_packed_device.argtypes = [C.c_int, vp, sz, sz, sz, vp, vp, vp, vp, vp]
+        G.vsgpu_packed_hit_bytes.restype = sz
         G.vsgpu_last_error.restype = C.c_char_p
         G.vsgpu_last_stats.argtypes = [vp, vp]
         _gpu_lib = G
@@ -78,6 +81,10 @@ class ShardedFlatIndex:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._store = None
         self._bufs = {}
+        self._stream = None
+        self._any_pin = None
+        self._last = None
+        self.redone_steps = 0
 
     def close(self):
         self.local.close()
@@ -88,6 +95,7 @@ class ShardedFlatIndex:
 
     def add_device_rows(self, tensor, first_label):
         assert tensor.is_cuda and tensor.is_contiguous()
+        torch.cuda.current_stream(self.device).synchronize()   # the rows were produced on the caller's stream
         return self.local.add_device_rows(tensor.data_ptr(), tensor.stride(0) * tensor.element_size(), tensor.shape[0],
                                           first_label)
 
@@ -102,8 +110,17 @@ class ShardedFlatIndex:
             self._bufs[key] = torch.empty(shape, dtype=dtype, device=self.device)
         return self._bufs[key]
 
+    def stream(self):
+        """The store's CUDA stream as a torch stream. Every step runs with it as torch's current stream, so the H2D copy
+        of the queries, the scan (enqueued by libvsgpu on that stream), NCCL and the merge are ordered by the stream
+        itself: no host synchronisation anywhere on the path."""
+        if self._stream is None:
+            self._stream = torch.cuda.ExternalStream(_vsgpu().vsgpu_store_stream(self.store()), device=self.device)
+        return self._stream
+
     def local_topk_device(self, q_dev, k, flags=0):
-        """q_dev: [nq, blob] processed queries on this GPU -> (scores [nq,k], labels [nq,k]) device tensors."""
+        """q_dev: [nq, blob] processed queries on this GPU -> (scores [nq,k], labels [nq,k]) device tensors.
+        Enqueued on the store's stream (the caller orders its own stream against it, see topk_device)."""
         G = _vsgpu()
         nq = q_dev.shape[0]
         sdt = torch.float64 if self.f64 else torch.float32
@@ -116,45 +133,107 @@ class ShardedFlatIndex:
         return scores, labels
 
     def topk_device(self, q_dev, k, flags=0):
-        """Global top-k on every rank: local scan -> all-gather -> device merge."""
+        """Global top-k on every rank: local scan -> ONE all-gather of packed (label, score, flag) hits -> device merge.
+        Everything is enqueued on the store's stream; results are final after finish()."""
+        caller = torch.cuda.current_stream(self.device)
+        st = self.stream()
+        st.wait_stream(caller)                      # q_dev may have been produced on the caller's stream
+        with torch.cuda.stream(st):
+            out = self._topk_enqueue(q_dev, k, flags)
+        caller.wait_stream(st)
+        return out
+
+    def _topk_enqueue(self, q_dev, k, flags):
         G = _vsgpu()
         scores, labels = self.local_topk_device(q_dev, k, flags)
-        if self.world == 1:
-            G.vsgpu_store_sync(self.store())
-            return scores, labels
         nq = q_dev.shape[0]
-        G.vsgpu_store_sync(self.store())          # NCCL runs on torch's stream
-        all_s = self._buf("as", (self.world, nq, k), scores.dtype)
-        all_l = self._buf("al", (self.world, nq, k), torch.int64)
-        dist.all_gather_into_tensor(all_s, scores, group=self.group)
-        dist.all_gather_into_tensor(all_l, labels, group=self.group)
-        out_s = self._buf("os", (nq, k), scores.dtype)
-        out_l = self._buf("ol", (nq, k), torch.int64)
-        stream = torch.cuda.current_stream(self.device)
-        rc = G.vsgpu_merge_topk_device(self.device.index, C.c_void_p(stream.cuda_stream), int(self.f64), self.world, nq, k,
-                                       all_s.data_ptr(), all_l.data_ptr(), out_s.data_ptr(), out_l.data_ptr())
+        self._last = (q_dev, k, nq)
+        if self.world == 1:
+            return scores, labels
+        if self.f64:  # fp64 indexes never take the tensor path: no flags to carry, scores do not fit the packed hit
+            all_s = self._buf("as", (self.world, nq, k), scores.dtype)
+            all_l = self._buf("al", (self.world, nq, k), torch.int64)
+            dist.all_gather_into_tensor(all_s, scores, group=self.group)
+            dist.all_gather_into_tensor(all_l, labels, group=self.group)
+            out_s = self._buf("os", (nq, k), scores.dtype)
+            out_l = self._buf("ol", (nq, k), torch.int64)
+            rc = G.vsgpu_merge_topk_device(self.device.index, C.c_void_p(self.stream().cuda_stream), 1, self.world, nq, k,
+                                           all_s.data_ptr(), all_l.data_ptr(), out_s.data_ptr(), out_l.data_ptr())
+            if rc != 0:
+                raise RuntimeError("vsgpu_merge_topk_device: " + G.vsgpu_last_error().decode())
+            return out_s, out_l
+        return self._gather_merge(scores, labels, nq, k)
+
+    def _gather_merge(self, scores, labels, nq, k):
+        G = _vsgpu()
+        hb = G.vsgpu_packed_hit_bytes()
+        mine = self._buf("pk", (nq, k, hb), torch.uint8)
+        rc = G.vsgpu_pack_topk_device(self.store(), nq, k, scores.data_ptr(), labels.data_ptr(), mine.data_ptr())
         if rc != 0:
-            raise RuntimeError("vsgpu_merge_topk_device: " + G.vsgpu_last_error().decode())
+            raise RuntimeError("vsgpu_pack_topk_device: " + G.vsgpu_last_error().decode())
+        everyone = self._buf("pa", (self.world, nq, k, hb), torch.uint8)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        out_s = self._buf("os", (nq, k), torch.float32)
+        out_l = self._buf("ol", (nq, k), torch.int64)
+        any_flag = self._buf("af", (1,), torch.int32)
+        any_flag.zero_()
+        rc = G.vsgpu_merge_packed_device(self.device.index, C.c_void_p(self.stream().cuda_stream), self.world, nq, k,
+                                         everyone.data_ptr(), out_s.data_ptr(), out_l.data_ptr(), None, any_flag.data_ptr())
+        if rc != 0:
+            raise RuntimeError("vsgpu_merge_packed_device: " + G.vsgpu_last_error().decode())
+        if self._any_pin is None:
+            self._any_pin = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._any_pin.copy_(any_flag, non_blocking=True)
         return out_s, out_l
+
+    def finish(self):
+        """Wait for the last topk_device and make its result final: when some shard flagged a query (its tensor-path
+        candidate buffer overflowed — adversarial ties), every rank sees the flag in the gathered hits; the shards redo
+        their flagged queries on the exact path (vsgpu_store_sync) and the lists are gathered and merged once more.
+        Returns the (scores, labels) device tensors of the step."""
+        G = _vsgpu()
+        st = self.stream()
+        st.synchronize()
+        redo = self.world > 1 and not self.f64 and self._any_pin is not None and int(self._any_pin[0]) != 0
+        rc = G.vsgpu_store_sync(self.store())       # resolves this shard's own overflowed queries (no-op otherwise)
+        if rc != 0:
+            raise RuntimeError("vsgpu_store_sync: " + G.vsgpu_last_error().decode())
+        if redo:
+            _, k, nq = self._last
+            with torch.cuda.stream(st):
+                self._gather_merge(self._buf("ls", (nq, k), torch.float32), self._buf("ll", (nq, k), torch.int64), nq, k)
+            st.synchronize()
+            self.redone_steps += 1
+        if self.world == 1:
+            _, k, nq = self._last
+            return self._buf("ls", (nq, k), torch.float64 if self.f64 else torch.float32), self._buf("ll", (nq, k), torch.int64)
+        _, k, nq = self._last
+        return self._buf("os", (nq, k), torch.float64 if self.f64 else torch.float32), self._buf("ol", (nq, k), torch.int64)
 
     def knn_batch(self, queries, k, flags=0):
         """Host queries (processed blobs, numpy [nq, blob] or a pinned uint8 tensor) -> host (labels int64 [nq,k], scores
-        float64 [nq,k]). One H2D copy, the sharded search, one D2H copy per output into pinned buffers, one sync."""
+        float64 [nq,k]). One H2D copy, the sharded search, one D2H copy per output into pinned buffers, one sync at the
+        end; everything in between is ordered by the store's stream."""
         if isinstance(queries, torch.Tensor):
             q = queries
         else:
             q = torch.from_numpy(np.ascontiguousarray(queries).view(np.uint8).reshape(queries.shape[0], -1))
         nq = q.shape[0]
-        q_dev = self._buf("qd", tuple(q.shape), torch.uint8)
-        q_dev.copy_(q, non_blocking=True)
-        out_s, out_l = self.topk_device(q_dev, k, flags)
+        st = self.stream()
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            q_dev = self._buf("qd", tuple(q.shape), torch.uint8)
+            q_dev.copy_(q, non_blocking=True)
+            self._topk_enqueue(q_dev, k, flags)
+        out_s, out_l = self.finish()
         key = ("pin", nq, k, out_s.dtype)
         if key not in self._bufs:
             self._bufs[key] = (torch.empty((nq, k), dtype=out_s.dtype).pin_memory(), torch.empty((nq, k), dtype=torch.int64).pin_memory())
         pin_s, pin_l = self._bufs[key]
-        pin_s.copy_(out_s, non_blocking=True)
-        pin_l.copy_(out_l, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        with torch.cuda.stream(st):
+            pin_s.copy_(out_s, non_blocking=True)
+            pin_l.copy_(out_l, non_blocking=True)
+        st.synchronize()
         return pin_l.numpy().copy(), pin_s.numpy().astype(np.float64)  # the pinned buffers are reused by the next call
 
     # ---- range query and batch iterator across shards (SURVEY.md §8e): variable-length per-shard replies ----
