@@ -240,6 +240,14 @@ long VecSimGPU_AppendDeviceRows(VecSimIndex *index, const void *device_rows, siz
 int VecSimGPU_SetDevice(int device);
 int VecSimGPU_GetDevice(void);
 int VecSimGPU_DeviceCount(void);
+/* Several devices (SURVEY.md §5, §8b "Additions"): flat (single-value, non-fp64) indexes created afterwards keep their
+ * rows sharded over `devices` — one process, one host thread and one stream per device, per-shard top-k lists gathered
+ * over NVLink peer copies and merged on devices[0] — behind the unchanged VecSimIndex_* calls. n == 1 is
+ * VecSimGPU_SetDevice. Labels are routed by (label mod n); rows bulk-ingested with VecSimGPU_AppendDeviceRows stay on the
+ * device they were on (which must be one of `devices`). A device may be listed more than once. Returns 0, or -1 for an
+ * unknown device. */
+int VecSimGPU_Configure(const int *devices, size_t n);
+size_t VecSimGPU_ShardCount(VecSimIndex *index); /* 1 for an index that lives on one device */
 /* 0 auto, 1 exact scan only, 2 tensor path only (see include/vsgpu.h flags). */
 void VecSimGPU_SetTopKMode(int mode);
 /* Counters of the last query on this index: path (0 exact, 1 tensor), kernel launches, candidates,

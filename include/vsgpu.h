@@ -135,6 +135,25 @@ int vsgpu_pack_topk_device(vsgpu_store *s, size_t nq, size_t k, const float *sco
 int vsgpu_merge_packed_device(int device, void *stream, size_t parts, size_t nq, size_t k, const void *packed,
                               float *out_scores, uint64_t *out_labels, uint32_t *out_flags, uint32_t *any_flag);
 
+/* ---- one process, several devices ------------------------------------------------------------------------------------
+ * A group binds the stores (one per device) of a sharded flat index. A batched top-k runs as:
+ *   vsgpu_group_topk_begin   (one thread)   stage the processed queries in pinned memory
+ *   vsgpu_group_topk_shard   (per shard, concurrently from several threads)  H2D, local top-k, pack, peer copy of the packed
+ *                            list into the root device's gather buffer — all on the shard's stream
+ *   vsgpu_group_topk_finish  (one thread)   root stream waits for the shards' events, merges, copies the reply to the host;
+ *                            returns 1 when a shard flagged an overflowed query (then: vsgpu_store_sync on every shard,
+ *                            _shard with repush = 1, _finish again)
+ * The first store's device is the root. */
+typedef struct vsgpu_group vsgpu_group;
+vsgpu_group *vsgpu_group_create(vsgpu_store **stores, size_t n);
+void vsgpu_group_destroy(vsgpu_group *g);
+size_t vsgpu_group_size(const vsgpu_group *g);
+int vsgpu_group_topk_begin(vsgpu_group *g, const void *queries, size_t nq, size_t qstride, size_t k);
+int vsgpu_group_topk_shard(vsgpu_group *g, size_t shard, size_t nq, size_t k, unsigned flags, int repush);
+int vsgpu_group_topk_finish(vsgpu_group *g, size_t nq, size_t k, uint64_t *out_labels, double *out_scores);
+float vsgpu_group_last_ms(const vsgpu_group *g); /* device time of the last batch, root stream */
+int vsgpu_pointer_device(const void *device_ptr); /* owning device of a device pointer, -1 if not device memory */
+
 /* ---- HNSW (algorithms/hnsw/hnsw.h) -----------------------------------------------------------
  * A graph over the rows of a store (internal id = row index). Level-0 records hold up to 2M links,
  * upper levels M. Traversal results are identical to HNSWIndex::topKQuery / rangeQuery on the same

@@ -168,6 +168,44 @@ def test_bf16_midpoint_rows_are_not_dropped(capi, port, metric, k):
     P.close()
 
 
+@pytest.mark.parametrize("vtype,metric,dim,n,k,nq", [
+    (0, 1, 128, 60000, 500, 40),     # the reference's own benchmark grid runs k = 500 (docs/benchmarks.md:55-64)
+    (0, 0, 96, 50000, 1000, 16),     # L2, the largest k the tensor path serves; 16 queries (8 <= nq < 32 also takes it)
+    (2, 1, 128, 60000, 500, 9),      # bf16 store
+])
+def test_tensor_path_large_k_and_small_batches(capi, port, vtype, metric, dim, n, k, nq):
+    dist = "normal" if metric == 1 else "uniform"
+    X = make_vectors(vtype, n, dim, seed=n + dim, dist=dist)
+    Q = make_vectors(vtype, nq, dim, seed=n + dim + 1, dist=dist)
+    G = _index(capi, vtype, dim, metric, X)
+    P = port.PortIndex(vtype, dim, metric)
+    P.add_many(X)
+    st = _check_against(capi, G, P, Q, k, mode=0)            # auto mode must choose the tensor path by itself
+    assert st["path"] == 1 and st["fallback_queries"] == 0, st
+    G.close()
+    P.close()
+
+
+def test_mixed_row_norms_keep_the_band_narrow(capi, port):
+    """The error bound is per row (e1[q] * ||row||): a handful of very long rows must not widen the admission band of the
+    short ones (with a store-wide bound every short row falls inside the band and the queries overflow to the exact
+    path)."""
+    n, dim, k, nq = 50000, 128, 10, 32
+    rng = np.random.default_rng(5)
+    X = (0.05 * rng.standard_normal((n, dim))).astype(np.float32)
+    X[rng.choice(n, 20, replace=False)] *= 400.0               # 20 rows ~400x longer than the rest
+    Q = rng.standard_normal((nq, dim)).astype(np.float32)
+    for metric in (1, 0):
+        G = _index(capi, 0, dim, metric, X)
+        P = port.PortIndex(0, dim, metric)
+        P.add_many(X)
+        st = _check_against(capi, G, P, Q, k, mode=2)
+        assert st["path"] == 1 and st["fallback_queries"] == 0, (metric, st)
+        assert st["candidates"] / nq < 6000, st
+        G.close()
+        P.close()
+
+
 def test_candidate_overflow_falls_back_to_exact(capi, port):
     """Near-duplicate rows: every row is within the coarse error bound of the k-th score, the
     candidate buffers overflow, and the affected queries are redone on the exact path."""

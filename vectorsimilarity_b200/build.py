@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 CUDA_SOURCES = ["vsgpu_api.cu", "vsgpu_exact.cu", "vsgpu_select.cu", "vsgpu_tensor.cu", "vsgpu_hnsw.cu", "vsgpu_scan.cu", "vsgpu_tensor_i8.cu", "vsgpu_shard.cu"]
-HOST_SOURCES = ["host/vecsim_flat.cpp", "host/vecsim_flat_multi.cpp", "host/vecsim_hnsw.cpp", "host/vecsim_tiered.cpp", "host/vecsim_hnsw_file.cpp", "host/vecsim_api.cpp"]
+HOST_SOURCES = ["host/vecsim_flat.cpp", "host/vecsim_flat_multi.cpp", "host/vecsim_flat_sharded.cpp", "host/vecsim_hnsw.cpp", "host/vecsim_tiered.cpp", "host/vecsim_hnsw_file.cpp", "host/vecsim_api.cpp"]
 NVCC_FLAGS = ["-std=c++20", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 GXX_FLAGS = ["-std=c++20", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra"]

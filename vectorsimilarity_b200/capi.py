@@ -117,6 +117,7 @@ EXPORTS = [
     "VecSimBatchIterator_Next", "VecSimBatchIterator_HasNext", "VecSimBatchIterator_Free", "VecSimBatchIterator_Reset",
     "VecSimIndex_TopKQueryBatch", "VecSimIndex_TopKQueryBatchRaw", "VecSimIndex_AddVectorBatch",
     "VecSimGPU_SetDevice", "VecSimGPU_GetDevice", "VecSimGPU_DeviceCount", "VecSimGPU_SetTopKMode",
+    "VecSimGPU_Configure", "VecSimGPU_ShardCount",
     "VecSimGPU_LastQueryStats", "VecSimGPU_GetStore", "VecSimGPU_LastError", "VecSimGPU_AppendDeviceRows",
     "VecSimGPU_HNSWLoadIndex", "VecSimGPU_HNSWSaveIndex",
     "VecSimGPU_GetGraph", "VecSimGPU_HNSWImportGraph", "VecSimGPU_HNSWExportGraph", "VecSimGPU_HNSWLastStats",
@@ -229,6 +230,9 @@ def lib():
     L.VecSimTieredIndex_GC.argtypes = [vp]
     L.VecSimTieredIndex_AcquireSharedLocks.argtypes = [vp]
     L.VecSimTieredIndex_ReleaseSharedLocks.argtypes = [vp]
+    L.VecSimGPU_Configure.argtypes = [C.POINTER(C.c_int), C.c_size_t]
+    L.VecSimGPU_ShardCount.restype = C.c_size_t
+    L.VecSimGPU_ShardCount.argtypes = [vp]
     _lib = L
     return L
 
@@ -279,6 +283,13 @@ def device_count():
 def set_device(d):
     if lib().VecSimGPU_SetDevice(d) != 0:
         raise RuntimeError("no such CUDA device %d" % d)
+
+
+def configure_devices(devices):
+    """VecSimGPU_Configure: flat indexes created afterwards shard their rows over `devices` (one process, all GPUs)."""
+    arr = (C.c_int * len(devices))(*devices)
+    if lib().VecSimGPU_Configure(arr, len(devices)) != 0:
+        raise RuntimeError("VecSimGPU_Configure: bad device list %r" % (devices,))
 
 
 def normalize(blob, dim, vtype):
@@ -411,6 +422,9 @@ class VecSimIndex:
                                        C.byref(scan), C.byref(total))
         return dict(path=path.value, kernel_launches=launches.value, candidates=cand.value, fallback_queries=fb.value,
                     scan_ms=scan.value, total_ms=total.value)
+
+    def shard_count(self):
+        return lib().VecSimGPU_ShardCount(self._h)
 
     def device_store(self):
         return lib().VecSimGPU_GetStore(self._h)

@@ -86,6 +86,16 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
                 }
                 return midx;
             }
+            if (globals().devices.size() > 1 && p.type != VecSimType_FLOAT64) {
+                // VecSimGPU_Configure named several devices: the rows are sharded over them (vecsim_flat_sharded.cpp)
+                auto *sidx = new ShardedFlatIndex(p, params->logCtx, globals().devices);
+                if (!sidx->ok()) {
+                    g_api_err = std::string("sharded device stores: ") + vsgpu_last_error();
+                    delete sidx;
+                    return nullptr;
+                }
+                return sidx;
+            }
             auto *idx = new FlatIndex(p, params->logCtx);
             if (!idx->ok()) {
                 g_api_err = std::string("device store: ") + vsgpu_last_error();
@@ -430,6 +440,7 @@ long VecSimIndex_AddVectorBatch(VecSimIndex *index, const void *blobs, size_t n,
 }
 
 long VecSimGPU_AppendDeviceRows(VecSimIndex *index, const void *device_rows, size_t stride_bytes, size_t n, size_t first_label) {
+    if (auto *sh = dynamic_cast<ShardedFlatIndex *>(index)) return sh->appendDeviceRows(device_rows, stride_bytes, n, first_label);
     auto *flat = dynamic_cast<FlatIndex *>(index);
     if (!flat) return -1;
     return flat->appendDeviceRows(device_rows, stride_bytes, n, first_label);
@@ -438,7 +449,22 @@ long VecSimGPU_AppendDeviceRows(VecSimIndex *index, const void *device_rows, siz
 int VecSimGPU_SetDevice(int device) {
     if (device < 0 || device >= vsgpu_device_count()) return -1;
     globals().device = device;
+    globals().devices.clear();
     return 0;
+}
+int VecSimGPU_Configure(const int *devices, size_t n) {
+    if (!devices || n == 0) return -1;
+    const int have = vsgpu_device_count();
+    std::vector<int> d(devices, devices + n);
+    for (size_t i = 0; i < n; i++)
+        if (d[i] < 0 || d[i] >= have) return -1; // a device may be named more than once (several shards on one GPU)
+    globals().device = d[0];
+    globals().devices = n > 1 ? d : std::vector<int>();
+    return 0;
+}
+size_t VecSimGPU_ShardCount(VecSimIndex *index) {
+    auto *sh = dynamic_cast<ShardedFlatIndex *>(index);
+    return sh ? sh->shardCount() : 1;
 }
 int VecSimGPU_GetDevice(void) { return globals().device; }
 int VecSimGPU_DeviceCount(void) { return vsgpu_device_count(); }

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <stdexcept>
 
@@ -53,10 +54,10 @@ void normalize_blob(void *blob, size_t dim, VecSimType type) {
 static constexpr size_t FLUSH_ROWS = 8192;
 static constexpr size_t FLUSH_BYTES = (size_t)64 << 20;
 
-FlatIndex::FlatIndex(const BFParams &p, void *logCtx)
+FlatIndex::FlatIndex(const BFParams &p, void *logCtx, int device)
     : type_(p.type), metric_(p.metric), dim_(p.dim), block_size_(p.blockSize ? p.blockSize : 1024),
       data_size_(type_size(p.type) * p.dim), stored_size_(stored_size(p.type, p.dim, p.metric)), log_ctx_(logCtx) {
-    store_ = vsgpu_store_create(globals().device, (int)type_, (int)metric_, dim_, p.initialCapacity);
+    store_ = vsgpu_store_create(device >= 0 ? device : globals().device, (int)type_, (int)metric_, dim_, p.initialCapacity);
 }
 
 FlatIndex::~FlatIndex() {
@@ -434,16 +435,16 @@ int FlatIndex::allScores(const void *processed_query, std::vector<std::pair<doub
     return 0;
 }
 
-namespace {
 // bf_batch_iterator.h:59-214 — first call scores every row (on the device), later calls only select.
 class FlatBatchIterator final : public VecSimBatchIterator {
   public:
-    FlatBatchIterator(FlatIndex *idx, std::vector<uint8_t> q, void *tctx)
-        : idx_(idx), query_(std::move(q)), tctx_(tctx), label_count_(idx->indexLabelCount()) {}
+    using ScoreFn = std::function<int(const void *, std::vector<std::pair<double, size_t>> &)>;
+    FlatBatchIterator(ScoreFn score_all, size_t label_count, std::vector<uint8_t> q, void *tctx)
+        : score_all_(std::move(score_all)), query_(std::move(q)), tctx_(tctx), label_count_(label_count) {}
     VecSimQueryReply *next(size_t n, VecSimQueryReply_Order order) override {
         auto *rep = new VecSimQueryReply();
         if (!computed_) {
-            if (idx_->allScores(query_.data(), scores_) != 0) return rep;
+            if (score_all_(query_.data(), scores_) != 0) return rep;
             label_count_ = scores_.size();
             computed_ = true;
         }
@@ -473,7 +474,7 @@ class FlatBatchIterator final : public VecSimBatchIterator {
     }
 
   private:
-    FlatIndex *idx_;
+    ScoreFn score_all_;
     std::vector<uint8_t> query_;
     void *tctx_;
     size_t label_count_;
@@ -481,10 +482,15 @@ class FlatBatchIterator final : public VecSimBatchIterator {
     bool computed_ = false;
     size_t pos_ = 0, returned_ = 0;
 };
-} // namespace
+
+VecSimBatchIterator *new_flat_batch_iterator(std::function<int(const void *, std::vector<std::pair<double, size_t>> &)> score_all,
+                                             size_t label_count, std::vector<uint8_t> query, void *tctx) {
+    return new FlatBatchIterator(std::move(score_all), label_count, std::move(query), tctx);
+}
 
 VecSimBatchIterator *FlatIndex::newBatchIterator(const void *blob, VecSimQueryParams *qp) {
-    return new FlatBatchIterator(this, preprocessQuery(blob), qp ? qp->timeoutCtx : nullptr);
+    return new_flat_batch_iterator([this](const void *q, std::vector<std::pair<double, size_t>> &out) { return allScores(q, out); },
+                                   indexLabelCount(), preprocessQuery(blob), qp ? qp->timeoutCtx : nullptr);
 }
 
 VecSimIndexBasicInfo FlatIndex::basicInfo() {

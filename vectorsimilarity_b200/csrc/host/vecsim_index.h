@@ -6,6 +6,7 @@
 #include "../../../include/vecsim_b200.h"
 #include "../../../include/vsgpu.h"
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <atomic>
 #include <mutex>
@@ -37,6 +38,7 @@ struct Globals {
     bool mem_set = false;
     VecSimWriteMode write_mode = VecSim_WriteAsync;
     int device = 0;
+    std::vector<int> devices; // VecSimGPU_Configure: more than one entry -> new flat indexes are sharded over them
     int topk_mode = 0;
 };
 Globals &globals();
@@ -93,9 +95,14 @@ namespace vsb {
 
 class FlatIndex final : public VecSimIndexInterface {
   public:
-    FlatIndex(const BFParams &p, void *logCtx);
+    FlatIndex(const BFParams &p, void *logCtx, int device = -1); // device < 0: the process-wide default (VecSimGPU_SetDevice)
     ~FlatIndex() override;
     bool ok() const { return store_ != nullptr; }
+    // labels grow with the internal id: the device's (score, id) order is the reference's (score, label) reply order
+    bool labelsMonotone() {
+        std::lock_guard<std::mutex> g(mu_);
+        return labels_monotone_;
+    }
 
     int addVector(const void *blob, size_t label) override;
     long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) override;
@@ -203,6 +210,59 @@ class FlatMultiIndex final : public VecSimIndexInterface {
     std::unordered_map<size_t, std::vector<idType>> label_to_ids_;
     std::vector<uint8_t> pending_rows_;
     std::vector<uint64_t> pending_labels_;
+    VecSearchMode last_mode_ = EMPTY_MODE;
+    std::mutex mu_;
+};
+
+// Flat, rows sharded over several devices of one process: vecsim_flat_sharded.cpp
+class ShardWorkers;
+class ShardedFlatIndex final : public VecSimIndexInterface {
+  public:
+    ShardedFlatIndex(const BFParams &p, void *logCtx, const std::vector<int> &devices);
+    ~ShardedFlatIndex() override;
+    bool ok() const { return group_ != nullptr; }
+    int addVector(const void *blob, size_t label) override;
+    long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) override;
+    int deleteVector(size_t label) override;
+    double getDistanceFrom(size_t label, const void *blob) override;
+    size_t indexSize() override;
+    size_t indexLabelCount() override { return indexSize(); }
+    VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) override;
+    int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels, double *scores,
+                  uint32_t *counts) override;
+    VecSimQueryReply *rangeQuery(const void *blob, double radius, VecSimQueryParams *qp,
+                                 VecSimQueryReply_Order order) override;
+    VecSimBatchIterator *newBatchIterator(const void *blob, VecSimQueryParams *qp) override;
+    VecSimIndexBasicInfo basicInfo() override;
+    VecSimIndexDebugInfo debugInfo() override;
+    VecSimIndexStatsInfo statsInfo() override;
+    bool preferAdHocSearch(size_t subsetSize, size_t k, bool initial_check) override;
+    void setLastSearchMode(VecSearchMode m) override { last_mode_ = m; }
+    void exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) override;
+    std::vector<uint8_t> preprocessQuery(const void *blob) override;
+    vsgpu_store *deviceStore() override;
+    void lastStats(vsgpu_stats *out) override;
+
+    size_t shardCount() const { return shards_.size(); }
+    FlatIndex *shard(size_t i) { return shards_[i].get(); }
+    // rows already in the memory of one of the shards' devices: appended to that shard (labels first_label + i)
+    long appendDeviceRows(const void *dev_rows, size_t stride, size_t n, size_t first_label);
+    int allScores(const void *processed_query, std::vector<std::pair<double, size_t>> &out);
+
+  private:
+    size_t route(size_t label) const;
+    struct Range {
+        size_t first, last; // labels [first, last]
+        size_t shard;
+    };
+    std::vector<std::unique_ptr<FlatIndex>> shards_;
+    std::vector<int> devices_;
+    std::vector<Range> ranges_; // bulk-ingested label ranges, sorted by first
+    std::unique_ptr<ShardWorkers> workers_;
+    vsgpu_group *group_ = nullptr;
+    BFParams params_;
+    size_t data_size_, stored_size_;
+    float last_ms_ = 0.f;
     VecSearchMode last_mode_ = EMPTY_MODE;
     std::mutex mu_;
 };
@@ -344,6 +404,8 @@ class TieredIndex final : public VecSimIndexInterface {
     std::shared_ptr<std::atomic<bool>> alive_;
 };
 
+VecSimBatchIterator *new_flat_batch_iterator(std::function<int(const void *, std::vector<std::pair<double, size_t>> &)> score_all,
+                                             size_t label_count, std::vector<uint8_t> query, void *tctx);
 VecSimIndexInterface *load_hnsw_file(const char *path, std::string &err);
 size_t tiered_merge_for_test(const size_t *a_ids, const double *a_scores, size_t na, const size_t *b_ids, const double *b_scores,
                              size_t nb, size_t limit, size_t *out_ids, double *out_scores, size_t *taken);

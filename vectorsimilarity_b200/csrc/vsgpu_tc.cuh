@@ -83,9 +83,8 @@ __device__ __forceinline__ void lds_f32x32(uint32_t saddr, float (&t)[32]) {
 // ballots so that lane j owns column j and reserves that column's slots with ONE atomic — 32 different counters in a
 // single instruction, one round trip per chunk. (One atomic per hit serialised ~30 dependent round trips per chunk at
 // the 1-8 % pass rates of the early phases and left the epilogue, not the MMAs, as the critical path.)
-template <uint32_t CAP>
 __device__ __forceinline__ void warp_append_hits(uint32_t hit, uint32_t q0, uint32_t row, const uint32_t (&r)[32],
-                                                 uint32_t *__restrict__ cnt, uint2 *__restrict__ cand, int lane) {
+                                                 uint32_t *__restrict__ cnt, uint2 *__restrict__ cand, int lane, uint32_t CAP) {
     const uint32_t any = __reduce_or_sync(0xffffffffu, hit);
     if (!any) return;
     uint32_t mine = 0; // rows of this warp that hit column `lane`
@@ -151,6 +150,13 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc,
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }

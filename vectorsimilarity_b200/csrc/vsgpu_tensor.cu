@@ -36,13 +36,19 @@ constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int MAX_NQ = 4096;          // thresholds of the whole batch sit in smem
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
-constexpr uint32_t CAND_CAP = 3072;   // candidate ids per query and phase
+// candidate ids per query and phase / survivors kept per query between phases: the small pair serves k <= 384 (the merge
+// kernel's tables fit 48 KB of shared memory, seven blocks per SM), the large pair k up to 1024 (docs/benchmarks.md:55-64
+// of the reference runs k = 500)
+constexpr uint32_t CAND_CAP = 3072, CAND_CAP_BIG = 8192;
+constexpr uint32_t RUN_CAP_BIG = 4096;
+constexpr size_t K_SMALL_MAX = 384, K_MAX = 1024;
 
 struct GemmSmem {
     // operand ring (1024-byte aligned for SWIZZLE_128B)
     uint8_t a[STAGES][A_BYTES];
     uint8_t b[STAGES][B_BYTES];
     float athr[MAX_NQ];
+    float e1[MAX_NQ];
     uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
 };
@@ -59,9 +65,13 @@ struct GemmArgs {
     uint32_t nq;         // valid queries
     uint32_t n_qtiles;   // ceil(nq / BN)
     uint32_t k_blocks;   // ceil(dim / BK)
-    const float *athr;   // [nq] admit when acc >= athr[q]
+    const float *athr;   // [nq] admit when acc + e1[q] * ||row|| >= athr[q]
+    const float *e1;     // [nq] error of the coarse score per unit of row norm
+    const float *row_l2; // [rows] ||row||_2, rounded up
+    float c_l2;          // L2: the reference's own fp32 score rounds within c_l2 (||q|| + ||row||)^2
     uint32_t *cnt;       // [nq] candidate counters
-    uint2 *cand;         // [nq][CAND_CAP] (row id, coarse accumulator bits)
+    uint2 *cand;         // [nq][cand_cap] (row id, coarse accumulator bits)
+    uint32_t cand_cap;
     float *dump;         // debug: [rows][dump_ld] raw accumulators (else NULL)
     uint32_t dump_ld;
     uint32_t idesc;      // IDESC_BF16 / IDESC_FP16
@@ -97,8 +107,10 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x) {
         sm.athr[i] = i < g.nq ? g.athr[i] : __int_as_float(0x7f800000);
+        sm.e1[i] = (i < g.nq && g.e1) ? g.e1[i] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -155,8 +167,11 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
             const uint32_t row = g.row0 + mt * BM + quad * 32 + (uint32_t)lane;
             const bool row_ok = row < g.row_end;
+            const float nr = (row_ok && g.row_l2) ? g.row_l2[row] : 0.f;
             float ra = 0.f;
-            if constexpr (SUB) ra = row_ok ? g.row_sub[row] : 0.f;
+            // L2: what is filtered (and stored) is a'' = a.q - ||a||^2 / 2 + c_l2 ||a||^2 — the row's own share of the L2
+            // rounding term rides on the per-row constant, so it costs nothing per accumulator (rounded so a'' errs upwards)
+            if constexpr (SUB) ra = row_ok ? __fmaf_rd(__fmul_ru(g.c_l2, nr), -nr, g.row_sub[row]) : 0.f;
             mbar_wait(&sm.tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1
@@ -176,15 +191,19 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                         }
                     }
                 } else {
-                    // all 32 compares first (independent, no branch in between), then the hits of the whole warp
+                    // admit when the row's coarse score plus ITS error bound e1[q] * ||row|| reaches the query's bound: one FFMA
+                    // and one compare per accumulator, all 32 first (independent, no branch in between), then the hits
+                    // of the whole warp
                     uint32_t hit = 0;
                     if constexpr (SUB) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__fsub_rn(__uint_as_float(r[j]), ra));
                     }
+                    float e1v[32];
+                    lds_f32x32(smem_u32(&sm.e1[nt * BN + col]), e1v);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) hit |= (__uint_as_float(r[j]) >= thr[j] ? 1u : 0u) << j;
-                    warp_append_hits<CAND_CAP>(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane);
+                    for (int j = 0; j < 32; j++) hit |= (__fmaf_rn(e1v[j], nr, __uint_as_float(r[j])) >= thr[j] ? 1u : 0u) << j;
+                    warp_append_hits(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane, g.cand_cap);
                 }
             }
             tc_fence_before();
@@ -213,6 +232,7 @@ struct PairSmem {
     uint8_t a[PSTAGES][A_BYTES];
     uint8_t b[PSTAGES][BH_BYTES];
     float athr[MAX_NQ];
+    float e1[MAX_NQ];
     uint64_t full[PSTAGES], empty[PSTAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
 };
@@ -247,8 +267,10 @@ coarse_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
-    for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x) {
         sm.athr[i] = i < g.nq ? g.athr[i] : __int_as_float(0x7f800000);
+        sm.e1[i] = (i < g.nq && g.e1) ? g.e1[i] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all(); // both CTAs' barriers exist before anything is signalled across the pair
@@ -306,8 +328,11 @@ coarse_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             const uint32_t pt = item / g.n_qtiles, nt = item % g.n_qtiles;
             const uint32_t row = g.row0 + pt * 2 * BM + rank * BM + quad * 32 + (uint32_t)lane;
             const bool row_ok = row < g.row_end;
+            const float nr = (row_ok && g.row_l2) ? g.row_l2[row] : 0.f;
             float ra = 0.f;
-            if constexpr (SUB) ra = row_ok ? g.row_sub[row] : 0.f;
+            // L2: what is filtered (and stored) is a'' = a.q - ||a||^2 / 2 + c_l2 ||a||^2 — the row's own share of the L2
+            // rounding term rides on the per-row constant, so it costs nothing per accumulator (rounded so a'' errs upwards)
+            if constexpr (SUB) ra = row_ok ? __fmaf_rd(__fmul_ru(g.c_l2, nr), -nr, g.row_sub[row]) : 0.f;
             mbar_wait(&sm.tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1
@@ -332,9 +357,11 @@ coarse_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 #pragma unroll
                         for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__fsub_rn(__uint_as_float(r[j]), ra));
                     }
+                    float e1v[32];
+                    lds_f32x32(smem_u32(&sm.e1[nt * BN + col]), e1v);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) hit |= (__uint_as_float(r[j]) >= thr[j] ? 1u : 0u) << j;
-                    warp_append_hits<CAND_CAP>(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane);
+                    for (int j = 0; j < 32; j++) hit |= (__fmaf_rn(e1v[j], nr, __uint_as_float(r[j])) >= thr[j] ? 1u : 0u) << j;
+                    warp_append_hits(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane, g.cand_cap);
                 }
             }
             tc_fence_before();
@@ -387,7 +414,8 @@ __global__ void shadow_rows_kernel(const float *__restrict__ rows, size_t row_st
             row_l2[first + i] = nrm;
             if (row_hsq) row_hsq[first + i] = 0.5f * ss;
             atomicMax(max_l2_bits, __float_as_uint(nrm));
-            atomicMax(max_l2_bits + 1, __float_as_uint(sqrtf(se) * up)); // max ||a - a^|| (mirror rounding)
+            // max over rows of ||a - a^|| / ||a|| (what rounding to bf16 cost, relative to the row's norm), rounded up
+            if (ss > 0.f) atomicMax(max_l2_bits + 1, __float_as_uint(__fdiv_ru(sqrtf(se) * up, __fdiv_rd(sqrtf(ss), up))));
         }
     }
 }
@@ -415,14 +443,18 @@ __global__ void bf16_norms_kernel(const __nv_bfloat16 *__restrict__ rows, size_t
     }
 }
 
-// queries -> bf16 operand matrix [nq][qb_stride] (zero padded) + per-query error bound:
-//   a^.q^ - a.q = (a^ - a).q^ + a.(q^ - q)  =>  |coarse - exact| <= ||q^|| max||a^ - a|| + max||a|| ||q^ - q||  (Cauchy-Schwarz)
-// plus c_rel ||q|| max||a|| for the fp32 accumulation on both sides. The two rounding terms are MEASURED (the mirror
-// kernel records max ||a - a^||, this kernel ||q - q^||), not the worst case 2^-8 per operand: for real-valued data they
-// are ~0.4 of it, and for stores that already hold 16-bit rows they vanish.
+// queries -> bf16 operand matrix [nq][qb_stride] (zero padded) + per-query error coefficients:
+//   a^.q^ - a.q = (a^ - a).q^ + a.(q^ - q)  =>  |coarse - exact| <= ||q^|| ||a^ - a|| + ||a|| ||q^ - q||   (Cauchy-Schwarz)
+//                                                               <= (||q^|| rho + ||q^ - q|| + c_rel ||q||) ||a|| = e1[q] ||a||
+// with rho = max over rows of ||a^ - a|| / ||a|| and c_rel ||q|| ||a|| for the fp32 accumulation on both sides. The
+// rounding terms are MEASURED (the mirror kernel records rho, this kernel ||q - q^||), not the worst case 2^-8 per
+// operand: for real-valued data they are ~0.4 of it, and for stores that already hold 16-bit rows they vanish. The bound
+// is per row (e1[q] times THAT row's norm): a few long rows do not widen the band of the short ones.
+// e2[q]: L2 only, the part that does not scale with the row.
 __global__ void prep_coarse_queries_kernel(const uint8_t *__restrict__ q, size_t q_stride, int is_f32, size_t dim, size_t nq,
                                            __nv_bfloat16 *__restrict__ qb, size_t qb_stride, float c_rel,
-                                           const unsigned *__restrict__ max_l2_bits, float *__restrict__ eps, float c_l2) {
+                                           const unsigned *__restrict__ max_l2_bits, float *__restrict__ eps, float c_l2,
+                                           float *__restrict__ eps2) {
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -461,10 +493,15 @@ __global__ void prep_coarse_queries_kernel(const uint8_t *__restrict__ q, size_t
             // differences, all within c_l2 (|q| + R)^2
             const float up = norm_slack(dim);
             const float qn = sqrtf(ss) * up, qbn = sqrtf(sb) * up, qe = sqrtf(se) * up;
-            const float R = __uint_as_float(max_l2_bits[0]), EA = __uint_as_float(max_l2_bits[1]);
-            float e = __fmaf_ru(qbn, EA, __fmul_ru(R, qe));
-            e = __fmaf_ru(__fmul_ru(c_rel, qn), R, e);
-            eps[i] = __fmaf_ru(__fmul_ru(c_l2, qn + R), qn + R, e);
+            const float R = __uint_as_float(max_l2_bits[0]), rho = __uint_as_float(max_l2_bits[1]);
+            (void)R;
+            float e = __fmaf_ru(qbn, rho, __fmaf_ru(c_rel, qn, qe));
+            // L2: c_l2 (||q|| + ||a||)^2 = c_l2 ||q||^2 (e2, per query) + 2 c_l2 ||q|| ||a|| (joins e1) + c_l2 ||a||^2 (per row)
+            if (eps2) {
+                e = __fmaf_ru(__fmul_ru(2.0f * c_l2, qn), 1.0f, e);
+                eps2[i] = __fmul_ru(__fmul_ru(c_l2, qn), qn);
+            }
+            eps[i] = e;
         }
     }
 }
@@ -481,30 +518,39 @@ __device__ __forceinline__ float key2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-constexpr uint32_t RUN_CAP = 1024;   // survivors kept per query between phases
+constexpr uint32_t RUN_CAP = 1024;   // survivors kept per query between phases (k <= 384)
 
 struct MergeArgs {
     uint32_t nq, k;
     uint2 *run;              // [nq][RUN_CAP] (row id, coarse acc bits) of rows that can still make the top-k
     uint32_t *run_cnt;       // [nq]
     uint32_t *cnt;           // [nq] candidates appended this phase (reset to 0 here)
-    const uint2 *cand;       // [nq][CAND_CAP]
-    const float *eps;        // [nq] bound on |coarse acc - exact sum|
-    float *athr;             // [nq] admission bound for the next phase (accumulator space)
+    const uint2 *cand;       // [nq][cand_cap]
+    uint32_t run_cap, cand_cap;
+    const float *e1;         // [nq] |coarse acc - exact sum| <= e1[q] * ||row|| (+ e2[q])
+    const float *e2;         // [nq] or NULL (L2: the part of the bound that does not scale with the row)
+    const float *row_l2;     // [rows] ||row||, rounded up
+    float c_l2;              // L2: per-row share c_l2 ||row||^2 of the bound (already added to the stored value), else 0
+    float *athr;             // [nq] admission bound for the next phase: admit when acc + e1 ||row|| >= athr
     uint32_t *overflow;      // [nq] set when a buffer overflowed: the query is redone exactly
     unsigned long long *total_cand;
 };
 
-// One block per query over (survivors U this phase's candidates). With A_K the k-th largest coarse accumulator seen so
-// far, every row of the exact top-k — including every row tied with the k-th exact score — has acc >= A_K - 2*eps
-// (DESIGN.md §5.3), so that is both the survivor cut and the next phase's admission bound. Only A_K is needed, not an
-// order: an 8-bit radix select over (key - min key) finds it in at most four histogram passes over shared memory (the
-// first version sorted all <= 4096 pairs bitonically, 78 block-wide stages: 130 us per phase at 1024 queries); the
-// survivors are then compacted in any order (the re-rank orders the final list by exact score and id).
+// One block per query over (survivors U this phase's candidates). Row r's exact sum lies in [lo_r, hi_r] =
+// acc_r -+ (e1 ||r|| + e2). With L_K the k-th largest lo over the rows seen so far, the k-th largest exact sum is >= L_K, so
+// every row of the exact top-k — including every row tied with the k-th exact score — has hi_r >= L_K:
+// that is both the survivor cut and the next phase's admission test. Only L_K is needed, not an order: an 8-bit radix
+// select over (key - min key) finds it in at most four histogram passes over shared memory (the first version sorted all
+// <= 4096 pairs bitonically, 78 block-wide stages: 130 us per phase at 1024 queries); the survivors are then compacted
+// in any order (the re-rank orders the final list by exact score and id).
 constexpr int MERGE_THREADS = 256;
 __global__ void __launch_bounds__(MERGE_THREADS) merge_phase_kernel(MergeArgs a) {
-    __shared__ uint32_t s_key[RUN_CAP + CAND_CAP]; // ~key(acc): ascending key = descending acc
-    __shared__ uint32_t s_rid[RUN_CAP];            // run[] is rewritten in place: stage the survivors' ids
+    extern __shared__ __align__(16) uint8_t merge_smem[];
+    const uint32_t RUN_CAP = a.run_cap, CAND_CAP = a.cand_cap;
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(merge_smem);        // [run + cand] ~key(lo): ascending key = descending lo
+    float *s_hi = reinterpret_cast<float *>(s_key + RUN_CAP + CAND_CAP); // [run + cand] acc + e1 ||row|| (rounded up)
+    uint32_t *s_rid = reinterpret_cast<uint32_t *>(s_hi + RUN_CAP + CAND_CAP); // run[] is rewritten in place: stage ids, accs
+    uint32_t *s_racc = s_rid + RUN_CAP;
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_red[2 * (MERGE_THREADS / 32)];
     __shared__ uint32_t s_digit, s_below, s_keep;
@@ -520,16 +566,22 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_phase_kernel(MergeArgs a)
     const uint32_t total = rcnt + cnt;
     const uint2 *run_q = a.run + (size_t)q * RUN_CAP;
     const uint2 *cand_q = a.cand + (size_t)q * CAND_CAP;
+    const float e1 = a.e1[q], e2 = a.e2 ? a.e2[q] : 0.f;
     uint32_t kmin = 0xffffffffu, kmax = 0;
     for (uint32_t i = threadIdx.x; i < total; i += MERGE_THREADS) {
         uint2 e;
         if (i < rcnt) {
             e = run_q[i];
             s_rid[i] = e.x;
+            s_racc[i] = e.y;
         } else {
             e = cand_q[i - rcnt];
         }
-        const uint32_t key = ~f2key(__uint_as_float(e.y));
+        // stored value: acc (IP) or a'' = a' + c_l2 ||row||^2 (L2). exact sum in [v - w - 2 w2, v + w] (+- e2)
+        const float nr = a.row_l2[e.x];
+        const float acc = __uint_as_float(e.y), w = __fmul_ru(e1, nr), w2 = __fmul_ru(__fmul_ru(2.0f * a.c_l2, nr), nr);
+        s_hi[i] = __fadd_ru(acc, w);
+        const uint32_t key = ~f2key(__fsub_rd(__fsub_rd(acc, w), w2));
         s_key[i] = key;
         kmin = min(kmin, key);
         kmax = max(kmax, key);
@@ -591,17 +643,16 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_phase_kernel(MergeArgs a)
             prefix |= s_digit << shift;
             want -= s_below;
         }
-        const float ak = key2f(~(kmin + prefix));
-        bound = __fsub_rd(ak, __fmul_ru(2.0f, a.eps[q]));
-        bound = __fsub_rd(bound, fabsf(bound) * 1e-6f);
+        const float lk = key2f(~(kmin + prefix));              // k-th largest lower end (before e2)
+        bound = __fsub_rd(lk, __fmul_ru(2.0f, e2));            // hi_r + e2 >= L_K - e2
+        bound = __fsub_rd(bound, fabsf(bound) * 1e-6f);        // the epilogue's FFMA rounds to nearest
     }
     // survivors, in any order
     uint2 *run_out = a.run + (size_t)q * RUN_CAP;
     for (uint32_t i = threadIdx.x; i < total; i += MERGE_THREADS) {
-        const float acc = key2f(~s_key[i]);
-        if (acc >= bound) {
+        if (s_hi[i] >= bound) {
             const uint32_t slot = atomicAdd(&s_keep, 1u);
-            if (slot < RUN_CAP) run_out[slot] = make_uint2(i < rcnt ? s_rid[i] : cand_q[i - rcnt].x, __float_as_uint(acc));
+            if (slot < RUN_CAP) run_out[slot] = i < rcnt ? make_uint2(s_rid[i], s_racc[i]) : cand_q[i - rcnt];
         }
     }
     __syncthreads();
@@ -690,9 +741,9 @@ bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k) {
     if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_BFLOAT16 && s->type != VSGPU_FLOAT16) return false;
     if (s->type == VSGPU_FLOAT16 && s->plan.kind != CK_LANES) return false; // dim >= 16: the fp32-accumulating tier
     if (s->plan.kind == CK_SEQ) return false;
-    if (nq < 32 || k > 384 || k == 0) return false;
+    if (nq < 8 || k > K_MAX || k == 0) return false; // from 8 queries on one pass over the 16-bit rows beats the SIMT scan
     if (s->dim < 64 || s->dim > 8192) return false;
-    if (s->count < 32768 || s->count < 16 * k) return false;
+    if (s->count < 32768 || s->count < 32 * k) return false;
     if (!encode_fn()) return false;
     static int cc_major[64] = {0};
     if (s->device < 64 && !cc_major[s->device]) {
@@ -740,11 +791,15 @@ int tensor_sync_mirrors(vsgpu_store *s) {
             t->mirrored = s->count;
         }
     } else {
+        if (!s->row_l2) {
+            VS_CUDA(cudaMalloc(&s->row_l2, s->capacity * sizeof(float)));
+            t->mirrored = 0;
+        }
         if (t->mirrored < s->count) {
             const size_t n = s->count - t->mirrored;
             const unsigned blocks = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)t->sms * 16);
             bf16_norms_kernel<<<blocks, 256, 0, s->stream>>>((const __nv_bfloat16 *)s->rows, s->row_stride / 2, s->dim, t->mirrored,
-                                                            n, nullptr, t->max_l2_bits, s->type == VSGPU_FLOAT16 ? 1 : 0, t->row_hsq);
+                                                            n, s->row_l2, t->max_l2_bits, s->type == VSGPU_FLOAT16 ? 1 : 0, t->row_hsq);
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
             t->mirrored = s->count;
@@ -818,7 +873,11 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
     CUtensorMap map_a;
     VS_TRY(make_map(&map_a, a_base, n, s->dim, a_stride, BM));
 
-    const std::vector<std::pair<uint32_t, uint32_t>> phases = make_phases(n, k, CAND_CAP, BM);
+    const uint32_t run_cap = k <= K_SMALL_MAX ? RUN_CAP : RUN_CAP_BIG, cand_cap = k <= K_SMALL_MAX ? CAND_CAP : CAND_CAP_BIG;
+    const std::vector<std::pair<uint32_t, uint32_t>> phases = make_phases(n, k, cand_cap, BM);
+    const size_t merge_smem = (size_t)(run_cap + cand_cap) * 8 + (size_t)run_cap * 8;
+    if (merge_smem > 48 * 1024)
+        VS_CUDA(cudaFuncSetAttribute(merge_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
     const size_t chunks = (nq_all + MAX_NQ - 1) / MAX_NQ;
     uint32_t *ovf_all = nullptr;
     unsigned long long *tot_all = nullptr;
@@ -832,13 +891,14 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         // scratch layout in s->cand
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
-        const size_t o_qb = take(nq_pad * qb_stride * 2), o_eps = take(nq * 4), o_athr = take(nq * 4), o_cnt = take(nq * 4),
-                     o_rcnt = take(nq * 4), o_run = take(nq * RUN_CAP * 8), o_cand = take(nq * CAND_CAP * 8),
-                     o_rid = take(nq * RUN_CAP * 4), o_rsc = take(nq * RUN_CAP * 4);
+        const size_t o_qb = take(nq_pad * qb_stride * 2), o_eps = take(nq * 4), o_eps2 = take(nq * 4), o_athr = take(nq * 4), o_cnt = take(nq * 4),
+                     o_rcnt = take(nq * 4), o_run = take(nq * (size_t)run_cap * 8), o_cand = take(nq * (size_t)cand_cap * 8),
+                     o_rid = take(nq * (size_t)run_cap * 4), o_rsc = take(nq * (size_t)run_cap * 4);
         VS_TRY(ensure_scratch(s, s->cand, off));
         uint8_t *base = (uint8_t *)s->cand.ptr;
         auto *qb = (__nv_bfloat16 *)(base + o_qb);
         float *eps = (float *)(base + o_eps), *athr = (float *)(base + o_athr);
+        float *eps2 = s->metric == VSGPU_L2 ? (float *)(base + o_eps2) : nullptr;
         uint32_t *cnt = (uint32_t *)(base + o_cnt), *ovf = ovf_all + q0, *rcnt = (uint32_t *)(base + o_rcnt);
         uint2 *run = (uint2 *)(base + o_run), *cand = (uint2 *)(base + o_cand);
         uint32_t *rid = (uint32_t *)(base + o_rid);
@@ -850,7 +910,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         VS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)((uint8_t *)run - (uint8_t *)cnt), s->stream));
         fill_t<float><<<64, 256, 0, s->stream>>>(athr, -INFINITY, nq);
         prep_coarse_queries_kernel<<<(unsigned)std::min<size_t>((nq + 7) / 8, 1024), 256, 0, s->stream>>>(
-            qp, q_stride, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps, c_l2);
+            qp, q_stride, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, c_rel, t->max_l2_bits, eps, c_l2, eps2);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches += 2;
         CUtensorMap map_b, map_bh;
@@ -865,8 +925,12 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             g.n_qtiles = (uint32_t)(nq_pad / BN);
             g.k_blocks = (uint32_t)((s->dim + BK - 1) / BK);
             g.athr = athr;
+            g.e1 = eps;
+            g.row_l2 = s->row_l2;
+            g.c_l2 = c_l2;
             g.cnt = cnt;
             g.cand = cand;
+            g.cand_cap = cand_cap;
             g.dump = nullptr;
             g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
             g.row_sub = s->metric == VSGPU_L2 ? t->row_hsq : nullptr;
@@ -883,20 +947,25 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             m.run_cnt = rcnt;
             m.cnt = cnt;
             m.cand = cand;
-            m.eps = eps;
+            m.run_cap = run_cap;
+            m.cand_cap = cand_cap;
+            m.e1 = eps;
+            m.e2 = eps2;
+            m.row_l2 = s->row_l2;
+            m.c_l2 = c_l2;
             m.athr = athr;
             m.overflow = ovf;
             m.total_cand = tot;
-            merge_phase_kernel<<<(unsigned)nq, MERGE_THREADS, 0, s->stream>>>(m);
+            merge_phase_kernel<<<(unsigned)nq, MERGE_THREADS, merge_smem, s->stream>>>(m);
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
         }
         // exact scores of the survivors (bit-identical to the CPU reference), then the final order
-        unpack_ids_kernel<<<256, 256, 0, s->stream>>>(run, nq * RUN_CAP, rid);
+        unpack_ids_kernel<<<256, 256, 0, s->stream>>>(run, nq * (size_t)run_cap, rid);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches++;
-        VS_TRY(launch_exact_gather(s, qp, nq, q_stride, nullptr, rid, RUN_CAP, rcnt, RUN_CAP, rsc, RUN_CAP));
-        VS_TRY(launch_sort_candidates(s, nq, k, rid, rsc, RUN_CAP, rcnt, k, out_ids ? out_ids + q0 * k : nullptr,
+        VS_TRY(launch_exact_gather(s, qp, nq, q_stride, nullptr, rid, run_cap, rcnt, run_cap, rsc, run_cap));
+        VS_TRY(launch_sort_candidates(s, nq, k, rid, rsc, run_cap, rcnt, k, out_ids ? out_ids + q0 * k : nullptr,
                                       out_scores ? (float *)out_scores + q0 * k : nullptr,
                                       out_labels ? out_labels + q0 * k : nullptr));
     }
@@ -946,7 +1015,7 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
     VS_CUDA(cudaMemsetAsync(qb, 0, nq_pad * qb_stride * 2, s->stream));
     VS_CUDA(cudaMemsetAsync(dump, 0, nrows * nq * 4, s->stream));
     prep_coarse_queries_kernel<<<64, 256, 0, s->stream>>>(d_q, s->row_bytes, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, 0.f,
-                                                         t->max_l2_bits, eps, 0.f);
+                                                         t->max_l2_bits, eps, 0.f, nullptr);
     CUtensorMap map_a, map_b;
     VS_TRY(make_map(&map_a, f32 ? (const void *)s->shadow : (const void *)s->rows, s->count, s->dim,
                     f32 ? s->shadow_stride * 2 : s->row_stride, BM));

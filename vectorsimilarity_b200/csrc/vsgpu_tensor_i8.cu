@@ -46,6 +46,7 @@ struct I8Smem {
 
 struct I8Args {
     uint32_t row0, row_end, nq, n_qtiles, k_blocks, idesc;
+    uint32_t mma_only; // measurement: the epilogue only drains TMEM (no test, no append) -> the pipeline's own ceiling
     const float *cq;      // [nq] admit when float(dot) >= cq * row_mul + row_add (loosened)
     const float *row_mul; // per row, or NULL = 1 (cosine: the stored norm)
     const float *row_add; // per row, or NULL = 0 (L2: sum a^2 / 2)
@@ -157,13 +158,18 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             if (q < g.nq) g.dump[(size_t)(row - g.row0) * g.dump_ld + q] = (int)r[j];
                         }
                     }
+                } else if (g.mma_only) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) x ^= r[j];
+                    if (x == 0xdeadbeefu && cq[0] == 12345.f) g.cnt[0] = x; // keeps the loads alive, never true in practice
                 } else {
                     // 3 instructions per accumulator (I2F, FFMA, FSETP), all 32 first, then the hits of the whole warp;
                     // padded query columns carry c_q = +inf
                     uint32_t hit = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) hit |= (__int2float_rn((int)r[j]) >= fmaf(cq[j], rm, ra2) ? 1u : 0u) << j;
-                    warp_append_hits<CAND_CAP>(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane);
+                    warp_append_hits(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane, CAND_CAP);
                 }
             }
             tc_fence_before();
@@ -176,6 +182,154 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    }
+}
+
+// ---- CTA-pair variant: tcgen05.mma.cta_group::2, a 256-row x 256-query tile per cluster of two ----------------------
+// The single-CTA kernel moves (128 + 256) x 128 operand bytes per k-block for 128 x 256 x 128 MACs and runs at the L2 -> SM
+// bandwidth cap, far below the int8 MMA rate. Here each CTA stages its own 128 rows and HALF of the query
+// tile: (128 + 128) x 128 bytes for the same MACs per CTA — a third less operand traffic per MAC. The leader (cluster rank
+// 0) issues the MMAs; both CTAs' operands complete on the leader's `full` barriers; commits are multicast to both CTAs.
+constexpr int PSTAGES = 6;
+constexpr int BH_BYTES = (BN / 2) * BKB; // 16 KB: this CTA's half of the query tile
+struct I8PairSmem {
+    uint8_t a[PSTAGES][A_BYTES];
+    uint8_t b[PSTAGES][BH_BYTES];
+    float cq[MAX_NQ];
+    uint64_t full[PSTAGES], empty[PSTAGES], tfull[2], tempty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bh, I8Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    I8PairSmem &sm = *reinterpret_cast<I8PairSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const uint32_t p_tiles = (g.row_end - g.row0 + 2 * BM - 1) / (2 * BM);
+    const uint32_t items = p_tiles * g.n_qtiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < PSTAGES; i++) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&sm.tfull[i], 1);
+            mbar_init(&sm.tempty[i], 2 * EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bh) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x)
+        sm.cq[i] = (i < g.nq && g.cq) ? g.cq[i] : __int_as_float(0x7f800000);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all(); // both CTAs' barriers exist before anything is signalled across the pair
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) { // ===== TMA producer (both CTAs): own rows, own half of the queries =====
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = cluster_id; item < items; item += n_clusters) {
+                const uint32_t pt = item / g.n_qtiles, nt = item % g.n_qtiles;
+                const int row = (int)(g.row0 + pt * 2 * BM + rank * BM), qrow = (int)(nt * BN + rank * (BN / 2));
+                for (uint32_t kb = 0; kb < g.k_blocks; kb++) {
+                    mbar_wait(&sm.empty[stage], phase ^ 1);
+                    if (leader) mbar_expect_tx(&sm.full[stage], 2 * (A_BYTES + BH_BYTES));
+                    const uint32_t full0 = mapa_u32(smem_u32(&sm.full[stage]), 0);
+                    tma_load_2d_pair(sm.a[stage], &map_a, full0, (int)(kb * BKB), row);
+                    tma_load_2d_pair(sm.b[stage], &map_bh, full0, (int)(kb * BKB), qrow);
+                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) { // ===== MMA issuer: one thread of the leader CTA =====
+            const uint32_t idesc2 = (g.idesc & ~(0x1fu << 24)) | ((uint32_t)(256 >> 4) << 24);
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            for (uint32_t item = cluster_id; item < items; item += n_clusters) {
+                mbar_wait(&sm.tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + as * BN;
+                for (uint32_t kb = 0; kb < g.k_blocks; kb++) {
+                    mbar_wait(&sm.full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc(smem_u32(sm.a[stage]));
+                    const uint64_t bdesc = make_desc(smem_u32(sm.b[stage]));
+#pragma unroll
+                    for (int k = 0; k < BKB / UKB; k++)
+                        tc_mma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc2, (kb | (uint32_t)k) != 0);
+                    tc_commit_pair(&sm.empty[stage]);
+                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_pair(&sm.tfull[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): this CTA's 128 rows x 256 queries =====
+        const int ew = warp - 4;
+        const uint32_t quad = (uint32_t)(warp & 3);
+        const uint32_t half = (uint32_t)(ew >> 2);
+        uint32_t as = 0, aphase = 0;
+        for (uint32_t item = cluster_id; item < items; item += n_clusters) {
+            const uint32_t pt = item / g.n_qtiles, nt = item % g.n_qtiles;
+            const uint32_t row = g.row0 + pt * 2 * BM + rank * BM + quad * 32 + (uint32_t)lane;
+            const bool row_ok = row < g.row_end;
+            const float rm = (row_ok && g.row_mul) ? g.row_mul[row] : 1.0f;
+            const float ra = (row_ok && g.row_add) ? g.row_add[row] : 0.0f;
+            const float ra2 = ra - fabsf(ra) * 3.8146973e-6f - 2.0f;
+            mbar_wait(&sm.tfull[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t col = half * 128 + c * 32;
+                uint32_t r[32];
+                tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
+                tc_wait_ld();
+                float cq[32];
+                lds_f32x32(smem_u32(&sm.cq[nt * BN + col]), cq);
+                if (g.dump) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const uint32_t q = nt * BN + col + j;
+                            if (q < g.nq) g.dump[(size_t)(row - g.row0) * g.dump_ld + q] = (int)r[j];
+                        }
+                    }
+                } else if (g.mma_only) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) x ^= r[j];
+                    if (x == 0xdeadbeefu && cq[0] == 12345.f) g.cnt[0] = x;
+                } else {
+                    uint32_t hit = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) hit |= (__int2float_rn((int)r[j]) >= fmaf(cq[j], rm, ra2) ? 1u : 0u) << j;
+                    warp_append_hits(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane, CAND_CAP);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sm.tempty[as]), 0));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all(); // nobody signals the leader's barriers or reads TMEM any more
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
     }
 }
 
@@ -337,7 +491,7 @@ struct I8State {
     uint32_t *row_sq = nullptr;
     float *row_add = nullptr;
     int sms = 0;
-    bool attr_set = false;
+    bool attr_set = false, pair_attr_set = false;
 };
 
 int make_map_u8(CUtensorMap *map, const void *base, size_t rows, size_t dim_bytes, size_t stride_bytes, int box_rows) {
@@ -380,7 +534,7 @@ void tensor_i8_release(vsgpu_store *s) {
 
 bool tensor_i8_supported(const vsgpu_store *s, size_t nq, size_t k) {
     if (s->type != VSGPU_INT8 && s->type != VSGPU_UINT8) return false;
-    if (nq < 32 || k == 0 || k > RUN_CAP) return false;
+    if (nq < 8 || k == 0 || k > RUN_CAP) return false;
     if (s->dim < 32 || s->dim > 33024) return false; // int32 accumulator: the reference's own cap (spaces.h:57-66)
     if (s->count < 32768 || s->count < 16 * k) return false;
     if (!tc_encode_fn()) return false;
@@ -419,7 +573,33 @@ static int i8_sync_side(vsgpu_store *s, I8State *t) {
     return VSGPU_OK;
 }
 
-static int i8_launch_gemm(vsgpu_store *s, I8State *t, const CUtensorMap &ma, const CUtensorMap &mb, I8Args &g) {
+static int env_flag(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static bool i8_pair_enabled() {
+    static const bool on = env_flag("VSGPU_I8_PAIR", 1) != 0; // cta_group::2 by default (A/B: VSGPU_I8_PAIR=0)
+    return on;
+}
+
+// mbh: the query matrix as [128 x 128 B] boxes (the pair kernel stages half a query tile per CTA), NULL = single-CTA kernel
+static int i8_launch_gemm(vsgpu_store *s, I8State *t, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap *mbh,
+                          I8Args &g) {
+    static const int mma_only = env_flag("VSGPU_I8_MMA_ONLY", 0);
+    g.mma_only = g.dump ? 0u : (uint32_t)mma_only;
+    if (mbh) {
+        const size_t psmem = sizeof(I8PairSmem) + 1024;
+        if (!t->pair_attr_set) {
+            VS_CUDA(cudaFuncSetAttribute(i8_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            t->pair_attr_set = true;
+        }
+        const uint32_t p_tiles = (g.row_end - g.row0 + 2 * BM - 1) / (2 * BM);
+        const unsigned clusters = (unsigned)std::min<uint32_t>(p_tiles * g.n_qtiles, (uint32_t)(t->sms / 2));
+        i8_gemm_pair_kernel<<<2 * clusters, GEMM_THREADS, psmem, s->stream>>>(ma, *mbh, g);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+        return VSGPU_OK;
+    }
     const size_t smem = sizeof(I8Smem) + 1024;
     if (!t->attr_set) {
         VS_CUDA(cudaFuncSetAttribute(i8_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -479,8 +659,9 @@ int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_st
                                                                                                   uns, nq, qq);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches++;
-        CUtensorMap map_b;
+        CUtensorMap map_b, map_bh;
         VS_TRY(make_map_u8(&map_b, qp, nq, s->dim, q_stride, BN));
+        if (i8_pair_enabled()) VS_TRY(make_map_u8(&map_bh, qp, nq, s->dim, q_stride, BN / 2));
         for (size_t p = 0; p < phases.size(); p++) {
             I8Args g{};
             g.row0 = phases[p].first;
@@ -494,7 +675,7 @@ int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_st
             g.row_add = s->metric == VSGPU_L2 ? t->row_add : nullptr;
             g.cnt = cnt;
             g.cand = cand;
-            VS_TRY(i8_launch_gemm(s, t, map_a, map_b, g));
+            VS_TRY(i8_launch_gemm(s, t, map_a, map_b, i8_pair_enabled() ? &map_bh : nullptr, g));
             I8MergeArgs m{};
             m.nq = (uint32_t)nq;
             m.k = (uint32_t)k;
@@ -553,9 +734,10 @@ extern "C" int vsgpu_debug_i8(vsgpu_store *s, const void *queries, size_t nq, si
     VS_CUDA(cudaMemset(d_q, 0, nq * s->row_stride));
     VS_CUDA(cudaMemcpy2D(d_q, s->row_stride, queries, qstride, s->row_bytes, nq, cudaMemcpyHostToDevice));
     VS_CUDA(cudaMemsetAsync(dump, 0, nrows * nq * 4, s->stream));
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_bh;
     VS_TRY(make_map_u8(&map_a, s->rows, s->count, s->dim, s->row_stride, BM));
     VS_TRY(make_map_u8(&map_b, d_q, nq, s->dim, s->row_stride, BN));
+    if (i8_pair_enabled()) VS_TRY(make_map_u8(&map_bh, d_q, nq, s->dim, s->row_stride, BN / 2));
     I8Args g{};
     g.row0 = (uint32_t)row0;
     g.row_end = (uint32_t)(row0 + nrows);
@@ -565,7 +747,7 @@ extern "C" int vsgpu_debug_i8(vsgpu_store *s, const void *queries, size_t nq, si
     g.idesc = i8_idesc(s);
     g.dump = dump;
     g.dump_ld = (uint32_t)nq;
-    VS_TRY(i8_launch_gemm(s, t, map_a, map_b, g));
+    VS_TRY(i8_launch_gemm(s, t, map_a, map_b, i8_pair_enabled() ? &map_bh : nullptr, g));
     VS_CUDA(cudaStreamSynchronize(s->stream));
     VS_CUDA(cudaMemcpy(out, dump, nrows * nq * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_q);
