@@ -164,6 +164,9 @@ typedef struct vsgpu_hnsw vsgpu_hnsw;
 vsgpu_hnsw *vsgpu_hnsw_create(vsgpu_store *s, size_t M, size_t ef_construction);
 void vsgpu_hnsw_destroy(vsgpu_hnsw *g);
 size_t vsgpu_hnsw_size(const vsgpu_hnsw *g);
+/* Several rows per label (HNSWIndex_Multi, hnsw_multi.h:62-71,103-106): top-k and the batch iterator key their result set by
+ * label (updatable_max_heap, utils/updatable_heap.h:66-111) — each label once, with its best score. */
+void vsgpu_hnsw_set_multi(vsgpu_hnsw *g, int multi);
 size_t vsgpu_hnsw_device_bytes(const vsgpu_hnsw *g);
 int vsgpu_hnsw_entry(const vsgpu_hnsw *g, long *entry, long *max_level); /* -1/-1 when empty */
 /* Index the next n rows of the store (ids size()..size()+n-1, appended beforehand) with the given
@@ -198,6 +201,9 @@ typedef struct vsgpu_hnsw_iter vsgpu_hnsw_iter;
 vsgpu_hnsw_iter *vsgpu_hnsw_iter_create(vsgpu_hnsw *g, const void *query, size_t ef);
 void vsgpu_hnsw_iter_destroy(vsgpu_hnsw_iter *it);
 int vsgpu_hnsw_iter_reset(vsgpu_hnsw_iter *it);
+/* Multi-value graphs (HNSWMulti_BatchIterator::returned, hnsw_multi_batch_iterator.h:39-57): after a batch, the caller names
+ * every row of every label that batch returned; later batches skip them. HOST ids. */
+int vsgpu_hnsw_iter_mark_returned(vsgpu_hnsw_iter *it, const uint32_t *ids, size_t n);
 int vsgpu_hnsw_iter_next(vsgpu_hnsw_iter *it, size_t n_res, size_t label_count, uint64_t *out_labels, double *out_scores,
                          uint32_t *out_ids, size_t *out_count, int *depleted);
 /* Counters of the last traversal / insert call: distance evaluations, expanded nodes, device ms. */

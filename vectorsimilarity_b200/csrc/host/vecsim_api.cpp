@@ -107,10 +107,6 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
         if (params->algo == VecSimAlgo_HNSWLIB) {
             const HNSWParams &p = params->algoParams.hnswParams;
             if (p.dim == 0 || p.type > VecSimType_UINT8 || p.metric > VecSimMetric_Cosine) return nullptr;
-            if (p.multi) {
-                g_api_err = "multi-value HNSW indexes are not built yet (SURVEY §8 row f2)";
-                return nullptr;
-            }
             auto *idx = new HnswIndex(p, params->logCtx);
             if (!idx->ok()) {
                 g_api_err = std::string("HNSW index: ") + vsgpu_last_error();

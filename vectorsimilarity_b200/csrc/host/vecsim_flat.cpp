@@ -7,7 +7,9 @@
 #include "vecsim_hybrid.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <functional>
 #include <limits>
 #include <stdexcept>
@@ -18,6 +20,35 @@ Globals &globals() {
     static Globals g;
     return g;
 }
+
+namespace {
+struct alignas(16) HookHeader {
+    size_t size;
+    void (*free_fn)(void *);
+};
+std::atomic<size_t> g_hook_bytes{0};
+} // namespace
+
+void *hook_alloc(size_t n) {
+    const Globals &g = globals();
+    void *(*alloc_fn)(size_t) = (g.mem_set && g.mem.allocFunction) ? g.mem.allocFunction : std::malloc;
+    void (*free_fn)(void *) = (g.mem_set && g.mem.allocFunction && g.mem.freeFunction) ? g.mem.freeFunction : std::free;
+    auto *h = static_cast<HookHeader *>(alloc_fn(n + sizeof(HookHeader)));
+    if (!h) throw std::bad_alloc();
+    h->size = n;
+    h->free_fn = free_fn;
+    g_hook_bytes.fetch_add(n + sizeof(HookHeader), std::memory_order_relaxed);
+    return h + 1;
+}
+
+void hook_free(void *p) noexcept {
+    if (!p) return;
+    HookHeader *h = static_cast<HookHeader *>(p) - 1;
+    g_hook_bytes.fetch_sub(h->size + sizeof(HookHeader), std::memory_order_relaxed);
+    h->free_fn(h);
+}
+
+size_t hook_bytes() { return g_hook_bytes.load(std::memory_order_relaxed); }
 
 size_t type_size(VecSimType t) {
     switch (t) {

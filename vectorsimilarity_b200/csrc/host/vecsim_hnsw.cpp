@@ -27,8 +27,19 @@ HnswIndex::HnswIndex(const HNSWParams &p, void *logCtx)
     if (M_ <= 1 || 2 * M_ > 512) return; // the reference throws for M<=1 (hnsw.h:1644); >256 is a device limit
     mult_ = 1.0 / std::log(1.0 * (double)M_);
     level_gen_.seed(100); // hnsw.h:230 default random_seed
+    multi_ = p.multi;
     store_ = vsgpu_store_create(globals().device, (int)type_, (int)metric_, dim_, p.initialCapacity);
     if (store_) graph_ = vsgpu_hnsw_create(store_, M_, efc_);
+    if (graph_) vsgpu_hnsw_set_multi(graph_, multi_ ? 1 : 0);
+}
+
+std::vector<idType> HnswIndex::idsOfLocked(size_t label) const {
+    if (multi_) {
+        auto it = label_to_ids_.find(label);
+        return it == label_to_ids_.end() ? std::vector<idType>() : it->second;
+    }
+    auto it = label_to_id_.find(label);
+    return it == label_to_id_.end() ? std::vector<idType>() : std::vector<idType>{it->second};
 }
 
 HnswIndex::~HnswIndex() {
@@ -80,9 +91,19 @@ size_t HnswIndex::abortPending() {
     const size_t n = pending_labels_.size();
     for (size_t i = 0; i < n; i++) {
         const size_t id = id_to_label_.size() - 1;
-        auto it = label_to_id_.find(id_to_label_[id]);
-        if (it != label_to_id_.end() && it->second == (idType)id) label_to_id_.erase(it);
+        if (multi_) {
+            auto it = label_to_ids_.find(id_to_label_[id]);
+            if (it != label_to_ids_.end()) {
+                auto &v = it->second;
+                v.erase(std::remove(v.begin(), v.end(), (idType)id), v.end());
+                if (v.empty()) label_to_ids_.erase(it);
+            }
+        } else {
+            auto it = label_to_id_.find(id_to_label_[id]);
+            if (it != label_to_id_.end() && it->second == (idType)id) label_to_id_.erase(it);
+        }
         id_to_label_.pop_back();
+        id_deleted_.pop_back();
     }
     pending_rows_.clear();
     pending_labels_.clear();
@@ -93,18 +114,22 @@ size_t HnswIndex::abortPending() {
 int HnswIndex::addVector(const void *blob, size_t label) {
     std::lock_guard<std::mutex> g(mu_);
     int ret = 1;
-    auto it = label_to_id_.find(label);
-    if (it != label_to_id_.end()) {
-        // hnsw_single.h:153-163 deletes the old vector and appends the new one. The old node is
-        // tombstoned here instead of being cut out of the graph.
-        if (markDeletedLocked(it->second) != 0) return -1;
-        label_to_id_.erase(it);
-        ret = 0;
+    if (!multi_) {
+        auto it = label_to_id_.find(label);
+        if (it != label_to_id_.end()) {
+            // hnsw_single.h:153-163 deletes the old vector and appends the new one. The old node is
+            // tombstoned here instead of being cut out of the graph.
+            if (markDeletedLocked(it->second) != 0) return -1;
+            label_to_id_.erase(it);
+            ret = 0;
+        }
     }
     const size_t id = id_to_label_.size();
     if (id >= 0xfffffffeull) return -1;
     id_to_label_.push_back(label);
-    label_to_id_[label] = (idType)id;
+    id_deleted_.push_back(0);
+    if (multi_) label_to_ids_[label].push_back((idType)id); // hnsw_multi.h:186-196: another vector under the label, always new
+    else label_to_id_[label] = (idType)id;
     const size_t off = pending_rows_.size();
     pending_rows_.resize(off + stored_size_);
     preprocess(blob, pending_rows_.data() + off);
@@ -127,13 +152,24 @@ long HnswIndex::addVectorBatch(const void *blobs, size_t n, const size_t *labels
 
 int HnswIndex::markDeletedLocked(idType id) {
     if (flush() != 0) return -1;
+    if (id < id_deleted_.size() && id_deleted_[id]) return 0;
     if (vsgpu_hnsw_set_deleted(graph_, id, 1) != VSGPU_OK) return -1;
+    if (id < id_deleted_.size()) id_deleted_[id] = 1;
     num_deleted_++;
     return 0;
 }
 
 int HnswIndex::deleteVector(size_t label) {
     std::lock_guard<std::mutex> g(mu_);
+    if (multi_) { // hnsw_multi.h:221-247: every vector of the label
+        auto it = label_to_ids_.find(label);
+        if (it == label_to_ids_.end()) return 0;
+        int n = 0;
+        for (idType id : it->second)
+            if (markDeletedLocked(id) == 0) n++;
+        label_to_ids_.erase(it);
+        return n;
+    }
     auto it = label_to_id_.find(label);
     if (it == label_to_id_.end()) return 0;
     if (markDeletedLocked(it->second) != 0) return 0;
@@ -144,13 +180,14 @@ int HnswIndex::deleteVector(size_t label) {
 double HnswIndex::getDistanceFrom(size_t label, const void *blob) {
     std::lock_guard<std::mutex> g(mu_);
     const double nan = std::numeric_limits<double>::quiet_NaN();
-    auto it = label_to_id_.find(label);
-    if (it == label_to_id_.end()) return nan;
+    const std::vector<idType> ids = idsOfLocked(label);
+    if (ids.empty()) return nan;
     if (flush() != 0) return nan;
-    const uint32_t id = it->second;
-    double out = nan;
-    if (vsgpu_distances(store_, blob, &id, 1, &out) != VSGPU_OK) return nan;
-    return out;
+    std::vector<double> d(ids.size());
+    if (vsgpu_distances(store_, blob, ids.data(), ids.size(), d.data()) != VSGPU_OK) return nan;
+    double best = d[0]; // hnsw_multi.h:81-95: the closest of the label's vectors
+    for (double v : d) best = (best < v) ? best : v;
+    return best;
 }
 
 void HnswIndex::exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) {
@@ -160,16 +197,16 @@ void HnswIndex::exactDistances(const void *processed_query, const size_t *labels
     if (flush() != 0) return;
     std::vector<uint32_t> ids;
     std::vector<size_t> pos;
-    for (size_t i = 0; i < n; i++) {
-        auto it = label_to_id_.find(labels[i]);
-        if (it == label_to_id_.end()) continue;
-        ids.push_back(it->second);
-        pos.push_back(i);
-    }
+    for (size_t i = 0; i < n; i++)
+        for (idType id : idsOfLocked(labels[i])) {
+            ids.push_back(id);
+            pos.push_back(i);
+        }
     if (ids.empty()) return;
     std::vector<double> d(ids.size());
     if (vsgpu_distances(store_, processed_query, ids.data(), ids.size(), d.data()) != VSGPU_OK) return;
-    for (size_t j = 0; j < ids.size(); j++) out[pos[j]] = d[j];
+    for (size_t j = 0; j < ids.size(); j++)
+        if (!(out[pos[j]] <= d[j])) out[pos[j]] = d[j]; // minimum over a label's vectors (NaN = not set yet)
 }
 
 int HnswIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *out_labels,
@@ -219,7 +256,7 @@ VecSimQueryReply *HnswIndex::topKQuery(const void *blob, size_t k, VecSimQueryPa
         last_mode_ = STANDARD_KNN;
         return rep;
     }
-    const size_t cap = std::min(k, id_to_label_.size());
+    const size_t cap = std::min(k, multi_ ? indexLabelCount() : id_to_label_.size());
     std::vector<size_t> labels(cap);
     std::vector<double> scores(cap);
     uint32_t cnt = 0;
@@ -263,6 +300,16 @@ VecSimQueryReply *HnswIndex::rangeQuery(const void *blob, double radius, VecSimQ
     }
     rep->results.resize(count);
     for (size_t i = 0; i < count; i++) rep->results[i] = {(size_t)lab[i], sc[i]};
+    if (multi_ && count > 1) {
+        // unique_results_container (utils/query_result_utils.h, hnsw_multi.h:73-79): each label once, with its best score
+        std::sort(rep->results.begin(), rep->results.end(), [](const VecSimQueryResult &a, const VecSimQueryResult &b) {
+            if (a.id != b.id) return a.id < b.id;
+            return a.score < b.score;
+        });
+        rep->results.erase(std::unique(rep->results.begin(), rep->results.end(),
+                                       [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id == b.id; }),
+                           rep->results.end());
+    }
     if (order == BY_ID)
         std::sort(rep->results.begin(), rep->results.end(),
                   [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id < b.id; });
@@ -334,8 +381,16 @@ int HnswIndex::iterNext(vsgpu_hnsw_iter *it, size_t n, size_t *labels, double *s
     std::lock_guard<std::mutex> g(mu_);
     if (flush() != 0) return -1;
     static_assert(sizeof(size_t) == sizeof(uint64_t), "labelType is 64-bit");
-    return vsgpu_hnsw_iter_next(it, n, label_to_id_.size(), (uint64_t *)labels, scores, nullptr, count, depleted) == VSGPU_OK ? 0
-                                                                                                                              : -1;
+    if (vsgpu_hnsw_iter_next(it, n, multi_ ? label_to_ids_.size() : label_to_id_.size(), (uint64_t *)labels, scores, nullptr, count,
+                             depleted) != VSGPU_OK)
+        return -1;
+    if (multi_) { // HNSWMulti_BatchIterator::returned: later batches skip every vector of the labels handed out now
+        std::vector<uint32_t> ids;
+        for (size_t i = 0; i < *count; i++)
+            for (idType id : idsOfLocked(labels[i])) ids.push_back(id);
+        if (vsgpu_hnsw_iter_mark_returned(it, ids.data(), ids.size()) != VSGPU_OK) return -1;
+    }
+    return 0;
 }
 void HnswIndex::iterReset(vsgpu_hnsw_iter *it) {
     std::lock_guard<std::mutex> g(mu_);
@@ -351,7 +406,7 @@ VecSimIndexBasicInfo HnswIndex::basicInfo() {
     b.algo = VecSimAlgo_HNSWLIB;
     b.metric = metric_;
     b.type = type_;
-    b.isMulti = false;
+    b.isMulti = multi_;
     b.isTiered = false;
     b.isDisk = false;
     b.blockSize = block_size_;
@@ -361,7 +416,8 @@ VecSimIndexBasicInfo HnswIndex::basicInfo() {
 
 VecSimIndexStatsInfo HnswIndex::statsInfo() {
     VecSimIndexStatsInfo s{};
-    s.memory = sizeof(*this) + id_to_label_.capacity() * sizeof(size_t) + label_to_id_.size() * 32 + pending_rows_.capacity() +
+    s.memory = sizeof(*this) + id_to_label_.capacity() * (sizeof(size_t) + 1) + (label_to_id_.size() + label_to_ids_.size()) * 32 +
+               (multi_ ? id_to_label_.size() * sizeof(idType) : 0) + pending_rows_.capacity() +
                (store_ ? vsgpu_store_device_bytes(store_) : 0) + (graph_ ? vsgpu_hnsw_device_bytes(graph_) : 0);
     s.numberOfMarkedDeleted = num_deleted_;
     return s;
@@ -373,7 +429,7 @@ VecSimIndexDebugInfo HnswIndex::debugInfo() {
     VecSimIndexDebugInfo d{};
     d.commonInfo.basicInfo = basicInfo();
     d.commonInfo.indexSize = id_to_label_.size() - num_deleted_;
-    d.commonInfo.indexLabelCount = label_to_id_.size();
+    d.commonInfo.indexLabelCount = multi_ ? label_to_ids_.size() : label_to_id_.size();
     d.commonInfo.memory = statsInfo().memory;
     d.commonInfo.lastMode = last_mode_;
     long ep = -1, ml = -1;
@@ -425,6 +481,7 @@ void HnswIndex::lastStats(vsgpu_stats *out) {
 int HnswIndex::elementNeighbors(size_t label, int ***out) {
     std::lock_guard<std::mutex> g(mu_);
     *out = nullptr;
+    if (multi_) return VecSimDebugCommandCode_MultiNotSupported; // hnsw_multi.h: one label has several nodes
     auto it = label_to_id_.find(label);
     if (it == label_to_id_.end()) return VecSimDebugCommandCode_LabelNotExists;
     if (flush() != 0) return VecSimDebugCommandCode_BadIndex;
@@ -460,7 +517,11 @@ int HnswIndex::importGraph(const void *blobs, int processed, size_t n, const siz
     if (vsgpu_store_append(store_, rows.data(), stored_size_, lab.data(), n) != VSGPU_OK) return -1;
     if (vsgpu_hnsw_import(graph_, n, levels, l0, upper, upper_records, entry, max_level) != VSGPU_OK) return -1;
     id_to_label_.assign(lab.begin(), lab.end());
-    for (size_t i = 0; i < n; i++) label_to_id_[lab[i]] = (idType)i;
+    id_deleted_.assign(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        if (multi_) label_to_ids_[lab[i]].push_back((idType)i);
+        else label_to_id_[lab[i]] = (idType)i;
+    }
     return 0;
 }
 

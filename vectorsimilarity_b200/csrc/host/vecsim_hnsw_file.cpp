@@ -9,6 +9,7 @@
 // The traversal never reads the "incoming unidirectional edges" lists, so the reader skips them; the writer derives them
 // from the links (u -> v without v -> u) so that the reference can load the file and pass its integrity check.
 #include "vecsim_index.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -102,10 +103,6 @@ VecSimIndexInterface *load_hnsw_file(const char *path, std::string &err) {
     if (!r.ok || p.dim == 0 || p.dim > (1u << 24) || p.type > VecSimType_UINT8 || p.metric > VecSimMetric_Cosine ||
         M0 != 2 * p.M || p.M < 2 || p.M > 256) {
         err = "Cannot load index: corrupted header";
-        return nullptr;
-    }
-    if (p.multi) {
-        err = "Cannot load index: multi-value HNSW indexes are not built yet (SURVEY §8 row f2)";
         return nullptr;
     }
     std::vector<size_t> labels(n);
@@ -238,6 +235,15 @@ int HnswIndex::markDeletedById(idType id) {
     std::lock_guard<std::mutex> g(mu_);
     if (id >= id_to_label_.size()) return -1;
     if (markDeletedLocked(id) != 0) return -1;
+    if (multi_) {
+        auto it = label_to_ids_.find(id_to_label_[id]);
+        if (it != label_to_ids_.end()) {
+            auto &v = it->second;
+            v.erase(std::remove(v.begin(), v.end(), id), v.end());
+            if (v.empty()) label_to_ids_.erase(it);
+        }
+        return 0;
+    }
     auto it = label_to_id_.find(id_to_label_[id]);
     if (it != label_to_id_.end() && it->second == id) label_to_id_.erase(it);
     return 0;
@@ -295,7 +301,7 @@ int HnswIndex::saveFile(const char *path) {
     put<int>(out, type_);
     put<int>(out, metric_);
     put<size_t>(out, block_size_);
-    put<bool>(out, false);
+    put<bool>(out, multi_);
     put<size_t>(out, (n + block_size_ - 1) / block_size_ * block_size_); // maxElements: whole blocks
     put<size_t>(out, M_);
     put<size_t>(out, 2 * M_);
@@ -309,9 +315,7 @@ int HnswIndex::saveFile(const char *path) {
     put<idType>(out, entry < 0 ? (idType)-1 : (idType)entry);
     for (size_t i = 0; i < n; i++) {
         put<size_t>(out, id_to_label_[i]);
-        auto it = label_to_id_.find(id_to_label_[i]);
-        const bool deleted = it == label_to_id_.end() || it->second != (idType)i;
-        put<uint8_t>(out, deleted ? DELETE_MARK : 0);
+        put<uint8_t>(out, id_deleted_[i] ? DELETE_MARK : 0);
     }
     out.write((const char *)rows.data(), (std::streamsize)rows.size());
     for (size_t b = 0; b * block_size_ < n; b++) {

@@ -17,11 +17,37 @@
 #include <utility>
 #include <vector>
 
+namespace vsb {
+// Host allocations that live as long as an index, a reply or an iterator go through the caller's hooks
+// (VecSim_SetMemoryFunctions, /root/reference/src/VecSim/vec_sim.h:281, memory/vecsim_malloc.cpp:27-65): RediSearch hands
+// in RedisModule_Alloc / Free so the memory shows up in Redis' accounting. A 16-byte header keeps the size and the free
+// function that matches the allocation (hooks may be installed after some objects exist); the live total is what
+// hook_bytes() reports.
+void *hook_alloc(size_t n);
+void hook_free(void *p) noexcept;
+size_t hook_bytes();
+template <class T> struct HookAlloc {
+    using value_type = T;
+    HookAlloc() = default;
+    template <class U> HookAlloc(const HookAlloc<U> &) {}
+    T *allocate(size_t n) { return static_cast<T *>(hook_alloc(n * sizeof(T))); }
+    void deallocate(T *p, size_t) noexcept { hook_free(p); }
+    template <class U> bool operator==(const HookAlloc<U> &) const { return true; }
+    template <class U> bool operator!=(const HookAlloc<U> &) const { return false; }
+};
+template <class T> using hvec = std::vector<T, HookAlloc<T>>;
+template <class K, class V> using hmap = std::unordered_map<K, V, std::hash<K>, std::equal_to<K>, HookAlloc<std::pair<const K, V>>>;
+struct Hooked { // objects handed to the caller (indexes, replies, iterators)
+    static void *operator new(size_t n) { return hook_alloc(n); }
+    static void operator delete(void *p) noexcept { hook_free(p); }
+};
+} // namespace vsb
+
 struct VecSimQueryResult {
     size_t id;
     double score;
 };
-struct VecSimQueryReply {
+struct VecSimQueryReply : vsb::Hooked {
     std::vector<VecSimQueryResult> results;
     VecSimQueryReply_Code code = VecSim_QueryReply_OK;
 };
@@ -54,14 +80,14 @@ struct VecSimDebugInfoIterator {
     size_t pos = 0;
 };
 
-struct VecSimBatchIterator {
+struct VecSimBatchIterator : vsb::Hooked {
     virtual ~VecSimBatchIterator() = default;
     virtual VecSimQueryReply *next(size_t n, VecSimQueryReply_Order order) = 0;
     virtual bool hasNext() = 0;
     virtual void reset() = 0;
 };
 
-struct VecSimIndexInterface {
+struct VecSimIndexInterface : vsb::Hooked {
     virtual ~VecSimIndexInterface() = default;
     virtual int addVector(const void *blob, size_t label) = 0;
     virtual long addVectorBatch(const void *blobs, size_t n, const size_t *labels, size_t first_label) = 0;
@@ -155,12 +181,12 @@ class FlatIndex final : public VecSimIndexInterface {
     vsgpu_store *store_ = nullptr;
     size_t count_ = 0;
     bool identity_ = true;
-    std::unordered_map<size_t, idType> label_to_id_;
-    std::vector<size_t> id_to_label_;
+    hmap<size_t, idType> label_to_id_;
+    hvec<size_t> id_to_label_;
     bool labels_monotone_ = true;
     size_t max_label_ = 0;
-    std::vector<uint8_t> pending_rows_;
-    std::vector<uint64_t> pending_labels_;
+    hvec<uint8_t> pending_rows_;
+    hvec<uint64_t> pending_labels_;
     VecSearchMode last_mode_ = EMPTY_MODE;
     std::mutex mu_;
 };
@@ -206,10 +232,10 @@ class FlatMultiIndex final : public VecSimIndexInterface {
     size_t dim_, block_size_, data_size_, stored_size_;
     void *log_ctx_;
     vsgpu_store *store_ = nullptr;
-    std::vector<size_t> id_to_label_;
-    std::unordered_map<size_t, std::vector<idType>> label_to_ids_;
-    std::vector<uint8_t> pending_rows_;
-    std::vector<uint64_t> pending_labels_;
+    hvec<size_t> id_to_label_;
+    hmap<size_t, std::vector<idType>> label_to_ids_;
+    hvec<uint8_t> pending_rows_;
+    hvec<uint64_t> pending_labels_;
     VecSearchMode last_mode_ = EMPTY_MODE;
     std::mutex mu_;
 };
@@ -267,7 +293,8 @@ class ShardedFlatIndex final : public VecSimIndexInterface {
     std::mutex mu_;
 };
 
-// HNSW (single value per label): vecsim_hnsw.cpp
+// HNSW: vecsim_hnsw.cpp. Single value per label (HNSWIndex_Single) or, with HNSWParams.multi, several vectors per label
+// (HNSWIndex_Multi, hnsw_multi.h): queries then return each label once, with the best score among its vectors.
 class HnswIndex final : public VecSimIndexInterface {
   public:
     HnswIndex(const HNSWParams &p, void *logCtx);
@@ -279,7 +306,7 @@ class HnswIndex final : public VecSimIndexInterface {
     int deleteVector(size_t label) override;
     double getDistanceFrom(size_t label, const void *blob) override;
     size_t indexSize() override { return id_to_label_.size() - num_deleted_; }
-    size_t indexLabelCount() override { return label_to_id_.size(); }
+    size_t indexLabelCount() override { return multi_ ? label_to_ids_.size() : label_to_id_.size(); }
     VecSimQueryReply *topKQuery(const void *blob, size_t k, VecSimQueryParams *qp) override;
     int topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryParams *qp, size_t *labels, double *scores,
                   uint32_t *counts) override;
@@ -299,8 +326,9 @@ class HnswIndex final : public VecSimIndexInterface {
     vsgpu_hnsw *deviceGraph();
     bool hasLabel(size_t label) {
         std::lock_guard<std::mutex> g(mu_);
-        return label_to_id_.count(label) != 0;
+        return multi_ ? label_to_ids_.count(label) != 0 : label_to_id_.count(label) != 0;
     }
+    bool isMulti() const { return multi_; }
     // pushes staged vectors to the device store and graph now (the tiered index ingests from its worker threads)
     int sync() {
         std::lock_guard<std::mutex> g(mu_);
@@ -308,6 +336,8 @@ class HnswIndex final : public VecSimIndexInterface {
     }
     size_t abortPending();
     int iterNext(vsgpu_hnsw_iter *it, size_t n, size_t *labels, double *scores, size_t *count, int *depleted);
+    // ids of the live rows of `label` (empty when unknown); caller holds mu_
+    std::vector<idType> idsOfLocked(size_t label) const;
     void iterReset(vsgpu_hnsw_iter *it);
     void iterDestroy(vsgpu_hnsw_iter *it);
     size_t efRuntime() const { return ef_; }
@@ -334,12 +364,15 @@ class HnswIndex final : public VecSimIndexInterface {
     std::default_random_engine level_gen_;
     vsgpu_store *store_ = nullptr;
     vsgpu_hnsw *graph_ = nullptr;
-    std::unordered_map<size_t, idType> label_to_id_;
-    std::vector<size_t> id_to_label_;
+    bool multi_ = false;
+    hmap<size_t, idType> label_to_id_;               // single value per label
+    hmap<size_t, std::vector<idType>> label_to_ids_; // multi: the live rows of each label
+    hvec<size_t> id_to_label_;
+    hvec<uint8_t> id_deleted_; // tombstones, by id
     size_t num_deleted_ = 0;
-    std::vector<uint8_t> pending_rows_;
-    std::vector<uint64_t> pending_labels_;
-    std::vector<uint32_t> pending_levels_;
+    hvec<uint8_t> pending_rows_;
+    hvec<uint64_t> pending_labels_;
+    hvec<uint32_t> pending_levels_;
     VecSearchMode last_mode_ = EMPTY_MODE;
     std::mutex mu_;
 };

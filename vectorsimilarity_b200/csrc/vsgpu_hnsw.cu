@@ -151,6 +151,49 @@ template <typename CT_, int G_, bool FTZ, bool L2, int ST> struct PolChain {
             out[r] = v;
         }
     }
+    // NR rows against the staged pivot with every load of a 4-step slice in flight at once (plans without a residual:
+    // chain c reads element G*s + c). Same chains, same order, same butterfly as dists<true>: bit-identical results.
+    // Used by the warp-per-query traversal, where one warp has to hide the row latency on its own.
+    template <int NR>
+    __device__ static void dists_fast(const KCtx &k, const void *pv_, const uint32_t (&a)[NR], int c, DT (&out)[NR]) {
+        const DT *pv = (const DT *)pv_ + c;
+        const uint8_t *ra[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) ra[r] = k.rows + (size_t)(a[r] == INV ? 0 : a[r]) * k.row_stride;
+        DT acc[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) acc[r] = DT(0);
+        const int S = k.plan.S;
+        for (int s0 = 0; s0 < S; s0 += 4) {
+            DT x[NR][4];
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+#pragma unroll
+                for (int r = 0; r < NR; r++) x[r][t] = s0 + t < S ? load_st<ST, DT>(ra[r], G * (s0 + t) + c) : DT(0);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (s0 + t < S) {
+                    const DT y = pv[(s0 + t) * G];
+#pragma unroll
+                    for (int r = 0; r < NR; r++) {
+                        if constexpr (L2) {
+                            const DT d = sub_rn(x[r][t], y);
+                            acc[r] = fma_step<FTZ>(d, d, acc[r]);
+                        } else {
+                            acc[r] = fma_step<FTZ>(x[r][t], y, acc[r]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            DT v = butterfly<DT, G>(acc[r]);
+            if (!L2) v = sub_rn(DT(1), v);
+            out[r] = v;
+        }
+    }
+    static constexpr bool HAS_FAST = true;
     // one thread evaluates a whole (row, row) pair: the G chain sums live in registers and are folded
     // with the same pairing tree as the warp butterfly (acc[c] + acc[c + w], w = G/2 .. 1). Used where
     // many independent pairs are wanted at once (neighbour-selection heuristic), so a thread per pair
@@ -214,6 +257,7 @@ template <bool U> struct PolInt {
     using DT = float;
     static constexpr int G = 8;
     static constexpr int RU = 2;
+    static constexpr bool HAS_FAST = false;
     static size_t pivot_bytes(const vsgpu_store *s) { return s->row_stride + sizeof(IntPivotTail); }
     // src: dim bytes zero padded to row_stride (a stored row, or a staged query)
     __device__ static void load_pivot(const KCtx &k, void *pv_, const uint8_t *src, float norm) {
@@ -280,6 +324,7 @@ template <typename CT_> struct PolSeq {
     using DT = CT_;
     static constexpr int G = 1;
     static constexpr int RU = 1;
+    static constexpr bool HAS_FAST = false;
     static size_t pivot_bytes(const vsgpu_store *s) { return s->dim * sizeof(DT); }
     __device__ static void load_pivot(const KCtx &k, void *pv_, const uint8_t *src, float) {
         DT *pv = (DT *)pv_;
@@ -676,10 +721,12 @@ __device__ __forceinline__ bool cand_insert(Work<DT> &w, int &cand_n, DT d, uint
 // searchLayer / searchBottomLayer (hnsw.h:682-721, 1983-2035) from entry w.sc[SC_CUR]. Result set in
 // w.top_* (SC_TOPN entries, ascending under TopLess). labels != nullptr: query flavour (keyed by
 // label); else builder flavour (keyed by id, admissions logged). Status through w.sc[SC_STATUS].
+// `multi` (HNSWIndex_Multi, hnsw_multi.h:62-71,103-106): the result set is an updatable_max_heap keyed by LABEL
+// (utils/updatable_heap.h:66-111) — a label already in the set only ever improves its score, it never takes a second slot.
 template <class P>
 __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::DT> &w, int level, int ef,
                              const uint64_t *labels, const Visited &vis, unsigned long long &evals,
-                             unsigned long long &hops) {
+                             unsigned long long &hops, bool multi = false) {
     using DT = typename P::DT;
     TopLess<DT> tl{labels};
     CandLess<DT> cl;
@@ -694,6 +741,33 @@ __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::
     const bool regtop = ef <= 64 && !w.no_regtop;
     DT t0d = DT(0), t1d = DT(0);
     uint32_t t0i = 0, t1i = 0;
+    // multi, register-resident set: position of the entry that carries `lab`, or -1 (labels are fetched per probe: the
+    // probe is one global load per lane, off the critical path of single-value searches, which never call this)
+    auto reg_find_label = [&](uint64_t lab) -> int {
+        const bool p0 = lane < top_n && labels[t0i] == lab;
+        const bool p1 = lane + 32 < top_n && labels[t1i] == lab;
+        const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+        return b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : -1);
+    };
+    auto reg_dist_at = [&](int p) -> DT {
+        const DT a = __shfl_sync(0xffffffffu, t0d, p & 31), b = __shfl_sync(0xffffffffu, t1d, p & 31);
+        return p < 32 ? a : b;
+    };
+    auto reg_remove = [&](int p) { // entries after p move down by one
+        const DT d0 = __shfl_down_sync(0xffffffffu, t0d, 1), d1 = __shfl_down_sync(0xffffffffu, t1d, 1);
+        const uint32_t i0 = __shfl_down_sync(0xffffffffu, t0i, 1), i1 = __shfl_down_sync(0xffffffffu, t1i, 1);
+        const DT f1d = __shfl_sync(0xffffffffu, t1d, 0); // entry 32 becomes entry 31
+        const uint32_t f1i = __shfl_sync(0xffffffffu, t1i, 0);
+        if (lane >= p) {
+            t0d = lane == 31 ? f1d : d0;
+            t0i = lane == 31 ? f1i : i0;
+        }
+        if (lane + 32 >= p) {
+            t1d = d1;
+            t1i = i1;
+        }
+        top_n--;
+    };
     auto reg_insert = [&](DT d, uint32_t id) {
         const bool p0 = lane < top_n && tl(t0d, t0i, d, id);
         const bool p1 = lane + 32 < top_n && tl(t1d, t1i, d, id);
@@ -812,13 +886,55 @@ __device__ void search_layer(const KCtx &k, const GraphDev &g, Work<typename P::
                         break;
                     }
                     if (!w.nb_del[j0 + b]) {
-                        if (regtop) reg_insert(d, id);
-                        else sorted_insert(w.top_d, w.top_id, top_n, d, id, tl);
-                        if (lane == 0 && adm_n < w.adm_cap) {
+                        bool take = true;
+                        if (multi) { // emplace by label: a known label keeps its better score, a better one replaces it
+                            const uint64_t lab = labels[id];
+                            if (regtop) {
+                                const int p = reg_find_label(lab);
+                                if (p >= 0) {
+                                    if (reg_dist_at(p) > d) reg_remove(p);
+                                    else take = false;
+                                }
+                            } else {
+                                int p = -1;
+                                for (int i0 = 0; i0 < top_n && p < 0; i0 += 32) {
+                                    const int i = i0 + lane;
+                                    const unsigned m = __ballot_sync(0xffffffffu, i < top_n && labels[w.top_id[i]] == lab);
+                                    if (m) p = i0 + __ffs(m) - 1;
+                                }
+                                if (p >= 0) {
+                                    if (w.top_d[p] > d) {
+                                        for (int lo = p + 1; lo < top_n; lo += 32) { // shift the tail down by one
+                                            const int i = lo + lane;
+                                            DT td = DT(0);
+                                            uint32_t ti = 0;
+                                            if (i < top_n) {
+                                                td = w.top_d[i];
+                                                ti = w.top_id[i];
+                                            }
+                                            __syncwarp();
+                                            if (i < top_n) {
+                                                w.top_d[i - 1] = td;
+                                                w.top_id[i - 1] = ti;
+                                            }
+                                            __syncwarp();
+                                        }
+                                        top_n--;
+                                    } else {
+                                        take = false;
+                                    }
+                                }
+                            }
+                        }
+                        if (take) {
+                            if (regtop) reg_insert(d, id);
+                            else sorted_insert(w.top_d, w.top_id, top_n, d, id, tl);
+                        }
+                        if (take && lane == 0 && adm_n < w.adm_cap) {
                             w.adm_d[adm_n] = d;
                             w.adm_id[adm_n] = id;
                         }
-                        adm_n++;
+                        if (take) adm_n++;
                     }
                     if (top_n > ef) top_n--;
                     if (top_n > 0) lower = regtop ? reg_last() : w.top_d[top_n - 1];
@@ -876,6 +992,7 @@ struct SearchArgs {
     size_t range_cap;
     int profile; // VSGPU_HNSW_PROFILE: per-phase cycle counters
     int no_regtop; // VSGPU_HNSW_NO_REGTOP
+    int multi;     // HNSWIndex_Multi: result set keyed by label
 };
 
 template <typename DT> __device__ __forceinline__ Work<DT> carve(unsigned char *smem, size_t pivot_bytes, int max_links,
@@ -958,7 +1075,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_k
             tp = clock64();
         }
         Visited vis{a.visited + q * a.vis_words, 0};
-        search_layer<P>(a.k, a.g, w, 0, a.ef, a.labels, vis, evals, hops);
+        search_layer<P>(a.k, a.g, w, 0, a.ef, a.labels, vis, evals, hops, a.multi != 0);
         if (a.profile && threadIdx.x == 0) s_prof[4] = clock64() - tp;
         count = min(w.sc[SC_TOPN], a.k_out); // ascending (score, label): the k best are the first k
         for (int i = threadIdx.x; i < count; i += blockDim.x) {
@@ -987,6 +1104,387 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_k
                 for (int i = 0; i < 6; i++) atomicAdd(&a.counters[2 + i], (unsigned long long)s_prof[i]);
                 atomicMax(&a.counters[8], hops);
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-query traversal (top-k, ef <= 64). The CTA-per-query kernel above pays three block-wide barriers per hop and
+// leaves seven of its eight warps idle while warp 0 pops and admits: a hop cost 6-11 us for ~2 dependent memory round
+// trips of work (r1 profile: barrier stall 21 cycles per issue, issue slots 9 % busy). Here ONE warp owns a query from the
+// entry point to the reply — pop, link gather, visited test, distances (eight rows per slice, every load in flight),
+// admission — with no barrier at all after the queries are staged, and a CTA carries several independent queries.
+// Same algorithm, same order of admissions, same arithmetic: the results are identical (hnsw.h:530-613, 682-721,
+// 1210-1258, 1983-2084); anything this kernel does not take (ef > 64, candidate set overflow) goes to the kernel above.
+constexpr int WQ_MAX_WARPS = 8;
+
+template <typename DT> struct WarpTop { // the result set in registers: lane L holds entries L and L + 32, ascending
+    DT d0 = DT(0), d1 = DT(0);
+    uint32_t i0 = 0, i1 = 0;
+    int n = 0;
+    __device__ __forceinline__ void insert(DT d, uint32_t id, int lane, const TopLess<DT> &tl) {
+        const bool p0 = lane < n && tl(d0, i0, d, id);
+        const bool p1 = lane + 32 < n && tl(d1, i1, d, id);
+        const int cnt = __popc(__ballot_sync(0xffffffffu, p0)) + __popc(__ballot_sync(0xffffffffu, p1));
+        const DT u0d = __shfl_up_sync(0xffffffffu, d0, 1);
+        const uint32_t u0i = __shfl_up_sync(0xffffffffu, i0, 1);
+        DT u1d = __shfl_up_sync(0xffffffffu, d1, 1);
+        uint32_t u1i = __shfl_up_sync(0xffffffffu, i1, 1);
+        const DT l31d = __shfl_sync(0xffffffffu, d0, 31);
+        const uint32_t l31i = __shfl_sync(0xffffffffu, i0, 31);
+        if (lane == 0) {
+            u1d = l31d;
+            u1i = l31i;
+        }
+        if (lane == cnt) {
+            d0 = d;
+            i0 = id;
+        } else if (lane > cnt) {
+            d0 = u0d;
+            i0 = u0i;
+        }
+        if (lane + 32 == cnt) {
+            d1 = d;
+            i1 = id;
+        } else if (lane + 32 > cnt) {
+            d1 = u1d;
+            i1 = u1i;
+        }
+        n = min(n + 1, 64);
+    }
+    __device__ __forceinline__ DT dist_at(int p) const {
+        const DT a = __shfl_sync(0xffffffffu, d0, p & 31), b = __shfl_sync(0xffffffffu, d1, p & 31);
+        return p < 32 ? a : b;
+    }
+    __device__ __forceinline__ int find_label(uint64_t lab, int lane, const uint64_t *labels) const {
+        const bool p0 = lane < n && labels[i0] == lab;
+        const bool p1 = lane + 32 < n && labels[i1] == lab;
+        const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+        return b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : -1);
+    }
+    __device__ __forceinline__ void remove(int p, int lane) {
+        const DT e0 = __shfl_down_sync(0xffffffffu, d0, 1), e1 = __shfl_down_sync(0xffffffffu, d1, 1);
+        const uint32_t j0 = __shfl_down_sync(0xffffffffu, i0, 1), j1 = __shfl_down_sync(0xffffffffu, i1, 1);
+        const DT f1d = __shfl_sync(0xffffffffu, d1, 0);
+        const uint32_t f1i = __shfl_sync(0xffffffffu, i1, 0);
+        if (lane >= p) {
+            d0 = lane == 31 ? f1d : e0;
+            i0 = lane == 31 ? f1i : j0;
+        }
+        if (lane + 32 >= p) {
+            d1 = e1;
+            i1 = j1;
+        }
+        n--;
+    }
+};
+
+struct WarpScratch { // per-warp slices of shared memory
+    void *pivot;
+    uint32_t *nb_ids;
+    uint8_t *nb_del;
+    void *nb_dist;
+    void *cand_d;
+    uint32_t *cand_id;
+};
+__host__ __device__ inline size_t wq_warp_bytes(size_t dt, size_t pivot_bytes, int max_links, int cand_cap) {
+    auto al = [](size_t b) { return (b + 15) / 16 * 16; };
+    return al(pivot_bytes) + al((size_t)max_links * 4) + al((size_t)max_links) + al((size_t)max_links * dt) + al((size_t)cand_cap * dt) +
+           al((size_t)cand_cap * 4);
+}
+__device__ __forceinline__ WarpScratch wq_carve(unsigned char *p, size_t dt, size_t pivot_bytes, int max_links, int cand_cap) {
+    auto al = [](size_t b) { return (b + 15) / 16 * 16; };
+    WarpScratch w;
+    w.pivot = p;
+    p += al(pivot_bytes);
+    w.nb_ids = (uint32_t *)p;
+    p += al((size_t)max_links * 4);
+    w.nb_del = p;
+    p += al((size_t)max_links);
+    w.nb_dist = p;
+    p += al((size_t)max_links * dt);
+    w.cand_d = p;
+    p += al((size_t)cand_cap * dt);
+    w.cand_id = (uint32_t *)p;
+    return w;
+}
+
+// links of `node` at `level` that were not visited yet, in link order (warp-wide; see gather_unvisited)
+template <typename DT>
+__device__ __forceinline__ int wq_gather(const KCtx &k, const GraphDev &g, const WarpScratch &w, uint32_t node, int level,
+                                         const Visited *vis, int lane) {
+    const uint32_t *rec = links_of(g, node, level);
+    const int width = level == 0 ? g.M0 : g.M;
+    int base = 0, cnt = 0;
+    for (int i0 = 0; i0 < width; i0 += 32) {
+        const int i = i0 + lane;
+        const uint32_t id = i < width ? rec[1 + i] : INV;
+        if (i0 == 0) cnt = (int)rec[0];
+        if (i0 >= cnt) break;
+        bool take = false;
+        uint8_t del = 0;
+        if (i < cnt) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(k.rows + (size_t)id * k.row_stride));
+            del = g.flags[id];
+            take = vis ? !test_and_set(*vis, id) : true;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const int pos = base + __popc(m & ((1u << lane) - 1));
+            w.nb_ids[pos] = id;
+            w.nb_del[pos] = del & 1;
+        }
+        base += __popc(m);
+    }
+    __syncwarp();
+    return base;
+}
+
+// nb_dist[j] = dist(row nb_ids[j], query) for j < n (warp-wide)
+template <class P> __device__ __forceinline__ void wq_eval(const KCtx &k, const WarpScratch &w, int n, int lane) {
+    using DT = typename P::DT;
+    DT *out = (DT *)w.nb_dist;
+    constexpr int GPW = 32 / P::G;
+    const int c = lane % P::G, grp = lane / P::G;
+    int base = 0;
+    if constexpr (P::HAS_FAST && P::G == 32) {
+        if (k.plan.kind == CK_LANES && k.plan.prefix == 0) {
+            constexpr int NR = 8;
+            for (; base + NR <= n || (base < n && n - base > 4); base += NR) {
+                uint32_t a[NR];
+#pragma unroll
+                for (int r = 0; r < NR; r++) a[r] = base + r < n ? w.nb_ids[base + r] : INV;
+                DT o[NR];
+                P::template dists_fast<NR>(k, w.pivot, a, c, o);
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++)
+                        if (base + r < n) out[base + r] = o[r];
+                }
+            }
+        }
+    }
+    constexpr int RU = P::RU;
+    for (; base < n; base += GPW * RU) {
+        const int j0 = base + grp * RU;
+        uint32_t a[RU], b[RU];
+#pragma unroll
+        for (int r = 0; r < RU; r++) {
+            a[r] = j0 + r < n ? w.nb_ids[j0 + r] : INV;
+            b[r] = INV;
+        }
+        DT o[RU];
+        P::template dists<true>(k, w.pivot, a, b, c, o);
+        if (c == 0) {
+#pragma unroll
+            for (int r = 0; r < RU; r++)
+                if (a[r] != INV) out[j0 + r] = o[r];
+        }
+    }
+    __syncwarp();
+}
+
+template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_search_warp_kernel(SearchArgs a, int wpc, size_t nq) {
+    using DT = typename P::DT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = wq_warp_bytes(sizeof(DT), a.pivot_bytes, a.max_links, a.cand_cap);
+    // stage the CTA's queries: P::load_pivot is CTA-cooperative, one call per warp slot
+    for (int ws = 0; ws < wpc; ws++) {
+        const size_t qq = (size_t)blockIdx.x * wpc + ws;
+        if (qq < nq) P::load_pivot(a.k, smem_raw + (size_t)ws * per_warp, a.q + qq * a.q_stride, a.q_norms ? a.q_norms[qq] : 0.f);
+    }
+    __syncthreads(); // the only block-wide barrier
+    const size_t q = (size_t)blockIdx.x * wpc + warp;
+    if (q >= nq) return;
+    const WarpScratch w = wq_carve(smem_raw + (size_t)warp * per_warp, sizeof(DT), a.pivot_bytes, a.max_links, a.cand_cap);
+    DT *nb_dist = (DT *)w.nb_dist, *cand_d = (DT *)w.cand_d;
+    const KCtx &k = a.k;
+    const GraphDev &g = a.g;
+    unsigned long long evals = 0, hops = 0;
+    int count = 0;
+    uint32_t status = 0;
+    const int ep0 = g.state[0], maxl = g.state[1];
+    if (ep0 >= 0) {
+        // ---- greedy descent to level 1 (searchBottomLayerEP, greedySearchLevel) ----
+        uint32_t cur = (uint32_t)ep0;
+        if (lane == 0) w.nb_ids[0] = cur;
+        __syncwarp();
+        wq_eval<P>(k, w, 1, lane);
+        DT cur_d = nb_dist[0];
+        evals += 1;
+        for (int level = maxl; level > 0; level--) {
+            for (;;) {
+                __syncwarp();
+                const int n = wq_gather<DT>(k, g, w, cur, level, nullptr, lane);
+                wq_eval<P>(k, w, n, lane);
+                evals += n;
+                bool changed = false;
+                for (int j = 0; j < n; j++) { // sequential scan in link order, uniform across the warp
+                    const DT dj = nb_dist[j];
+                    if (dj < cur_d) {
+                        cur_d = dj;
+                        cur = w.nb_ids[j];
+                        changed = true;
+                    }
+                }
+                if (!changed) break;
+            }
+        }
+        // ---- bottom layer (searchBottomLayer_WithTimeout) ----
+        const Visited vis{a.visited + q * a.vis_words, 0};
+        const TopLess<DT> tl{a.labels};
+        const CandLess<DT> cl;
+        const int ef = a.ef;
+        const bool multi = a.multi != 0;
+        WarpTop<DT> top;
+        int cand_n = 0;
+        DT lower;
+        __syncwarp();
+        if (!is_deleted(g, cur)) {
+            lower = cur_d;
+            top.insert(lower, cur, lane, tl);
+        } else {
+            lower = dt_max<DT>();
+        }
+        if (lane == 0) {
+            cand_d[0] = lower;
+            w.cand_id[0] = cur;
+            test_and_set(vis, cur);
+        }
+        cand_n = 1;
+        __syncwarp();
+        for (;;) {
+            // pop the best candidate: maximum under pair(-dist, id)
+            DT bd = DT(0);
+            uint32_t bid = 0;
+            int bi = -1;
+            for (int i = lane; i < cand_n; i += 32) {
+                const DT d = cand_d[i];
+                const uint32_t id = w.cand_id[i];
+                if (bi < 0 || cl(bd, bid, d, id)) {
+                    bd = d;
+                    bid = id;
+                    bi = i;
+                }
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const DT od = __shfl_xor_sync(0xffffffffu, bd, m);
+                const uint32_t oid = __shfl_xor_sync(0xffffffffu, bid, m);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+                if (oi >= 0 && (bi < 0 || cl(bd, bid, od, oid))) {
+                    bd = od;
+                    bid = oid;
+                    bi = oi;
+                }
+            }
+            if (bi < 0) break;
+            if (bd > lower && top.n >= ef) break;
+            __syncwarp();
+            if (lane == 0) {
+                cand_d[bi] = cand_d[cand_n - 1];
+                w.cand_id[bi] = w.cand_id[cand_n - 1];
+            }
+            cand_n--;
+            hops++;
+            __syncwarp();
+            const int n = wq_gather<DT>(k, g, w, bid, 0, &vis, lane);
+            wq_eval<P>(k, w, n, lane);
+            evals += n;
+            bool failed = false;
+            for (int j0 = 0; j0 < n && !failed; j0 += 32) {
+                const int j = j0 + lane;
+                const DT dj = j < n ? nb_dist[j] : DT(0);
+                // whoever fails the test now fails it later too (the bound only shrinks once the set is full)
+                unsigned mask = __ballot_sync(0xffffffffu, j < n && (lower > dj || top.n < ef));
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const DT d = __shfl_sync(0xffffffffu, dj, b);
+                    if (!(lower > d || top.n < ef)) continue;
+                    const uint32_t id = w.nb_ids[j0 + b];
+                    if (cand_n >= a.cand_cap) {
+                        if (top.n >= ef) { // drop entries that can never be expanded (see cand_insert)
+                            int out = 0;
+                            for (int base = 0; base < cand_n; base += 32) {
+                                const int i = base + lane;
+                                DT td = DT(0);
+                                uint32_t ti = 0;
+                                bool keep = false;
+                                if (i < cand_n) {
+                                    td = cand_d[i];
+                                    ti = w.cand_id[i];
+                                    keep = !(td > lower);
+                                }
+                                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                                __syncwarp();
+                                if (keep) {
+                                    const int pos = out + __popc(m & ((1u << lane) - 1));
+                                    cand_d[pos] = td;
+                                    w.cand_id[pos] = ti;
+                                }
+                                __syncwarp();
+                                out += __popc(m);
+                            }
+                            cand_n = out;
+                        }
+                        if (cand_n >= a.cand_cap) {
+                            failed = true;
+                            break;
+                        }
+                    }
+                    if (lane == 0) {
+                        cand_d[cand_n] = d;
+                        w.cand_id[cand_n] = id;
+                    }
+                    __syncwarp();
+                    cand_n++;
+                    if (!w.nb_del[j0 + b]) {
+                        bool take = true;
+                        if (multi) {
+                            const int p = top.find_label(a.labels[id], lane, a.labels);
+                            if (p >= 0) {
+                                if (top.dist_at(p) > d) top.remove(p, lane);
+                                else take = false;
+                            }
+                        }
+                        if (take) top.insert(d, id, lane, tl);
+                    }
+                    if (top.n > ef) top.n--;
+                    if (top.n > 0) lower = top.dist_at(top.n - 1);
+                }
+            }
+            if (failed) {
+                status = 1; // the host redoes this query on the CTA kernel with a spill area
+                break;
+            }
+        }
+        count = min(top.n, a.k_out);
+        const size_t o0 = q * a.out_ld;
+        if (lane < count) {
+            if (a.out_ids) a.out_ids[o0 + lane] = top.i0;
+            if (a.out_scores) ((DT *)a.out_scores)[o0 + lane] = top.d0;
+            if (a.out_labels) a.out_labels[o0 + lane] = a.labels[top.i0];
+        }
+        if (lane + 32 < count) {
+            if (a.out_ids) a.out_ids[o0 + lane + 32] = top.i1;
+            if (a.out_scores) ((DT *)a.out_scores)[o0 + lane + 32] = top.d1;
+            if (a.out_labels) a.out_labels[o0 + lane + 32] = a.labels[top.i1];
+        }
+    }
+    for (int j = count + lane; j < a.k_out; j += 32) {
+        const size_t o = q * a.out_ld + j;
+        if (a.out_ids) a.out_ids[o] = INV;
+        if (a.out_scores) ((DT *)a.out_scores)[o] = dt_nan<DT>();
+        if (a.out_labels) a.out_labels[o] = ~0ull;
+    }
+    if (lane == 0) {
+        if (a.status) a.status[q] = status;
+        if (a.out_counts) a.out_counts[q] = (uint32_t)count;
+        if (a.counters) {
+            atomicAdd(&a.counters[0], evals);
+            atomicAdd(&a.counters[1], hops);
         }
     }
 }
@@ -1143,6 +1641,11 @@ struct BiArgs {
     uint32_t *out_count;
     size_t pivot_bytes;
     unsigned long long *counters;
+    // HNSWMulti_BatchIterator (hnsw_multi_batch_iterator.h:39-99): the result set is keyed by label (a flat array here:
+    // emplace = find the label, keep the better score) and rows whose label was handed out by an earlier batch are
+    // skipped — the host marks every row of a returned label in `returned_bits` between calls
+    int multi;
+    const uint32_t *returned_bits;
 };
 // std::greater on pair<DistType, key>: min-heap. Expressed as the "less" our max-heap helpers take.
 template <typename DT> struct MinLess {
@@ -1178,6 +1681,33 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_bi_kerne
     DT lower = DT(0);
     const int ef = a.ef;
     bool skip_scan = false;
+    // multi-value flavour, thread 0 only: `top` as a flat array (one entry per label)
+    auto was_returned = [&](uint32_t id) { return (a.returned_bits[id >> 5] >> (id & 31)) & 1u; };
+    auto m_max = [&]() { // index of the largest entry under (score, label)
+        int m = 0;
+        for (int i = 1; i < top_n; i++)
+            if (tl(top_d[m], a.top_id[m], top_d[i], a.top_id[i])) m = i;
+        return m;
+    };
+    auto m_remove = [&](int i) {
+        top_d[i] = top_d[top_n - 1];
+        a.top_id[i] = a.top_id[top_n - 1];
+        top_n--;
+    };
+    auto m_emplace = [&](DT d, uint32_t id) {
+        const uint64_t lab = a.labels[id];
+        for (int i = 0; i < top_n; i++)
+            if (a.labels[a.top_id[i]] == lab) {
+                if (top_d[i] > d) {
+                    top_d[i] = d;
+                    a.top_id[i] = id;
+                }
+                return;
+            }
+        top_d[top_n] = d;
+        a.top_id[top_n] = id;
+        top_n++;
+    };
     if (threadIdx.x == 0) {
         cand_n = (int)st->cand_n;
         extra_n = (int)st->extra_n;
@@ -1215,7 +1745,11 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_bi_kerne
     if (threadIdx.x == 0) {
         // fillFromExtras
         while (top_n < ef && extra_n > 0) {
-            heap_push(top_d, a.top_id, top_n, extra_d[0], a.extra_id[0], tl);
+            if (a.multi) {
+                if (!was_returned(a.extra_id[0])) m_emplace(extra_d[0], a.extra_id[0]);
+            } else {
+                heap_push(top_d, a.top_id, top_n, extra_d[0], a.extra_id[0], tl);
+            }
             heap_pop(extra_d, a.extra_id, extra_n, el);
         }
         skip_scan = top_n == ef;
@@ -1232,7 +1766,18 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_bi_kerne
                 else {
                     const DT d = cand_d[0];
                     const uint32_t id = a.cand_id[0];
-                    if (!is_deleted(a.g, id)) {
+                    if (!is_deleted(a.g, id) && a.multi) {
+                        // updateHeaps, label-keyed (hnsw_multi_batch_iterator.h:59-84)
+                        if ((lower > d || top_n < ef) && !was_returned(id)) {
+                            m_emplace(d, id);
+                            if (top_n > ef) {
+                                const int m = m_max();
+                                heap_push(extra_d, a.extra_id, extra_n, top_d[m], a.top_id[m], el);
+                                m_remove(m);
+                            }
+                            lower = top_d[m_max()];
+                        }
+                    } else if (!is_deleted(a.g, id)) {
                         // updateHeaps
                         if (top_n < ef) {
                             heap_push(top_d, a.top_id, top_n, d, id, tl);
@@ -1267,16 +1812,20 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS) hnsw_bi_kerne
         if (!skip_scan && top_n < ef) st->depleted = 1;
         // prepareResults: spare results go back to the extras
         while (top_n > a.n_res) {
-            heap_push(extra_d, a.extra_id, extra_n, top_d[0], a.top_id[0], el);
-            heap_pop(top_d, a.top_id, top_n, tl);
+            const int m = a.multi ? m_max() : 0;
+            heap_push(extra_d, a.extra_id, extra_n, top_d[m], a.top_id[m], el);
+            if (a.multi) m_remove(m);
+            else heap_pop(top_d, a.top_id, top_n, tl);
         }
         const int count = top_n;
         for (int i = count - 1; i >= 0; i--) {
-            const uint32_t id = a.top_id[0];
+            const int m = a.multi ? m_max() : 0;
+            const uint32_t id = a.top_id[m];
             a.out_ids[i] = id;
-            ((DT *)a.out_scores)[i] = top_d[0];
+            ((DT *)a.out_scores)[i] = top_d[m];
             a.out_labels[i] = a.labels[id];
-            heap_pop(top_d, a.top_id, top_n, tl);
+            if (a.multi) m_remove(m);
+            else heap_pop(top_d, a.top_id, top_n, tl);
         }
         *a.out_count = (uint32_t)count;
         st->returned += (unsigned long long)count;
@@ -1321,12 +1870,6 @@ struct InsertArgs {
     void *res_d;          // [slots][BATCH_MAX_LEVELS][M] DistType
     uint32_t *mod_stamp;  // [capacity] id of the last inserted element that rewrote the node's links
     uint32_t *committed;  // mode 2: number of elements committed
-    // mode 3 (parallel build, opt-in): CTA b connects element first + b without validation; neighbours' records are
-    // guarded by per-node spin locks (a warp holds at most one lock at a time), the entry point by locks[capacity].
-    // Like the reference's multi-threaded ingestion, elements of one round do not see each other and the graph
-    // depends on timing; it is a valid HNSW graph, not the sequential one.
-    uint32_t *locks;
-    uint32_t state_lock_idx;
 };
 constexpr int BATCH_MAX_LEVELS = 16;
 
@@ -1549,15 +2092,6 @@ __device__ bool warp_revisit(const KCtx &k, const GraphDev &g, const RvScratch<t
     return __shfl_sync(0xffffffffu, changed, 0) != 0;
 }
 
-__device__ __forceinline__ void node_lock(uint32_t *locks, uint32_t i) {
-    while (atomicCAS(&locks[i], 0u, 1u) != 0u) __nanosleep(64);
-    __threadfence();
-}
-__device__ __forceinline__ void node_unlock(uint32_t *locks, uint32_t i) {
-    __threadfence();
-    atomicExch(&locks[i], 0u);
-}
-
 template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_insert_kernel(InsertArgs a) {
     using DT = typename P::DT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1585,16 +2119,16 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
     long long tp = 0;
 
     __shared__ int s_rlog_n, s_valid;
-    const bool per_cta = a.mode == 1 || a.mode == 3;
+    const bool per_cta = a.mode == 1;
     const uint32_t e_begin = per_cta ? a.first + blockIdx.x : a.first;
     const uint32_t e_end = per_cta ? e_begin + 1 : a.first + a.n;
     for (uint32_t e = e_begin; e < e_end; e++) {
         __syncthreads();
         const uint32_t slot = e - a.first;
         int *meta = a.res_meta ? a.res_meta + (size_t)slot * (4 + BATCH_MAX_LEVELS) : nullptr;
-        const bool commit_mode = a.mode == 2 || a.mode == 3;
+        const bool commit_mode = a.mode == 2;
         // mode 3 works from the state its search saw (other CTAs may be raising the entry point right now)
-        const int ep = a.mode == 3 ? meta[1] : a.g.state[0], maxl = a.mode == 3 ? meta[2] : a.g.state[1];
+        const int ep = a.g.state[0], maxl = a.g.state[1];
         const int lvl = (int)a.g.levels[e];
         if (a.mode == 1) {
             if (threadIdx.x == 0) {
@@ -1609,7 +2143,6 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
             __syncthreads();
             if (!meta[0]) return;
         }
-        if (a.mode == 3 && !meta[0]) return; // could not be recorded: the host inserts it sequentially afterwards
         if (a.mode == 2) {
             // valid while the graph state and every link list this element's search read are as it saw them
             if (threadIdx.x == 0) s_valid = (meta[0] == 1 && meta[1] == ep && meta[2] == maxl && meta[3] <= a.rlog_cap) ? 1 : 0;
@@ -1777,11 +2310,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
                     for (int si = warp; si < ns; si += a.rv_warps) {
                         const uint32_t nb = sel_id[si];
                         if (is_deleted(a.g, nb)) continue;
-                        volatile uint32_t *nb_rec = links_of(a.g, nb, level); // volatile: other CTAs rewrite it (mode 3)
-                        if (a.mode == 3) {
-                            if ((threadIdx.x & 31) == 0) node_lock(a.locks, nb);
-                            __syncwarp();
-                        }
+                        volatile uint32_t *nb_rec = links_of(a.g, nb, level);
                         bool changed = true;
                         if ((int)nb_rec[0] < maxMcur) {
                             if ((threadIdx.x & 31) == 0) {
@@ -1795,10 +2324,6 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
                         // a full neighbour that rejects the new element and keeps all its links is untouched: later
                         // elements of the round that read its list are still valid
                         if (a.mod_stamp && changed && (threadIdx.x & 31) == 0) a.mod_stamp[nb] = e;
-                        if (a.mode == 3) {
-                            __syncwarp();
-                            if ((threadIdx.x & 31) == 0) node_unlock(a.locks, nb);
-                        }
                     }
                 }
                 __syncthreads();
@@ -1875,17 +2400,7 @@ template <class P> __global__ void __launch_bounds__(HNSW_THREADS, 1) hnsw_inser
             if (threadIdx.x == 0) meta[3] = s_rlog_n;
             break;
         }
-        if (threadIdx.x == 0 && a.mode == 3) {
-            if (lvl > maxl) { // re-check under the lock: several elements of the round may be taller than the graph
-                node_lock(a.locks, a.state_lock_idx);
-                volatile int *st = a.g.state;
-                if (lvl > st[1]) {
-                    st[0] = (int)e;
-                    st[1] = lvl;
-                }
-                node_unlock(a.locks, a.state_lock_idx);
-            }
-        } else if (threadIdx.x == 0 && lvl > maxl) {
+        if (threadIdx.x == 0 && lvl > maxl) {
             a.g.state[0] = (int)e;
             a.g.state[1] = lvl;
         }
@@ -1909,6 +2424,7 @@ using namespace vsgpu;
 struct vsgpu_hnsw {
     vsgpu_store *s = nullptr;
     int M = 0, M0 = 0, efc = 0;
+    bool multi = false;    // several rows per label: queries key their result set by label
     size_t capacity = 0;   // nodes the arrays are sized for
     size_t count = 0;      // nodes in the graph
     uint32_t *l0 = nullptr, *up = nullptr, *up_off = nullptr, *levels = nullptr, *tags = nullptr, *tag_counter = nullptr;
@@ -2068,6 +2584,7 @@ void vsgpu_hnsw_destroy(vsgpu_hnsw *g) {
 }
 
 size_t vsgpu_hnsw_size(const vsgpu_hnsw *g) { return g->count; }
+void vsgpu_hnsw_set_multi(vsgpu_hnsw *g, int multi) { g->multi = multi != 0; }
 size_t vsgpu_hnsw_device_bytes(const vsgpu_hnsw *g) {
     return g->capacity * ((size_t)(g->M0 + 1) * 4 + 4 + 4 + 4 + 1) + g->up_capacity * (size_t)(g->M + 1) * 4 +
            g->visited.bytes + g->spill.bytes + g->out.bytes + g->misc.bytes;
@@ -2384,6 +2901,7 @@ static int hnsw_search_core(vsgpu_hnsw *g, const void *q, size_t nq, size_t q_st
     a.range_cap = range_cap;
     a.profile = getenv("VSGPU_HNSW_PROFILE") != nullptr;
     a.no_regtop = getenv("VSGPU_HNSW_NO_REGTOP") != nullptr;
+    a.multi = g->multi ? 1 : 0;
     if (with_spill) {
         VS_TRY(ensure_scratch(s, g->spill, nq * (g->count + 1) * (dt + 4)));
         a.spill = g->spill.ptr;
@@ -2405,6 +2923,28 @@ static int hnsw_search_core(vsgpu_hnsw *g, const void *q, size_t nq, size_t q_st
             return (int)VSGPU_ERR_ARG;
         }
         a.cand_cap = cand_cap;
+        // top-k with ef <= 64: one warp per query (VSGPU_HNSW_CTA=1 forces the CTA-per-query kernel for A/B runs)
+        static const bool force_cta = getenv("VSGPU_HNSW_CTA") != nullptr;
+        if (!range && !with_spill && ef <= 64 && !force_cta && !a.profile) {
+            int sms = 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+            sms = std::max(sms, 1);
+            const int wq_cand = (int)(2 * ef + 64);
+            const size_t per_warp = wq_warp_bytes(dt, a.pivot_bytes, a.max_links, wq_cand);
+            // enough queries per CTA to fill the machine, few enough that every SM gets work at small batches
+            int wpc = (int)std::min<size_t>(WQ_MAX_WARPS, std::max<size_t>(1, (nq + 2 * (size_t)sms - 1) / (2 * (size_t)sms)));
+            while (wpc > 1 && (size_t)wpc * per_warp > limit / 2) wpc--;
+            if ((size_t)wpc * per_warp <= limit) {
+                SearchArgs w = a;
+                w.cand_cap = wq_cand;
+                auto kern = hnsw_search_warp_kernel<P>;
+                const size_t wsmem = (size_t)wpc * per_warp;
+                VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                kern<<<(unsigned)((nq + wpc - 1) / wpc), wpc * 32, wsmem, s->stream>>>(w, wpc, nq);
+                VS_CUDA(cudaGetLastError());
+                return (int)VSGPU_OK;
+            }
+        }
         if (range) {
             auto kern = hnsw_range_kernel<P>;
             VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2582,6 +3122,9 @@ struct vsgpu_hnsw_iter {
     size_t top_cap = 0;
     void *out = nullptr;
     size_t out_cap = 0;
+    uint32_t *returned = nullptr;        // multi-value: one bit per row whose label was handed out already (device)
+    std::vector<uint32_t> returned_host; // host mirror
+    bool returned_dirty = false;
 };
 
 static int iter_reset_state(vsgpu_hnsw_iter *it) {
@@ -2591,6 +3134,11 @@ static int iter_reset_state(vsgpu_hnsw_iter *it) {
     st.lower = std::numeric_limits<double>::infinity();
     VS_CUDA(cudaMemcpyAsync(it->state, &st, sizeof(st), cudaMemcpyHostToDevice, s->stream));
     VS_CUDA(cudaMemsetAsync(it->visited, 0, ((it->cap + 31) / 32) * 4, s->stream));
+    if (it->returned) {
+        VS_CUDA(cudaMemsetAsync(it->returned, 0, ((it->cap + 31) / 32) * 4, s->stream));
+        std::fill(it->returned_host.begin(), it->returned_host.end(), 0u);
+        it->returned_dirty = false;
+    }
     VS_CUDA(cudaStreamSynchronize(s->stream));
     return VSGPU_OK;
 }
@@ -2606,6 +3154,10 @@ vsgpu_hnsw_iter *vsgpu_hnsw_iter_create(vsgpu_hnsw *g, const void *query, size_t
     bool ok = cudaMalloc(&it->query, s->row_stride + 256) == cudaSuccess;
     ok = ok && cudaMalloc(&it->visited, ((it->cap + 31) / 32) * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&it->state, sizeof(BiState)) == cudaSuccess;
+    if (ok && g->multi) {
+        ok = cudaMalloc(&it->returned, ((it->cap + 31) / 32) * 4) == cudaSuccess;
+        it->returned_host.assign((it->cap + 31) / 32, 0u);
+    }
     ok = ok && cudaMalloc(&it->cand_d, (it->cap + 1) * dt) == cudaSuccess && cudaMalloc(&it->cand_id, (it->cap + 1) * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&it->extra_d, (it->cap + 1) * dt) == cudaSuccess && cudaMalloc(&it->extra_id, (it->cap + 1) * 4) == cudaSuccess;
     if (ok) {
@@ -2639,9 +3191,18 @@ void vsgpu_hnsw_iter_destroy(vsgpu_hnsw_iter *it) {
     cudaSetDevice(it->g->s->device);
     cudaStreamSynchronize(it->g->s->stream);
     for (void *p : {(void *)it->query, (void *)it->visited, (void *)it->state, it->cand_d, (void *)it->cand_id, it->extra_d,
-                    (void *)it->extra_id, it->top_d, (void *)it->top_id, it->out})
+                    (void *)it->extra_id, it->top_d, (void *)it->top_id, it->out, (void *)it->returned})
         if (p) cudaFree(p);
     delete it;
+}
+
+// multi-value graphs: rows (every row of every label the last batch returned) that later batches must skip
+int vsgpu_hnsw_iter_mark_returned(vsgpu_hnsw_iter *it, const uint32_t *ids, size_t n) {
+    if (!it->returned) return VSGPU_OK;
+    for (size_t i = 0; i < n; i++)
+        if (ids[i] < it->cap) it->returned_host[ids[i] >> 5] |= 1u << (ids[i] & 31);
+    it->returned_dirty = it->returned_dirty || n > 0;
+    return VSGPU_OK;
 }
 
 int vsgpu_hnsw_iter_reset(vsgpu_hnsw_iter *it) {
@@ -2704,6 +3265,12 @@ int vsgpu_hnsw_iter_next(vsgpu_hnsw_iter *it, size_t n_res, size_t label_count, 
     a.out_labels = d_lab;
     a.out_count = d_cnt;
     a.counters = g->counters;
+    a.multi = g->multi ? 1 : 0;
+    a.returned_bits = it->returned;
+    if (it->returned && it->returned_dirty) {
+        VS_CUDA(cudaMemcpyAsync(it->returned, it->returned_host.data(), it->returned_host.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        it->returned_dirty = false;
+    }
     VS_CUDA(cudaMemsetAsync(g->counters, 0, 128, s->stream));
     const int rc = dispatch_policy(s, [&]<class P>() -> int {
         a.pivot_bytes = P::pivot_bytes(s);

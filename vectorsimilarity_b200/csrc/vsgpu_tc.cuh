@@ -110,6 +110,18 @@ __device__ __forceinline__ void warp_append_hits(uint32_t hit, uint32_t q0, uint
     }
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, naming the registers a preceding tcgen05.ld fills as read-write operands: the compiler may otherwise move
+// plain reads of those registers above the wait (nothing else ties them to it) — seen as stale accumulators once two
+// loads were kept in flight.
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 
 // K-major, SWIZZLE_128B operand descriptor: rows at a 128-byte pitch, 8-row groups 1024 bytes apart
 // (SBO = 64 x 16 B), LBO unused (1), descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.

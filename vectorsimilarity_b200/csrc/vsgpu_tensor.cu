@@ -179,7 +179,7 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const uint32_t col = half * 128 + c * 32;
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
-                tc_wait_ld();
+                tc_wait_ld(r);
                 float thr[32];
                 lds_f32x32(smem_u32(&sm.athr[nt * BN + col]), thr);
                 if (g.dump) {
@@ -340,7 +340,7 @@ coarse_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 const uint32_t col = half * 128 + c * 32;
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
-                tc_wait_ld();
+                tc_wait_ld(r);
                 float thr[32];
                 lds_f32x32(smem_u32(&sm.athr[nt * BN + col]), thr);
                 if (g.dump) {

@@ -147,7 +147,7 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 const uint32_t col = half * 128 + c * 32;
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
-                tc_wait_ld();
+                tc_wait_ld(r);
                 float cq[32];
                 lds_f32x32(smem_u32(&sm.cq[nt * BN + col]), cq);
                 if (g.dump) {
@@ -295,7 +295,7 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const uint32_t col = half * 128 + c * 32;
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
-                tc_wait_ld();
+                tc_wait_ld(r);
                 float cq[32];
                 lds_f32x32(smem_u32(&sm.cq[nt * BN + col]), cq);
                 if (g.dump) {
@@ -578,7 +578,7 @@ static int env_flag(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 static bool i8_pair_enabled() {
-    static const bool on = env_flag("VSGPU_I8_PAIR", 1) != 0; // cta_group::2 by default (A/B: VSGPU_I8_PAIR=0)
+    static const bool on = env_flag("VSGPU_I8_PAIR", 0) != 0; // cta_group::2 variant: opt-in (measured slower)
     return on;
 }
 
