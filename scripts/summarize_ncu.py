@@ -29,6 +29,13 @@ KEYS = [
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "gpc__cycles_elapsed.max", "sm__cycles_active.avg",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_elapsed",
+    "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+    "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.sum.per_second",
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "smsp__mem_tensor_reads_op_ldt.sum",
 ]
 
 

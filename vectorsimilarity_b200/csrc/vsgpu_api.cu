@@ -266,6 +266,14 @@ static int topk_core(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stri
         return tensor_topk(s, q_dev, nq, q_stride, q_norms, k_eff, out_ids, out_scores, out_labels);
     }
     s->stats.path = 0;
+    // small batches on the staged scan: selection fused into the scan (per-CTA running top-k in shared memory) — no score
+    // matrix, 2 launches per pass of up to 8 queries instead of 1 + 13
+    if (fused_topk_supported(s, std::min<size_t>(nq, 8), k_eff) && nq <= 8) {
+        VS_CUDA(cudaEventRecord(s->ev2, s->stream));
+        VS_TRY(launch_fused_topk(s, q_dev, nq, q_stride, k_eff, out_ld, out_ids, out_scores, out_labels));
+        VS_CUDA(cudaEventRecord(s->ev3, s->stream));
+        return VSGPU_OK;
+    }
     // exact path: chunks of queries sized so the score matrix stays within ~1/16 of HBM or 2 GB
     const size_t ld = (n + 63) / 64 * 64;
     // one launch = one pass over the store for up to 16 queries (the kernel's register tile)

@@ -193,6 +193,68 @@ template <typename CT_, int G_, bool FTZ, bool L2, int ST> struct PolChain {
             out[r] = v;
         }
     }
+    // Whole hop for one warp (G == 32, plan without residual): out[j] = dist(row ids[j], pivot), j < n. Rows are taken eight at
+    // a time in 4-step slices, and the loads of slice i + 1 are issued BEFORE the FMAs of slice i: one memory round trip is
+    // always in flight behind the arithmetic (a single warp has nobody else to hide it). Chains, order and butterfly as above.
+    __device__ static void eval_rows_pipelined(const KCtx &k, const void *pv_, const uint32_t *ids, int n, DT *out, int lane) {
+        constexpr int NR = 8;
+        const DT *pv = (const DT *)pv_ + lane;
+        const int S = k.plan.S, chunks = (S + 3) / 4;
+        const int groups = (n + NR - 1) / NR, items = groups * chunks;
+        DT xa[NR][4], xb[NR][4];
+        auto load = [&](int item, DT (&x)[NR][4]) {
+            const int grp = item / chunks, s0 = (item % chunks) * 4;
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                const int j = grp * NR + r;
+                const uint8_t *row = k.rows + (size_t)(j < n ? ids[j] : ids[0]) * k.row_stride;
+#pragma unroll
+                for (int t = 0; t < 4; t++) x[r][t] = s0 + t < S ? load_st<ST, DT>(row, G * (s0 + t) + lane) : DT(0);
+            }
+        };
+        DT acc[NR];
+        auto compute = [&](int item, DT (&x)[NR][4]) {
+            const int grp = item / chunks, ch = item % chunks, s0 = ch * 4;
+            if (ch == 0) {
+#pragma unroll
+                for (int r = 0; r < NR; r++) acc[r] = DT(0);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (s0 + t < S) {
+                    const DT y = pv[(s0 + t) * G];
+#pragma unroll
+                    for (int r = 0; r < NR; r++) {
+                        if constexpr (L2) {
+                            const DT d = sub_rn(x[r][t], y);
+                            acc[r] = fma_step<FTZ>(d, d, acc[r]);
+                        } else {
+                            acc[r] = fma_step<FTZ>(x[r][t], y, acc[r]);
+                        }
+                    }
+                }
+            }
+            if (ch == chunks - 1) {
+#pragma unroll
+                for (int r = 0; r < NR; r++) {
+                    DT v = butterfly<DT, G>(acc[r]);
+                    if (!L2) v = sub_rn(DT(1), v);
+                    const int j = grp * NR + r;
+                    if (lane == 0 && j < n) out[j] = v;
+                }
+            }
+        };
+        if (items == 0) return;
+        load(0, xa);
+        for (int item = 0; item < items; item += 2) {
+            if (item + 1 < items) load(item + 1, xb);
+            compute(item, xa);
+            if (item + 1 < items) {
+                if (item + 2 < items) load(item + 2, xa);
+                compute(item + 1, xb);
+            }
+        }
+    }
     static constexpr bool HAS_FAST = true;
     // one thread evaluates a whole (row, row) pair: the G chain sums live in registers and are folded
     // with the same pairing tree as the warp butterfly (acc[c] + acc[c + w], w = G/2 .. 1). Used where
@@ -1224,7 +1286,10 @@ __device__ __forceinline__ int wq_gather(const KCtx &k, const GraphDev &g, const
         bool take = false;
         uint8_t del = 0;
         if (i < cnt) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(k.rows + (size_t)id * k.row_stride));
+            // every 128-byte line of the row (one prefetch fetches one line), capped at 2 KB per row
+            const uint8_t *rp = k.rows + (size_t)id * k.row_stride;
+            const int lines = (int)min((k.row_stride + 127) / 128, (size_t)16);
+            for (int l = 0; l < lines; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 128 * l));
             del = g.flags[id];
             take = vis ? !test_and_set(*vis, id) : true;
         }
@@ -1249,19 +1314,9 @@ template <class P> __device__ __forceinline__ void wq_eval(const KCtx &k, const 
     int base = 0;
     if constexpr (P::HAS_FAST && P::G == 32) {
         if (k.plan.kind == CK_LANES && k.plan.prefix == 0) {
-            constexpr int NR = 8;
-            for (; base + NR <= n || (base < n && n - base > 4); base += NR) {
-                uint32_t a[NR];
-#pragma unroll
-                for (int r = 0; r < NR; r++) a[r] = base + r < n ? w.nb_ids[base + r] : INV;
-                DT o[NR];
-                P::template dists_fast<NR>(k, w.pivot, a, c, o);
-                if (lane == 0) {
-#pragma unroll
-                    for (int r = 0; r < NR; r++)
-                        if (base + r < n) out[base + r] = o[r];
-                }
-            }
+            P::eval_rows_pipelined(k, w.pivot, w.nb_ids, n, out, lane);
+            __syncwarp();
+            return;
         }
     }
     constexpr int RU = P::RU;
@@ -1304,6 +1359,8 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_sea
     unsigned long long evals = 0, hops = 0;
     int count = 0;
     uint32_t status = 0;
+    long long prof[6] = {0, 0, 0, 0, 0, 0}; // VSGPU_HNSW_PROFILE cycles: gather, eval, admit, pop, bottom layer, descent
+    const long long tstart = a.profile ? clock64() : 0;
     const int ep0 = g.state[0], maxl = g.state[1];
     if (ep0 >= 0) {
         // ---- greedy descent to level 1 (searchBottomLayerEP, greedySearchLevel) ----
@@ -1354,6 +1411,9 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_sea
         }
         cand_n = 1;
         __syncwarp();
+        long long tpop = a.profile ? clock64() : 0;
+        const long long tbottom = tpop;
+        prof[5] = tpop - tstart;
         for (;;) {
             // pop the best candidate: maximum under pair(-dist, id)
             DT bd = DT(0);
@@ -1389,8 +1449,17 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_sea
             cand_n--;
             hops++;
             __syncwarp();
+            long long t0 = 0, t1 = 0, t2 = 0;
+            if (a.profile) t0 = clock64();
             const int n = wq_gather<DT>(k, g, w, bid, 0, &vis, lane);
+            if (a.profile) t1 = clock64();
             wq_eval<P>(k, w, n, lane);
+            if (a.profile) {
+                t2 = clock64();
+                prof[0] += t1 - t0;
+                prof[1] += t2 - t1;
+                prof[3] += t0 - tpop;
+            }
             evals += n;
             bool failed = false;
             for (int j0 = 0; j0 < n && !failed; j0 += 32) {
@@ -1459,7 +1528,13 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_sea
                 status = 1; // the host redoes this query on the CTA kernel with a spill area
                 break;
             }
+            if (a.profile) {
+                const long long t3 = clock64();
+                prof[2] += t3 - t2;
+                tpop = t3;
+            }
         }
+        if (a.profile) prof[4] = clock64() - tbottom;
         count = min(top.n, a.k_out);
         const size_t o0 = q * a.out_ld;
         if (lane < count) {
@@ -1485,6 +1560,10 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_sea
         if (a.counters) {
             atomicAdd(&a.counters[0], evals);
             atomicAdd(&a.counters[1], hops);
+            if (a.profile) {
+                for (int i = 0; i < 6; i++) atomicAdd(&a.counters[2 + i], (unsigned long long)prof[i]);
+                atomicMax(&a.counters[8], hops);
+            }
         }
     }
 }
@@ -2925,7 +3004,7 @@ static int hnsw_search_core(vsgpu_hnsw *g, const void *q, size_t nq, size_t q_st
         a.cand_cap = cand_cap;
         // top-k with ef <= 64: one warp per query (VSGPU_HNSW_CTA=1 forces the CTA-per-query kernel for A/B runs)
         static const bool force_cta = getenv("VSGPU_HNSW_CTA") != nullptr;
-        if (!range && !with_spill && ef <= 64 && !force_cta && !a.profile) {
+        if (!range && !with_spill && ef <= 64 && !force_cta) {
             int sms = 0;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
             sms = std::max(sms, 1);
@@ -2990,8 +3069,8 @@ int vsgpu_hnsw_topk_device(vsgpu_hnsw *g, const void *queries, size_t nq, size_t
     g->last_evals = ctr[0];
     g->last_hops = ctr[1];
     if (getenv("VSGPU_HNSW_PROFILE"))
-        fprintf(stderr, "[vsgpu_hnsw_topk] nq=%zu ms=%.3f evals=%llu hops=%llu max_hops=%llu cycles/query: gather=%llu eval=%llu admit=%llu bottom=%llu descent=%llu\n",
-                nq, g->last_ms, ctr[0], ctr[1], ctr[8], ctr[2] / nq, ctr[3] / nq, ctr[4] / nq, ctr[6] / nq, ctr[7] / nq);
+        fprintf(stderr, "[vsgpu_hnsw_topk] nq=%zu ms=%.3f evals=%llu hops=%llu max_hops=%llu cycles/query: gather=%llu eval=%llu admit=%llu pop=%llu bottom=%llu descent=%llu\n",
+                nq, g->last_ms, ctr[0], ctr[1], ctr[8], ctr[2] / nq, ctr[3] / nq, ctr[4] / nq, ctr[5] / nq, ctr[6] / nq, ctr[7] / nq);
     const size_t dt = s->type == VSGPU_FLOAT64 ? 8 : 4;
     for (size_t i = 0; i < nq; i++) {
         if (!st[i]) continue;

@@ -178,6 +178,10 @@ int launch_exact_gather(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_s
 // ---- staged streaming scan (vsgpu_scan.cu): fp32 / fp16 stores, dim % 32 == 0, <= 16 raw queries per pass ----
 bool tma_scan_supported(const vsgpu_store *s);
 int launch_tma_scan(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, void *scores, size_t ld);
+// scan + selection in one pass (per-CTA running top-k in shared memory + one merge launch): <= 8 queries, k <= 128
+bool fused_topk_supported(const vsgpu_store *s, size_t nq, size_t k);
+int launch_fused_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, size_t k, size_t out_ld, uint32_t *out_ids,
+                      void *out_scores, uint64_t *out_labels);
 
 // ---- selection (vsgpu_select.cu) ----
 // For each of nq score rows (DistType, length n, leading dim ld): the k smallest by (score, id),

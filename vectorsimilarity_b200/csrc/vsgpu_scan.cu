@@ -95,14 +95,48 @@ struct ScanTmaArgs {
     int nq;
     float *scores; // [nq][ld]
     size_t ld;
+    // fused selection (TOPK kernels): per-CTA running top-k in shared memory, only k (key, id) pairs per CTA and query leave
+    int k;          // <= FUSED_K_MAX
+    uint2 *part;    // [nq][gridDim.x][k] (score key, row id), ascending (key, id); unused slots carry id = 0xffffffff
 };
+
+// Fused top-k: the k best (score, id) pairs a CTA has seen per query live in shared memory; a row is appended only when it
+// beats the CTA's current k-th score, and the buffer is cut back to k by a block-wide bitonic sort whenever it fills
+// (a few times per CTA: the number of appends is ~ k (1 + ln(rows per CTA / k))).
+constexpr int FUSED_K_MAX = 128;
+constexpr int FUSED_CAP = 512;      // buffer entries per query
+constexpr int FUSED_CHECK_TILES = 4; // occupancy is checked every that many tiles (<= 64 appends per tile and query)
+
+__device__ __forceinline__ uint32_t score_key32(float v) { // order-preserving, NaN last (as vsgpu_select.cu)
+    const uint32_t u = __float_as_uint(v);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory"); }
+
+// sort buf[0 .. FUSED_CAP) ascending (entries are key << 32 | id; empty slots = ~0), consumer threads only
+__device__ __forceinline__ void fused_sort(unsigned long long *buf) {
+    for (int size = 2; size <= FUSED_CAP; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < FUSED_CAP / 2; t += CONSUMER_WARPS * 32) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const unsigned long long x = buf[lo], y = buf[hi];
+                if ((x > y) == asc) {
+                    buf[lo] = y;
+                    buf[hi] = x;
+                }
+            }
+            consumer_barrier();
+        }
+}
 
 template <typename ET> __device__ __forceinline__ float elem_to_float(ET v);
 template <> __device__ __forceinline__ float elem_to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float elem_to_float<__half>(__half v) { return __half2float(v); }
 
 // QP = query pairs per pass (2, 4 or 8)
-template <typename ET, int QP, bool L2>
+template <typename ET, int QP, bool L2, bool TOPK>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const __grid_constant__ CUtensorMap map, ScanTmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int QC = 2 * QP;
@@ -110,7 +144,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const __grid_
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MAX_STAGES;
     float2 *qs = reinterpret_cast<float2 *>(smem + 128);                           // [QP][dim]
-    unsigned char *stage0 = smem + 128 + (((size_t)QP * a.dim * sizeof(float2) + 127) / 128) * 128;
+    unsigned char *after_q = smem + 128 + (((size_t)QP * a.dim * sizeof(float2) + 127) / 128) * 128;
+    // TOPK: [QC] buffers of FUSED_CAP (key << 32 | id) entries, then per query the append cursor and the admission key
+    unsigned long long *tk_buf = reinterpret_cast<unsigned long long *>(after_q);
+    uint32_t *tk_cnt = reinterpret_cast<uint32_t *>(after_q + (size_t)QC * FUSED_CAP * 8);
+    uint32_t *tk_thr = tk_cnt + QC;
+    unsigned char *stage0 = TOPK ? after_q + (size_t)QC * FUSED_CAP * 8 + 128 : after_q;
     const size_t seg_bytes = (size_t)a.kc * sizeof(ET);
     const size_t stage_bytes = (size_t)TILE_ROWS * seg_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,6 +170,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const __grid_
         if (2 * p < a.nq) v.x = elem_to_float<ET>(reinterpret_cast<const ET *>(a.q + (size_t)(2 * p) * a.q_stride)[e]);
         if (2 * p + 1 < a.nq) v.y = elem_to_float<ET>(reinterpret_cast<const ET *>(a.q + (size_t)(2 * p + 1) * a.q_stride)[e]);
         qs[i] = v;
+    }
+    if constexpr (TOPK) {
+        for (int i = threadIdx.x; i < QC * FUSED_CAP; i += blockDim.x) tk_buf[i] = ~0ull;
+        if (threadIdx.x < QC) {
+            tk_cnt[threadIdx.x] = 0;
+            tk_thr[threadIdx.x] = 0xffffffffu; // admit everything until k rows are known
+        }
     }
     __syncthreads();
 
@@ -155,6 +201,26 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const __grid_
 
     // ---- consumers ----
     uint32_t it = 0;
+    // TOPK: cut query q's buffer back to its k best when it could overflow before the next check (block-uniform decision)
+    auto compact = [&](bool force) {
+        consumer_barrier(); // every append of the tiles so far is visible
+        for (int q = 0; q < a.nq; q++) {
+            const uint32_t c = tk_cnt[q];
+            if (!force && c <= (uint32_t)(FUSED_CAP - 64 * FUSED_CHECK_TILES)) continue;
+            unsigned long long *buf = tk_buf + (size_t)q * FUSED_CAP;
+            consumer_barrier();
+            fused_sort(buf);
+            const uint32_t keep = min(c, (uint32_t)a.k);
+            for (int i = (int)keep + threadIdx.x; i < FUSED_CAP; i += CONSUMER_WARPS * 32) buf[i] = ~0ull;
+            if (threadIdx.x == 0) {
+                tk_cnt[q] = keep;
+                // rows are visited in ascending id order within a CTA: a later row that only ties the k-th score loses
+                if (keep == (uint32_t)a.k) tk_thr[q] = (uint32_t)(buf[a.k - 1] >> 32);
+            }
+            consumer_barrier();
+        }
+    };
+    int tiles_done = 0;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         u64 acc[ROWS_PER_WARP][QP];
 #pragma unroll
@@ -215,13 +281,112 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_tma_kernel(const __grid_
         // lane L now holds value indices L * (V/32) + j: row L >> 2, queries (L & 3) * (QC/4) + j
         constexpr int PER = V / 32;
         const size_t row = tile * TILE_ROWS + (size_t)warp * ROWS_PER_WARP + (lane >> 2);
-        if (row < a.n) {
+        if constexpr (TOPK) {
+            if (row < a.n) {
 #pragma unroll
-            for (int j = 0; j < PER; j++) {
-                const int q = (lane & 3) * PER + j;
-                if (q < a.nq) a.scores[(size_t)q * a.ld + row] = L2 ? v[j] : __fsub_rn(1.0f, v[j]);
+                for (int j = 0; j < PER; j++) {
+                    const int q = (lane & 3) * PER + j;
+                    if (q < a.nq) {
+                        const uint32_t key = score_key32(L2 ? v[j] : __fsub_rn(1.0f, v[j]));
+                        if (key < tk_thr[q] || tk_thr[q] == 0xffffffffu) {
+                            const uint32_t slot = atomicAdd(&tk_cnt[q], 1u);
+                            if (slot < (uint32_t)FUSED_CAP) tk_buf[(size_t)q * FUSED_CAP + slot] = ((unsigned long long)key << 32) | (uint32_t)row;
+                        }
+                    }
+                }
+            }
+            if (++tiles_done % FUSED_CHECK_TILES == 0) compact(false);
+        } else {
+            if (row < a.n) {
+#pragma unroll
+                for (int j = 0; j < PER; j++) {
+                    const int q = (lane & 3) * PER + j;
+                    if (q < a.nq) a.scores[(size_t)q * a.ld + row] = L2 ? v[j] : __fsub_rn(1.0f, v[j]);
+                }
             }
         }
+    }
+    if constexpr (TOPK) {
+        compact(true);
+        for (int i = threadIdx.x; i < a.nq * a.k; i += CONSUMER_WARPS * 32) {
+            const int q = i / a.k, j = i % a.k;
+            const unsigned long long e = tk_buf[(size_t)q * FUSED_CAP + j];
+            a.part[((size_t)q * gridDim.x + blockIdx.x) * a.k + j] = make_uint2((uint32_t)(e >> 32), e == ~0ull ? 0xffffffffu : (uint32_t)e);
+        }
+    }
+}
+
+// Merge of the per-CTA lists (one block per query): the k-th best overall is no worse than any single CTA's k-th, so only
+// entries up to T = min over CTAs of their k-th key can matter; they are gathered into shared memory FUSED_MERGE_CAP at a
+// time, sorted by (key, id) and cut back to k — any number of ties at T is handled by repeating.
+constexpr int FUSED_MERGE_CAP = 2048;
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) fused_merge_kernel(const uint2 *__restrict__ part, int parts, int k, const uint64_t *__restrict__ labels,
+                                                              uint32_t out_ld, uint32_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                                                              uint64_t *__restrict__ out_labels) {
+    __shared__ unsigned long long buf[FUSED_MERGE_CAP];
+    __shared__ uint32_t s_T, s_n;
+    const int q = blockIdx.x;
+    const uint2 *mine = part + (size_t)q * parts * k;
+    if (threadIdx.x == 0) {
+        s_T = 0xffffffffu;
+        s_n = 0;
+    }
+    for (int i = threadIdx.x; i < FUSED_MERGE_CAP; i += THREADS) buf[i] = ~0ull;
+    __syncthreads();
+    for (int p = threadIdx.x; p < parts; p += THREADS) {
+        const uint2 last = mine[(size_t)p * k + (k - 1)];
+        if (last.y != 0xffffffffu) atomicMin(&s_T, last.x); // this CTA alone holds k rows at or below its k-th key
+    }
+    __syncthreads();
+    const uint32_t T = s_T;
+    const int total = parts * k;
+    auto sort_and_cut = [&]() {
+        for (int size = 2; size <= FUSED_MERGE_CAP; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < FUSED_MERGE_CAP / 2; t += THREADS) {
+                    const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                    const bool asc = (lo & size) == 0;
+                    const unsigned long long x = buf[lo], y = buf[hi];
+                    if ((x > y) == asc) {
+                        buf[lo] = y;
+                        buf[hi] = x;
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = k + threadIdx.x; i < FUSED_MERGE_CAP; i += THREADS) buf[i] = ~0ull;
+        if (threadIdx.x == 0) s_n = min(s_n, (uint32_t)k);
+        __syncthreads();
+    };
+    for (int base = 0; base < total; base += THREADS) {
+        const int i = base + threadIdx.x;
+        bool take = false;
+        uint2 e = make_uint2(0, 0);
+        if (i < total) {
+            e = mine[i];
+            take = e.y != 0xffffffffu && e.x <= T;
+        }
+        // room for a whole round of THREADS entries, else sort and cut first (block-uniform)
+        if (s_n + THREADS > FUSED_MERGE_CAP) sort_and_cut();
+        if (take) {
+            const uint32_t slot = atomicAdd(&s_n, 1u);
+            buf[slot] = ((unsigned long long)e.x << 32) | e.y;
+        }
+        __syncthreads();
+    }
+    sort_and_cut();
+    for (uint32_t i = threadIdx.x; i < out_ld; i += THREADS) {
+        const unsigned long long e = i < (uint32_t)k ? buf[i] : ~0ull;
+        const bool ok = e != ~0ull;
+        const uint32_t id = ok ? (uint32_t)e : 0xffffffffu, key = (uint32_t)(e >> 32);
+        if (out_ids) out_ids[(size_t)q * out_ld + i] = id;
+        if (out_scores) {
+            const float sc = !ok || key == 0xffffffffu ? __uint_as_float(0x7fc00000u)
+                                                       : __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+            out_scores[(size_t)q * out_ld + i] = sc;
+        }
+        if (out_labels) out_labels[(size_t)q * out_ld + i] = ok ? labels[id] : ~0ull;
     }
 }
 
@@ -249,7 +414,7 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <typename ET, bool L2> int launch_t(vsgpu_store *s, ScanTmaArgs &a, size_t smem_bytes) {
+template <typename ET, bool L2, bool TOPK = false> int launch_t(vsgpu_store *s, ScanTmaArgs &a, size_t smem_bytes, unsigned grid = 0) {
     CUtensorMap map;
     {
         cuuint64_t gdim[2] = {(cuuint64_t)a.dim, (cuuint64_t)a.n};
@@ -267,14 +432,21 @@ template <typename ET, bool L2> int launch_t(vsgpu_store *s, ScanTmaArgs &a, siz
     }
 #define VS_LAUNCH_TMA(QPV)                                                                                             \
     do {                                                                                                               \
-        auto kern = scan_tma_kernel<ET, QPV, L2>;                                                                      \
+        auto kern = scan_tma_kernel<ET, QPV, L2, TOPK>;                                                                \
         VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));             \
-        kern<<<(unsigned)std::min<size_t>((size_t)sm_count(s->device), (a.n + TILE_ROWS - 1) / TILE_ROWS), SCAN_THREADS, \
-               smem_bytes, s->stream>>>(map, a);                                                                            \
+        kern<<<grid ? grid : (unsigned)std::min<size_t>((size_t)sm_count(s->device), (a.n + TILE_ROWS - 1) / TILE_ROWS), \
+               SCAN_THREADS, smem_bytes, s->stream>>>(map, a);                                                              \
     } while (0)
     if (a.nq <= 4) VS_LAUNCH_TMA(2);
     else if (a.nq <= 8) VS_LAUNCH_TMA(4);
-    else VS_LAUNCH_TMA(8);
+    else {
+        if constexpr (TOPK) {
+            set_error("fused scan: at most 8 queries per pass");
+            return VSGPU_ERR_ARG;
+        } else {
+            VS_LAUNCH_TMA(8);
+        }
+    }
 #undef VS_LAUNCH_TMA
     VS_CUDA(cudaGetLastError());
     s->stats.kernel_launches++;
@@ -288,6 +460,81 @@ bool tma_scan_supported(const vsgpu_store *s) {
     if (p.kind != CK_LANES || p.G != 32 || p.prefix != 0) return false;
     if (s->type != VSGPU_FLOAT32 && s->type != VSGPU_FLOAT16) return false;
     return s->dim % 32 == 0 && s->dim <= 4096 && encode_fn() != nullptr;
+}
+
+// stage geometry of the staged scan for `qp` query pairs; `extra` bytes of shared memory are taken by the caller
+static bool scan_geometry(const vsgpu_store *s, int qp, size_t extra, int *kc_out, int *nst_out, size_t *smem_out) {
+    const int dim = (int)s->dim;
+    const size_t esz = s->elem;
+    const size_t q_bytes = (((size_t)qp * dim * sizeof(float2) + 127) / 128) * 128;
+    int dev_smem = 0;
+    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device) != cudaSuccess || dev_smem <= 0)
+        dev_smem = 227 * 1024;
+    if ((size_t)dev_smem < 128 + q_bytes + 1024 + extra + 3 * (size_t)TILE_ROWS * 32 * esz) return false;
+    const size_t budget = (size_t)dev_smem - 128 - q_bytes - 1024 - extra;
+    int kc = 0, nst = 0;
+    for (int c = std::min(dim, 256); c >= 32; c -= 32) {
+        if (dim % c) continue;
+        const size_t stage = (size_t)TILE_ROWS * c * esz;
+        const int n = (int)std::min<size_t>(budget / stage, MAX_STAGES);
+        if (n >= 3) {
+            kc = c;
+            nst = n;
+            break;
+        }
+    }
+    if (!kc) return false;
+    nst = std::min(nst, 6);
+    *kc_out = kc;
+    *nst_out = nst;
+    *smem_out = 128 + q_bytes + extra + (size_t)nst * TILE_ROWS * kc * esz;
+    return true;
+}
+
+// Scan + selection in one pass (north star: "only K scores ever leave the SM"): the k best (score, id) of up to 8 queries,
+// ascending, into out_* ([nq][out_ld]). Two launches: the staged scan with a per-CTA running top-k, and the merge.
+bool fused_topk_supported(const vsgpu_store *s, size_t nq, size_t k) {
+    static const bool off = getenv("VSGPU_NO_FUSED_TOPK") != nullptr; // A/B switch
+    return !off && tma_scan_supported(s) && nq >= 1 && nq <= 8 && k >= 1 && k <= (size_t)FUSED_K_MAX && k <= s->count;
+}
+
+int launch_fused_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, size_t k, size_t out_ld, uint32_t *out_ids,
+                      void *out_scores, uint64_t *out_labels) {
+    const int qp = nq <= 4 ? 2 : 4;
+    const size_t extra = (size_t)(2 * qp) * FUSED_CAP * 8 + 128;
+    int kc = 0, nst = 0;
+    size_t smem_bytes = 0;
+    if (!scan_geometry(s, qp, extra, &kc, &nst, &smem_bytes)) {
+        set_error("launch_fused_topk: dimension too large for the staged scan");
+        return VSGPU_ERR_ARG;
+    }
+    const size_t ntiles = (s->count + TILE_ROWS - 1) / TILE_ROWS;
+    // short stores: fewer CTAs than SMs would each hold a whole list of k; keep >= 2 k rows per CTA so the lists stay useful
+    unsigned grid = (unsigned)std::min<size_t>((size_t)sm_count(s->device), ntiles);
+    grid = (unsigned)std::max<size_t>(1, std::min<size_t>(grid, s->count / std::max<size_t>(2 * k, 64) + 1));
+    VS_TRY(ensure_scratch(s, s->sel_state, nq * (size_t)grid * k * sizeof(uint2) + 256));
+    ScanTmaArgs a{};
+    a.rows = s->rows;
+    a.row_stride = s->row_stride;
+    a.n = s->count;
+    a.dim = (int)s->dim;
+    a.kc = kc;
+    a.nstages = nst;
+    a.q = (const uint8_t *)q_dev;
+    a.q_stride = q_stride;
+    a.nq = (int)nq;
+    a.k = (int)k;
+    a.part = (uint2 *)s->sel_state.ptr;
+    const bool l2 = s->plan.is_l2;
+    int rc;
+    if (s->type == VSGPU_FLOAT32) rc = l2 ? launch_t<float, true, true>(s, a, smem_bytes, grid) : launch_t<float, false, true>(s, a, smem_bytes, grid);
+    else rc = l2 ? launch_t<__half, true, true>(s, a, smem_bytes, grid) : launch_t<__half, false, true>(s, a, smem_bytes, grid);
+    VS_TRY(rc);
+    fused_merge_kernel<256><<<(unsigned)nq, 256, 0, s->stream>>>(a.part, (int)grid, (int)k, s->labels, (uint32_t)out_ld, out_ids,
+                                                                (float *)out_scores, out_labels);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
 }
 
 // scores[q * ld + id] for up to 16 queries (raw blobs on the device)

@@ -163,15 +163,28 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         const uint32_t quad = (uint32_t)(warp & 3);       // TMEM lane quadrant this warp may read
         const uint32_t half = (uint32_t)(ew >> 2);         // which 128 of the 256 columns
         uint32_t as = 0, aphase = 0;
+        // the per-row terms of the NEXT tile are fetched while this one is filtered (no global load in front of a tile's
+        // first compare)
+        auto row_terms = [&](uint32_t item, float &nr_o, float &sub_o) {
+            const uint32_t r = g.row0 + (item / g.n_qtiles) * BM + quad * 32 + (uint32_t)lane;
+            const bool ok = item < items && r < g.row_end;
+            nr_o = (ok && g.row_l2) ? __ldg(g.row_l2 + r) : 0.f;
+            sub_o = 0.f;
+            if constexpr (SUB) sub_o = ok ? __ldg(g.row_sub + r) : 0.f;
+        };
+        float nr_n, sub_n;
+        row_terms(blockIdx.x, nr_n, sub_n);
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
             const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
             const uint32_t row = g.row0 + mt * BM + quad * 32 + (uint32_t)lane;
             const bool row_ok = row < g.row_end;
-            const float nr = (row_ok && g.row_l2) ? g.row_l2[row] : 0.f;
+            const float nr = nr_n, sub = sub_n;
+            row_terms(item + gridDim.x, nr_n, sub_n);
             float ra = 0.f;
             // L2: what is filtered (and stored) is a'' = a.q - ||a||^2 / 2 + c_l2 ||a||^2 — the row's own share of the L2
             // rounding term rides on the per-row constant, so it costs nothing per accumulator (rounded so a'' errs upwards)
-            if constexpr (SUB) ra = row_ok ? __fmaf_rd(__fmul_ru(g.c_l2, nr), -nr, g.row_sub[row]) : 0.f;
+            if constexpr (SUB) ra = row_ok ? __fmaf_rd(__fmul_ru(g.c_l2, nr), -nr, sub) : 0.f;
+            (void)sub;
             mbar_wait(&sm.tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1

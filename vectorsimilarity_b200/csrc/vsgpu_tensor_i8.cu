@@ -31,7 +31,11 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BKB; // 16 KB
 constexpr int B_BYTES = BN * BKB; // 32 KB
 constexpr int MAX_NQ = 4096;
-constexpr int EPI_WARPS = 8;
+// 16 epilogue warps (four per TMEM lane quadrant, 64 accumulator columns each): with 8 the epilogue — TMEM load latency,
+// I2F + FFMA + FSETP per accumulator, the append's atomic round trip — was the critical path at two warps per scheduler
+// (13.6 ms against 9.2 ms with the epilogue compiled out, profiles/r2_i8_epilogue_ab.md)
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_COLS = 4 * 256 / EPI_WARPS; // accumulator columns per epilogue warp
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t CAND_CAP = 3072; // candidates per query and phase
 constexpr uint32_t RUN_CAP = 1024;  // k <= RUN_CAP
@@ -129,22 +133,32 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // ===== epilogue: TMEM int32 -> bound test -> (row, dot) candidates =====
         const int ew = warp - 4;
         const uint32_t quad = (uint32_t)(warp & 3);
-        const uint32_t half = (uint32_t)(ew >> 2);
+        const uint32_t half = (uint32_t)(ew >> 2); // which EPI_COLS-wide slice of the 256 columns
         uint32_t as = 0, aphase = 0;
+        // the per-row terms of the NEXT tile are fetched while this one is tested: a global load in front of every tile's
+        // first compare was ~a fifth of the tile time (long-scoreboard stalls, profiles/r2_i8_gemm_ncu.md)
+        auto row_terms = [&](uint32_t item, float &rm_o, float &ra_o) {
+            const uint32_t r = g.row0 + (item / g.n_qtiles) * BM + quad * 32 + (uint32_t)lane;
+            const bool ok = item < items && r < g.row_end;
+            rm_o = (ok && g.row_mul) ? __ldg(g.row_mul + r) : 1.0f;
+            ra_o = (ok && g.row_add) ? __ldg(g.row_add + r) : 0.0f;
+        };
+        float rm_n, ra_n;
+        row_terms(blockIdx.x, rm_n, ra_n);
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
             const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
             const uint32_t row = g.row0 + mt * BM + quad * 32 + (uint32_t)lane;
             const bool row_ok = row < g.row_end;
             // admit when float(dot) >= c_q * rm + ra2: c_q arrives already lowered by the merge kernel, ra2 is the
             // row's additive term lowered by a few ulps and two dot units (the admitted set must be a superset)
-            const float rm = (row_ok && g.row_mul) ? g.row_mul[row] : 1.0f;
-            const float ra = (row_ok && g.row_add) ? g.row_add[row] : 0.0f;
+            const float rm = rm_n, ra = ra_n;
+            row_terms(item + gridDim.x, rm_n, ra_n);
             const float ra2 = ra - fabsf(ra) * 3.8146973e-6f - 2.0f;
             mbar_wait(&sm.tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1
-            for (uint32_t c = 0; c < 4; c++) {
-                const uint32_t col = half * 128 + c * 32;
+            for (uint32_t c = 0; c < EPI_COLS / 32; c++) {
+                const uint32_t col = half * EPI_COLS + c * 32;
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
                 tc_wait_ld(r);
@@ -158,7 +172,7 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             if (q < g.nq) g.dump[(size_t)(row - g.row0) * g.dump_ld + q] = (int)r[j];
                         }
                     }
-                } else if (g.mma_only) {
+                } else if (g.mma_only == 1) {
                     uint32_t x = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) x ^= r[j];
@@ -169,7 +183,11 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     uint32_t hit = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) hit |= (__int2float_rn((int)r[j]) >= fmaf(cq[j], rm, ra2) ? 1u : 0u) << j;
-                    warp_append_hits(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane, CAND_CAP);
+                    if (g.mma_only == 2) { // measurement: the test without the append
+                        if (hit == 0xdeadbeefu && cq[0] == 12345.f) g.cnt[0] = hit;
+                    } else {
+                        warp_append_hits(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane, CAND_CAP);
+                    }
                 }
             }
             tc_fence_before();
@@ -291,8 +309,8 @@ i8_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_wait(&sm.tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1
-            for (uint32_t c = 0; c < 4; c++) {
-                const uint32_t col = half * 128 + c * 32;
+            for (uint32_t c = 0; c < EPI_COLS / 32; c++) {
+                const uint32_t col = half * EPI_COLS + c * 32;
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
                 tc_wait_ld(r);
