@@ -286,7 +286,7 @@ class FlatRun:
             index.finish()
         self.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches, cands, fallbacks, path, scan_ms = 0, 0, 0, 0, []
+        launches, cands, fallbacks, path, scan_ms, local_ms = 0, 0, 0, 0, [], []
         self.barrier()
         t0 = time.perf_counter()
         ev0.record(st)
@@ -299,6 +299,7 @@ class FlatRun:
             fallbacks += s["fallback_queries"]
             path = s["path"]
             scan_ms.append(s["scan_ms"])
+            local_ms.append(s["total_ms"])
         ev1.record(st)
         self.barrier()
         wall = time.perf_counter() - t0
@@ -307,7 +308,8 @@ class FlatRun:
             self.env["dist"].all_reduce(t, op=self.env["dist"].ReduceOp.MAX)
         ms = float(t.item()) / steps
         return {"ms_per_step": ms, "qps": self.batch / (ms / 1e3), "launches": launches, "candidates": cands,
-                "fallbacks": fallbacks, "path": path, "scan_ms": float(np.mean(scan_ms)) if scan_ms else 0.0, "wall": wall}
+                "fallbacks": fallbacks, "path": path, "scan_ms": float(np.mean(scan_ms)) if scan_ms else 0.0,
+                "local_ms": float(np.mean(local_ms)) if local_ms else 0.0, "wall": wall}
 
     def time_e2e(self, steps, warmup, mode):
         """The same steps through the reference-facing call with HOST buffers (H2D of the queries and D2H of the reply
@@ -419,6 +421,67 @@ def sub_config(env, wl_name, rows_total, steps, warmup, mode, peaks, e2e=True):
         out.update(r.bounds(res["ms_per_step"], peaks))
     r.close()
     return out
+
+
+def single_process_sharded(env, wl_name, n_total, steps, warmup, mode):
+    """The same workload through the sharding INSIDE the C library (VecSimGPU_Configure + VecSimIndex_New(VecSimAlgo_BF),
+    one process driving every GPU of the box; csrc/host/vecsim_flat_sharded.cpp): what RediSearch gets by linking
+    libvecsim_b200.so. Runs on rank 0 only, after the SPMD measurement, with HOST query / result buffers
+    (VecSimIndex_TopKQueryBatchRaw: H2D to every device, per-shard scan, peer-copy gather, merge on device 0, D2H)."""
+    torch, capi = env["torch"], env["capi"]
+    tname, mname, _, dim, k, batch = WORKLOADS[wl_name]
+    ndev = env["world"]
+    capi.configure_devices(list(range(ndev)))
+    capi.set_topk_mode(mode)
+    try:
+        G = capi.BFIndex(capi.BFParams(type=TYPE_ID[tname], dim=dim, metric=METRIC_ID[mname], multi=False, initialCapacity=n_total,
+                                       blockSize=1024))
+        assert G.shard_count() == ndev
+        t0 = time.perf_counter()
+        for d in range(ndev):
+            lo, hi = env["sharded"].shard_bounds(n_total, ndev, d)
+            dev = torch.device("cuda", d)
+            row = lo
+            while row < hi:
+                c = row // CHUNK
+                x = gen_chunk_torch(torch, tname, c, CHUNK, dim, dev)
+                a, b = row - c * CHUNK, min(hi - c * CHUNK, CHUNK)
+                part = x[a:b].contiguous()
+                torch.cuda.synchronize(dev)
+                assert G.add_device_rows(part.data_ptr(), part.stride(0) * part.element_size(), b - a, row) == b - a
+                row = c * CHUNK + b
+                del x, part
+        ingest_s = time.perf_counter() - t0
+        assert G.index_size() == n_total
+        Q = gen_queries_numpy(tname, batch, dim)
+        labels_out = np.empty((batch, k), dtype=np.uint64)
+        scores_out = np.empty((batch, k), dtype=np.float64)
+        L = capi.lib()
+
+        def step():
+            rc = L.VecSimIndex_TopKQueryBatchRaw(G._h, Q.ctypes.data, batch, k, None, labels_out.ctypes.data, scores_out.ctypes.data)
+            assert rc == 0, L.VecSimGPU_LastError()
+
+        for _ in range(max(warmup, 1)):
+            step()
+        dev_ms = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+            dev_ms.append(G.last_query_stats()["total_ms"])
+        secs = time.perf_counter() - t0
+        st = G.last_query_stats()
+        out = {"devices": ndev, "rows": n_total, "batch": batch, "k": k,
+               "e2e": {"value": batch * steps / secs, "unit": "queries/s", "h2d_bytes_per_step": int(Q.nbytes) * ndev,
+                       "d2h_bytes_per_step": int(batch * k * 12)},
+               "device_ms_per_step": float(np.mean(dev_ms)), "value": batch / (float(np.mean(dev_ms)) / 1e3) if np.mean(dev_ms) > 0 else None,
+               "path": "tensor coarse + exact re-rank" if st["path"] == 1 else "exact scan", "gpu_launches": st["kernel_launches"] * steps,
+               "fallback_queries": st["fallback_queries"], "ingest_s": round(ingest_s, 2),
+               "how": "one process, one host thread + stream per GPU, peer-copy gather of packed per-shard top-K, merge on device 0"}
+        G.close()
+        return out
+    finally:
+        capi.set_device(env["device"].index)
 
 
 def cfg1_latency(env):
@@ -602,6 +665,19 @@ def main():
             guarded("cfg5_hnsw_fp32_l2_1M", lambda: cfg5_hnsw(env, max(5, args.steps), 3))
             guarded("cfg1_flat_fp32_l2_100k_single_query", lambda: cfg1_latency(env))
 
+    # ---- N > 1: the sharding inside the C library, one process over all the GPUs (rank 0; the other ranks wait on the CPU) ----
+    single = None
+    if world > 1 and args.extras != "none" and tname != "fp64":
+        cpu_group = dist.new_group(backend="gloo")
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                single = single_process_sharded(env, args.workload, n_total, max(3, min(args.steps, 10)), 3, args.mode)
+            except Exception as e:
+                single = {"error": repr(e)}
+        dist.barrier(group=cpu_group)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": res["qps"], "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -615,7 +691,9 @@ def main():
             "e2e": e2e, "gpu_launches": int(res["launches"]), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
             "hbm_fraction": frac["hbm_fraction"], "tensor_fraction": frac["tensor_fraction"],
             "candidates_per_query": res["candidates"] / max(1, args.steps * batch), "fallback_queries": res["fallbacks"],
-            "wall_s_timed_region": res["wall"], "sweep": sweep, "configs": configs,
+            "step_breakdown_ms": {"dominant_kernel": res["scan_ms"], "local_topk_all_kernels": res["local_ms"],
+                                  "gather_merge_sync": max(0.0, res["ms_per_step"] - res["local_ms"]), "step": res["ms_per_step"]},
+            "wall_s_timed_region": res["wall"], "sweep": sweep, "configs": configs, "single_process": single,
         }
         print(json.dumps(line))
     if world > 1:

@@ -50,7 +50,8 @@ enum {
 
 typedef struct vsgpu_store vsgpu_store;
 
-const char *vsgpu_last_error(void);
+const char *vsgpu_last_error(void); /* per calling thread */
+void vsgpu_set_last_error(const char *msg); /* hand an error text from a worker thread to the thread that reports it */
 int vsgpu_device_count(void);
 /* free / total bytes of HBM on `device` */
 int vsgpu_mem_info(int device, size_t *free_bytes, size_t *total_bytes);
@@ -92,8 +93,18 @@ int vsgpu_topk(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, s
  * enqueued on the store's stream; call vsgpu_store_sync before reading. */
 int vsgpu_topk_device(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k,
                       unsigned flags, uint64_t *out_labels, void *out_scores, uint32_t *out_ids);
+/* Two-step variant for sharded callers: _begin stops a tensor-path call after the coarse phases and writes each query's
+ * admission bound to bound_out ([nq] fp32, DEVICE; -inf when the call already did all its work). The caller reduces the
+ * bounds over the shards (max — every shard's bound is a valid lower bound of the global k-th score) and hands the result
+ * to _finish, which drops the survivors below it before the exact re-rank. Same outputs as vsgpu_topk_device. */
+int vsgpu_topk_device_begin(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k, unsigned flags,
+                            uint64_t *out_labels, void *out_scores, uint32_t *out_ids, float *bound_out);
+int vsgpu_topk_device_finish(vsgpu_store *s, const float *bound_in);
 int vsgpu_store_sync(vsgpu_store *s);
 void *vsgpu_store_stream(vsgpu_store *s); /* cudaStream_t */
+/* Run the store's work on a stream of the caller's (a framework's pooled stream, say) from now on; the store never
+ * destroys it, and it must outlive the store. */
+int vsgpu_store_set_stream(vsgpu_store *s, void *stream);
 
 /* Range scan for ONE query: every row with score <= radius (already cast to the DistType by the
  * caller). Unordered. Returns VSGPU_ERR_OVERFLOW and sets *out_count to the needed capacity when

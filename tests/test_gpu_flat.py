@@ -342,3 +342,43 @@ def test_debug_info_iterator_flat(capi):
     out = C.POINTER(C.POINTER(C.c_int))()
     assert rc(G._h, 0, C.byref(out)) == 1
     G.close()
+
+
+def test_concurrent_single_query_callers_are_combined(capi, port):
+    """SURVEY §8b "Threading": RediSearch calls VecSimIndex_TopKQuery from its worker threads concurrently. Callers that
+    arrive while a device call is running are served together by the next one (flat combining in FlatIndex::topKQuery);
+    every caller gets exactly the reply it would get alone — also with different k per caller."""
+    import threading
+    n, dim = 30000, 64
+    X = make_vectors(0, n, dim, seed=71)
+    Q = make_vectors(0, 64, dim, seed=72)
+    G = capi.BFIndex(capi.BFParams(type=0, dim=dim, metric=0, multi=False, initialCapacity=n, blockSize=1024))
+    G.add_vectors(X)
+    P = port.PortIndex(0, dim, 0)
+    P.add_many(X)
+    want = {}
+    for i in range(len(Q)):
+        k = 5 + (i % 4) * 7
+        l, s, _ = P.topk(Q[i], k)
+        want[i] = (l.astype(np.int64), s)
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(6):
+                for i in range(t, len(Q), 8):
+                    k = 5 + (i % 4) * 7
+                    l, s = G.knn_query(Q[i], k)
+                    if not (np.array_equal(l[0], want[i][0]) and np.array_equal(s[0], want[i][1])):
+                        errors.append((t, i))
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
+    G.close()
+    P.close()

@@ -392,20 +392,71 @@ VecSimQueryReply *FlatIndex::topKQuery(const void *blob, size_t k, VecSimQueryPa
         last_mode_ = STANDARD_KNN;
         return rep;
     }
-    const size_t cap = std::min(k, indexSize());
-    std::vector<size_t> labels(std::max<size_t>(cap, 1));
-    std::vector<double> scores(std::max<size_t>(cap, 1));
-    uint32_t cnt = 0;
-    if (cap == 0) {
+    if (indexSize() == 0) {
         last_mode_ = STANDARD_KNN;
         if (timed_out(qp ? qp->timeoutCtx : nullptr)) rep->code = VecSim_QueryReply_TimedOut;
         return rep;
     }
-    const int rc = topKBatch(blob, 1, cap, qp, labels.data(), scores.data(), &cnt);
-    if (rc == 1) rep->code = VecSim_QueryReply_TimedOut;
-    if (rc != 0) return rep;
-    rep->results.resize(cnt);
-    for (uint32_t i = 0; i < cnt; i++) rep->results[i] = {labels[i], scores[i]};
+    auto run_one = [&](const void *b, size_t kk, VecSimQueryParams *p, VecSimQueryReply *out) {
+        const size_t cap = std::min(kk, indexSize());
+        if (cap == 0) return;
+        std::vector<size_t> labels(cap);
+        std::vector<double> scores(cap);
+        uint32_t cnt = 0;
+        const int rc = topKBatch(b, 1, cap, p, labels.data(), scores.data(), &cnt);
+        if (rc == 1) out->code = VecSim_QueryReply_TimedOut;
+        if (rc != 0) return;
+        out->results.resize(cnt);
+        for (uint32_t i = 0; i < cnt; i++) out->results[i] = {labels[i], scores[i]};
+    };
+    if (qp && qp->timeoutCtx) { // a caller with its own timeout context is served on its own
+        run_one(blob, k, qp, rep);
+        return rep;
+    }
+    // Flat combining: whoever finds no leader becomes one and serves every query that is waiting — its own included — as ONE
+    // batched device call; callers that arrive while that call runs wait and are served by the next round. A lone caller pays
+    // nothing; N concurrent callers share one pass over the store instead of queueing N passes behind the index mutex.
+    PendingQuery me{blob, k, rep};
+    std::unique_lock<std::mutex> ql(q_mu_);
+    q_wait_.push_back(&me);
+    if (q_leader_) {
+        q_cv_.wait(ql, [&] { return me.done || !q_leader_; });
+        if (me.done) return rep;
+    }
+    q_leader_ = true;
+    while (!q_wait_.empty()) {
+        std::vector<PendingQuery *> batch;
+        batch.swap(q_wait_);
+        ql.unlock();
+        if (batch.size() == 1) {
+            run_one(batch[0]->blob, batch[0]->k, nullptr, batch[0]->rep);
+        } else {
+            size_t kmax = 0;
+            for (PendingQuery *p : batch) kmax = std::max(kmax, p->k);
+            kmax = std::min(kmax, indexSize());
+            const size_t nq = batch.size();
+            std::vector<uint8_t> qbuf(nq * data_size_);
+            for (size_t i = 0; i < nq; i++) std::memcpy(qbuf.data() + i * data_size_, batch[i]->blob, data_size_);
+            std::vector<size_t> labels(nq * std::max<size_t>(kmax, 1));
+            std::vector<double> scores(nq * std::max<size_t>(kmax, 1));
+            std::vector<uint32_t> cnt(nq, 0);
+            const int rc = kmax ? topKBatch(qbuf.data(), nq, kmax, nullptr, labels.data(), scores.data(), cnt.data()) : 0;
+            for (size_t i = 0; i < nq; i++) {
+                if (rc != 0) continue;
+                // the k best of a query are a prefix of its kmax best (same total order)
+                const size_t take = std::min<size_t>(std::min<size_t>(cnt[i], batch[i]->k), kmax);
+                batch[i]->rep->results.resize(take);
+                for (size_t j = 0; j < take; j++) batch[i]->rep->results[j] = {labels[i * kmax + j], scores[i * kmax + j]};
+            }
+        }
+        ql.lock();
+        combined_batches_++;
+        combined_queries_ += batch.size();
+        for (PendingQuery *p : batch) p->done = true;
+        q_cv_.notify_all();
+    }
+    q_leader_ = false;
+    q_cv_.notify_all(); // a caller that slipped in after the last swap takes over as leader
     return rep;
 }
 

@@ -208,10 +208,21 @@ int ShardedFlatIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSim
         }
         if (vsgpu_group_topk_begin(group_, qbuf.data(), nq, stored_size_, k) != VSGPU_OK) return -1;
         std::vector<int> rcs(shards_.size(), 0);
+        std::vector<std::string> errs(shards_.size());
         const unsigned mode = (unsigned)globals().topk_mode;
-        workers_->run([&](size_t sh) { rcs[sh] = vsgpu_group_topk_shard(group_, sh, nq, k, mode, 0); });
-        for (int rc : rcs)
-            if (rc != VSGPU_OK) return -1;
+        auto failed = [&]() { // error texts are per thread in libvsgpu: carry the first one over to the caller's thread
+            for (size_t sh = 0; sh < rcs.size(); sh++)
+                if (rcs[sh] != VSGPU_OK) {
+                    vsgpu_set_last_error(("shard " + std::to_string(sh) + ": " + errs[sh]).c_str());
+                    return true;
+                }
+            return false;
+        };
+        workers_->run([&](size_t sh) {
+            rcs[sh] = vsgpu_group_topk_shard(group_, sh, nq, k, mode, 0);
+            if (rcs[sh] != VSGPU_OK) errs[sh] = vsgpu_last_error();
+        });
+        if (failed()) return -1;
         std::vector<uint64_t> lab(nq * k);
         std::vector<double> sc(nq * k);
         int rc = vsgpu_group_topk_finish(group_, nq, k, lab.data(), sc.data());
@@ -220,9 +231,9 @@ int ShardedFlatIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSim
             workers_->run([&](size_t sh) {
                 rcs[sh] = vsgpu_store_sync(shards_[sh]->deviceStore());
                 if (rcs[sh] == VSGPU_OK) rcs[sh] = vsgpu_group_topk_shard(group_, sh, nq, k, mode, 1);
+                if (rcs[sh] != VSGPU_OK) errs[sh] = vsgpu_last_error();
             });
-            for (int r2 : rcs)
-                if (r2 != VSGPU_OK) return -1;
+            if (failed()) return -1;
             rc = vsgpu_group_topk_finish(group_, nq, k, lab.data(), sc.data());
             if (rc == 1) rc = VSGPU_OK; // flags are sticky for the batch; the lists are exact now
         } else {

@@ -9,6 +9,7 @@
 #include <functional>
 #include <memory>
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <shared_mutex>
 #include <random>
@@ -158,6 +159,13 @@ class FlatIndex final : public VecSimIndexInterface {
     vsgpu_store *deviceStore() override;
     void lastStats(vsgpu_stats *out) override;
 
+    // batches formed out of concurrent single-query calls so far, and the queries they carried (see topKQuery)
+    void combinerStats(size_t *batches, size_t *queries) {
+        std::lock_guard<std::mutex> g(q_mu_);
+        *batches = combined_batches_;
+        *queries = combined_queries_;
+    }
+
     // resolves the reference's admission/tie rule for one query from the
     // (score, id)-ordered candidates the device returned
     static void resolve(const size_t *labels, const double *scores, const uint32_t *ids, size_t cnt, size_t k,
@@ -189,6 +197,19 @@ class FlatIndex final : public VecSimIndexInterface {
     hvec<uint64_t> pending_labels_;
     VecSearchMode last_mode_ = EMPTY_MODE;
     std::mutex mu_;
+    // Concurrent single-query callers (RediSearch's worker threads, vec_sim.h:147-148) are combined: the first caller to
+    // arrive runs the device call for everybody who queued up meanwhile, as one batch (SURVEY §8b "Threading")
+    struct PendingQuery {
+        const void *blob;
+        size_t k;
+        VecSimQueryReply *rep;
+        bool done = false;
+    };
+    std::mutex q_mu_;
+    std::condition_variable q_cv_;
+    std::vector<PendingQuery *> q_wait_;
+    bool q_leader_ = false;
+    size_t combined_batches_ = 0, combined_queries_ = 0;
 };
 
 

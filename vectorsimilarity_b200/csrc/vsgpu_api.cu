@@ -234,7 +234,8 @@ static size_t score_size(const vsgpu_store *s) { return s->type == VSGPU_FLOAT64
 
 // queries staged on the device -> device outputs [nq][out_ld]
 static int topk_core(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, size_t k,
-                     size_t out_ld, unsigned flags, uint32_t *out_ids, void *out_scores, uint64_t *out_labels) {
+                     size_t out_ld, unsigned flags, uint32_t *out_ids, void *out_scores, uint64_t *out_labels,
+                     float *bound_out = nullptr) {
     const size_t n = s->count;
     const size_t k_eff = std::min(k, n);
     const size_t ssz = score_size(s);
@@ -263,7 +264,7 @@ static int topk_core(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stri
             return VSGPU_ERR_ARG;
         }
         s->stats.path = 1;
-        return tensor_topk(s, q_dev, nq, q_stride, q_norms, k_eff, out_ids, out_scores, out_labels);
+        return tensor_topk(s, q_dev, nq, q_stride, q_norms, k_eff, out_ids, out_scores, out_labels, bound_out);
     }
     s->stats.path = 0;
     // small batches on the staged scan: selection fused into the scan (per-CTA running top-k in shared memory) — no score
@@ -300,6 +301,7 @@ using namespace vsgpu;
 extern "C" {
 
 const char *vsgpu_last_error(void) { return g_err.c_str(); }
+void vsgpu_set_last_error(const char *msg) { g_err = msg ? msg : ""; }
 
 int vsgpu_device_count(void) {
     int n = 0;
@@ -369,8 +371,22 @@ void vsgpu_store_destroy(vsgpu_store *s) {
     if (s->norms) cudaFree(s->norms);
     for (cudaEvent_t e : {s->ev0, s->ev1, s->ev2, s->ev3})
         if (e) cudaEventDestroy(e);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->stream && s->own_stream) cudaStreamDestroy(s->stream);
     delete s;
+}
+
+int vsgpu_store_set_stream(vsgpu_store *s, void *stream) {
+    if (!s || !stream) {
+        set_error("vsgpu_store_set_stream: bad arguments");
+        return VSGPU_ERR_ARG;
+    }
+    VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
+    VS_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->own_stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)stream;
+    s->own_stream = false;
+    return VSGPU_OK;
 }
 
 size_t vsgpu_store_size(const vsgpu_store *s) { return s->count; }
@@ -531,6 +547,35 @@ int vsgpu_topk_device(vsgpu_store *s, const void *queries, size_t nq, size_t qst
     const float *qn = nullptr;
     VS_TRY(stage_queries_device(s, queries, nq, qstride, &q, &qs, &qn));
     VS_TRY(topk_core(s, q, nq, qs, qn, k, k, flags, out_ids, out_scores, out_labels));
+    VS_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return VSGPU_OK;
+}
+
+// Two-step variant for sharded callers. _begin: as vsgpu_topk_device, but a tensor-path call stops after the coarse phases
+// and writes each query's admission bound to bound_out ([nq] fp32, DEVICE; -inf when the call did all its work already).
+// The caller reduces the bounds over the shards (max) and calls _finish with the result: survivors below the reduced bound
+// are dropped before the exact re-rank — a shard then re-ranks its share of ONE band instead of a whole band of its own.
+int vsgpu_topk_device_begin(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k, unsigned flags,
+                            uint64_t *out_labels, void *out_scores, uint32_t *out_ids, float *bound_out) {
+    if (nq == 0 || k == 0) return VSGPU_OK;
+    if (!bound_out) return vsgpu_topk_device(s, queries, nq, qstride, k, flags, out_labels, out_scores, out_ids);
+    VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(resolve_pending_topk(s));
+    s->stats = vsgpu_stats{};
+    VS_CUDA(cudaEventRecord(s->ev0, s->stream));
+    fill_kernel<float><<<16, 256, 0, s->stream>>>(bound_out, -std::numeric_limits<float>::infinity(), nq);
+    const void *q = nullptr;
+    size_t qs = 0;
+    const float *qn = nullptr;
+    VS_TRY(stage_queries_device(s, queries, nq, qstride, &q, &qs, &qn));
+    VS_TRY(topk_core(s, q, nq, qs, qn, k, k, flags, out_ids, out_scores, out_labels, bound_out));
+    VS_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return VSGPU_OK;
+}
+
+int vsgpu_topk_device_finish(vsgpu_store *s, const float *bound_in) {
+    VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(tensor_topk_finish(s, bound_in));
     VS_CUDA(cudaEventRecord(s->ev1, s->stream));
     return VSGPU_OK;
 }

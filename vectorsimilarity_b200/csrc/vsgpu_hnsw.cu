@@ -255,6 +255,53 @@ template <typename CT_, int G_, bool FTZ, bool L2, int ST> struct PolChain {
             }
         }
     }
+    // Rows staged in shared memory by cp.async (slot p = link position, raw storage type): out value for compacted entry j
+    // (slot pos[j]) lands on lane j. Lane c is chain c; the 32 chain sums of all (<= 32) rows are folded by ONE transposing
+    // butterfly (31 shuffles, same pairing tree as 32 separate butterflies — see vsgpu_scan.cu), so lane j ends with row j.
+    __device__ static DT eval_staged(const KCtx &k, const void *pv_, const uint8_t *slots, size_t slot_stride, const uint8_t *pos,
+                                     int n, int lane) {
+        const DT *pv = (const DT *)pv_ + lane;
+        const int S = k.plan.S;
+        DT v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = DT(0);
+        for (int s = 0; s < S; s++) {
+            const DT y = pv[s * G];
+            const int e = G * s + lane;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                if (j < n) { // warp-uniform
+                    const uint8_t *row = slots + (size_t)pos[j] * slot_stride;
+                    DT x;
+                    if constexpr (ST == VSGPU_FLOAT32) x = (DT) reinterpret_cast<const float *>(row)[e];
+                    else if constexpr (ST == VSGPU_FLOAT64) x = (DT) reinterpret_cast<const double *>(row)[e];
+                    else if constexpr (ST == VSGPU_BFLOAT16) x = (DT)__uint_as_float((unsigned)reinterpret_cast<const unsigned short *>(row)[e] << 16);
+                    else x = (DT)__half2float(__ushort_as_half(reinterpret_cast<const unsigned short *>(row)[e]));
+                    if constexpr (L2) {
+                        const DT d = sub_rn(x, y);
+                        v[j] = fma_step<FTZ>(d, d, v[j]);
+                    } else {
+                        v[j] = fma_step<FTZ>(x, y, v[j]);
+                    }
+                }
+            }
+        }
+        int half = 16;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (i < half) {
+                    const DT lo = v[i], hi = v[i + half];
+                    const DT send = up ? lo : hi, keep = up ? hi : lo;
+                    v[i] = add_rn(keep, __shfl_xor_sync(0xffffffffu, send, m));
+                }
+            }
+            half >>= 1;
+        }
+        return L2 ? v[0] : sub_rn(DT(1), v[0]);
+    }
     static constexpr bool HAS_FAST = true;
     // one thread evaluates a whole (row, row) pair: the G chain sums live in registers and are folded
     // with the same pairing tree as the warp butterfly (acc[c] + acc[c + w], w = G/2 .. 1). Used where
@@ -1055,6 +1102,7 @@ struct SearchArgs {
     int profile; // VSGPU_HNSW_PROFILE: per-phase cycle counters
     int no_regtop; // VSGPU_HNSW_NO_REGTOP
     int multi;     // HNSWIndex_Multi: result set keyed by label
+    int wq_row_slots; // warp-per-query kernel: rows staged per hop in shared memory (0 = read rows from global memory)
 };
 
 template <typename DT> __device__ __forceinline__ Work<DT> carve(unsigned char *smem, size_t pivot_bytes, int max_links,
@@ -1248,11 +1296,13 @@ struct WarpScratch { // per-warp slices of shared memory
     void *nb_dist;
     void *cand_d;
     uint32_t *cand_id;
+    uint8_t *nb_pos;  // link position (= row slot) of each gathered neighbour
+    uint8_t *rows;    // staged rows: `row_slots` slots of row_stride bytes (0 slots: rows are read from global memory)
 };
-__host__ __device__ inline size_t wq_warp_bytes(size_t dt, size_t pivot_bytes, int max_links, int cand_cap) {
+__host__ __device__ inline size_t wq_warp_bytes(size_t dt, size_t pivot_bytes, int max_links, int cand_cap, size_t row_slot_bytes = 0) {
     auto al = [](size_t b) { return (b + 15) / 16 * 16; };
     return al(pivot_bytes) + al((size_t)max_links * 4) + al((size_t)max_links) + al((size_t)max_links * dt) + al((size_t)cand_cap * dt) +
-           al((size_t)cand_cap * 4);
+           al((size_t)cand_cap * 4) + al((size_t)max_links) + al(row_slot_bytes);
 }
 __device__ __forceinline__ WarpScratch wq_carve(unsigned char *p, size_t dt, size_t pivot_bytes, int max_links, int cand_cap) {
     auto al = [](size_t b) { return (b + 15) / 16 * 16; };
@@ -1268,6 +1318,10 @@ __device__ __forceinline__ WarpScratch wq_carve(unsigned char *p, size_t dt, siz
     w.cand_d = p;
     p += al((size_t)cand_cap * dt);
     w.cand_id = (uint32_t *)p;
+    p += al((size_t)cand_cap * 4);
+    w.nb_pos = p;
+    p += al((size_t)max_links);
+    w.rows = p;
     return w;
 }
 
@@ -1286,10 +1340,7 @@ __device__ __forceinline__ int wq_gather(const KCtx &k, const GraphDev &g, const
         bool take = false;
         uint8_t del = 0;
         if (i < cnt) {
-            // every 128-byte line of the row (one prefetch fetches one line), capped at 2 KB per row
-            const uint8_t *rp = k.rows + (size_t)id * k.row_stride;
-            const int lines = (int)min((k.row_stride + 127) / 128, (size_t)16);
-            for (int l = 0; l < lines; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 128 * l));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(k.rows + (size_t)id * k.row_stride));
             del = g.flags[id];
             take = vis ? !test_and_set(*vis, id) : true;
         }
@@ -1339,11 +1390,11 @@ template <class P> __device__ __forceinline__ void wq_eval(const KCtx &k, const 
     __syncwarp();
 }
 
-template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_search_warp_kernel(SearchArgs a, int wpc, size_t nq) {
+template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32, 1) hnsw_search_warp_kernel(SearchArgs a, int wpc, size_t nq) {
     using DT = typename P::DT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = wq_warp_bytes(sizeof(DT), a.pivot_bytes, a.max_links, a.cand_cap);
+    const size_t per_warp = wq_warp_bytes(sizeof(DT), a.pivot_bytes, a.max_links, a.cand_cap, (size_t)a.wq_row_slots * a.k.row_stride);
     // stage the CTA's queries: P::load_pivot is CTA-cooperative, one call per warp slot
     for (int ws = 0; ws < wpc; ws++) {
         const size_t qq = (size_t)blockIdx.x * wpc + ws;
@@ -1451,9 +1502,53 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_sea
             __syncwarp();
             long long t0 = 0, t1 = 0, t2 = 0;
             if (a.profile) t0 = clock64();
-            const int n = wq_gather<DT>(k, g, w, bid, 0, &vis, lane);
-            if (a.profile) t1 = clock64();
-            wq_eval<P>(k, w, n, lane);
+            int n;
+            DT staged_d = DT(0);
+            bool staged = false;
+            if constexpr (P::HAS_FAST && P::G == 32) {
+                // Staged hop (plans without residual, all links fit the slots): the moment the link record arrives, every
+                // linked row is requested with cp.async — one 16-byte chunk per lane and row, no registers held — BEFORE the
+                // visited / deleted tests, whose own round trip to memory then overlaps the rows'. A hop is two dependent
+                // memory round trips (links; rows || flags) plus ~600 cycles of arithmetic.
+                const uint32_t *rec = links_of(g, bid, 0);
+                const int cnt = (int)rec[0];
+                if (a.wq_row_slots > 0 && cnt <= a.wq_row_slots && cnt <= 32 && k.plan.kind == CK_LANES && k.plan.prefix == 0) {
+                    staged = true;
+                    const uint32_t id = lane < cnt ? rec[1 + lane] : INV;
+                    const int chunks = (int)(k.row_stride / 16);
+                    for (int p = 0; p < cnt; p++) {
+                        const uint32_t idp = __shfl_sync(0xffffffffu, id, p);
+                        const uint8_t *src = k.rows + (size_t)idp * k.row_stride;
+                        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(w.rows + (size_t)p * k.row_stride);
+                        for (int c = lane; c < chunks; c += 32)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src + 16 * c) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    bool take = false;
+                    uint8_t del = 0;
+                    if (lane < cnt) {
+                        del = g.flags[id];
+                        take = !test_and_set(vis, id);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, take);
+                    if (take) {
+                        const int pos = __popc(m & ((1u << lane) - 1));
+                        w.nb_ids[pos] = id;
+                        w.nb_del[pos] = del & 1;
+                        w.nb_pos[pos] = (uint8_t)lane;
+                    }
+                    n = __popc(m);
+                    if (a.profile) t1 = clock64();
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    staged_d = P::eval_staged(k, w.pivot, w.rows, k.row_stride, w.nb_pos, n, lane);
+                }
+            }
+            if (!staged) {
+                n = wq_gather<DT>(k, g, w, bid, 0, &vis, lane);
+                if (a.profile) t1 = clock64();
+                wq_eval<P>(k, w, n, lane);
+            }
             if (a.profile) {
                 t2 = clock64();
                 prof[0] += t1 - t0;
@@ -1464,7 +1559,7 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_sea
             bool failed = false;
             for (int j0 = 0; j0 < n && !failed; j0 += 32) {
                 const int j = j0 + lane;
-                const DT dj = j < n ? nb_dist[j] : DT(0);
+                const DT dj = staged ? staged_d : (j < n ? nb_dist[j] : DT(0));
                 // whoever fails the test now fails it later too (the bound only shrinks once the set is full)
                 unsigned mask = __ballot_sync(0xffffffffu, j < n && (lower > dj || top.n < ef));
                 while (mask) {
@@ -3009,13 +3104,17 @@ static int hnsw_search_core(vsgpu_hnsw *g, const void *q, size_t nq, size_t q_st
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
             sms = std::max(sms, 1);
             const int wq_cand = (int)(2 * ef + 64);
-            const size_t per_warp = wq_warp_bytes(dt, a.pivot_bytes, a.max_links, wq_cand);
+            // rows of one hop staged in shared memory when a full level-0 record (<= 32 links) fits 20 KB per warp
+            static const bool no_stage = getenv("VSGPU_HNSW_NO_STAGE") != nullptr; // A/B switch
+            const int slots = (!no_stage && g->M0 <= 32 && (size_t)g->M0 * s->row_stride <= 20 * 1024) ? g->M0 : 0;
+            const size_t per_warp = wq_warp_bytes(dt, a.pivot_bytes, a.max_links, wq_cand, (size_t)slots * s->row_stride);
             // enough queries per CTA to fill the machine, few enough that every SM gets work at small batches
             int wpc = (int)std::min<size_t>(WQ_MAX_WARPS, std::max<size_t>(1, (nq + 2 * (size_t)sms - 1) / (2 * (size_t)sms)));
             while (wpc > 1 && (size_t)wpc * per_warp > limit / 2) wpc--;
             if ((size_t)wpc * per_warp <= limit) {
                 SearchArgs w = a;
                 w.cand_cap = wq_cand;
+                w.wq_row_slots = slots;
                 auto kern = hnsw_search_warp_kernel<P>;
                 const size_t wsmem = (size_t)wpc * per_warp;
                 VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));

@@ -135,6 +135,7 @@ struct vsgpu_store {
     float max_row_l2 = 0.f;
     bool shadow_valid_upto_count = false;
     cudaStream_t stream = nullptr;
+    bool own_stream = true; // false: adopted from the caller (vsgpu_store_set_stream), never destroyed here
     vsgpu::ChainPlan plan{};
     // scratch (grown on demand, owned by the store)
     vsgpu::Scratch q_raw, q_dev, scores, sel_state, out_dev, cand, misc;
@@ -199,7 +200,8 @@ int launch_range_compact(vsgpu_store *s, const void *scores, size_t n, double ra
 // ---- tensor path (vsgpu_tensor.cu) ----
 bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k);
 int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, size_t k,
-                uint32_t *out_ids, void *out_scores, uint64_t *out_labels);
+                uint32_t *out_ids, void *out_scores, uint64_t *out_labels, float *bound_out = nullptr);
+int tensor_topk_finish(vsgpu_store *s, const float *bound_in);
 int tensor_sync_mirrors(vsgpu_store *s);
 void tensor_release(vsgpu_store *s);
 // int8 / uint8 stores: exact integer GEMM on tcgen05 kind::i8 (vsgpu_tensor_i8.cu)

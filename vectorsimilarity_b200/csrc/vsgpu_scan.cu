@@ -400,17 +400,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeTiledFn fn = [] { // initialised once, also under concurrent first calls (sharded index threads)
         void *p = nullptr;
         cudaDriverEntryPointQueryResult qres;
+        EncodeTiledFn f = nullptr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
+            f = (EncodeTiledFn)p;
         cudaGetLastError();
-    }
+        return f;
+    }();
     return fn;
 }
 

@@ -188,16 +188,20 @@ __global__ void __launch_bounds__(256) sel_compact_kernel(const ST *__restrict__
 template <typename ST, typename KT>
 __global__ void __launch_bounds__(1024) sort_pairs_kernel(const KT *__restrict__ in_keys, const ST *__restrict__ in_scores,
                                                           const uint32_t *__restrict__ in_ids, size_t in_ld,
-                                                          const uint32_t *__restrict__ counts, uint32_t fixed_count, int P,
+                                                          const uint32_t *__restrict__ counts, uint32_t fixed_count, int P_max,
                                                           uint32_t k, uint32_t out_ld, const uint64_t *__restrict__ labels,
                                                           uint32_t *__restrict__ out_ids, ST *__restrict__ out_scores,
                                                           uint64_t *__restrict__ out_labels) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KT *sk = reinterpret_cast<KT *>(smem_raw);
-    uint32_t *si = reinterpret_cast<uint32_t *>(smem_raw + (size_t)P * sizeof(KT));
+    uint32_t *si = reinterpret_cast<uint32_t *>(smem_raw + (size_t)P_max * sizeof(KT));
     const int q = blockIdx.x;
     uint32_t cnt = counts ? counts[q] : fixed_count;
-    if (cnt > (uint32_t)P) cnt = P;
+    if (cnt > (uint32_t)P_max) cnt = P_max;
+    // the network is sized for THIS list (block-uniform): a pruned candidate list of a few dozen entries does not pay for
+    // the P_max = 1024-wide sort its buffer could hold
+    int P = 2; // <= P_max: cnt <= P_max and P_max is a power of two
+    while (P < (int)cnt) P <<= 1;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         KT key = ~KT(0);
         uint32_t id = 0xffffffffu;

@@ -186,17 +186,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 inline EncodeTiledFn tc_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised exactly once even when several shard threads arrive together
+    static const EncodeTiledFn fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult qres;
+        EncodeTiledFn f = nullptr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
+            f = (EncodeTiledFn)p;
         cudaGetLastError();
-    }
+        return f;
+    }();
     return fn;
 }
 

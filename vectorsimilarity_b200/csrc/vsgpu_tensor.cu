@@ -720,7 +720,43 @@ struct TensorState {
     float *row_hsq = nullptr;     // L2 stores: ||row||^2 / 2 per row
     int sms = 0;
     bool attr_set = false, pair_attr_set = false;
+    // two-step top-k (vsgpu_topk_device_begin / _finish): the coarse phases ran, the survivors wait for the re-rank
+    struct Split {
+        bool armed = false;
+        const uint8_t *qp = nullptr;
+        size_t nq = 0, q_stride = 0, k = 0, n_ev = 0;
+        uint32_t run_cap = 0;
+        uint2 *run = nullptr;
+        uint32_t *rcnt = nullptr, *rid = nullptr;
+        float *rsc = nullptr, *e1 = nullptr, *athr = nullptr;
+        uint32_t *out_ids = nullptr;
+        void *out_scores = nullptr;
+        uint64_t *out_labels = nullptr;
+        const float *q_norms = nullptr;
+    } split;
 };
+
+// survivors whose upper score estimate does not reach the (cross-shard) bound cannot be in the global result: drop them
+__global__ void __launch_bounds__(256) prune_run_kernel(uint2 *__restrict__ run, uint32_t *__restrict__ run_cnt, uint32_t run_cap,
+                                                        const float *__restrict__ e1, const float *__restrict__ row_l2,
+                                                        const float *__restrict__ bound) {
+    extern __shared__ uint2 s_keep[];
+    __shared__ uint32_t s_n;
+    const uint32_t q = blockIdx.x;
+    const uint32_t cnt = run_cnt[q];
+    const float b = bound[q], e = e1[q];
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    uint2 *mine = run + (size_t)q * run_cap;
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint2 v = mine[i];
+        const float hi = __fadd_ru(__uint_as_float(v.y), __fmul_ru(e, row_l2[v.x]));
+        if (hi >= b) s_keep[atomicAdd(&s_n, 1u)] = v;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < s_n; i += blockDim.x) mine[i] = s_keep[i];
+    if (threadIdx.x == 0) run_cnt[q] = s_n;
+}
 
 static TensorState *state(vsgpu_store *s) {
     if (!s->tmap_cache) s->tmap_cache = new TensorState();
@@ -758,13 +794,9 @@ bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k) {
     if (s->dim < 64 || s->dim > 8192) return false;
     if (s->count < 32768 || s->count < 32 * k) return false;
     if (!encode_fn()) return false;
-    static int cc_major[64] = {0};
-    if (s->device < 64 && !cc_major[s->device]) {
-        int v = 0;
-        cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, s->device);
-        cc_major[s->device] = v ? v : -1;
-    }
-    return s->device < 64 && cc_major[s->device] == 10;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, s->device);
+    return v == 10;
 }
 
 // bring the bf16 mirror (fp32 stores) and the row norms up to date with the store
@@ -867,11 +899,28 @@ static int launch_gemm(vsgpu_store *s, TensorState *t, const CUtensorMap &ma, co
     return VSGPU_OK;
 }
 
+static int tensor_rerank(vsgpu_store *s, TensorState *t, const uint8_t *qp, size_t nq, size_t q_stride, size_t k, uint32_t run_cap,
+                         uint2 *run, uint32_t *rcnt, uint32_t *rid, float *rsc, uint32_t *out_ids, void *out_scores,
+                         uint64_t *out_labels) {
+    (void)t;
+    // exact scores of the survivors (bit-identical to the CPU reference), then the final order
+    unpack_ids_kernel<<<256, 256, 0, s->stream>>>(run, nq * (size_t)run_cap, rid);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    VS_TRY(launch_exact_gather(s, qp, nq, q_stride, nullptr, rid, run_cap, rcnt, run_cap, rsc, run_cap));
+    VS_TRY(launch_sort_candidates(s, nq, k, rid, rsc, run_cap, rcnt, k, out_ids, out_scores, out_labels));
+    return VSGPU_OK;
+}
+
+// bound_out != NULL (two-step call, single chunk of queries only): stop after the coarse phases, hand out the admission
+// bounds and leave the survivors for tensor_topk_finish
 int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_stride, const float *q_norms, size_t k,
-                uint32_t *out_ids, void *out_scores, uint64_t *out_labels) {
+                uint32_t *out_ids, void *out_scores, uint64_t *out_labels, float *bound_out) {
     if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8)
         return tensor_i8_topk(s, q_dev, nq_all, q_stride, q_norms, k, out_ids, out_scores, out_labels);
     TensorState *t = state(s);
+    t->split.armed = false;
+    const bool two_step = bound_out != nullptr && nq_all <= MAX_NQ;
     VS_TRY(tensor_sync_mirrors(s));
     const size_t n = s->count;
     const bool f32 = s->type == VSGPU_FLOAT32;
@@ -973,17 +1022,51 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             VS_CUDA(cudaGetLastError());
             s->stats.kernel_launches++;
         }
-        // exact scores of the survivors (bit-identical to the CPU reference), then the final order
-        unpack_ids_kernel<<<256, 256, 0, s->stream>>>(run, nq * (size_t)run_cap, rid);
-        VS_CUDA(cudaGetLastError());
-        s->stats.kernel_launches++;
-        VS_TRY(launch_exact_gather(s, qp, nq, q_stride, nullptr, rid, run_cap, rcnt, run_cap, rsc, run_cap));
-        VS_TRY(launch_sort_candidates(s, nq, k, rid, rsc, run_cap, rcnt, k, out_ids ? out_ids + q0 * k : nullptr,
-                                      out_scores ? (float *)out_scores + q0 * k : nullptr,
-                                      out_labels ? out_labels + q0 * k : nullptr));
+        if (two_step) {
+            VS_CUDA(cudaMemcpyAsync(bound_out, athr, nq * 4, cudaMemcpyDeviceToDevice, s->stream));
+            auto &sp = t->split;
+            sp.armed = true;
+            sp.qp = qp;
+            sp.nq = nq;
+            sp.q_stride = q_stride;
+            sp.k = k;
+            sp.n_ev = n_ev;
+            sp.run_cap = run_cap;
+            sp.run = run;
+            sp.rcnt = rcnt;
+            sp.rid = rid;
+            sp.rsc = rsc;
+            sp.e1 = eps;
+            sp.athr = athr;
+            sp.out_ids = out_ids;
+            sp.out_scores = out_scores;
+            sp.out_labels = out_labels;
+            sp.q_norms = q_norms;
+            return VSGPU_OK;
+        }
+        VS_TRY(tensor_rerank(s, t, qp, nq, q_stride, k, run_cap, run, rcnt, rid, rsc, out_ids ? out_ids + q0 * k : nullptr,
+                             out_scores ? (float *)out_scores + q0 * k : nullptr, out_labels ? out_labels + q0 * k : nullptr));
     }
     // overflowed queries are redone on the exact path by whoever synchronises next (no host wait here)
     VS_TRY(pending_arm(s, q_dev, nq_all, q_stride, q_norms, k, out_ids, out_scores, out_labels, n_ev, chunks));
+    return VSGPU_OK;
+}
+
+// second half of a two-step call: prune with the reduced bound (may be NULL), re-rank, write the lists
+int tensor_topk_finish(vsgpu_store *s, const float *bound_in) {
+    auto *t = (TensorState *)s->tmap_cache;
+    if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8 || !t || !t->split.armed) return VSGPU_OK;
+    auto &sp = t->split;
+    sp.armed = false;
+    if (bound_in) {
+        prune_run_kernel<<<(unsigned)sp.nq, 256, (size_t)sp.run_cap * sizeof(uint2), s->stream>>>(sp.run, sp.rcnt, sp.run_cap, sp.e1,
+                                                                                                s->row_l2, bound_in);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+    }
+    VS_TRY(tensor_rerank(s, t, sp.qp, sp.nq, sp.q_stride, sp.k, sp.run_cap, sp.run, sp.rcnt, sp.rid, sp.rsc, sp.out_ids, sp.out_scores,
+                         sp.out_labels));
+    VS_TRY(pending_arm(s, sp.qp, sp.nq, sp.q_stride, sp.q_norms, sp.k, sp.out_ids, sp.out_scores, sp.out_labels, sp.n_ev, 1));
     return VSGPU_OK;
 }
 

@@ -509,7 +509,7 @@ struct I8State {
     uint32_t *row_sq = nullptr;
     float *row_add = nullptr;
     int sms = 0;
-    bool attr_set = false, pair_attr_set = false;
+    bool attr_set = false, pair_attr_set = false, merge_attr_set = false;
 };
 
 int make_map_u8(CUtensorMap *map, const void *base, size_t rows, size_t dim_bytes, size_t stride_bytes, int box_rows) {
@@ -710,10 +710,9 @@ int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_st
             m.overflow = ovf;
             m.total_cand = tot;
             const size_t msm = 2 * 4096 * 4;
-            static bool mattr = false;
-            if (!mattr) {
+            if (!t->merge_attr_set) { // a per-device attribute: one flag per store, not per process
                 VS_CUDA(cudaFuncSetAttribute(i8_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
-                mattr = true;
+                t->merge_attr_set = true;
             }
             i8_merge_kernel<<<(unsigned)nq, I8_MERGE_THREADS, msm, s->stream>>>(m);
             VS_CUDA(cudaGetLastError());
