@@ -135,7 +135,34 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
         return nullptr;
     }
 }
-size_t VecSimIndex_EstimateInitialSize(const VecSimParams *) { return sizeof(FlatIndex); }
+// What an empty index costs before the first vector (index_factories/*_factory.cpp EstimateInitialSize): the host object(s)
+// plus what the constructor reserves on the device for `initialCapacity` rows (the reference ignores initialCapacity; here
+// it reserves HBM rows up front, so it is part of the estimate).
+size_t VecSimIndex_EstimateInitialSize(const VecSimParams *params) {
+    if (!params) return 0;
+    auto rows = [](VecSimType t, size_t dim, VecSimMetric m, size_t cap) {
+        const size_t stride = (type_size(t) * dim + 15) / 16 * 16;
+        const bool norm = m == VecSimMetric_Cosine && (t == VecSimType_INT8 || t == VecSimType_UINT8);
+        return cap * (stride + sizeof(uint64_t) + (norm ? sizeof(float) : 0));
+    };
+    switch (params->algo) {
+    case VecSimAlgo_BF: {
+        const BFParams &p = params->algoParams.bfParams;
+        return (p.multi ? sizeof(FlatMultiIndex) : sizeof(FlatIndex)) + rows(p.type, p.dim, p.metric, p.initialCapacity);
+    }
+    case VecSimAlgo_HNSWLIB: {
+        const HNSWParams &p = params->algoParams.hnswParams;
+        const size_t M = p.M ? p.M : 16;
+        return sizeof(HnswIndex) + rows(p.type, p.dim, p.metric, p.initialCapacity) +
+               p.initialCapacity * ((2 * M + 1) * sizeof(idType) + 3 * sizeof(uint32_t) + 1);
+    }
+    case VecSimAlgo_TIERED: {
+        const TieredIndexParams &tp = params->algoParams.tieredParams;
+        return sizeof(TieredIndex) + sizeof(FlatIndex) + (tp.primaryIndexParams ? VecSimIndex_EstimateInitialSize(tp.primaryIndexParams) : 0);
+    }
+    default: return 0;
+    }
+}
 size_t VecSimIndex_EstimateElementSize(const VecSimParams *params) {
     if (params && params->algo == VecSimAlgo_HNSWLIB) {
         // index_factories/hnsw_factory.cpp:123-148: level-0 record + expected upper levels + vector + metadata

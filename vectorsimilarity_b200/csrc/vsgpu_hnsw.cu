@@ -193,115 +193,6 @@ template <typename CT_, int G_, bool FTZ, bool L2, int ST> struct PolChain {
             out[r] = v;
         }
     }
-    // Whole hop for one warp (G == 32, plan without residual): out[j] = dist(row ids[j], pivot), j < n. Rows are taken eight at
-    // a time in 4-step slices, and the loads of slice i + 1 are issued BEFORE the FMAs of slice i: one memory round trip is
-    // always in flight behind the arithmetic (a single warp has nobody else to hide it). Chains, order and butterfly as above.
-    __device__ static void eval_rows_pipelined(const KCtx &k, const void *pv_, const uint32_t *ids, int n, DT *out, int lane) {
-        constexpr int NR = 8;
-        const DT *pv = (const DT *)pv_ + lane;
-        const int S = k.plan.S, chunks = (S + 3) / 4;
-        const int groups = (n + NR - 1) / NR, items = groups * chunks;
-        DT xa[NR][4], xb[NR][4];
-        auto load = [&](int item, DT (&x)[NR][4]) {
-            const int grp = item / chunks, s0 = (item % chunks) * 4;
-#pragma unroll
-            for (int r = 0; r < NR; r++) {
-                const int j = grp * NR + r;
-                const uint8_t *row = k.rows + (size_t)(j < n ? ids[j] : ids[0]) * k.row_stride;
-#pragma unroll
-                for (int t = 0; t < 4; t++) x[r][t] = s0 + t < S ? load_st<ST, DT>(row, G * (s0 + t) + lane) : DT(0);
-            }
-        };
-        DT acc[NR];
-        auto compute = [&](int item, DT (&x)[NR][4]) {
-            const int grp = item / chunks, ch = item % chunks, s0 = ch * 4;
-            if (ch == 0) {
-#pragma unroll
-                for (int r = 0; r < NR; r++) acc[r] = DT(0);
-            }
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                if (s0 + t < S) {
-                    const DT y = pv[(s0 + t) * G];
-#pragma unroll
-                    for (int r = 0; r < NR; r++) {
-                        if constexpr (L2) {
-                            const DT d = sub_rn(x[r][t], y);
-                            acc[r] = fma_step<FTZ>(d, d, acc[r]);
-                        } else {
-                            acc[r] = fma_step<FTZ>(x[r][t], y, acc[r]);
-                        }
-                    }
-                }
-            }
-            if (ch == chunks - 1) {
-#pragma unroll
-                for (int r = 0; r < NR; r++) {
-                    DT v = butterfly<DT, G>(acc[r]);
-                    if (!L2) v = sub_rn(DT(1), v);
-                    const int j = grp * NR + r;
-                    if (lane == 0 && j < n) out[j] = v;
-                }
-            }
-        };
-        if (items == 0) return;
-        load(0, xa);
-        for (int item = 0; item < items; item += 2) {
-            if (item + 1 < items) load(item + 1, xb);
-            compute(item, xa);
-            if (item + 1 < items) {
-                if (item + 2 < items) load(item + 2, xa);
-                compute(item + 1, xb);
-            }
-        }
-    }
-    // Rows staged in shared memory by cp.async (slot p = link position, raw storage type): out value for compacted entry j
-    // (slot pos[j]) lands on lane j. Lane c is chain c; the 32 chain sums of all (<= 32) rows are folded by ONE transposing
-    // butterfly (31 shuffles, same pairing tree as 32 separate butterflies — see vsgpu_scan.cu), so lane j ends with row j.
-    __device__ static DT eval_staged(const KCtx &k, const void *pv_, const uint8_t *slots, size_t slot_stride, const uint8_t *pos,
-                                     int n, int lane) {
-        const DT *pv = (const DT *)pv_ + lane;
-        const int S = k.plan.S;
-        DT v[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = DT(0);
-        for (int s = 0; s < S; s++) {
-            const DT y = pv[s * G];
-            const int e = G * s + lane;
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                if (j < n) { // warp-uniform
-                    const uint8_t *row = slots + (size_t)pos[j] * slot_stride;
-                    DT x;
-                    if constexpr (ST == VSGPU_FLOAT32) x = (DT) reinterpret_cast<const float *>(row)[e];
-                    else if constexpr (ST == VSGPU_FLOAT64) x = (DT) reinterpret_cast<const double *>(row)[e];
-                    else if constexpr (ST == VSGPU_BFLOAT16) x = (DT)__uint_as_float((unsigned)reinterpret_cast<const unsigned short *>(row)[e] << 16);
-                    else x = (DT)__half2float(__ushort_as_half(reinterpret_cast<const unsigned short *>(row)[e]));
-                    if constexpr (L2) {
-                        const DT d = sub_rn(x, y);
-                        v[j] = fma_step<FTZ>(d, d, v[j]);
-                    } else {
-                        v[j] = fma_step<FTZ>(x, y, v[j]);
-                    }
-                }
-            }
-        }
-        int half = 16;
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            const bool up = (lane & m) != 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if (i < half) {
-                    const DT lo = v[i], hi = v[i + half];
-                    const DT send = up ? lo : hi, keep = up ? hi : lo;
-                    v[i] = add_rn(keep, __shfl_xor_sync(0xffffffffu, send, m));
-                }
-            }
-            half >>= 1;
-        }
-        return L2 ? v[0] : sub_rn(DT(1), v[0]);
-    }
     static constexpr bool HAS_FAST = true;
     // one thread evaluates a whole (row, row) pair: the G chain sums live in registers and are folded
     // with the same pairing tree as the warp butterfly (acc[c] + acc[c + w], w = G/2 .. 1). Used where
@@ -1102,7 +993,6 @@ struct SearchArgs {
     int profile; // VSGPU_HNSW_PROFILE: per-phase cycle counters
     int no_regtop; // VSGPU_HNSW_NO_REGTOP
     int multi;     // HNSWIndex_Multi: result set keyed by label
-    int wq_row_slots; // warp-per-query kernel: rows staged per hop in shared memory (0 = read rows from global memory)
 };
 
 template <typename DT> __device__ __forceinline__ Work<DT> carve(unsigned char *smem, size_t pivot_bytes, int max_links,
@@ -1296,13 +1186,11 @@ struct WarpScratch { // per-warp slices of shared memory
     void *nb_dist;
     void *cand_d;
     uint32_t *cand_id;
-    uint8_t *nb_pos;  // link position (= row slot) of each gathered neighbour
-    uint8_t *rows;    // staged rows: `row_slots` slots of row_stride bytes (0 slots: rows are read from global memory)
 };
-__host__ __device__ inline size_t wq_warp_bytes(size_t dt, size_t pivot_bytes, int max_links, int cand_cap, size_t row_slot_bytes = 0) {
+__host__ __device__ inline size_t wq_warp_bytes(size_t dt, size_t pivot_bytes, int max_links, int cand_cap) {
     auto al = [](size_t b) { return (b + 15) / 16 * 16; };
     return al(pivot_bytes) + al((size_t)max_links * 4) + al((size_t)max_links) + al((size_t)max_links * dt) + al((size_t)cand_cap * dt) +
-           al((size_t)cand_cap * 4) + al((size_t)max_links) + al(row_slot_bytes);
+           al((size_t)cand_cap * 4);
 }
 __device__ __forceinline__ WarpScratch wq_carve(unsigned char *p, size_t dt, size_t pivot_bytes, int max_links, int cand_cap) {
     auto al = [](size_t b) { return (b + 15) / 16 * 16; };
@@ -1318,10 +1206,6 @@ __device__ __forceinline__ WarpScratch wq_carve(unsigned char *p, size_t dt, siz
     w.cand_d = p;
     p += al((size_t)cand_cap * dt);
     w.cand_id = (uint32_t *)p;
-    p += al((size_t)cand_cap * 4);
-    w.nb_pos = p;
-    p += al((size_t)max_links);
-    w.rows = p;
     return w;
 }
 
@@ -1357,7 +1241,7 @@ __device__ __forceinline__ int wq_gather(const KCtx &k, const GraphDev &g, const
 }
 
 // nb_dist[j] = dist(row nb_ids[j], query) for j < n (warp-wide)
-template <class P> __device__ __forceinline__ void wq_eval(const KCtx &k, const WarpScratch &w, int n, int lane) {
+template <class P, int WIDE> __device__ __forceinline__ void wq_eval(const KCtx &k, const WarpScratch &w, int n, int lane) {
     using DT = typename P::DT;
     DT *out = (DT *)w.nb_dist;
     constexpr int GPW = 32 / P::G;
@@ -1365,9 +1249,33 @@ template <class P> __device__ __forceinline__ void wq_eval(const KCtx &k, const 
     int base = 0;
     if constexpr (P::HAS_FAST && P::G == 32) {
         if (k.plan.kind == CK_LANES && k.plan.prefix == 0) {
-            P::eval_rows_pipelined(k, w.pivot, w.nb_ids, n, out, lane);
-            __syncwarp();
-            return;
+            // eight rows per slice, all their loads in flight before the first FMA. (Tried and dropped, r2: issuing slice
+            // i + 1's loads before slice i's FMAs — no gain, the FMAs are too short to hide a memory round trip; and staging a
+            // whole hop's rows in shared memory with cp.async before the visited test — 1.46 ms against 0.88 ms per batch of
+            // 256: the extra registers and 16 KB per warp cost more occupancy than the overlap returns.)
+            auto slice = [&]<int NR>() {
+                uint32_t a[NR];
+#pragma unroll
+                for (int r = 0; r < NR; r++) a[r] = base + r < n ? w.nb_ids[base + r] : INV;
+                DT o[NR];
+                P::template dists_fast<NR>(k, w.pivot, a, c, o);
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++)
+                        if (base + r < n) out[base + r] = o[r];
+                }
+                base += NR;
+            };
+            // WIDE (small batches, latency-bound): sixteen rows per slice while more than eight are left — 64 loads in flight per
+            // lane, a hop's ~30 rows cost two memory round trips instead of four (0.72 against 0.81 ms per batch of 256 on the
+            // 1 M-node graph) at 204 registers; large batches are throughput-bound and keep the 8-row slices at 128 registers
+            // (2.1 M against 1.4 M QPS at batch 4096)
+            if constexpr (WIDE) {
+                while (n - base > 8) slice.template operator()<16>();
+                if (n - base > 4) slice.template operator()<8>();
+            } else {
+                while (n - base > 4) slice.template operator()<8>();
+            }
         }
     }
     constexpr int RU = P::RU;
@@ -1390,11 +1298,11 @@ template <class P> __device__ __forceinline__ void wq_eval(const KCtx &k, const 
     __syncwarp();
 }
 
-template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32, 1) hnsw_search_warp_kernel(SearchArgs a, int wpc, size_t nq) {
+template <class P, int WIDE> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32) hnsw_search_warp_kernel(SearchArgs a, int wpc, size_t nq) {
     using DT = typename P::DT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = wq_warp_bytes(sizeof(DT), a.pivot_bytes, a.max_links, a.cand_cap, (size_t)a.wq_row_slots * a.k.row_stride);
+    const size_t per_warp = wq_warp_bytes(sizeof(DT), a.pivot_bytes, a.max_links, a.cand_cap);
     // stage the CTA's queries: P::load_pivot is CTA-cooperative, one call per warp slot
     for (int ws = 0; ws < wpc; ws++) {
         const size_t qq = (size_t)blockIdx.x * wpc + ws;
@@ -1418,14 +1326,14 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32, 1) hnsw_
         uint32_t cur = (uint32_t)ep0;
         if (lane == 0) w.nb_ids[0] = cur;
         __syncwarp();
-        wq_eval<P>(k, w, 1, lane);
+        wq_eval<P, WIDE>(k, w, 1, lane);
         DT cur_d = nb_dist[0];
         evals += 1;
         for (int level = maxl; level > 0; level--) {
             for (;;) {
                 __syncwarp();
                 const int n = wq_gather<DT>(k, g, w, cur, level, nullptr, lane);
-                wq_eval<P>(k, w, n, lane);
+                wq_eval<P, WIDE>(k, w, n, lane);
                 evals += n;
                 bool changed = false;
                 for (int j = 0; j < n; j++) { // sequential scan in link order, uniform across the warp
@@ -1502,53 +1410,9 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32, 1) hnsw_
             __syncwarp();
             long long t0 = 0, t1 = 0, t2 = 0;
             if (a.profile) t0 = clock64();
-            int n;
-            DT staged_d = DT(0);
-            bool staged = false;
-            if constexpr (P::HAS_FAST && P::G == 32) {
-                // Staged hop (plans without residual, all links fit the slots): the moment the link record arrives, every
-                // linked row is requested with cp.async — one 16-byte chunk per lane and row, no registers held — BEFORE the
-                // visited / deleted tests, whose own round trip to memory then overlaps the rows'. A hop is two dependent
-                // memory round trips (links; rows || flags) plus ~600 cycles of arithmetic.
-                const uint32_t *rec = links_of(g, bid, 0);
-                const int cnt = (int)rec[0];
-                if (a.wq_row_slots > 0 && cnt <= a.wq_row_slots && cnt <= 32 && k.plan.kind == CK_LANES && k.plan.prefix == 0) {
-                    staged = true;
-                    const uint32_t id = lane < cnt ? rec[1 + lane] : INV;
-                    const int chunks = (int)(k.row_stride / 16);
-                    for (int p = 0; p < cnt; p++) {
-                        const uint32_t idp = __shfl_sync(0xffffffffu, id, p);
-                        const uint8_t *src = k.rows + (size_t)idp * k.row_stride;
-                        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(w.rows + (size_t)p * k.row_stride);
-                        for (int c = lane; c < chunks; c += 32)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src + 16 * c) : "memory");
-                    }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                    bool take = false;
-                    uint8_t del = 0;
-                    if (lane < cnt) {
-                        del = g.flags[id];
-                        take = !test_and_set(vis, id);
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, take);
-                    if (take) {
-                        const int pos = __popc(m & ((1u << lane) - 1));
-                        w.nb_ids[pos] = id;
-                        w.nb_del[pos] = del & 1;
-                        w.nb_pos[pos] = (uint8_t)lane;
-                    }
-                    n = __popc(m);
-                    if (a.profile) t1 = clock64();
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    __syncwarp();
-                    staged_d = P::eval_staged(k, w.pivot, w.rows, k.row_stride, w.nb_pos, n, lane);
-                }
-            }
-            if (!staged) {
-                n = wq_gather<DT>(k, g, w, bid, 0, &vis, lane);
-                if (a.profile) t1 = clock64();
-                wq_eval<P>(k, w, n, lane);
-            }
+            const int n = wq_gather<DT>(k, g, w, bid, 0, &vis, lane);
+            if (a.profile) t1 = clock64();
+            wq_eval<P, WIDE>(k, w, n, lane);
             if (a.profile) {
                 t2 = clock64();
                 prof[0] += t1 - t0;
@@ -1559,7 +1423,7 @@ template <class P> __global__ void __launch_bounds__(WQ_MAX_WARPS * 32, 1) hnsw_
             bool failed = false;
             for (int j0 = 0; j0 < n && !failed; j0 += 32) {
                 const int j = j0 + lane;
-                const DT dj = staged ? staged_d : (j < n ? nb_dist[j] : DT(0));
+                const DT dj = j < n ? nb_dist[j] : DT(0);
                 // whoever fails the test now fails it later too (the bound only shrinks once the set is full)
                 unsigned mask = __ballot_sync(0xffffffffu, j < n && (lower > dj || top.n < ef));
                 while (mask) {
@@ -3104,21 +2968,24 @@ static int hnsw_search_core(vsgpu_hnsw *g, const void *q, size_t nq, size_t q_st
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
             sms = std::max(sms, 1);
             const int wq_cand = (int)(2 * ef + 64);
-            // rows of one hop staged in shared memory when a full level-0 record (<= 32 links) fits 20 KB per warp
-            static const bool no_stage = getenv("VSGPU_HNSW_NO_STAGE") != nullptr; // A/B switch
-            const int slots = (!no_stage && g->M0 <= 32 && (size_t)g->M0 * s->row_stride <= 20 * 1024) ? g->M0 : 0;
-            const size_t per_warp = wq_warp_bytes(dt, a.pivot_bytes, a.max_links, wq_cand, (size_t)slots * s->row_stride);
+            const size_t per_warp = wq_warp_bytes(dt, a.pivot_bytes, a.max_links, wq_cand);
             // enough queries per CTA to fill the machine, few enough that every SM gets work at small batches
             int wpc = (int)std::min<size_t>(WQ_MAX_WARPS, std::max<size_t>(1, (nq + 2 * (size_t)sms - 1) / (2 * (size_t)sms)));
             while (wpc > 1 && (size_t)wpc * per_warp > limit / 2) wpc--;
             if ((size_t)wpc * per_warp <= limit) {
                 SearchArgs w = a;
                 w.cand_cap = wq_cand;
-                w.wq_row_slots = slots;
-                auto kern = hnsw_search_warp_kernel<P>;
                 const size_t wsmem = (size_t)wpc * per_warp;
-                VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-                kern<<<(unsigned)((nq + wpc - 1) / wpc), wpc * 32, wsmem, s->stream>>>(w, wpc, nq);
+                const unsigned grid = (unsigned)((nq + wpc - 1) / wpc);
+                if (nq <= 1024) { // latency-bound: wide slices
+                    auto kern = hnsw_search_warp_kernel<P, 1>;
+                    VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                    kern<<<grid, wpc * 32, wsmem, s->stream>>>(w, wpc, nq);
+                } else {
+                    auto kern = hnsw_search_warp_kernel<P, 0>;
+                    VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                    kern<<<grid, wpc * 32, wsmem, s->stream>>>(w, wpc, nq);
+                }
                 VS_CUDA(cudaGetLastError());
                 return (int)VSGPU_OK;
             }
