@@ -204,6 +204,9 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, c
 int tensor_topk_finish(vsgpu_store *s, const float *bound_in);
 int tensor_sync_mirrors(vsgpu_store *s);
 void tensor_release(vsgpu_store *s);
+// a single row changed (src != SIZE_MAX: row src was copied over row id): patch the tensor-path side data in place
+int tensor_row_changed(vsgpu_store *s, size_t id, size_t src);
+int tensor_i8_row_changed(vsgpu_store *s, size_t id, size_t src);
 // int8 / uint8 stores: exact integer GEMM on tcgen05 kind::i8 (vsgpu_tensor_i8.cu)
 bool tensor_i8_supported(const vsgpu_store *s, size_t nq, size_t k);
 int tensor_i8_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, size_t k,

@@ -782,6 +782,35 @@ void tensor_release(vsgpu_store *s) {
     s->shadow_stride = 0;
 }
 
+// One row changed: keep the mirror / norms in step instead of rebuilding them for the whole store (r1 rebuilt 15 GB of mirror
+// after any delete). `src` != SIZE_MAX: row `src` was copied over row `id` (delete-by-swap), else row `id` was rewritten.
+// The store-wide maxima (max ||row||, max relative rounding) only ever grow, so they stay valid upper bounds.
+int tensor_row_changed(vsgpu_store *s, size_t id, size_t src) {
+    if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8) return tensor_i8_row_changed(s, id, src);
+    auto *t = (TensorState *)s->tmap_cache;
+    if (!t) return VSGPU_OK;
+    if (id < t->mirrored) {
+        const bool f32 = s->type == VSGPU_FLOAT32;
+        if (src != (size_t)-1 && src < t->mirrored) {
+            if (f32 && s->shadow)
+                VS_CUDA(cudaMemcpyAsync(s->shadow + id * s->shadow_stride, s->shadow + src * s->shadow_stride, s->shadow_stride * 2,
+                                        cudaMemcpyDeviceToDevice, s->stream));
+            if (s->row_l2) VS_CUDA(cudaMemcpyAsync(s->row_l2 + id, s->row_l2 + src, 4, cudaMemcpyDeviceToDevice, s->stream));
+            if (t->row_hsq) VS_CUDA(cudaMemcpyAsync(t->row_hsq + id, t->row_hsq + src, 4, cudaMemcpyDeviceToDevice, s->stream));
+        } else if (f32 && s->shadow) {
+            shadow_rows_kernel<<<1, 32, 0, s->stream>>>((const float *)s->rows, s->row_stride / 4, s->dim, id, 1, (__nv_bfloat16 *)s->shadow,
+                                                       s->shadow_stride, s->row_l2, t->max_l2_bits, t->row_hsq);
+            VS_CUDA(cudaGetLastError());
+        } else if (!f32) {
+            bf16_norms_kernel<<<1, 32, 0, s->stream>>>((const __nv_bfloat16 *)s->rows, s->row_stride / 2, s->dim, id, 1, s->row_l2,
+                                                      t->max_l2_bits, s->type == VSGPU_FLOAT16 ? 1 : 0, t->row_hsq);
+            VS_CUDA(cudaGetLastError());
+        }
+    }
+    t->mirrored = std::min(t->mirrored, s->count);
+    return VSGPU_OK;
+}
+
 static bool g_tensor_disabled = false;
 
 bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k) {

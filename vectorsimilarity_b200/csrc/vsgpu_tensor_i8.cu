@@ -550,6 +550,23 @@ void tensor_i8_release(vsgpu_store *s) {
     s->tmap_cache = nullptr;
 }
 
+int tensor_i8_row_changed(vsgpu_store *s, size_t id, size_t src) {
+    auto *t = (I8State *)s->tmap_cache;
+    if (!t) return VSGPU_OK;
+    if (t->row_sq && id < t->synced) {
+        if (src != (size_t)-1 && src < t->synced) {
+            VS_CUDA(cudaMemcpyAsync(t->row_sq + id, t->row_sq + src, 4, cudaMemcpyDeviceToDevice, s->stream));
+            VS_CUDA(cudaMemcpyAsync(t->row_add + id, t->row_add + src, 4, cudaMemcpyDeviceToDevice, s->stream));
+        } else {
+            i8_row_sq_kernel<<<1, 32, 0, s->stream>>>(s->rows, s->row_stride, (int)(s->row_stride / 16), s->type == VSGPU_UINT8, id, 1,
+                                                     t->row_sq, t->row_add);
+            VS_CUDA(cudaGetLastError());
+        }
+    }
+    t->synced = std::min(t->synced, s->count);
+    return VSGPU_OK;
+}
+
 bool tensor_i8_supported(const vsgpu_store *s, size_t nq, size_t k) {
     if (s->type != VSGPU_INT8 && s->type != VSGPU_UINT8) return false;
     if (nq < 8 || k == 0 || k > RUN_CAP) return false;
