@@ -123,3 +123,66 @@ def test_multi_index_file_round_trip(capi, port, tmp_path):
     assert f["multi"] and f["n"] == n and f["num_deleted"] == 8 and int((f["flags"] & 1).sum()) == 8
     G.close()
     G2.close()
+
+
+def test_tiered_index_over_multi_value_backend(capi, port):
+    """VecSimAlgo_TIERED over a multi-value HNSW backend (hnsw_tiered.h with HNSWIndex_Multi / BruteForceIndex_Multi): a
+    repeated label is another vector; while some vectors of a label are still buffered and others already ingested, a query
+    returns the label once, with the best score over both tiers (merge_results<withSet = true>,
+    utils/query_result_utils.h:44-92). Checked against the oracle halves + the restated merge, and — once everything is
+    ingested — against the oracle's multi-value HNSW built in the same order."""
+    n, dim, n_labels = 600, 16, 60
+    labels = (np.arange(n) % n_labels).astype(np.uint64)          # ten vectors per label
+    X = make_vectors(0, n, dim, seed=21)
+    Q = make_vectors(0, 8, dim, seed=22)
+    T = capi.Tiered_HNSWIndex(capi.HNSWParams(type=0, dim=dim, metric=0, multi=True, initialCapacity=0, blockSize=1024, M=8,
+                                              efConstruction=40, efRuntime=60, epsilon=0.01), None, flat_buffer_size=1000)
+    for i in range(n):
+        assert T.add_vector(X[i], int(labels[i])) == 1
+    assert T.index_size() == n and T.get_curr_bf_size() == n
+    # everything buffered: the flat tier answers alone (exact multi-value scan)
+    PF = port.PortIndex(0, dim, 0, multi=True)
+    PF.add_many(X, labels=labels)
+    for q in Q:
+        l, s = T.knn_query(q, 10)
+        pl, ps, _ = PF.topk(q, 10)
+        assert np.array_equal(l[0], pl.astype(np.int64)) and np.array_equal(s[0], ps)
+    # one executed job drains everything pending at that moment into the backend, in submission order
+    T.run_jobs(max_jobs=1)
+    assert T.get_curr_bf_size() == 0 and T.index_size() == n
+    PB = port.PortHnsw(0, dim, 0, M=8, ef_construction=40, ef_runtime=60, multi=True)
+    PB.add_many(X, labels=labels)
+    for q in Q:
+        l, s = T.knn_query(q, 10)
+        pl, ps, _ = PB.topk(q, 10, ef_runtime=60)
+        assert np.array_equal(l[0], pl.astype(np.int64)) and np.array_equal(s[0], ps)
+        assert len(set(l[0].tolist())) == 10
+    # a second wave stays in the buffer: labels now live in BOTH tiers
+    X2 = make_vectors(0, 120, dim, seed=23)
+    lab2 = (np.arange(120) % n_labels).astype(np.uint64)
+    for i in range(120):
+        assert T.add_vector(X2[i], int(lab2[i])) == 1
+    assert T.get_curr_bf_size() == 120 and T.index_size() == n + 120
+    PF2 = port.PortIndex(0, dim, 0, multi=True)
+    PF2.add_many(X2, labels=lab2)
+    for q in Q:
+        fl, fs, _ = PF2.topk(q, 10)
+        bl, bs, _ = PB.topk(q, 10, ef_runtime=60)
+        want = {}
+        for lab, sc in list(zip(fl.tolist(), fs.tolist())) + list(zip(bl.tolist(), bs.tolist())):
+            want[lab] = min(sc, want.get(lab, np.inf))
+        want = sorted(want.items(), key=lambda t: (t[1], t[0]))[:10]
+        l, s = T.knn_query(q, 10)
+        assert l[0].tolist() == [w[0] for w in want] and s[0].tolist() == [w[1] for w in want]
+        assert len(set(l[0].tolist())) == 10
+    # deleting a label removes its vectors from both tiers and voids its pending jobs
+    removed = T.delete_vector(7)
+    assert removed == 10 + 2 and T.index_size() == n + 120 - 12
+    l, _ = T.knn_query(X[7], 60)
+    assert 7 not in l[0].tolist()
+    T.wait_for_index()
+    assert T.get_curr_bf_size() == 0
+    T.close()
+    PF.close()
+    PF2.close()
+    PB.close()

@@ -120,10 +120,9 @@ VecSimIndex *VecSimIndex_New(const VecSimParams *params) {
             auto *idx = new TieredIndex(params->algoParams.tieredParams, params->logCtx);
             if (!idx->ok()) {
                 const TieredIndexParams &tp = params->algoParams.tieredParams;
-                const bool shape_ok = tp.primaryIndexParams && tp.primaryIndexParams->algo == VecSimAlgo_HNSWLIB &&
-                                      !tp.primaryIndexParams->algoParams.hnswParams.multi;
+                const bool shape_ok = tp.primaryIndexParams && tp.primaryIndexParams->algo == VecSimAlgo_HNSWLIB;
                 g_api_err = shape_ok ? std::string("tiered index: ") + vsgpu_last_error()
-                                     : std::string("tiered index: the backend must be a single-value VecSimAlgo_HNSWLIB index");
+                                     : std::string("tiered index: the backend must be a VecSimAlgo_HNSWLIB index");
                 delete idx;
                 return nullptr;
             }

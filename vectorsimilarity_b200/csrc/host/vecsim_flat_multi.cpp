@@ -115,6 +115,20 @@ int FlatMultiIndex::deleteVector(size_t label) {
     return ret;
 }
 
+int FlatMultiIndex::deleteFirst(size_t label, size_t m) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = label_to_ids_.find(label);
+    if (it == label_to_ids_.end() || m == 0) return 0;
+    if (flush() != 0) return 0;
+    std::vector<idType> &ids = it->second; // insertion order; patched in place when one of its own rows moves
+    size_t done = 0;
+    for (; done < m && done < ids.size(); done++)
+        if (removeRow(ids[done]) != 0) break;
+    ids.erase(ids.begin(), ids.begin() + (ptrdiff_t)done);
+    if (ids.empty()) label_to_ids_.erase(it);
+    return (int)done;
+}
+
 double FlatMultiIndex::getDistanceFrom(size_t label, const void *blob) {
     std::lock_guard<std::mutex> g(mu_);
     const double nan = std::numeric_limits<double>::quiet_NaN();

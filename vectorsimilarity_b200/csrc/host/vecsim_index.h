@@ -243,6 +243,8 @@ class FlatMultiIndex final : public VecSimIndexInterface {
     int allScores(const void *processed_query, std::vector<std::pair<double, size_t>> &out);
     static bool reduce(const uint64_t *labels, const double *scores, size_t cnt, size_t want, bool exhausted,
                        std::vector<VecSimQueryResult> &out);
+    // the oldest m vectors of `label` (the tiered index moves vectors to its backend in insertion order)
+    int deleteFirst(size_t label, size_t m);
 
   private:
     void preprocess(const void *blob, uint8_t *out) const;
@@ -428,7 +430,7 @@ class TieredIndex final : public VecSimIndexInterface {
     void lastStats(vsgpu_stats *out) override;
     int elementNeighbors(size_t label, int ***out) override;
 
-    FlatIndex *frontend() { return front_.get(); }
+    VecSimIndexInterface *frontend() { return front_.get(); }
     HnswIndex *backend() { return back_.get(); }
     void acquireSharedLocks();
     void releaseSharedLocks();
@@ -443,15 +445,16 @@ class TieredIndex final : public VecSimIndexInterface {
     void executeInsertJob(AsyncJob *job);
     void invalidateJobLocked(size_t label);
 
-    std::unique_ptr<FlatIndex> front_;
+    std::unique_ptr<VecSimIndexInterface> front_; // FlatIndex, or FlatMultiIndex over a multi-value backend
     std::unique_ptr<HnswIndex> back_;
+    bool multi_ = false;
     void *job_queue_, *job_queue_ctx_;
     SubmitCB submit_;
     size_t flat_limit_, swap_threshold_;
     size_t data_size_ = 0;
     std::shared_mutex flat_guard_, main_guard_; // always taken in this order
     std::mutex drain_mu_;
-    std::unordered_map<size_t, AsyncJob *> label_to_job_; // one pending job per vector in the flat buffer
+    std::unordered_map<size_t, std::vector<AsyncJob *>> label_to_job_; // the pending job(s) of each label in the flat buffer
     std::vector<AsyncJob *> pending_;                      // the same jobs in submission order
     std::vector<AsyncJob *> parked_;                       // vectors the backend refused three times: they stay in the buffer
     std::atomic<size_t> direct_insertions_{0};

@@ -49,39 +49,46 @@ inline bool less_score_id(const VecSimQueryResult &a, const VecSimQueryResult &b
 
 // merge_results<withSet = false> (query_result_utils.h:44-92): both inputs ascending by (score, id); a result present in
 // both lists has the same score in both, meets itself during the merge and is emitted once.
+// with_set = merge_results<withSet = true> (multi-value tiers: a label may sit in both lists with DIFFERENT scores; the
+// better one comes first and the later one is dropped by the set of ids already emitted).
 std::pair<size_t, size_t> merge_results(std::vector<VecSimQueryResult> &out, const std::vector<VecSimQueryResult> &first,
-                                        const std::vector<VecSimQueryResult> &second, size_t limit) {
+                                        const std::vector<VecSimQueryResult> &second, size_t limit, bool with_set = false) {
     out.reserve(std::min(limit, first.size() + second.size()));
+    std::unordered_set<size_t> seen;
+    auto append = [&](const VecSimQueryResult &r) {
+        if (!with_set || seen.insert(r.id).second) {
+            out.push_back(r);
+            limit--;
+        }
+    };
     size_t i = 0, j = 0;
     while (limit && i < first.size() && j < second.size()) {
         const int c = cmp_score_then_id(first[i], second[j]);
-        if (c > 0) out.push_back(second[j++]);
-        else if (c < 0) out.push_back(first[i++]);
-        else {
+        if (c > 0) append(second[j++]);
+        else if (c < 0) append(first[i++]);
+        else { // an exact duplicate: it did not appear before and will not appear again
             out.push_back(first[i]);
             i++;
             j++;
+            limit--;
         }
-        limit--;
     }
     if (limit != 0) {
         if (i == first.size())
-            while (limit && j < second.size()) {
-                out.push_back(second[j++]);
-                limit--;
-            }
+            while (limit && j < second.size()) append(second[j++]);
         else
-            while (limit && i < first.size()) {
-                out.push_back(first[i++]);
-                limit--;
-            }
+            while (limit && i < first.size()) append(first[i++]);
     }
     return {i, j};
 }
 
-// filter_results_by_id<false> (query_result_utils.h:138-180): sort by id, keep one of each
+// filter_results_by_id (query_result_utils.h:138-180): sort by id, keep one of each — the better score of a label that
+// both tiers returned (multi-value); equal scores otherwise
 void unique_by_id(std::vector<VecSimQueryResult> &r) {
-    std::sort(r.begin(), r.end(), [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id < b.id; });
+    std::sort(r.begin(), r.end(), [](const VecSimQueryResult &a, const VecSimQueryResult &b) {
+        if (a.id != b.id) return a.id < b.id;
+        return a.score < b.score;
+    });
     r.erase(std::unique(r.begin(), r.end(), [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id == b.id; }),
             r.end());
 }
@@ -110,7 +117,7 @@ TieredIndex::TieredIndex(const TieredIndexParams &tp, void *logCtx)
       swap_threshold_(tp.specificParams.tieredHnswParams.swapJobThreshold), alive_(std::make_shared<std::atomic<bool>>(true)) {
     if (!tp.primaryIndexParams || tp.primaryIndexParams->algo != VecSimAlgo_HNSWLIB) return;
     const HNSWParams &hp = tp.primaryIndexParams->algoParams.hnswParams;
-    if (hp.multi) return; // multi-value backends: not built (HNSW half)
+    multi_ = hp.multi;
     if (swap_threshold_ == 0) swap_threshold_ = 1024; // DEFAULT_PENDING_SWAP_JOBS_THRESHOLD (tiered_factory.cpp)
     auto *h = new HnswIndex(hp, logCtx);
     if (!h->ok()) {
@@ -123,16 +130,26 @@ TieredIndex::TieredIndex(const TieredIndexParams &tp, void *logCtx)
     bp.type = hp.type;
     bp.dim = hp.dim;
     bp.metric = hp.metric;
-    bp.multi = false;
+    bp.multi = multi_;
     bp.initialCapacity = 0;
     bp.blockSize = hp.blockSize;
-    auto *f = new FlatIndex(bp, logCtx);
-    if (!f->ok()) {
-        delete f;
-        back_.reset();
-        return;
+    if (multi_) {
+        auto *f = new FlatMultiIndex(bp, logCtx);
+        if (!f->ok()) {
+            delete f;
+            back_.reset();
+            return;
+        }
+        front_.reset(f);
+    } else {
+        auto *f = new FlatIndex(bp, logCtx);
+        if (!f->ok()) {
+            delete f;
+            back_.reset();
+            return;
+        }
+        front_.reset(f);
     }
-    front_.reset(f);
     data_size_ = type_size(hp.type) * hp.dim;
 }
 
@@ -153,6 +170,7 @@ void TieredIndex::executeInsertJob(AsyncJob *job) {
     std::lock_guard<std::mutex> drain(drain_mu_);
     std::vector<AsyncJob *> batch;
     bool ok = true;
+    size_t dropped = 0;
     {
         // the flat guard is held (shared) until the labels are registered in the backend: an overwrite / delete of one of
         // them either invalidated its job before this point or finds the label in the backend afterwards
@@ -170,7 +188,7 @@ void TieredIndex::executeInsertJob(AsyncJob *job) {
         // store append + graph insertion on the device, under the exclusive main guard
         if (!ok || back_->sync() != 0) {
             ok = false;
-            const size_t dropped = back_->abortPending(); // whatever did not reach the device stays in the flat buffer only
+            dropped = back_->abortPending(); // whatever did not reach the device stays in the flat buffer only
             if (globals().log_cb) {
                 const std::string msg = "tiered index: the backend refused " + std::to_string(dropped) + " vector(s) (" +
                                         vsgpu_last_error() + "); they stay in the flat buffer";
@@ -178,14 +196,25 @@ void TieredIndex::executeInsertJob(AsyncJob *job) {
             }
         }
     }
+    // the backend takes vectors in order: the first (batch - dropped) of them are in, the rest are not
+    const size_t ingested = ok ? batch.size() : (dropped >= batch.size() ? 0 : batch.size() - dropped);
     AsyncJob *retry = nullptr;
     {
         std::unique_lock<std::shared_mutex> flat(flat_guard_);
-        for (AsyncJob *p : batch) {
+        for (size_t bi = 0; bi < batch.size(); bi++) {
+            AsyncJob *p = batch[bi];
             if (!p->isValid) continue; // deleted / overwritten while it was being ingested: already out of the flat buffer
-            if (ok || back_->hasLabel(p->label)) {
-                front_->deleteVector(p->label);
-                label_to_job_.erase(p->label);
+            if (bi < ingested) {
+                // out of the flat buffer: the label's only vector (single value), or its oldest one (multi value: the vectors
+                // of a label are ingested in the order they were added)
+                if (multi_) static_cast<FlatMultiIndex *>(front_.get())->deleteFirst(p->label, 1);
+                else front_->deleteVector(p->label);
+                auto it = label_to_job_.find(p->label);
+                if (it != label_to_job_.end()) {
+                    auto &v = it->second;
+                    v.erase(std::remove(v.begin(), v.end(), p), v.end());
+                    if (v.empty()) label_to_job_.erase(it);
+                }
                 p->isValid = false;
                 continue;
             }
@@ -194,7 +223,8 @@ void TieredIndex::executeInsertJob(AsyncJob *job) {
             p->attempts++;
             if (p != job) continue;
             auto *nj = new AsyncJob{0, executeJobWrapper, this, true, p->label, p->blob, alive_, p->attempts};
-            label_to_job_[p->label] = nj;
+            auto &v = label_to_job_[p->label];
+            std::replace(v.begin(), v.end(), p, nj);
             std::replace(pending_.begin(), pending_.end(), p, nj);
             p->isValid = false;
             if (nj->attempts < 3) retry = nj;
@@ -208,15 +238,37 @@ void TieredIndex::executeInsertJob(AsyncJob *job) {
 void TieredIndex::invalidateJobLocked(size_t label) {
     auto it = label_to_job_.find(label);
     if (it == label_to_job_.end()) return;
-    it->second->isValid = false;
-    // the job object stays with the queue (it frees itself when run); drop our references
-    pending_.erase(std::remove(pending_.begin(), pending_.end(), it->second), pending_.end());
+    for (AsyncJob *j : it->second) { // one job per buffered vector of the label (several under a multi-value backend)
+        j->isValid = false;
+        // the job object stays with the queue (it frees itself when run); drop our references
+        pending_.erase(std::remove(pending_.begin(), pending_.end(), j), pending_.end());
+    }
     label_to_job_.erase(it);
 }
 
 // ---- writes ----------------------------------------------------------------------------------------------------------
 int TieredIndex::addVector(const void *blob, size_t label) {
     int ret = 1;
+    if (multi_) {
+        // multi-value (hnsw_tiered.h:762-861 with HNSWIndex_Multi): a repeated label is another vector, never an overwrite
+        if (globals().write_mode == VecSim_WriteInPlace || !submit_ || front_->indexSize() >= flat_limit_) {
+            std::unique_lock<std::shared_mutex> main(main_guard_);
+            if (back_->addVector(blob, label) < 0) return -1;
+            ++direct_insertions_;
+            return 1;
+        }
+        AsyncJob *job = nullptr;
+        {
+            std::unique_lock<std::shared_mutex> flat(flat_guard_);
+            if (front_->addVector(blob, label) < 0) return -1;
+            job = new AsyncJob{0, executeJobWrapper, this, true, label, {}, alive_};
+            job->blob.assign((const uint8_t *)blob, (const uint8_t *)blob + data_size_);
+            label_to_job_[label].push_back(job);
+            pending_.push_back(job);
+        }
+        submit_(job_queue_, job_queue_ctx_, &job, &job->Execute, 1);
+        return 1;
+    }
     if (globals().write_mode == VecSim_WriteInPlace || !submit_) {
         ret -= deleteVector(label);
         std::unique_lock<std::shared_mutex> main(main_guard_);
@@ -243,7 +295,7 @@ int TieredIndex::addVector(const void *blob, size_t label) {
         if (front_->addVector(blob, label) < 0) return -1;
         job = new AsyncJob{0, executeJobWrapper, this, true, label, {}, alive_};
         job->blob.assign((const uint8_t *)blob, (const uint8_t *)blob + data_size_);
-        label_to_job_[label] = job;
+        label_to_job_[label] = {job};
         pending_.push_back(job);
     }
     // a worker may have ingested the previous vector of this label in the meantime: remove it from the backend before
@@ -299,12 +351,25 @@ size_t TieredIndex::indexLabelCount() {
 
 double TieredIndex::getDistanceFrom(size_t label, const void *blob) {
     const double d = front_->getDistanceFrom(label, blob);
-    if (!std::isnan(d)) return d; // hnsw_tiered.h:941-963 (single value: the flat copy is authoritative)
-    return back_->getDistanceFrom(label, blob);
+    if (!multi_) {
+        if (!std::isnan(d)) return d; // hnsw_tiered.h:941-963 (single value: the flat copy is authoritative)
+        return back_->getDistanceFrom(label, blob);
+    }
+    const double b = back_->getDistanceFrom(label, blob); // multi value: the closest vector of the label in either tier
+    if (std::isnan(d)) return b;
+    if (std::isnan(b)) return d;
+    return std::min(d, b);
 }
 
 void TieredIndex::exactDistances(const void *processed_query, const size_t *labels, double *out, size_t n) {
     front_->exactDistances(processed_query, labels, out, n);
+    if (multi_) { // the closest vector of each label over both tiers
+        std::vector<double> d(n);
+        back_->exactDistances(processed_query, labels, d.data(), n);
+        for (size_t i = 0; i < n; i++)
+            if (std::isnan(out[i]) || d[i] < out[i]) out[i] = d[i];
+        return;
+    }
     std::vector<size_t> miss;
     std::vector<size_t> pos;
     for (size_t i = 0; i < n; i++)
@@ -341,7 +406,7 @@ VecSimQueryReply *TieredIndex::topKQuery(const void *blob, size_t k, VecSimQuery
     std::sort(flat_res->results.begin(), flat_res->results.end(), less_score_id);
     std::sort(main_res->results.begin(), main_res->results.end(), less_score_id);
     auto *rep = new VecSimQueryReply();
-    merge_results(rep->results, main_res->results, flat_res->results, k);
+    merge_results(rep->results, main_res->results, flat_res->results, k, multi_);
     delete flat_res;
     delete main_res;
     return rep;
@@ -379,7 +444,7 @@ int TieredIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSimQuery
         for (uint32_t j = 0; j < fc[q]; j++) b.push_back({fl[q * k + j], fs[q * k + j]});
         std::sort(a.begin(), a.end(), less_score_id);
         std::sort(b.begin(), b.end(), less_score_id);
-        merge_results(out, a, b, k);
+        merge_results(out, a, b, k, multi_);
         for (size_t j = 0; j < k; j++) {
             if (labels) labels[q * k + j] = j < out.size() ? out[j].id : (size_t)-1;
             if (scores) scores[q * k + j] = j < out.size() ? out[j].score : nan;
@@ -412,7 +477,7 @@ VecSimQueryReply *TieredIndex::rangeQuery(const void *blob, double radius, VecSi
         rep->results.insert(rep->results.end(), flat_res->results.begin(), flat_res->results.end());
         unique_by_id(rep->results);
     } else {
-        merge_results(rep->results, main_res->results, flat_res->results, (size_t)-1);
+        merge_results(rep->results, main_res->results, flat_res->results, (size_t)-1, multi_);
     }
     delete flat_res;
     delete main_res;
@@ -457,6 +522,7 @@ class TieredBatchIterator final : public VecSimBatchIterator {
                 VecSimQueryReply *tail = flat_it_->next(n - flat_res_.size(), BY_SCORE_THEN_ID);
                 flat_res_.insert(flat_res_.end(), tail->results.begin(), tail->results.end());
                 delete tail;
+                if (idx_->multi_) filterReturned(flat_res_); // multi value: a label the backend already gave out
             }
             while (hnsw_res_.size() < n && state_ == ACTIVE && hnsw_code == VecSim_QueryReply_OK) {
                 VecSimQueryReply *tail = hnsw_it_->next(n - hnsw_res_.size(), BY_SCORE_THEN_ID);
@@ -464,7 +530,7 @@ class TieredBatchIterator final : public VecSimBatchIterator {
                 std::sort(tail->results.begin(), tail->results.end(), less_score_id);
                 // a new batch may hold better results than what is left of the previous one
                 std::vector<VecSimQueryResult> merged;
-                merge_results(merged, hnsw_res_, tail->results, n);
+                merge_results(merged, hnsw_res_, tail->results, n, idx_->multi_);
                 delete tail;
                 hnsw_res_.swap(merged);
                 filterReturned(hnsw_res_);
@@ -476,11 +542,16 @@ class TieredBatchIterator final : public VecSimBatchIterator {
             batch->code = hnsw_code;
             return batch;
         }
-        const auto [from_hnsw, from_flat] = merge_results(batch->results, hnsw_res_, flat_res_, n);
+        const auto [from_hnsw, from_flat] = merge_results(batch->results, hnsw_res_, flat_res_, n, idx_->multi_);
         // what the flat buffer returned must not come back from the backend in a later batch
         for (size_t i = 0; i < from_flat; i++) returned_.insert(flat_res_[i].id);
         flat_res_.erase(flat_res_.begin(), flat_res_.begin() + (ptrdiff_t)from_flat);
         hnsw_res_.erase(hnsw_res_.begin(), hnsw_res_.begin() + (ptrdiff_t)from_hnsw);
+        if (idx_->multi_) { // a label lives in both tiers with different vectors: whatever was handed out is done, in both
+            for (const VecSimQueryResult &r : batch->results) returned_.insert(r.id);
+            filterReturned(flat_res_);
+            filterReturned(hnsw_res_);
+        }
         if (order == BY_ID)
             std::sort(batch->results.begin(), batch->results.end(),
                       [](const VecSimQueryResult &a, const VecSimQueryResult &b) { return a.id < b.id; });
