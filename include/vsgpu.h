@@ -93,13 +93,21 @@ int vsgpu_topk(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, s
  * enqueued on the store's stream; call vsgpu_store_sync before reading. */
 int vsgpu_topk_device(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k,
                       unsigned flags, uint64_t *out_labels, void *out_scores, uint32_t *out_ids);
-/* Two-step variant for sharded callers: _begin stops a tensor-path call after the coarse phases and writes each query's
- * admission bound to bound_out ([nq] fp32, DEVICE; -inf when the call already did all its work). The caller reduces the
- * bounds over the shards (max — every shard's bound is a valid lower bound of the global k-th score) and hands the result
- * to _finish, which drops the survivors below it before the exact re-rank. Same outputs as vsgpu_topk_device. */
+/* Phased variant for sharded callers (`world` shards, one store each). A tensor-path call runs its coarse pass in `rounds`
+ * phases — _begin the first, every _next one more — and after each writes this shard's bounds to `bounds` ([2 nq] fp32,
+ * DEVICE): bounds[q] bounds its k-th best score from below, -bounds[nq + q] its ceil(k / world)-th best. Between the calls
+ * the caller reduces the whole buffer with MAX over the shards (one small all-reduce); max(bounds[q], -bounds[nq + q]) is then
+ * a lower bound of the k-th best score overall (world * ceil(k / world) >= k rows reach the smallest of the shards' second
+ * values). Every shard admits against it in its next phase and prunes against it in _finish, before the exact re-rank.
+ * Sequence: _begin, (reduce, _next) x (rounds - 1), reduce, _finish. `rounds` = vsgpu_topk_rounds() of a row count all the
+ * shards agree on — every shard runs exactly that many phases whatever its own size. Calls that take another path do all
+ * their work in _begin and leave neutral bounds. Same outputs as vsgpu_topk_device. world < 2 or bounds == NULL: plain call. */
 int vsgpu_topk_device_begin(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k, unsigned flags,
-                            uint64_t *out_labels, void *out_scores, uint32_t *out_ids, float *bound_out);
-int vsgpu_topk_device_finish(vsgpu_store *s, const float *bound_in);
+                            uint64_t *out_labels, void *out_scores, uint32_t *out_ids, unsigned world, unsigned rounds,
+                            float *bounds);
+int vsgpu_topk_device_next(vsgpu_store *s, float *bounds);
+int vsgpu_topk_device_finish(vsgpu_store *s, const float *bounds);
+size_t vsgpu_topk_rounds(size_t rows_per_shard, size_t k, unsigned world);
 int vsgpu_store_sync(vsgpu_store *s);
 void *vsgpu_store_stream(vsgpu_store *s); /* cudaStream_t */
 /* Run the store's work on a stream of the caller's (a framework's pooled stream, say) from now on; the store never

@@ -31,7 +31,11 @@ def main():
     port.set_tier(port.TIER_AVX512)
     checked = 0
     for vtype, metric, n, dim, k, nq, mode in [(0, 1, 20011, 96, 25, 40, 0), (0, 0, 5003, 128, 10, 3, 1), (4, 0, 3001, 6, 20, 9, 1),
-                                               (2, 1, 30011, 64, 50, 64, 0), (1, 2, 1001, 24, 7, 5, 1)]:
+                                               (2, 1, 30011, 64, 50, 64, 0), (1, 2, 1001, 24, 7, 5, 1),
+                                               # every shard large enough for the tensor path (forced): the phased call with
+                                               # its bound exchange after every phase
+                                               (0, 1, 40000 * world + 11, 64, 100, 96, 2), (0, 0, 36000 * world, 72, 10, 33, 2),
+                                               (2, 2, 34000 * world + 5, 64, 37, 24, 2), (4, 2, 40000 * world, 64, 10, 64, 2)]:
         X = make_vectors(vtype, n, dim, seed=11 + vtype)
         Q = make_vectors(vtype, nq, dim, seed=12 + vtype)
         if vtype == 4:  # coarse int8: many exact ties across the shard boundary

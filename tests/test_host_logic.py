@@ -195,6 +195,35 @@ def test_header_is_c_and_a_c_consumer_links(capi, tmp_path):
     assert lines[1].startswith("index ") and ("(ok)" in lines[1] or "tiered index:" in lines[1])
 
 
+def test_phase_schedule_of_sharded_phased_calls(capi):
+    """make_phases with `world` shards and a fixed number of rounds (vsgpu_topk_device_begin / _next / _finish): every shard
+    runs exactly `rounds` phases whatever its own row count (trailing ones may be empty), the schedule still tiles [0, n), and
+    exchanging the ceil(k / world)-th best affords fewer phases than a shard on its own needs."""
+    capi.lib()
+    G = C.CDLL(os.path.join(ROOT, "vectorsimilarity_b200", "libvsgpu.so"))
+    G.vsgpu_debug_phases.restype = C.c_size_t
+    G.vsgpu_debug_phases.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
+    G.vsgpu_debug_phases_sharded.restype = C.c_size_t
+    G.vsgpu_debug_phases_sharded.argtypes = [C.c_size_t, C.c_size_t, C.c_uint, C.c_size_t, C.c_void_p, C.c_size_t]
+    G.vsgpu_topk_rounds.restype = C.c_size_t
+    G.vsgpu_topk_rounds.argtypes = [C.c_size_t, C.c_size_t, C.c_uint]
+    buf = np.zeros(64, dtype=np.uint32)
+    for n, k, world in ((1_250_000, 100, 8), (2_500_000, 100, 4), (5_000_000, 100, 2), (6_250_000, 10, 8), (40_000, 384, 2),
+                        (1_250_000, 1000, 8)):
+        rounds = G.vsgpu_topk_rounds(n, k, world)
+        own = G.vsgpu_debug_phases(n, k, buf.ctypes.data, 64)
+        assert 1 <= rounds <= own
+        if world >= 4 and k <= 100:
+            assert rounds < own
+        for rows in (n, n - 1, n // 3, 1000, 128, 77):     # shards of any size follow the agreed number of rounds
+            m = G.vsgpu_debug_phases_sharded(rows, k, world, rounds, buf.ctypes.data, 64)
+            edges = buf[:m].astype(np.int64)
+            assert m == rounds and edges[-1] == rows and np.all(np.diff(edges) >= 0)
+            assert np.all(edges[edges < rows] % 128 == 0)
+    assert G.vsgpu_topk_rounds(1_250_000, 100, 8) == 3
+    assert G.vsgpu_topk_rounds(10_000_000, 100, 1) == G.vsgpu_debug_phases(10_000_000, 100, buf.ctypes.data, 64)
+
+
 def test_phase_schedule_of_the_filtered_gemm(capi):
     """make_phases (csrc/vsgpu_tc.cuh): phases tile [0, n) without gaps, every edge but the last is a multiple of the
     128-row tile, consecutive edges grow by at most the factor the candidate buffer affords (8 for k <= 150, less for

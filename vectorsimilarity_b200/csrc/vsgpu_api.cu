@@ -235,7 +235,7 @@ static size_t score_size(const vsgpu_store *s) { return s->type == VSGPU_FLOAT64
 // queries staged on the device -> device outputs [nq][out_ld]
 static int topk_core(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, size_t k,
                      size_t out_ld, unsigned flags, uint32_t *out_ids, void *out_scores, uint64_t *out_labels,
-                     float *bound_out = nullptr) {
+                     const PhasedCall *ph = nullptr) {
     const size_t n = s->count;
     const size_t k_eff = std::min(k, n);
     const size_t ssz = score_size(s);
@@ -264,7 +264,7 @@ static int topk_core(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stri
             return VSGPU_ERR_ARG;
         }
         s->stats.path = 1;
-        return tensor_topk(s, q_dev, nq, q_stride, q_norms, k_eff, out_ids, out_scores, out_labels, bound_out);
+        return tensor_topk(s, q_dev, nq, q_stride, q_norms, k_eff, out_ids, out_scores, out_labels, ph);
     }
     s->stats.path = 0;
     // small batches on the staged scan: selection fused into the scan (per-CTA running top-k in shared memory) — no score
@@ -551,34 +551,48 @@ int vsgpu_topk_device(vsgpu_store *s, const void *queries, size_t nq, size_t qst
     return VSGPU_OK;
 }
 
-// Two-step variant for sharded callers. _begin: as vsgpu_topk_device, but a tensor-path call stops after the coarse phases
-// and writes each query's admission bound to bound_out ([nq] fp32, DEVICE; -inf when the call did all its work already).
-// The caller reduces the bounds over the shards (max) and calls _finish with the result: survivors below the reduced bound
-// are dropped before the exact re-rank — a shard then re-ranks its share of ONE band instead of a whole band of its own.
+// Phased variant for sharded callers (`world` shards, one store each). A tensor-path call runs its coarse pass
+// in `rounds` phases — _begin the first, every _next one more — and after each writes this shard's bounds to `bounds`
+// ([2 nq] fp32, DEVICE): bounds[q] bounds its k-th best score from below, -bounds[nq + q] its ceil(k / world)-th best. The
+// caller reduces the whole buffer with MAX over the shards between the calls; max(bounds[q], -bounds[nq + q]) is then a lower
+// bound of the k-th best score overall, which every shard admits against in its next phase and prunes against in _finish
+// before the exact re-rank. Calls that take another path do all their work in _begin and leave neutral bounds.
 int vsgpu_topk_device_begin(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k, unsigned flags,
-                            uint64_t *out_labels, void *out_scores, uint32_t *out_ids, float *bound_out) {
+                            uint64_t *out_labels, void *out_scores, uint32_t *out_ids, unsigned world, unsigned rounds,
+                            float *bounds) {
     if (nq == 0 || k == 0) return VSGPU_OK;
-    if (!bound_out) return vsgpu_topk_device(s, queries, nq, qstride, k, flags, out_labels, out_scores, out_ids);
+    if (!bounds || world < 2 || rounds == 0) return vsgpu_topk_device(s, queries, nq, qstride, k, flags, out_labels, out_scores, out_ids);
     VS_CUDA(cudaSetDevice(s->device));
     VS_TRY(resolve_pending_topk(s));
     s->stats = vsgpu_stats{};
     VS_CUDA(cudaEventRecord(s->ev0, s->stream));
-    fill_kernel<float><<<16, 256, 0, s->stream>>>(bound_out, -std::numeric_limits<float>::infinity(), nq);
+    fill_kernel<float><<<16, 256, 0, s->stream>>>(bounds, -std::numeric_limits<float>::infinity(), nq);
+    fill_kernel<float><<<16, 256, 0, s->stream>>>(bounds + nq, std::numeric_limits<float>::infinity(), nq);
     const void *q = nullptr;
     size_t qs = 0;
     const float *qn = nullptr;
     VS_TRY(stage_queries_device(s, queries, nq, qstride, &q, &qs, &qn));
-    VS_TRY(topk_core(s, q, nq, qs, qn, k, k, flags, out_ids, out_scores, out_labels, bound_out));
+    const PhasedCall ph{world, rounds, bounds};
+    VS_TRY(topk_core(s, q, nq, qs, qn, k, k, flags, out_ids, out_scores, out_labels, &ph));
     VS_CUDA(cudaEventRecord(s->ev1, s->stream));
     return VSGPU_OK;
 }
 
-int vsgpu_topk_device_finish(vsgpu_store *s, const float *bound_in) {
+int vsgpu_topk_device_next(vsgpu_store *s, float *bounds) {
     VS_CUDA(cudaSetDevice(s->device));
-    VS_TRY(tensor_topk_finish(s, bound_in));
+    VS_TRY(tensor_topk_next(s, bounds));
     VS_CUDA(cudaEventRecord(s->ev1, s->stream));
     return VSGPU_OK;
 }
+
+int vsgpu_topk_device_finish(vsgpu_store *s, const float *bounds) {
+    VS_CUDA(cudaSetDevice(s->device));
+    VS_TRY(tensor_topk_finish(s, bounds));
+    VS_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return VSGPU_OK;
+}
+
+size_t vsgpu_topk_rounds(size_t rows_per_shard, size_t k, unsigned world) { return tensor_topk_rounds(rows_per_shard, k, world); }
 
 int vsgpu_topk(vsgpu_store *s, const void *queries, size_t nq, size_t qstride, size_t k, unsigned flags,
                uint64_t *out_labels, double *out_scores, uint32_t *out_ids, uint32_t *out_counts) {

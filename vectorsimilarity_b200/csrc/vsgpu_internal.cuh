@@ -199,9 +199,17 @@ int launch_range_compact(vsgpu_store *s, const void *scores, size_t n, double ra
 
 // ---- tensor path (vsgpu_tensor.cu) ----
 bool tensor_path_supported(const vsgpu_store *s, size_t nq, size_t k);
+// phased call of a sharded index (vsgpu_topk_device_begin / _next / _finish): `world` shards run `rounds` coarse phases
+// each and exchange `bounds` ([2 nq] fp32, device) after every one
+struct PhasedCall {
+    unsigned world, rounds;
+    float *bounds;
+};
 int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, size_t k,
-                uint32_t *out_ids, void *out_scores, uint64_t *out_labels, float *bound_out = nullptr);
-int tensor_topk_finish(vsgpu_store *s, const float *bound_in);
+                uint32_t *out_ids, void *out_scores, uint64_t *out_labels, const PhasedCall *ph = nullptr);
+int tensor_topk_next(vsgpu_store *s, float *bounds);
+int tensor_topk_finish(vsgpu_store *s, const float *bounds);
+size_t tensor_topk_rounds(size_t rows, size_t k, unsigned world);
 int tensor_sync_mirrors(vsgpu_store *s);
 void tensor_release(vsgpu_store *s);
 // a single row changed (src != SIZE_MAX: row src was copied over row id): patch the tensor-path side data in place

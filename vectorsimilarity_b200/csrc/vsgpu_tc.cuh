@@ -204,22 +204,43 @@ inline EncodeTiledFn tc_encode_fn() {
 // admits ~ (growth - 1) * k rows per query (growth is what the per-phase candidate buffer affords). The fewest phases
 // with that property, the last one ending exactly at n: every launch carries a fixed ~50-80 us (pipeline fill, tail,
 // the merge that follows), so a short trailing phase is the most expensive way to finish.
-inline std::vector<std::pair<uint32_t, uint32_t>> make_phases(size_t n, size_t k, size_t cand_cap, size_t bm) {
-    std::vector<std::pair<uint32_t, uint32_t>> phases;
+//
+// Sharded callers that exchange their bounds between the phases (vsgpu_topk_device_begin / _next / _finish, `world` shards):
+// the exchanged bound is the shards' ceil(k / world)-th best score, not the k-th, so a phase of G times the rows seen
+// admits ~ G * k / world rows per query and the same buffer affords a `world` times larger growth: 3 phases instead of 5
+// at 1.25 M rows per shard. All shards must run the same number of phases (`rounds`, from topk_rounds on a row count
+// every shard agrees on), whatever their own row count.
+inline double phase_growth(size_t k, size_t cand_cap, unsigned world) {
+    if (world <= 1) return std::max(3.0, std::min(8.0, (double)cand_cap / (2.5 * (double)k)));
+    const double m = (double)((k + world - 1) / world);
+    return std::max(3.0, std::min(64.0, (double)cand_cap / (4.0 * m))); // the min over the shards of an m-th order statistic is looser
+}
+inline size_t phase_first(size_t k, size_t cand_cap, size_t bm) {
     size_t s0 = std::max<size_t>(bm, std::min<size_t>(cand_cap, 2048) / bm * bm);
     s0 = std::max(s0, (std::min<size_t>(2 * k, cand_cap) + bm - 1) / bm * bm);
     if (const char *e = getenv("VSGPU_PHASE_S0")) { // experiments only
         const size_t v = (size_t)atol(e) / bm * bm;
         if (v >= s0 && v <= cand_cap) s0 = v;
     }
-    const double growth = std::max(3.0, std::min(8.0, (double)cand_cap / (2.5 * (double)k)));
+    return s0;
+}
+inline size_t topk_rounds(size_t n, size_t k, size_t cand_cap, size_t bm, unsigned world) {
+    const size_t s0 = phase_first(k, cand_cap, bm);
     size_t np = 1;
-    if (n > s0) np += (size_t)std::ceil(std::log((double)n / (double)s0) / std::log(growth) - 1e-9);
-    const double ratio = np > 1 ? std::pow((double)n / (double)s0, 1.0 / (double)(np - 1)) : 1.0;
+    if (n > s0) np += (size_t)std::ceil(std::log((double)n / (double)s0) / std::log(phase_growth(k, cand_cap, world)) - 1e-9);
+    return np;
+}
+// rounds == 0: as many phases as this n needs. rounds > 0: exactly that many (trailing ones may be empty: first == second)
+inline std::vector<std::pair<uint32_t, uint32_t>> make_phases(size_t n, size_t k, size_t cand_cap, size_t bm, unsigned world = 1,
+                                                              size_t rounds = 0) {
+    std::vector<std::pair<uint32_t, uint32_t>> phases;
+    const size_t s0 = phase_first(k, cand_cap, bm);
+    const size_t np = rounds ? rounds : topk_rounds(n, k, cand_cap, bm, world);
+    const double ratio = np > 1 && n > s0 ? std::pow((double)n / (double)s0, 1.0 / (double)(np - 1)) : 1.0;
     size_t a = 0;
     double edge = (double)std::min(n, s0);
-    for (size_t p = 0; p < np && a < n; p++) {
-        const size_t b = p + 1 == np ? n : std::min(n, std::max((size_t)edge / bm * bm, a + bm));
+    for (size_t p = 0; p < np; p++) {
+        const size_t b = a >= n ? n : p + 1 == np ? n : std::min(n, std::max((size_t)edge / bm * bm, a + bm));
         phases.emplace_back((uint32_t)a, (uint32_t)b);
         a = b;
         edge *= ratio;

@@ -547,6 +547,8 @@ struct MergeArgs {
     float *athr;             // [nq] admission bound for the next phase: admit when acc + e1 ||row|| >= athr
     uint32_t *overflow;      // [nq] set when a buffer overflowed: the query is redone exactly
     unsigned long long *total_cand;
+    uint32_t m;              // sharded, phased calls: also report the bound of the m-th best row, m = ceil(k / shards); else 0
+    float *bounds;           // [2 nq] out when m: bounds[q] = athr[q], bounds[nq + q] = -(bound of the m-th best), see below
 };
 
 // One block per query over (survivors U this phase's candidates). Row r's exact sum lies in [lo_r, hi_r] =
@@ -607,17 +609,18 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_phase_kernel(MergeArgs a)
     }
     if (threadIdx.x == 0) s_keep = 0;
     __syncthreads();
-    float bound = -__int_as_float(0x7f800000);
-    if (total >= a.k) {
+    float bound = -__int_as_float(0x7f800000), bound_m = bound;
 #pragma unroll
-        for (int w = 0; w < MERGE_THREADS / 32; w++) {
-            kmin = min(kmin, s_red[2 * w]);
-            kmax = max(kmax, s_red[2 * w + 1]);
-        }
-        const uint32_t range = kmax - kmin;
-        const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
-        uint32_t prefix = 0;      // digits of (k-th smallest key - kmin) decided so far
-        uint32_t want = a.k - 1;  // 0-based rank among the keys that share those digits
+    for (int w = 0; w < MERGE_THREADS / 32; w++) {
+        kmin = min(kmin, s_red[2 * w]);
+        kmax = max(kmax, s_red[2 * w + 1]);
+    }
+    const uint32_t range = kmax - kmin;
+    const int passes = range ? (32 - __clz(range) + 7) / 8 : 0;
+    // bound (in the admission test's units) of the (rank+1)-th largest lower end
+    auto select = [&](uint32_t rank) -> float {
+        uint32_t prefix = 0;      // digits of (rank-th smallest key - kmin) decided so far
+        uint32_t want = rank;     // 0-based rank among the keys that share those digits
         for (int shift = 8 * (passes - 1); shift >= 0; shift -= 8) {
             s_hist[threadIdx.x] = 0; // MERGE_THREADS == 256 bins
             __syncthreads();
@@ -656,10 +659,18 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_phase_kernel(MergeArgs a)
             prefix |= s_digit << shift;
             want -= s_below;
         }
-        const float lk = key2f(~(kmin + prefix));              // k-th largest lower end (before e2)
-        bound = __fsub_rd(lk, __fmul_ru(2.0f, e2));            // hi_r + e2 >= L_K - e2
-        bound = __fsub_rd(bound, fabsf(bound) * 1e-6f);        // the epilogue's FFMA rounds to nearest
-    }
+        const float lk = key2f(~(kmin + prefix));              // (rank+1)-th largest lower end (before e2)
+        float b = __fsub_rd(lk, __fmul_ru(2.0f, e2));          // hi_r + e2 >= L_K - e2
+        return __fsub_rd(b, fabsf(b) * 1e-6f);                 // the epilogue's FFMA rounds to nearest
+    };
+    if (total >= a.k) bound = select(a.k - 1);
+    // Sharded, phased call: with m = ceil(k / shards), every shard holds m rows whose exact score is at
+    // least its own m-th lower end, so shards * m >= k rows reach the smallest of those: the k-th best score overall does
+    // too. The caller reduces both halves of `bounds` with MAX over the shards; max(bounds[q], -bounds[nq + q]) is then a
+    // valid admission bound on every shard, and far tighter than any shard's own k-th.
+    if (a.m && a.m < a.k && total >= a.m) bound_m = select(a.m - 1);
+    else if (a.m >= a.k) bound_m = bound;
+    bound = fmaxf(bound, a.athr[q]);                           // what earlier phases (or other shards) established
     // survivors, in any order
     uint2 *run_out = a.run + (size_t)q * RUN_CAP;
     for (uint32_t i = threadIdx.x; i < total; i += MERGE_THREADS) {
@@ -678,7 +689,17 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_phase_kernel(MergeArgs a)
         a.run_cnt[q] = keep;
         a.cnt[q] = 0;
         a.athr[q] = bound;
+        if (a.m) {
+            a.bounds[q] = bound;
+            a.bounds[a.nq + q] = -bound_m;
+        }
     }
+}
+
+// reduced bounds of all shards -> this shard's admission bounds for its next phase
+__global__ void apply_bounds_kernel(float *__restrict__ athr, const float *__restrict__ bounds, uint32_t nq) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) athr[q] = fmaxf(athr[q], fmaxf(bounds[q], -bounds[nq + q]));
 }
 
 __global__ void unpack_ids_kernel(const uint2 *__restrict__ run, size_t total, uint32_t *__restrict__ ids) {
@@ -720,11 +741,12 @@ struct TensorState {
     float *row_hsq = nullptr;     // L2 stores: ||row||^2 / 2 per row
     int sms = 0;
     bool attr_set = false, pair_attr_set = false;
-    // two-step top-k (vsgpu_topk_device_begin / _finish): the coarse phases ran, the survivors wait for the re-rank
+    // phased top-k of a sharded caller (vsgpu_topk_device_begin / _next / _finish): what the remaining phases and the
+    // re-rank need
     struct Split {
         bool armed = false;
         const uint8_t *qp = nullptr;
-        size_t nq = 0, q_stride = 0, k = 0, n_ev = 0;
+        size_t nq = 0, q_stride = 0, k = 0, n_ev = 0, next = 0;
         uint32_t run_cap = 0;
         uint2 *run = nullptr;
         uint32_t *rcnt = nullptr, *rid = nullptr;
@@ -733,18 +755,23 @@ struct TensorState {
         void *out_scores = nullptr;
         uint64_t *out_labels = nullptr;
         const float *q_norms = nullptr;
+        std::vector<std::pair<uint32_t, uint32_t>> phases;
+        CUtensorMap map_a, map_b, map_bh;
+        GemmArgs g;
+        MergeArgs m;
+        size_t merge_smem = 0;
     } split;
 };
 
 // survivors whose upper score estimate does not reach the (cross-shard) bound cannot be in the global result: drop them
 __global__ void __launch_bounds__(256) prune_run_kernel(uint2 *__restrict__ run, uint32_t *__restrict__ run_cnt, uint32_t run_cap,
                                                         const float *__restrict__ e1, const float *__restrict__ row_l2,
-                                                        const float *__restrict__ bound) {
+                                                        const float *__restrict__ bounds) {
     extern __shared__ uint2 s_keep[];
     __shared__ uint32_t s_n;
     const uint32_t q = blockIdx.x;
     const uint32_t cnt = run_cnt[q];
-    const float b = bound[q], e = e1[q];
+    const float b = fmaxf(bounds[q], -bounds[gridDim.x + q]), e = e1[q];
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     uint2 *mine = run + (size_t)q * run_cap;
@@ -941,15 +968,33 @@ static int tensor_rerank(vsgpu_store *s, TensorState *t, const uint8_t *qp, size
     return VSGPU_OK;
 }
 
-// bound_out != NULL (two-step call, single chunk of queries only): stop after the coarse phases, hand out the admission
-// bounds and leave the survivors for tensor_topk_finish
+// one phase of the filtered GEMM and the merge of what it admitted
+static int run_phase(vsgpu_store *s, TensorState *t, const CUtensorMap &map_a, const CUtensorMap &map_b, const CUtensorMap *map_bh,
+                     GemmArgs &g, const MergeArgs &m, size_t merge_smem, std::pair<uint32_t, uint32_t> rows, size_t *n_ev) {
+    if (rows.first >= rows.second) return VSGPU_OK; // a shard with fewer rows than the agreed schedule covers
+    g.row0 = rows.first;
+    g.row_end = rows.second;
+    cudaEvent_t e0 = scan_event(s, 2 * *n_ev), e1 = scan_event(s, 2 * *n_ev + 1);
+    if (!e0 || !e1) return VSGPU_ERR_CUDA;
+    VS_CUDA(cudaEventRecord(e0, s->stream));
+    VS_TRY(launch_gemm(s, t, map_a, map_b, map_bh, g));
+    VS_CUDA(cudaEventRecord(e1, s->stream));
+    ++*n_ev;
+    merge_phase_kernel<<<m.nq, MERGE_THREADS, merge_smem, s->stream>>>(m);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    return VSGPU_OK;
+}
+
+// ph != NULL (phased call of a sharded index, single chunk of queries only): run the first phase only, hand out this
+// shard's bounds and leave the rest to tensor_topk_next / tensor_topk_finish
 int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_stride, const float *q_norms, size_t k,
-                uint32_t *out_ids, void *out_scores, uint64_t *out_labels, float *bound_out) {
+                uint32_t *out_ids, void *out_scores, uint64_t *out_labels, const PhasedCall *ph) {
     if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8)
         return tensor_i8_topk(s, q_dev, nq_all, q_stride, q_norms, k, out_ids, out_scores, out_labels);
     TensorState *t = state(s);
     t->split.armed = false;
-    const bool two_step = bound_out != nullptr && nq_all <= MAX_NQ;
+    const bool phased = ph != nullptr && ph->bounds != nullptr && ph->rounds > 0 && nq_all <= MAX_NQ;
     VS_TRY(tensor_sync_mirrors(s));
     const size_t n = s->count;
     const bool f32 = s->type == VSGPU_FLOAT32;
@@ -965,7 +1010,8 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
     VS_TRY(make_map(&map_a, a_base, n, s->dim, a_stride, BM));
 
     const uint32_t run_cap = k <= K_SMALL_MAX ? RUN_CAP : RUN_CAP_BIG, cand_cap = k <= K_SMALL_MAX ? CAND_CAP : CAND_CAP_BIG;
-    const std::vector<std::pair<uint32_t, uint32_t>> phases = make_phases(n, k, cand_cap, BM);
+    const std::vector<std::pair<uint32_t, uint32_t>> phases =
+        phased ? make_phases(n, k, cand_cap, BM, ph->world, ph->rounds) : make_phases(n, k, cand_cap, BM);
     const size_t merge_smem = (size_t)(run_cap + cand_cap) * 8 + (size_t)run_cap * 8;
     if (merge_smem > 48 * 1024)
         VS_CUDA(cudaFuncSetAttribute(merge_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
@@ -1008,51 +1054,40 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
         VS_TRY(make_map(&map_b, qb, nq_pad, s->dim, qb_stride * 2, BN));
         if (gemm_pair_enabled()) VS_TRY(make_map(&map_bh, qb, nq_pad, s->dim, qb_stride * 2, BN / 2));
 
-        for (size_t p = 0; p < phases.size(); p++) {
-            GemmArgs g{};
-            g.row0 = phases[p].first;
-            g.row_end = phases[p].second;
-            g.nq = (uint32_t)nq;
-            g.n_qtiles = (uint32_t)(nq_pad / BN);
-            g.k_blocks = (uint32_t)((s->dim + BK - 1) / BK);
-            g.athr = athr;
-            g.e1 = eps;
-            g.row_l2 = s->row_l2;
-            g.c_l2 = c_l2;
-            g.cnt = cnt;
-            g.cand = cand;
-            g.cand_cap = cand_cap;
-            g.dump = nullptr;
-            g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
-            g.row_sub = s->metric == VSGPU_L2 ? t->row_hsq : nullptr;
-            cudaEvent_t e0 = scan_event(s, 2 * n_ev), e1 = scan_event(s, 2 * n_ev + 1);
-            if (!e0 || !e1) return VSGPU_ERR_CUDA;
-            VS_CUDA(cudaEventRecord(e0, s->stream));
-            VS_TRY(launch_gemm(s, t, map_a, map_b, gemm_pair_enabled() ? &map_bh : nullptr, g));
-            VS_CUDA(cudaEventRecord(e1, s->stream));
-            n_ev++;
-            MergeArgs m{};
-            m.nq = (uint32_t)nq;
-            m.k = (uint32_t)k;
-            m.run = run;
-            m.run_cnt = rcnt;
-            m.cnt = cnt;
-            m.cand = cand;
-            m.run_cap = run_cap;
-            m.cand_cap = cand_cap;
-            m.e1 = eps;
-            m.e2 = eps2;
-            m.row_l2 = s->row_l2;
-            m.c_l2 = c_l2;
-            m.athr = athr;
-            m.overflow = ovf;
-            m.total_cand = tot;
-            merge_phase_kernel<<<(unsigned)nq, MERGE_THREADS, merge_smem, s->stream>>>(m);
-            VS_CUDA(cudaGetLastError());
-            s->stats.kernel_launches++;
-        }
-        if (two_step) {
-            VS_CUDA(cudaMemcpyAsync(bound_out, athr, nq * 4, cudaMemcpyDeviceToDevice, s->stream));
+        GemmArgs g{};
+        g.nq = (uint32_t)nq;
+        g.n_qtiles = (uint32_t)(nq_pad / BN);
+        g.k_blocks = (uint32_t)((s->dim + BK - 1) / BK);
+        g.athr = athr;
+        g.e1 = eps;
+        g.row_l2 = s->row_l2;
+        g.c_l2 = c_l2;
+        g.cnt = cnt;
+        g.cand = cand;
+        g.cand_cap = cand_cap;
+        g.dump = nullptr;
+        g.idesc = s->type == VSGPU_FLOAT16 ? IDESC_FP16 : IDESC_BF16;
+        g.row_sub = s->metric == VSGPU_L2 ? t->row_hsq : nullptr;
+        MergeArgs m{};
+        m.nq = (uint32_t)nq;
+        m.k = (uint32_t)k;
+        m.run = run;
+        m.run_cnt = rcnt;
+        m.cnt = cnt;
+        m.cand = cand;
+        m.run_cap = run_cap;
+        m.cand_cap = cand_cap;
+        m.e1 = eps;
+        m.e2 = eps2;
+        m.row_l2 = s->row_l2;
+        m.c_l2 = c_l2;
+        m.athr = athr;
+        m.overflow = ovf;
+        m.total_cand = tot;
+        if (phased) {
+            m.m = (uint32_t)((k + ph->world - 1) / ph->world);
+            m.bounds = ph->bounds;
+            VS_TRY(run_phase(s, t, map_a, map_b, gemm_pair_enabled() ? &map_bh : nullptr, g, m, merge_smem, phases[0], &n_ev));
             auto &sp = t->split;
             sp.armed = true;
             sp.qp = qp;
@@ -1060,6 +1095,7 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             sp.q_stride = q_stride;
             sp.k = k;
             sp.n_ev = n_ev;
+            sp.next = 1;
             sp.run_cap = run_cap;
             sp.run = run;
             sp.rcnt = rcnt;
@@ -1071,8 +1107,17 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
             sp.out_scores = out_scores;
             sp.out_labels = out_labels;
             sp.q_norms = q_norms;
+            sp.phases = phases;
+            sp.map_a = map_a;
+            sp.map_b = map_b;
+            sp.map_bh = map_bh;
+            sp.g = g;
+            sp.m = m;
+            sp.merge_smem = merge_smem;
             return VSGPU_OK;
         }
+        for (size_t p = 0; p < phases.size(); p++)
+            VS_TRY(run_phase(s, t, map_a, map_b, gemm_pair_enabled() ? &map_bh : nullptr, g, m, merge_smem, phases[p], &n_ev));
         VS_TRY(tensor_rerank(s, t, qp, nq, q_stride, k, run_cap, run, rcnt, rid, rsc, out_ids ? out_ids + q0 * k : nullptr,
                              out_scores ? (float *)out_scores + q0 * k : nullptr, out_labels ? out_labels + q0 * k : nullptr));
     }
@@ -1081,15 +1126,42 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
     return VSGPU_OK;
 }
 
-// second half of a two-step call: prune with the reduced bound (may be NULL), re-rank, write the lists
-int tensor_topk_finish(vsgpu_store *s, const float *bound_in) {
+// phased call, after the caller reduced `bounds` over the shards: tighten this shard's admission bounds, run its next phase
+// and write its new bounds. A no-op once the phases are done (or when _begin did all the work on another path).
+int tensor_topk_next(vsgpu_store *s, float *bounds) {
+    auto *t = (TensorState *)s->tmap_cache;
+    if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8 || !t || !t->split.armed) return VSGPU_OK;
+    auto &sp = t->split;
+    if (sp.next >= sp.phases.size()) return VSGPU_OK;
+    const auto rows = sp.phases[sp.next++];
+    if (rows.first >= rows.second) return VSGPU_OK;
+    apply_bounds_kernel<<<(unsigned)((sp.nq + 255) / 256), 256, 0, s->stream>>>(sp.athr, bounds, (uint32_t)sp.nq);
+    VS_CUDA(cudaGetLastError());
+    s->stats.kernel_launches++;
+    sp.m.bounds = bounds;
+    return run_phase(s, t, sp.map_a, sp.map_b, gemm_pair_enabled() ? &sp.map_bh : nullptr, sp.g, sp.m, sp.merge_smem, rows, &sp.n_ev);
+}
+
+// last step of a phased call: any phases left (a caller that exchanged fewer times than agreed), prune with the reduced
+// bounds (may be NULL), re-rank, write the lists
+int tensor_topk_finish(vsgpu_store *s, const float *bounds) {
     auto *t = (TensorState *)s->tmap_cache;
     if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8 || !t || !t->split.armed) return VSGPU_OK;
     auto &sp = t->split;
     sp.armed = false;
-    if (bound_in) {
+    if (bounds && sp.next < sp.phases.size()) {
+        apply_bounds_kernel<<<(unsigned)((sp.nq + 255) / 256), 256, 0, s->stream>>>(sp.athr, bounds, (uint32_t)sp.nq);
+        VS_CUDA(cudaGetLastError());
+        s->stats.kernel_launches++;
+    }
+    const bool ran_more = sp.next < sp.phases.size();
+    sp.m.m = 0; // nobody reads the bounds of these phases
+    for (; sp.next < sp.phases.size(); sp.next++)
+        VS_TRY(run_phase(s, t, sp.map_a, sp.map_b, gemm_pair_enabled() ? &sp.map_bh : nullptr, sp.g, sp.m, sp.merge_smem,
+                         sp.phases[sp.next], &sp.n_ev));
+    if (bounds && !ran_more) {
         prune_run_kernel<<<(unsigned)sp.nq, 256, (size_t)sp.run_cap * sizeof(uint2), s->stream>>>(sp.run, sp.rcnt, sp.run_cap, sp.e1,
-                                                                                                s->row_l2, bound_in);
+                                                                                                s->row_l2, bounds);
         VS_CUDA(cudaGetLastError());
         s->stats.kernel_launches++;
     }
@@ -1099,10 +1171,19 @@ int tensor_topk_finish(vsgpu_store *s, const float *bound_in) {
     return VSGPU_OK;
 }
 
+size_t tensor_topk_rounds(size_t rows, size_t k, unsigned world) {
+    return topk_rounds(rows, k, k <= K_SMALL_MAX ? CAND_CAP : CAND_CAP_BIG, BM, world);
+}
+
 } // namespace vsgpu
 
 // Host-logic test hook (no device needed): the phase schedule of the filtered GEMM for n rows and top-k. Writes up to `cap`
 // phase end rows to `edges`, returns the number of phases.
+extern "C" size_t vsgpu_debug_phases_sharded(size_t n, size_t k, unsigned world, size_t rounds, uint32_t *edges, size_t cap) {
+    const auto ph = vsgpu::make_phases(n, k, k <= vsgpu::K_SMALL_MAX ? vsgpu::CAND_CAP : vsgpu::CAND_CAP_BIG, vsgpu::BM, world, rounds);
+    for (size_t i = 0; i < ph.size() && i < cap; i++) edges[i] = ph[i].second;
+    return ph.size();
+}
 extern "C" size_t vsgpu_debug_phases(size_t n, size_t k, uint32_t *edges, size_t cap) {
     const auto ph = vsgpu::make_phases(n, k, vsgpu::CAND_CAP, vsgpu::BM);
     for (size_t i = 0; i < ph.size() && i < cap; i++) edges[i] = ph[i].second;

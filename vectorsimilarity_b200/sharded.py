@@ -27,8 +27,11 @@ def _vsgpu():
         vp, sz = C.c_void_p, C.c_size_t
         G.vsgpu_topk_device.argtypes = [vp, vp, sz, sz, sz, C.c_uint, vp, vp, vp]
         G.vsgpu_store_sync.argtypes = [vp]
-        G.vsgpu_topk_device_begin.argtypes = [vp, vp, sz, sz, sz, C.c_uint, vp, vp, vp, vp]
+        G.vsgpu_topk_device_begin.argtypes = [vp, vp, sz, sz, sz, C.c_uint, vp, vp, vp, C.c_uint, C.c_uint, vp]
+        G.vsgpu_topk_device_next.argtypes = [vp, vp]
         G.vsgpu_topk_device_finish.argtypes = [vp, vp]
+        G.vsgpu_topk_rounds.restype = sz
+        G.vsgpu_topk_rounds.argtypes = [sz, sz, C.c_uint]
         G.vsgpu_store_stream.restype = vp
         G.vsgpu_store_stream.argtypes = [vp]
         G.vsgpu_store_set_stream.argtypes = [vp, vp]
@@ -89,6 +92,9 @@ class ShardedFlatIndex:
         self._last = None
         self.redone_steps = 0
         self.share_bounds = os.environ.get("VSGPU_SHARE_BOUNDS", "1") != "0"   # A/B switch
+        self.n_total = n_total          # rows over all shards; agreed on lazily after the rows changed (see _total)
+        self._total_stale = n_total is None
+        self.exchanges = 0
 
     def close(self):
         # torch's caching allocator ties a block to the stream it was allocated on: every buffer of this index is
@@ -103,13 +109,28 @@ class ShardedFlatIndex:
 
     # ---- ingest: the caller hands each rank its own rows (already sharded) ----
     def add_vectors(self, blobs, labels):
+        self._total_stale = True
         return self.local.add_vectors(blobs, labels=labels)
 
     def add_device_rows(self, tensor, first_label):
         assert tensor.is_cuda and tensor.is_contiguous()
         torch.cuda.current_stream(self.device).synchronize()   # the rows were produced on the caller's stream
+        self._total_stale = True
         return self.local.add_device_rows(tensor.data_ptr(), tensor.stride(0) * tensor.element_size(), tensor.shape[0],
                                           first_label)
+
+    def _total(self):
+        """Rows over all shards. Every rank calls every method (SPMD), so all ranks find the count stale at the same call
+        and join the one all-reduce that refreshes it (a host wait, once after ingestion — not on the query path)."""
+        if self._total_stale:
+            if self.world > 1:
+                t = torch.tensor([self.local.index_size()], dtype=torch.int64, device=self.device)
+                dist.all_reduce(t, group=self.group)
+                self.n_total = int(t.item())
+            else:
+                self.n_total = self.local.index_size()
+            self._total_stale = False
+        return self.n_total
 
     def store(self):
         if self._store is None:
@@ -145,19 +166,28 @@ class ShardedFlatIndex:
         sdt = torch.float64 if self.f64 else torch.float32
         scores = self._buf("ls", (nq, k), sdt)
         labels = self._buf("ll", (nq, k), torch.int64)
-        if self.world > 1 and not self.f64 and self.share_bounds:
-            # two-step: coarse phases, then ONE 4-byte-per-query all-reduce(max) of the shards' admission bounds — every
-            # shard's bound is a lower bound of the global k-th score — so that each shard re-ranks its share of one band
-            # instead of a whole band of its own (the re-rank did not shrink with the shard: SURVEY §8e, VERDICT r1 #3c)
-            bound = self._buf("bd", (nq,), torch.float32)
+        if self.world > 1 and not self.f64 and self.share_bounds and self._total() >= self.world:
+            # phased: every shard runs the same number of coarse phases and after each ONE small all-reduce(max) makes the
+            # shards' bounds global — the ceil(k / world)-th best of every shard bounds the k-th best overall — so the next
+            # phase admits, and the re-rank scores, a shard's share of ONE candidate band instead of a band of its own (the
+            # per-shard phases and the re-rank did not shrink with the shard: SURVEY §8e). The phase count
+            # comes from n_total / world, which all ranks know, not from the local row count.
+            rounds = int(G.vsgpu_topk_rounds((self.n_total + self.world - 1) // self.world, k, self.world))
+            bounds = self._buf("bd", (2 * nq,), torch.float32)
             rc = G.vsgpu_topk_device_begin(self.store(), q_dev.data_ptr(), nq, q_dev.stride(0) * q_dev.element_size(), k, flags,
-                                           labels.data_ptr(), scores.data_ptr(), None, bound.data_ptr())
+                                           labels.data_ptr(), scores.data_ptr(), None, self.world, rounds, bounds.data_ptr())
             if rc != 0:
                 raise RuntimeError("vsgpu_topk_device_begin: " + G.vsgpu_last_error().decode())
-            dist.all_reduce(bound, op=dist.ReduceOp.MAX, group=self.group)
-            rc = G.vsgpu_topk_device_finish(self.store(), bound.data_ptr())
+            for _ in range(rounds - 1):
+                dist.all_reduce(bounds, op=dist.ReduceOp.MAX, group=self.group)
+                rc = G.vsgpu_topk_device_next(self.store(), bounds.data_ptr())
+                if rc != 0:
+                    raise RuntimeError("vsgpu_topk_device_next: " + G.vsgpu_last_error().decode())
+            dist.all_reduce(bounds, op=dist.ReduceOp.MAX, group=self.group)
+            rc = G.vsgpu_topk_device_finish(self.store(), bounds.data_ptr())
             if rc != 0:
                 raise RuntimeError("vsgpu_topk_device_finish: " + G.vsgpu_last_error().decode())
+            self.exchanges = rounds
             return scores, labels
         rc = G.vsgpu_topk_device(self.store(), q_dev.data_ptr(), nq, q_dev.stride(0) * q_dev.element_size(), k, flags,
                                  labels.data_ptr(), scores.data_ptr(), None)
