@@ -48,7 +48,12 @@ def main():
         P.add_many(X)
         # processed queries (cosine: normalised like the index does)
         Qp = Q.copy()
-        if metric == 2:
+        if metric == 2 and vtype >= 4:   # int8 / uint8 cosine blobs carry their norm after the dim bytes
+            Qp = np.zeros((nq, dim + 4), dtype=Q.dtype)
+            Qp[:, :dim] = Q
+            for q in Qp:
+                port.normalize(vtype, dim, q)
+        elif metric == 2:
             Qp = np.stack([port.normalize(vtype, dim, q.copy()) for q in Qp])
         labels, scores = S.knn_batch(Qp, k, flags=mode)
         for i in range(nq):
