@@ -109,6 +109,68 @@ __device__ __forceinline__ void warp_append_hits(uint32_t hit, uint32_t q0, uint
         }
     }
 }
+// Sparse hits (the long late phases: a hit in 1-10 % of the chunks, almost always a single one): the ballot-transposed append
+// above stalls the warp for the full round trip of its returning atomic — measured at ~2 chunk times per call, which made a
+// phase with hits in 9 % of its chunks 20 % slower than one without (profiles/r2_launches_i8_shard.md). Here a lane with a hit
+// reserves its slot with its own atomic and only RECORDS (slot, query, row, value); the store that needs the slot happens
+// when the record is recycled two sparse appends later (or at the end of the kernel), so the round trip overlaps the following
+// chunks' loads and compares. Chunks where some lane has more than one hit take the dense path.
+struct DeferredHits {
+    uint32_t slot0, q0, row0, val0, slot1, q1, row1, val1;
+    uint32_t which; // warp-uniform: the record the next sparse append recycles
+    __device__ __forceinline__ void init() {
+        q0 = q1 = 0xffffffffu;
+        slot0 = slot1 = row0 = row1 = val0 = val1 = 0;
+        which = 0;
+    }
+    __device__ __forceinline__ void flush(uint2 *__restrict__ cand, uint32_t CAP) {
+        if (q0 != 0xffffffffu && slot0 < CAP) cand[(size_t)q0 * CAP + slot0] = make_uint2(row0, val0);
+        if (q1 != 0xffffffffu && slot1 < CAP) cand[(size_t)q1 * CAP + slot1] = make_uint2(row1, val1);
+        q0 = q1 = 0xffffffffu;
+    }
+};
+__device__ __forceinline__ void warp_append_hits_deferred(uint32_t hit, uint32_t qbase, uint32_t row, const uint32_t (&r)[32],
+                                                          uint32_t *__restrict__ cnt, uint2 *__restrict__ cand, int lane, uint32_t CAP,
+                                                          DeferredHits &d) {
+    const uint32_t any = __reduce_or_sync(0xffffffffu, hit);
+    if (!any) return;
+    if (__any_sync(0xffffffffu, (hit & (hit - 1u)) != 0u)) { // some row hit several queries of this chunk: dense path
+        warp_append_hits(hit, qbase, row, r, cnt, cand, lane, CAP);
+        return;
+    }
+    // the value of the single hit column, without indexing the register array dynamically
+    uint32_t v16[16], v8[8], v4[4], v2[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v16[i] = (hit & 0xaaaaaaaau) ? r[2 * i + 1] : r[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v8[i] = (hit & 0xccccccccu) ? v16[2 * i + 1] : v16[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) v4[i] = (hit & 0xf0f0f0f0u) ? v8[2 * i + 1] : v8[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) v2[i] = (hit & 0xff00ff00u) ? v4[2 * i + 1] : v4[2 * i];
+    const uint32_t val = (hit & 0xffff0000u) ? v2[1] : v2[0];
+    const uint32_t q = qbase + (uint32_t)(__ffs((int)hit) - 1);
+    if (d.which == 0) { // warp-uniform
+        if (d.q0 != 0xffffffffu && d.slot0 < CAP) cand[(size_t)d.q0 * CAP + d.slot0] = make_uint2(d.row0, d.val0);
+        d.q0 = 0xffffffffu;
+        if (hit) {
+            d.slot0 = atomicAdd(&cnt[q], 1u);
+            d.q0 = q;
+            d.row0 = row;
+            d.val0 = val;
+        }
+    } else {
+        if (d.q1 != 0xffffffffu && d.slot1 < CAP) cand[(size_t)d.q1 * CAP + d.slot1] = make_uint2(d.row1, d.val1);
+        d.q1 = 0xffffffffu;
+        if (hit) {
+            d.slot1 = atomicAdd(&cnt[q], 1u);
+            d.q1 = q;
+            d.row1 = row;
+            d.val1 = val;
+        }
+    }
+    d.which ^= 1u;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // The same wait, naming the registers a preceding tcgen05.ld fills as read-write operands: the compiler may otherwise move
 // plain reads of those registers above the wait (nothing else ties them to it) — seen as stale accumulators once two

@@ -174,6 +174,8 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         };
         float nr_n, sub_n;
         row_terms(blockIdx.x, nr_n, sub_n);
+        DeferredHits dh;
+        dh.init();
         for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
             const uint32_t mt = item / g.n_qtiles, nt = item % g.n_qtiles;
             const uint32_t row = g.row0 + mt * BM + quad * 32 + (uint32_t)lane;
@@ -216,13 +218,14 @@ coarse_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     lds_f32x32(smem_u32(&sm.e1[nt * BN + col]), e1v);
 #pragma unroll
                     for (int j = 0; j < 32; j++) hit |= (__fmaf_rn(e1v[j], nr, __uint_as_float(r[j])) >= thr[j] ? 1u : 0u) << j;
-                    warp_append_hits(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane, g.cand_cap);
+                    warp_append_hits_deferred(row_ok ? hit : 0u, nt * BN + col, row, r, g.cnt, g.cand, lane, g.cand_cap, dh);
                 }
             }
             tc_fence_before();
             mbar_arrive(&sm.tempty[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        dh.flush(g.cand, g.cand_cap);
     }
     tc_fence_before();
     __syncthreads();
