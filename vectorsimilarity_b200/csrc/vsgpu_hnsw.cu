@@ -2598,6 +2598,7 @@ vsgpu_hnsw *vsgpu_hnsw_create(vsgpu_store *s, size_t M, size_t ef_construction) 
         const int st[2] = {-1, -1};
         ok = cudaMemcpy(g->state, st, sizeof(st), cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMemset(g->tag_counter, 0, sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaDeviceSynchronize() == cudaSuccess; // default-stream work: the store's stream does not wait for it
     }
     if (!ok) {
         set_error("vsgpu_hnsw_create: device allocation failed");

@@ -1221,6 +1221,9 @@ extern "C" int vsgpu_debug_coarse(vsgpu_store *s, const void *queries, size_t nq
     VS_CUDA(cudaMalloc(&athr, nq * 4));
     VS_CUDA(cudaMalloc(&dump, nrows * nq * 4));
     VS_CUDA(cudaMemcpy2D(d_q, s->row_bytes, queries, qstride, s->row_bytes, nq, cudaMemcpyHostToDevice));
+    // a copy from pageable memory may return before its DMA has landed, and the store's stream does not wait for the
+    // default stream
+    VS_CUDA(cudaDeviceSynchronize());
     VS_CUDA(cudaMemsetAsync(qb, 0, nq_pad * qb_stride * 2, s->stream));
     VS_CUDA(cudaMemsetAsync(dump, 0, nrows * nq * 4, s->stream));
     prep_coarse_queries_kernel<<<64, 256, 0, s->stream>>>(d_q, s->row_bytes, f32 ? 1 : (s->type == VSGPU_FLOAT16 ? 2 : 0), s->dim, nq, qb, qb_stride, 0.f,

@@ -847,6 +847,9 @@ extern "C" int vsgpu_debug_i8(vsgpu_store *s, const void *queries, size_t nq, si
     VS_CUDA(cudaMalloc(&dump, nrows * nq * 4));
     VS_CUDA(cudaMemset(d_q, 0, nq * s->row_stride));
     VS_CUDA(cudaMemcpy2D(d_q, s->row_stride, queries, qstride, s->row_bytes, nq, cudaMemcpyHostToDevice));
+    // the clear and the copy ran on the default stream, which the store's (non-blocking) stream does not wait for — and a
+    // copy from pageable memory may return before its DMA has landed
+    VS_CUDA(cudaDeviceSynchronize());
     VS_CUDA(cudaMemsetAsync(dump, 0, nrows * nq * 4, s->stream));
     CUtensorMap map_a, map_b, map_bh;
     VS_TRY(make_map_u8(&map_a, s->rows, s->count, s->dim, s->row_stride, BM));
