@@ -44,6 +44,7 @@ struct I8Smem {
     uint8_t a[STAGES][A_BYTES];
     uint8_t b[STAGES][B_BYTES];
     float cq[MAX_NQ];
+    float cqmin[MAX_NQ / 32]; // the smallest admission constant of each 32-query chunk: the quick reject below
     uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
 };
@@ -87,6 +88,13 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     for (uint32_t i = threadIdx.x; i < g.n_qtiles * BN; i += blockDim.x)
         sm.cq[i] = (i < g.nq && g.cq) ? g.cq[i] : __int_as_float(0x7f800000);
+    __syncthreads();
+    for (uint32_t grp = (uint32_t)warp; grp < g.n_qtiles * BN / 32; grp += blockDim.x / 32) {
+        float m = sm.cq[grp * 32 + (uint32_t)lane];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) sm.cqmin[grp] = m;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -164,6 +172,18 @@ i8_gemm_filter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 uint32_t r[32];
                 tc_ld32(tmem + ((quad * 32) << 16) + as * BN + col, r);
                 tc_wait_ld(r);
+                if (!g.dump && g.mma_only == 0) {
+                    // Quick reject: a hit needs float(dot_j) >= fma(c_j, rm, ra2) for some j, so the row's largest dot must
+                    // reach the bound built from the chunk's smallest c_j (rm >= 0, fma and int -> float are monotone).
+                    // 11 integer max3 + one convert / fma / compare instead of four instructions per accumulator; in the
+                    // long late phases practically every chunk stops here — the compare loop was the busiest pipe of
+                    // this kernel (ALU 62 %, tensor 54 %: profiles/r2_i8_gemm_final_ncu.md).
+                    int m = (int)r[0];
+#pragma unroll
+                    for (int j = 1; j < 32; j++) m = max(m, (int)r[j]);
+                    const float tmin = fmaf(sm.cqmin[(nt * BN + col) >> 5], rm, ra2);
+                    if (!__any_sync(0xffffffffu, row_ok && __int2float_rn(m) >= tmin)) continue;
+                }
                 float cq[32];
                 lds_f32x32(smem_u32(&sm.cq[nt * BN + col]), cq);
                 if (g.dump) {
