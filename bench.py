@@ -326,9 +326,8 @@ class FlatRun:
                                                      labels_out.ctypes.data, scores_out.ctypes.data)
                 assert rc == 0, L.VecSimGPU_LastError()
             else:
-                l, s = self.index.knn_batch(self.q_host, k, mode)   # pinned host queries in, host labels / scores out
-                labels_out[:] = l.view(np.uint64)
-                scores_out[:] = s
+                # pinned host queries in, host labels / scores out
+                self.index.knn_batch(self.q_host, k, mode, out_labels=labels_out, out_scores=scores_out)
 
         for _ in range(max(1, min(warmup, 2))):
             step()

@@ -331,8 +331,15 @@ int FlatIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryPa
     }
     if (flush() != 0) return -1;
     const size_t n = count_;
-    std::vector<uint8_t> qbuf(nq * stored_size_);
-    for (size_t q = 0; q < nq; q++) preprocess((const uint8_t *)queries + q * data_size_, qbuf.data() + q * stored_size_);
+    // L2 / IP queries need no preprocessing: hand the caller's buffer to the device layer as it is (it stages it in pinned
+    // memory once) instead of copying 3 MB of batch through a second host buffer first
+    const bool as_is = metric_ != VecSimMetric_Cosine && stored_size_ == data_size_;
+    std::vector<uint8_t> qbuf;
+    if (!as_is) {
+        qbuf.resize(nq * stored_size_);
+        for (size_t q = 0; q < nq; q++) preprocess((const uint8_t *)queries + q * data_size_, qbuf.data() + q * stored_size_);
+    }
+    const void *q_src = as_is ? queries : (const void *)qbuf.data();
     const bool fast = labels_monotone_;
     size_t k_sel = std::min(k, n);
     if (!fast) k_sel = (k > n / 2) ? n : std::min(2 * k, n);
@@ -352,7 +359,7 @@ int FlatIndex::topKBatch(const void *queries, size_t nq, size_t k, VecSimQueryPa
         sc_p = sc.data();
     }
     if (!fast) ids.resize(nq * k_sel);
-    const int rc = vsgpu_topk(store_, qbuf.data(), nq, stored_size_, k_sel, (unsigned)globals().topk_mode, lab_p, sc_p,
+    const int rc = vsgpu_topk(store_, q_src, nq, stored_size_, k_sel, (unsigned)globals().topk_mode, lab_p, sc_p,
                               fast ? nullptr : ids.data(), nullptr);
     if (rc != VSGPU_OK) return -1;
     if (timed_out(tctx)) {

@@ -273,10 +273,11 @@ class ShardedFlatIndex:
         _, k, nq = self._last
         return self._buf("os", (nq, k), torch.float64 if self.f64 else torch.float32), self._buf("ol", (nq, k), torch.int64)
 
-    def knn_batch(self, queries, k, flags=0):
+    def knn_batch(self, queries, k, flags=0, out_labels=None, out_scores=None):
         """Host queries (processed blobs, numpy [nq, blob] or a pinned uint8 tensor) -> host (labels int64 [nq,k], scores
         float64 [nq,k]). One H2D copy, the sharded search, one D2H copy per output into pinned buffers, one sync at the
-        end; everything in between is ordered by the store's stream."""
+        end; everything in between is ordered by the store's stream. out_labels (int64 / uint64 [nq,k]) and out_scores
+        (float64 [nq,k]), when given, receive the reply in one pass each instead of fresh arrays."""
         if isinstance(queries, torch.Tensor):
             q = queries
         else:
@@ -297,6 +298,10 @@ class ShardedFlatIndex:
             pin_s.copy_(out_s, non_blocking=True)
             pin_l.copy_(out_l, non_blocking=True)
         st.synchronize()
+        if out_labels is not None and out_scores is not None:
+            np.copyto(out_labels.view(np.int64), pin_l.numpy())
+            np.copyto(out_scores, pin_s.numpy())                      # widens fp32 -> fp64 on the way
+            return out_labels, out_scores
         return pin_l.numpy().copy(), pin_s.numpy().astype(np.float64)  # the pinned buffers are reused by the next call
 
     # ---- range query and batch iterator across shards: variable-length per-shard replies ----
