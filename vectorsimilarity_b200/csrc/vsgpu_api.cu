@@ -572,6 +572,7 @@ int vsgpu_topk_device_begin(vsgpu_store *s, const void *queries, size_t nq, size
     size_t qs = 0;
     const float *qn = nullptr;
     VS_TRY(stage_queries_device(s, queries, nq, qstride, &q, &qs, &qn));
+    tensor_topk_reset(s);
     const PhasedCall ph{world, rounds, bounds};
     VS_TRY(topk_core(s, q, nq, qs, qn, k, k, flags, out_ids, out_scores, out_labels, &ph));
     VS_CUDA(cudaEventRecord(s->ev1, s->stream));

@@ -207,6 +207,7 @@ struct PhasedCall {
 };
 int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq, size_t q_stride, const float *q_norms, size_t k,
                 uint32_t *out_ids, void *out_scores, uint64_t *out_labels, const PhasedCall *ph = nullptr);
+void tensor_topk_reset(vsgpu_store *s);
 int tensor_topk_next(vsgpu_store *s, float *bounds);
 int tensor_topk_finish(vsgpu_store *s, const float *bounds);
 size_t tensor_topk_rounds(size_t rows, size_t k, unsigned world);

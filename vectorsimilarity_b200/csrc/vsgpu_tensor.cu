@@ -1129,6 +1129,12 @@ int tensor_topk(vsgpu_store *s, const void *q_dev, size_t nq_all, size_t q_strid
     return VSGPU_OK;
 }
 
+// a phased call that was begun and never finished must not leak its phases into the next one
+void tensor_topk_reset(vsgpu_store *s) {
+    if (s->type == VSGPU_INT8 || s->type == VSGPU_UINT8) return;
+    if (auto *t = (TensorState *)s->tmap_cache) t->split.armed = false;
+}
+
 // phased call, after the caller reduced `bounds` over the shards: tighten this shard's admission bounds, run its next phase
 // and write its new bounds. A no-op once the phases are done (or when _begin did all the work on another path).
 int tensor_topk_next(vsgpu_store *s, float *bounds) {
