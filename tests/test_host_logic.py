@@ -195,6 +195,45 @@ def test_header_is_c_and_a_c_consumer_links(capi, tmp_path):
     assert lines[1].startswith("index ") and ("(ok)" in lines[1] or "tiered index:" in lines[1])
 
 
+def test_shard_bound_exchange_is_a_lower_bound_of_the_global_kth():
+    """The arithmetic behind vsgpu_topk_device_begin / _next / _finish, on a numpy model: every row has an
+    exact score inside [lo, hi]; a shard reports the k-th and the ceil(k / W)-th largest `lo` of the rows it has seen (or -inf);
+    B = max(max_s kth_s, min_s mth_s) must never exceed the k-th largest exact score over all shards, so every row of the global
+    top-k — ties at the k-th score included — passes the admission test hi >= B. Also with shards of very different sizes,
+    shards that have seen fewer than m rows, heavy ties and zero-width intervals."""
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        W = int(rng.integers(2, 9))
+        k = int(rng.integers(1, 40))
+        m = -(-k // W)
+        sizes = rng.integers(0, 60, size=W)
+        if trial % 3 == 0:
+            sizes[rng.integers(0, W)] = 200                       # one shard holds most of the rows
+        if sizes.sum() < k:
+            sizes[0] += k
+        exact, lo, hi = [], [], []
+        for n in sizes:
+            e = rng.normal(size=n)
+            if trial % 4 == 1:
+                e = np.round(e * 2) / 2                            # many exact ties
+            w = rng.uniform(0, 0.3, size=n) if trial % 5 else np.zeros(n)
+            shift = rng.uniform(-1, 1, size=n)
+            exact.append(e)
+            lo.append(e - w * (1 + shift) / 2 - 0.0)
+            hi.append(e + w * (1 - shift) / 2 + 0.0)
+        def nth_largest(a, r):
+            return -np.inf if len(a) < r else np.sort(a)[::-1][r - 1]
+        kth = max(nth_largest(l, k) for l in lo)
+        mth = min(nth_largest(l, m) for l in lo)
+        B = max(kth, mth)
+        all_exact = np.concatenate(exact)
+        true_kth = np.sort(all_exact)[::-1][k - 1]
+        assert B <= true_kth + 1e-12, (trial, B, true_kth)
+        all_hi = np.concatenate(hi)
+        in_topk = all_exact >= true_kth                             # the top-k and everything tied with its last member
+        assert np.all(all_hi[in_topk] >= B)
+
+
 def test_phase_schedule_of_sharded_phased_calls(capi):
     """make_phases with `world` shards and a fixed number of rounds (vsgpu_topk_device_begin / _next / _finish): every shard
     runs exactly `rounds` phases whatever its own row count (trailing ones may be empty), the schedule still tiles [0, n), and
